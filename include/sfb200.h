@@ -1,0 +1,111 @@
+/* sfb200.h -- C ABI of libsfb200.so: the B200 (sm_100a) kernels behind the Self-Forcing rollout
+ * hot path.  Plain pointers, sizes and a CUDA stream handle; no torch types.
+ *
+ * The reference (alazarteka/Self-Forcing) is pure Python: its "FFI" for this path is the set of
+ * torch / flash_attn calls listed below.  Each entry point names the reference call site(s)
+ * (file:line under the reference checkout) whose device work it replaces.  INTEGRATION.md shows
+ * the ctypes binding a maintainer would add on the reference side.
+ *
+ * Conventions
+ *   - every tensor is bf16 (2-byte) unless stated; "ld*" / "*_stride" are in ELEMENTS;
+ *   - every pointer is a device pointer that the caller owns (no allocation inside, no state
+ *     kept between calls); rows must be 16-byte aligned (strides multiples of 8 elements);
+ *   - `stream` is a cudaStream_t (CUstream) cast to void*; work is enqueued asynchronously;
+ *   - return value 0 = success, non-zero = error with text in sfb_last_error() (thread-local).
+ */
+#ifndef SFB200_H_
+#define SFB200_H_
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SFB_ABI_VERSION 1
+
+const char* sfb_last_error(void);
+int sfb_abi_version(void);
+
+/* Epilogues of sfb_gemm_bf16 (the elementwise ops the reference runs after each nn.Linear). */
+#define SFB_EPI_BIAS 0      /* y = bf16(acc + bias) */
+#define SFB_EPI_GELU 1      /* y = bf16(gelu_tanh(bf16(acc + bias)))        causal_model.py:278        */
+#define SFB_EPI_RESIDUAL 2  /* y = bf16(res + bf16(acc + bias))             causal_model.py:324        */
+#define SFB_EPI_GATE_RES 3  /* y = bf16(res + bf16(bf16(acc+bias) * gate))  causal_model.py:320,331-332 */
+
+/* Y[M,N] = epilogue(X[M,K] . W[N,K]^T + bias): tcgen05 GEMM, TMA-fed, fp32 accumulate in TMEM.
+ * Replaces nn.Linear (cuBLAS) at wan/modules/causal_model.py:112-114 (q,k,v -- one call with the
+ * three weights stacked and up to three output segments of `seg_cols` columns each), :240 (o),
+ * :277-279 (ffn), :351/:366 (head), :458-462 (patch/text embed); wan/modules/model.py:172,177-178,193.
+ * `gate` row for output row r is gate + (r / rows_per_gate) * gate_stride (per-frame adaLN gate).
+ * out may alias residual.  block_n: 0 = choose, else 64/128/256. */
+int sfb_gemm_bf16(const void* x, long long ldx, const void* w, long long ldw, const void* bias,
+                  int M, int N, int K, int epilogue,
+                  void* out0, long long ldo0, void* out1, long long ldo1, void* out2, long long ldo2, int seg_cols,
+                  const void* residual, long long ldr,
+                  const void* gate, long long gate_stride, int rows_per_gate,
+                  int block_n, void* stream);
+
+/* softmax(q k^T * scale) v without mask, head_dim 128, K/V read in place from a [B,S,H,128] cache
+ * window.  Replaces wan/modules/attention.py:32-202 (flash_attn_varlen_func at :136-150) as called
+ * from causal_model.py:230-234 (self-attention over the KV window) and model.py:189 (cross-attn). */
+int sfb_attention_fwd(const void* q, long long q_row_stride, long long q_batch_stride,
+                      const void* k, const void* v, long long kv_row_stride, long long kv_batch_stride,
+                      void* out, long long out_row_stride, long long out_batch_stride,
+                      int B, int Lq, int Skv, int H, int head_dim, float softmax_scale, void* stream);
+
+/* out[l][r][g][:] = bf16(mod[l][g][:] + e[r * e_row_stride + g * e_group_stride + :])
+ * adaLN tables for all layers at once: causal_model.py:310 (G=6) and :365 (head, G=2, broadcast e). */
+int sfb_modulation_table(const void* mod, const void* e, void* out, int NL, int R, int G, int C,
+                         long long e_row_stride, long long e_group_stride, void* stream);
+
+/* y = bf16(bf16(LN(x)) * bf16(1 + scale[g]) + shift[g]), g = row / rows_per_mod; LN eps, no affine.
+ * causal_model.py:315, :327-328, :366 with WanLayerNorm (model.py:89-99). */
+int sfb_ln_modulate(const void* x, long long ldx, void* y, long long ldy, int rows, int C, float eps,
+                    const void* shift, const void* scale, long long mod_stride, int rows_per_mod, void* stream);
+
+/* y = bf16(LN(x) * weight + bias)   (norm3, causal_model.py:268-270,324). */
+int sfb_ln_affine(const void* x, long long ldx, void* y, long long ldy, int rows, int C, float eps,
+                  const void* weight, const void* bias, void* stream);
+
+/* y = bf16(bf16(x * rsqrt(mean(x^2) + eps)) * weight) over the full width C (WanRMSNorm, model.py:70-86). */
+int sfb_rmsnorm(const void* x, long long ldx, void* y, long long ldy, int rows, int C, float eps,
+                const void* weight, void* stream);
+
+/* Fused QK-RMSNorm + 3-D RoPE + KV-cache append (model.py:70-86, causal_model.py:28-56,196-200,
+ * 222-229).  q_in/k_in/v_in: [B*L, C] projections.  RoPE tables cos/sin: fp32 [tab_rows, head_dim/2]
+ * (columns = frame | height | width ladders).  q -> q_out[b][n], k/v -> k_out/v_out[b][n] where the
+ * caller has already offset k_out/v_out to the cache write slot.  v_in == NULL skips the V copy. */
+int sfb_qk_norm_rope(const void* q_in, long long ldq, const void* k_in, long long ldk, const void* v_in, long long ldv,
+                     const void* wq, const void* wk, float eps, const float* cos_tab, const float* sin_tab,
+                     int tab_rows, int B, int L, int C, int head_dim, int F, int Hh, int Ww, int start_frame,
+                     void* q_out, long long q_out_row, long long q_out_batch,
+                     void* k_out, void* v_out, long long kv_out_row, long long kv_out_batch, void* stream);
+
+/* im2col of Conv3d(k = s = (1,2,2)) (causal_model.py:775-778): x[b][c][f][y][x] with element strides
+ * -> out[(b,f,y/2,x/2)][c*4 + (y%2)*2 + x%2]. */
+int sfb_patchify(const void* x, long long sb, long long sc, long long sf, long long sy, long long sx,
+                 void* out, int B, int Cin, int F, int H, int W, void* stream);
+
+/* sinusoidal_embedding_1d (model.py:15-25) in f64 -> bf16.  t_dtype: 0 f32, 1 i64, 2 f64, 3 bf16. */
+int sfb_sinusoid(const void* t, int t_dtype, void* out, int n, int freq_dim, void* stream);
+
+/* Few-row Linear: y = bf16(in(x) . W^T + b), in = identity | bf16(silu(.)).  The time MLPs at
+ * causal_model.py:464-467,829-832 (M = B*F rows). */
+int sfb_skinny_linear(const void* x, long long ldx, const void* w, long long ldw, const void* bias,
+                      void* y, long long ldy, int M, int N, int K, int silu_in, void* stream);
+
+/* unpatchify (causal_model.py:1081-1104) + flow -> x0 in f64 (wan_wrapper.py:204-228), sigma by
+ * nearest timestep (first argmin).  flow / x0 are written as contiguous [B,F,Cout,H,W]. */
+int sfb_head_finish(const void* head_out, long long ldh,
+                    const void* xt, long long xs_b, long long xs_f, long long xs_c, long long xs_y, long long xs_x,
+                    const void* timestep, int t_dtype, const float* timesteps, const float* sigmas, int n_tab,
+                    void* flow, void* x0, int B, int F, int Cout, int H, int W, void* stream);
+
+/* FlowMatchScheduler.add_noise (scheduler.py:159-176): out = bf16((1-sigma)*x0 + sigma*noise), fp32. */
+int sfb_add_noise(const void* x0, const void* noise, const void* timestep, int t_dtype,
+                  const float* timesteps, const float* sigmas, int n_tab, void* out, int n_frames, int per_frame,
+                  void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SFB200_H_ */

@@ -1,0 +1,66 @@
+"""ctypes binding of libsfb200.so (the C ABI declared in include/sfb200.h).
+
+There is no fallback: if the library is missing or a call fails the caller gets an exception.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+from ctypes import c_char_p, c_float, c_int, c_longlong, c_void_p
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "libsfb200.so")
+
+P, LL, I, F = c_void_p, c_longlong, c_int, c_float
+
+# name -> argtypes, mirroring include/sfb200.h one to one
+SIGNATURES = {
+    "sfb_gemm_bf16": [P, LL, P, LL, P, I, I, I, I, P, LL, P, LL, P, LL, I, P, LL, P, LL, I, I, P],
+    "sfb_attention_fwd": [P, LL, LL, P, P, LL, LL, P, LL, LL, I, I, I, I, I, F, P],
+    "sfb_modulation_table": [P, P, P, I, I, I, I, LL, LL, P],
+    "sfb_ln_modulate": [P, LL, P, LL, I, I, F, P, P, LL, I, P],
+    "sfb_ln_affine": [P, LL, P, LL, I, I, F, P, P, P],
+    "sfb_rmsnorm": [P, LL, P, LL, I, I, F, P, P],
+    "sfb_qk_norm_rope": [P, LL, P, LL, P, LL, P, P, F, P, P, I, I, I, I, I, I, I, I, I, P, LL, LL, P, P, LL, LL, P],
+    "sfb_patchify": [P, LL, LL, LL, LL, LL, P, I, I, I, I, I, P],
+    "sfb_sinusoid": [P, I, P, I, I, P],
+    "sfb_skinny_linear": [P, LL, P, LL, P, P, LL, I, I, I, I, P],
+    "sfb_head_finish": [P, LL, P, LL, LL, LL, LL, LL, P, I, P, P, I, P, P, I, I, I, I, I, P],
+    "sfb_add_noise": [P, P, P, I, P, P, I, P, I, I, P],
+}
+
+
+class SfbError(RuntimeError):
+    pass
+
+
+_lib = None
+
+
+def load(path: str | None = None) -> ctypes.CDLL:
+    """Load the shared library (once) and attach the prototypes.  Raises if it is not built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    path = path or os.environ.get("SFB200_LIB", LIB_PATH)
+    if not os.path.exists(path):
+        raise SfbError(
+            f"{path} not found: build it with `python -m self_forcing_b200.build` "
+            "(there is no CPU / PyTorch fallback for the B200 kernels)")
+    lib = ctypes.CDLL(path)
+    lib.sfb_last_error.restype = c_char_p
+    lib.sfb_last_error.argtypes = []
+    lib.sfb_abi_version.restype = c_int
+    lib.sfb_abi_version.argtypes = []
+    for name, argtypes in SIGNATURES.items():
+        fn = getattr(lib, name)
+        fn.argtypes = argtypes
+        fn.restype = c_int
+    _lib = lib
+    return lib
+
+
+def check(status: int, what: str) -> None:
+    if status != 0:
+        msg = load().sfb_last_error().decode("utf-8", "replace")
+        raise SfbError(f"{what} failed (status {status}): {msg}")

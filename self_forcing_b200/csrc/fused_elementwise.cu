@@ -1,0 +1,543 @@
+// HBM-bound fused kernels of the rollout hot path (one warp per token row, 16-byte vector
+// loads/stores, warp-shuffle reductions, fp32 math with the reference's bf16 rounding points).
+//
+//   sfb_modulation_table   e = modulation + e0                  causal_model.py:310, :365
+//   sfb_ln_modulate        LN(x) * (1 + scale) + shift          causal_model.py:315, :327-328, :366
+//   sfb_ln_affine          LN(x) * w + b  (norm3)               causal_model.py:324 / model.py:89-99
+//   sfb_qk_norm_rope       RMSNorm(q|k) -> 3-D RoPE -> q buffer / KV-cache slot (+ V copy)
+//                                                               model.py:70-86, causal_model.py:28-56,222-229
+//   sfb_rmsnorm            RMSNorm (cross-attention q / context k)   model.py:172,177
+//   sfb_patchify           Conv3d(k=s=(1,2,2)) im2col gather    causal_model.py:775-778
+//   sfb_sinusoid           timestep sinusoid table (f64)        model.py:15-25
+//   sfb_skinny_linear      few-row Linear (+SiLU) for the time MLPs   causal_model.py:464-467
+//   sfb_head_finish        unpatchify + flow -> x0 (f64)        causal_model.py:1081-1104, wan_wrapper.py:204-228
+//   sfb_add_noise          (1 - sigma) x0 + sigma noise         scheduler.py:159-176
+#include <math.h>
+
+#include <type_traits>
+
+#include "common.cuh"
+
+namespace sfb {
+
+__device__ __forceinline__ uint4 ldg16(const void* p) { return __ldg(reinterpret_cast<const uint4*>(p)); }
+__device__ __forceinline__ void unpack8(const uint4& q, float (&f)[8]) {
+  f[0] = bf_lo(q.x); f[1] = bf_hi(q.x); f[2] = bf_lo(q.y); f[3] = bf_hi(q.y);
+  f[4] = bf_lo(q.z); f[5] = bf_hi(q.z); f[6] = bf_lo(q.w); f[7] = bf_hi(q.w);
+}
+__device__ __forceinline__ uint4 pack8(const float (&f)[8]) {
+  uint4 q;
+  q.x = pack_bf16(f[0], f[1]); q.y = pack_bf16(f[2], f[3]);
+  q.z = pack_bf16(f[4], f[5]); q.w = pack_bf16(f[6], f[7]);
+  return q;
+}
+
+constexpr int ROW_WARPS = 8;   // warps (= rows) per block for the row kernels
+
+// ------------------------------------------------------------------------------------
+// modulation table: out[l][r][g][c] = bf16(mod[l][g][c] + e[r][g * e_group_stride + c])
+// ------------------------------------------------------------------------------------
+__global__ void modulation_table_kernel(const __nv_bfloat16* __restrict__ mod, const __nv_bfloat16* __restrict__ e,
+                                        __nv_bfloat16* __restrict__ out, int NL, int R, int G, int C,
+                                        long long e_row_stride, long long e_group_stride) {
+  const long long total = (long long)NL * R * G * (C / 8);
+  for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total;
+       idx += (long long)gridDim.x * blockDim.x) {
+    const int c8 = idx % (C / 8);
+    long long rest = idx / (C / 8);
+    const int g = rest % G; rest /= G;
+    const int r = rest % R;
+    const int l = rest / R;
+    float a[8], b[8];
+    unpack8(ldg16(mod + ((long long)l * G + g) * C + c8 * 8), a);
+    unpack8(ldg16(e + r * e_row_stride + g * e_group_stride + c8 * 8), b);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) a[i] += b[i];
+    *reinterpret_cast<uint4*>(out + (((long long)l * R + r) * G + g) * C + c8 * 8) = pack8(a);
+  }
+}
+
+// ------------------------------------------------------------------------------------
+// LayerNorm (no affine) + adaLN modulation, or LayerNorm with affine.  NV = C / 256.
+// ------------------------------------------------------------------------------------
+template <int NV, bool AFFINE>
+__global__ void __launch_bounds__(ROW_WARPS * 32)
+ln_kernel(const __nv_bfloat16* __restrict__ x, long long ldx, __nv_bfloat16* __restrict__ y, long long ldy, int rows,
+          float eps, const __nv_bfloat16* __restrict__ shift, const __nv_bfloat16* __restrict__ scale,
+          long long mod_stride, int rows_per_mod, const __nv_bfloat16* __restrict__ w,
+          const __nv_bfloat16* __restrict__ b) {
+  constexpr int C = NV * 256;
+  const int row = blockIdx.x * ROW_WARPS + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (row >= rows) return;
+  float v[NV][8];
+  float sum = 0.f;
+#pragma unroll
+  for (int k = 0; k < NV; ++k) {
+    unpack8(ldg16(x + row * ldx + (k * 32 + lane) * 8), v[k]);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) sum += v[k][i];
+  }
+  const float mean = warp_sum(sum) * (1.0f / C);
+  float sq = 0.f;
+#pragma unroll
+  for (int k = 0; k < NV; ++k)
+#pragma unroll
+    for (int i = 0; i < 8; ++i) { const float d = v[k][i] - mean; sq += d * d; }
+  const float rstd = rsqrtf(warp_sum(sq) * (1.0f / C) + eps);
+  const long long mrow = AFFINE ? 0 : (long long)(row / rows_per_mod) * mod_stride;
+#pragma unroll
+  for (int k = 0; k < NV; ++k) {
+    const int c0 = (k * 32 + lane) * 8;
+    float o[8];
+    if (AFFINE) {
+      float ww[8], bb[8];
+      unpack8(ldg16(w + c0), ww);
+      unpack8(ldg16(b + c0), bb);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) o[i] = (v[k][i] - mean) * rstd * ww[i] + bb[i];
+    } else {
+      float sc[8], sh[8];
+      unpack8(ldg16(scale + mrow + c0), sc);
+      unpack8(ldg16(shift + mrow + c0), sh);
+#pragma unroll
+      for (int i = 0; i < 8; ++i)
+        o[i] = bf16r(bf16r((v[k][i] - mean) * rstd) * bf16r(1.0f + sc[i])) + sh[i];
+    }
+    *reinterpret_cast<uint4*>(y + row * ldy + c0) = pack8(o);
+  }
+}
+
+// ------------------------------------------------------------------------------------
+// RMSNorm over the full channel width (+ optional 3-D RoPE), NV = C / 256
+// ------------------------------------------------------------------------------------
+struct RopeGeom {
+  int L;            // tokens per sample in this call
+  int Hh, Ww;       // token grid (height, width) of one frame
+  int start_frame;  // frame offset of the chunk (current_start // (Hh*Ww))
+  int n_f, n_h;     // complex pairs on the frame / height axes (22, 21 for d=128); rest is width
+};
+
+template <int NV>
+__device__ __forceinline__ void rms_row(const __nv_bfloat16* __restrict__ src, const __nv_bfloat16* __restrict__ w,
+                                        float eps, int lane, float (&v)[NV][8]) {
+  constexpr int C = NV * 256;
+  float sq = 0.f;
+#pragma unroll
+  for (int k = 0; k < NV; ++k) {
+    unpack8(ldg16(src + (k * 32 + lane) * 8), v[k]);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) sq += v[k][i] * v[k][i];
+  }
+  const float rstd = rsqrtf(warp_sum(sq) * (1.0f / C) + eps);
+#pragma unroll
+  for (int k = 0; k < NV; ++k) {
+    float ww[8];
+    unpack8(ldg16(w + (k * 32 + lane) * 8), ww);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) v[k][i] = bf16r(bf16r(v[k][i] * rstd) * ww[i]);
+  }
+}
+
+template <int NV>
+__global__ void __launch_bounds__(ROW_WARPS * 32)
+rmsnorm_kernel(const __nv_bfloat16* __restrict__ x, long long ldx, __nv_bfloat16* __restrict__ y, long long ldy,
+               int rows, float eps, const __nv_bfloat16* __restrict__ w) {
+  const int row = blockIdx.x * ROW_WARPS + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (row >= rows) return;
+  float v[NV][8];
+  rms_row<NV>(x + row * ldx, w, eps, lane, v);
+#pragma unroll
+  for (int k = 0; k < NV; ++k) *reinterpret_cast<uint4*>(y + row * ldy + (k * 32 + lane) * 8) = pack8(v[k]);
+}
+
+// One warp per token: q and k rows normalised + rotated; q -> q_out, k -> cache slot, v -> cache slot.
+// Rows are (sample b, token n): source row = b * L + n; destinations use their own batch strides.
+template <int NV>
+__global__ void __launch_bounds__(ROW_WARPS * 32)
+qk_norm_rope_kernel(const __nv_bfloat16* __restrict__ q_in, long long ldq, const __nv_bfloat16* __restrict__ k_in,
+                    long long ldk, const __nv_bfloat16* __restrict__ v_in, long long ldv,
+                    const __nv_bfloat16* __restrict__ wq, const __nv_bfloat16* __restrict__ wk, float eps,
+                    const float* __restrict__ cos_tab, const float* __restrict__ sin_tab, int head_dim,
+                    RopeGeom g, int rows, __nv_bfloat16* __restrict__ q_out, long long q_out_row,
+                    long long q_out_batch, __nv_bfloat16* __restrict__ k_out, __nv_bfloat16* __restrict__ v_out,
+                    long long kv_out_row, long long kv_out_batch) {
+  const int row = blockIdx.x * ROW_WARPS + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (row >= rows) return;
+  const int b = row / g.L, n = row - b * g.L;
+  const int fhw = g.Hh * g.Ww;
+  const int f = n / fhw, rem = n - f * fhw;
+  const int hh = rem / g.Ww, ww = rem - hh * g.Ww;
+  const int half = head_dim / 2;
+  const int pos_f = g.start_frame + f;
+
+  // rotation factors of this lane's 4 complex pairs per 16-byte vector (same for q and k)
+  float cs[NV][4], sn[NV][4];
+#pragma unroll
+  for (int k = 0; k < NV; ++k) {
+    const int c0 = (k * 32 + lane) * 8;
+    const int pair0 = (c0 % head_dim) / 2;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int pi = pair0 + i;
+      const int pos = pi < g.n_f ? pos_f : (pi < g.n_f + g.n_h ? hh : ww);
+      cs[k][i] = __ldg(cos_tab + pos * half + pi);
+      sn[k][i] = __ldg(sin_tab + pos * half + pi);
+    }
+  }
+  float v[NV][8];
+  rms_row<NV>(q_in + row * ldq, wq, eps, lane, v);
+  __nv_bfloat16* qo = q_out + b * q_out_batch + n * q_out_row;
+#pragma unroll
+  for (int k = 0; k < NV; ++k) {
+    float o[8];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      o[2 * i] = v[k][2 * i] * cs[k][i] - v[k][2 * i + 1] * sn[k][i];
+      o[2 * i + 1] = v[k][2 * i] * sn[k][i] + v[k][2 * i + 1] * cs[k][i];
+    }
+    *reinterpret_cast<uint4*>(qo + (k * 32 + lane) * 8) = pack8(o);
+  }
+  rms_row<NV>(k_in + row * ldk, wk, eps, lane, v);
+  __nv_bfloat16* ko = k_out + b * kv_out_batch + n * kv_out_row;
+#pragma unroll
+  for (int k = 0; k < NV; ++k) {
+    float o[8];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      o[2 * i] = v[k][2 * i] * cs[k][i] - v[k][2 * i + 1] * sn[k][i];
+      o[2 * i + 1] = v[k][2 * i] * sn[k][i] + v[k][2 * i + 1] * cs[k][i];
+    }
+    *reinterpret_cast<uint4*>(ko + (k * 32 + lane) * 8) = pack8(o);
+  }
+  if (v_in != nullptr) {
+    __nv_bfloat16* vo = v_out + b * kv_out_batch + n * kv_out_row;
+#pragma unroll
+    for (int k = 0; k < NV; ++k)
+      *reinterpret_cast<uint4*>(vo + (k * 32 + lane) * 8) = ldg16(v_in + row * ldv + (k * 32 + lane) * 8);
+  }
+}
+
+// ------------------------------------------------------------------------------------
+// patchify: x[b][c][f][y][x] (element strides) -> tokens[(b,f,hh,ww)][c*4 + ph*2 + pw]
+// ------------------------------------------------------------------------------------
+__global__ void patchify_kernel(const __nv_bfloat16* __restrict__ x, long long sb, long long sc, long long sf,
+                                long long sy, long long sx, __nv_bfloat16* __restrict__ out, int B, int Cin, int F,
+                                int Hh, int Ww) {
+  const long long total = (long long)B * F * Hh * Ww * Cin * 2;   // one thread per (token, c, ph): 2 pixels
+  const long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (idx >= total) return;
+  const int cp = idx % (Cin * 2);
+  long long tok = idx / (Cin * 2);
+  const int c = cp >> 1, ph = cp & 1;
+  const int ww = tok % Ww; long long r = tok / Ww;
+  const int hh = r % Hh; r /= Hh;
+  const int f = r % F;
+  const int b = r / F;
+  const __nv_bfloat16* src = x + b * sb + c * sc + f * sf + (2 * hh + ph) * sy + (2 * ww) * sx;
+  __nv_bfloat16* dst = out + tok * (Cin * 4) + c * 4 + ph * 2;
+  dst[0] = src[0];
+  dst[1] = src[sx];
+}
+
+// ------------------------------------------------------------------------------------
+// sinusoid: out[i][j] = cos(t_i w_j) (j < half) | sin(t_i w_{j-half}),  w_j = 10000^(-j/half), f64
+// ------------------------------------------------------------------------------------
+__device__ __forceinline__ double load_timestep(const void* t, int dtype, int i) {
+  switch (dtype) {
+    case 0: return (double)static_cast<const float*>(t)[i];
+    case 1: return (double)static_cast<const long long*>(t)[i];
+    case 2: return static_cast<const double*>(t)[i];
+    default: return (double)__bfloat162float(static_cast<const __nv_bfloat16*>(t)[i]);
+  }
+}
+
+__global__ void sinusoid_kernel(const void* __restrict__ t, int t_dtype, __nv_bfloat16* __restrict__ out, int n,
+                                int freq_dim) {
+  const int half = freq_dim / 2;
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= n * freq_dim) return;
+  const int i = idx / freq_dim, j = idx % freq_dim;
+  const int jj = j < half ? j : j - half;
+  const double w = pow(10000.0, -((double)jj / (double)half));
+  const double a = load_timestep(t, t_dtype, i) * w;
+  out[idx] = __double2bfloat16(j < half ? cos(a) : sin(a));
+}
+
+// ------------------------------------------------------------------------------------
+// skinny linear: y[m][n] = bf16(sum_k in(x[m][k]) w[n][k] + b[n]), M <= 8 per pass; in = id | silu
+// ------------------------------------------------------------------------------------
+constexpr int SKINNY_M = 8;
+__global__ void __launch_bounds__(256)
+skinny_linear_kernel(const __nv_bfloat16* __restrict__ x, long long ldx, const __nv_bfloat16* __restrict__ w,
+                     long long ldw, const __nv_bfloat16* __restrict__ bias, __nv_bfloat16* __restrict__ y,
+                     long long ldy, int M, int N, int K, int silu_in) {
+  extern __shared__ float xs[];   // [SKINNY_M][K] fp32 (already activated)
+  const int m0 = blockIdx.y * SKINNY_M;
+  const int mcount = min(SKINNY_M, M - m0);
+  for (int i = threadIdx.x; i < SKINNY_M * K; i += blockDim.x) {
+    const int m = i / K, k = i - m * K;
+    float v = 0.f;
+    if (m < mcount) {
+      v = __bfloat162float(x[(m0 + m) * ldx + k]);
+      if (silu_in) v = bf16r(v / (1.0f + __expf(-v)));
+    }
+    xs[i] = v;
+  }
+  __syncthreads();
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int n = blockIdx.x * 8 + warp;
+  if (n >= N) return;
+  float acc[SKINNY_M];
+#pragma unroll
+  for (int m = 0; m < SKINNY_M; ++m) acc[m] = 0.f;
+  for (int k0 = lane * 8; k0 < K; k0 += 256) {
+    float wv[8];
+    unpack8(ldg16(w + n * ldw + k0), wv);
+#pragma unroll
+    for (int m = 0; m < SKINNY_M; ++m) {
+      const float4 a = *reinterpret_cast<const float4*>(xs + m * K + k0);
+      const float4 c = *reinterpret_cast<const float4*>(xs + m * K + k0 + 4);
+      acc[m] += a.x * wv[0] + a.y * wv[1] + a.z * wv[2] + a.w * wv[3] + c.x * wv[4] + c.y * wv[5] + c.z * wv[6] +
+                c.w * wv[7];
+    }
+  }
+#pragma unroll
+  for (int m = 0; m < SKINNY_M; ++m) acc[m] = warp_sum(acc[m]);
+  if (lane == 0) {
+    const float bv = bias ? __bfloat162float(bias[n]) : 0.f;
+    for (int m = 0; m < mcount; ++m) y[(m0 + m) * ldy + n] = __float2bfloat16_rn(acc[m] + bv);
+  }
+}
+
+// ------------------------------------------------------------------------------------
+// nearest-timestep lookup shared by the sampler kernels (first index of the minimum, like
+// torch.argmin); returns sigma of that index.  All threads of the block must call it.
+// ------------------------------------------------------------------------------------
+template <typename T>
+__device__ T block_sigma_lookup(const float* __restrict__ timesteps, const float* __restrict__ sigmas, int n_tab,
+                                T t) {
+  __shared__ double s_best[32];
+  __shared__ int s_idx[32];
+  double best = 1e300;
+  int bi = 0x7fffffff;
+  for (int i = threadIdx.x; i < n_tab; i += blockDim.x) {
+    const T d = (T)timesteps[i] - t;
+    const double a = (double)(d < 0 ? -d : d);
+    if (a < best || (a == best && i < bi)) { best = a; bi = i; }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const double ob = __shfl_xor_sync(0xffffffffu, best, o);
+    const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+    if (ob < best || (ob == best && oi < bi)) { best = ob; bi = oi; }
+  }
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = (blockDim.x + 31) >> 5;
+  if (lane == 0) { s_best[warp] = best; s_idx[warp] = bi; }
+  __syncthreads();
+  if (warp == 0) {
+    best = lane < nw ? s_best[lane] : 1e300;
+    bi = lane < nw ? s_idx[lane] : 0x7fffffff;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      const double ob = __shfl_xor_sync(0xffffffffu, best, o);
+      const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+      if (ob < best || (ob == best && oi < bi)) { best = ob; bi = oi; }
+    }
+    if (lane == 0) s_idx[0] = bi;
+  }
+  __syncthreads();
+  return (T)sigmas[s_idx[0]];
+}
+
+// ------------------------------------------------------------------------------------
+// head_finish: head GEMM output [B*L][ (ph*2+pw)*Cout + c ] -> flow[b][f][c][y][x] and
+// x0 = x_t - sigma_t * flow in f64.  One block per (b, f, slab).
+// ------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+head_finish_kernel(const __nv_bfloat16* __restrict__ head_out, long long ldh, const __nv_bfloat16* __restrict__ xt,
+                   long long xs_b, long long xs_f, long long xs_c, long long xs_y, long long xs_x,
+                   const void* __restrict__ timestep, int t_dtype, const float* __restrict__ timesteps,
+                   const float* __restrict__ sigmas, int n_tab, __nv_bfloat16* __restrict__ flow,
+                   __nv_bfloat16* __restrict__ x0, int B, int F, int Cout, int Hh, int Ww) {
+  const int bf = blockIdx.x;
+  const int b = bf / F, f = bf % F;
+  const bool want_x0 = x0 != nullptr;   // block-uniform
+  double sigma = 0.0;
+  if (want_x0) sigma = block_sigma_lookup<double>(timesteps, sigmas, n_tab, load_timestep(timestep, t_dtype, bf));
+  const int H = Hh * 2, W = Ww * 2;
+  const int per_frame = Cout * H * W;
+  const long long L = (long long)F * Hh * Ww;
+  for (int idx = blockIdx.y * blockDim.x + threadIdx.x; idx < per_frame; idx += gridDim.y * blockDim.x) {
+    const int xw = idx % W;
+    int r = idx / W;
+    const int yh = r % H;
+    const int c = r / H;
+    const long long tok = (long long)b * L + (long long)f * Hh * Ww + (yh >> 1) * Ww + (xw >> 1);
+    const int feat = ((yh & 1) * 2 + (xw & 1)) * Cout + c;
+    const __nv_bfloat16 fl = head_out[tok * ldh + feat];
+    const double xv = want_x0 ? (double)__bfloat162float(xt[b * xs_b + f * xs_f + c * xs_c + yh * xs_y + xw * xs_x]) : 0.0;
+    const long long o = ((long long)bf * Cout + c) * H * W + (long long)yh * W + xw;
+    flow[o] = fl;
+    if (want_x0) x0[o] = __double2bfloat16(xv - sigma * (double)__bfloat162float(fl));
+  }
+}
+
+// ------------------------------------------------------------------------------------
+// add_noise: out = bf16((1 - sigma) * x0 + sigma * noise), fp32, sigma by nearest timestep (fp32)
+// ------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+add_noise_kernel(const __nv_bfloat16* __restrict__ x0, const __nv_bfloat16* __restrict__ noise,
+                 const void* __restrict__ timestep, int t_dtype, const float* __restrict__ timesteps,
+                 const float* __restrict__ sigmas, int n_tab, __nv_bfloat16* __restrict__ out, int per_frame) {
+  const int fr = blockIdx.x;
+  const float sigma = block_sigma_lookup<float>(timesteps, sigmas, n_tab, (float)load_timestep(timestep, t_dtype, fr));
+  const float one_minus = __fsub_rn(1.0f, sigma);
+  const long long base = (long long)fr * per_frame;
+  for (int idx = blockIdx.y * blockDim.x + threadIdx.x; idx < per_frame; idx += gridDim.y * blockDim.x) {
+    const float a = __fmul_rn(one_minus, __bfloat162float(x0[base + idx]));
+    const float c = __fmul_rn(sigma, __bfloat162float(noise[base + idx]));
+    out[base + idx] = __float2bfloat16_rn(__fadd_rn(a, c));
+  }
+}
+
+template <typename F>
+static int dispatch_nv(int C, const char* who, F&& f) {
+  switch (C) {
+    case 256: return f(std::integral_constant<int, 1>{});
+    case 512: return f(std::integral_constant<int, 2>{});
+    case 1024: return f(std::integral_constant<int, 4>{});
+    case 1536: return f(std::integral_constant<int, 6>{});
+    case 2048: return f(std::integral_constant<int, 8>{});
+    case 5120: return f(std::integral_constant<int, 20>{});
+  }
+  set_error("%s: channel width %d unsupported (256/512/1024/1536/2048/5120)", who, C);
+  return SFB_ERR_INVALID;
+}
+
+}  // namespace sfb
+
+using namespace sfb;
+typedef __nv_bfloat16 bf16;
+
+extern "C" int sfb_modulation_table(const void* mod, const void* e, void* out, int NL, int R, int G, int C,
+                                    long long e_row_stride, long long e_group_stride, void* stream) {
+  if (C % 8 || NL <= 0 || R <= 0 || G <= 0) { set_error("sfb_modulation_table: bad shape"); return SFB_ERR_INVALID; }
+  const long long total = (long long)NL * R * G * (C / 8);
+  const int blocks = (int)((total + 255) / 256);
+  modulation_table_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>((const bf16*)mod, (const bf16*)e, (bf16*)out, NL, R,
+                                                                   G, C, e_row_stride, e_group_stride);
+  return check_cuda(cudaGetLastError(), "modulation_table launch");
+}
+
+extern "C" int sfb_ln_modulate(const void* x, long long ldx, void* y, long long ldy, int rows, int C, float eps,
+                               const void* shift, const void* scale, long long mod_stride, int rows_per_mod,
+                               void* stream) {
+  if (rows <= 0 || rows_per_mod <= 0 || (ldx % 8) || (ldy % 8) || (mod_stride % 8)) { set_error("sfb_ln_modulate: bad arguments"); return SFB_ERR_INVALID; }
+  return dispatch_nv(C, "sfb_ln_modulate", [&](auto nv) {
+    ln_kernel<decltype(nv)::value, false><<<(rows + ROW_WARPS - 1) / ROW_WARPS, ROW_WARPS * 32, 0, (cudaStream_t)stream>>>(
+        (const bf16*)x, ldx, (bf16*)y, ldy, rows, eps, (const bf16*)shift, (const bf16*)scale, mod_stride, rows_per_mod,
+        nullptr, nullptr);
+    return check_cuda(cudaGetLastError(), "ln_modulate launch");
+  });
+}
+
+extern "C" int sfb_ln_affine(const void* x, long long ldx, void* y, long long ldy, int rows, int C, float eps,
+                             const void* weight, const void* bias, void* stream) {
+  if (rows <= 0 || (ldx % 8) || (ldy % 8) || !weight || !bias) { set_error("sfb_ln_affine: bad arguments"); return SFB_ERR_INVALID; }
+  return dispatch_nv(C, "sfb_ln_affine", [&](auto nv) {
+    ln_kernel<decltype(nv)::value, true><<<(rows + ROW_WARPS - 1) / ROW_WARPS, ROW_WARPS * 32, 0, (cudaStream_t)stream>>>(
+        (const bf16*)x, ldx, (bf16*)y, ldy, rows, eps, nullptr, nullptr, 0, 1, (const bf16*)weight, (const bf16*)bias);
+    return check_cuda(cudaGetLastError(), "ln_affine launch");
+  });
+}
+
+extern "C" int sfb_rmsnorm(const void* x, long long ldx, void* y, long long ldy, int rows, int C, float eps,
+                           const void* weight, void* stream) {
+  if (rows <= 0 || (ldx % 8) || (ldy % 8) || !weight) { set_error("sfb_rmsnorm: bad arguments"); return SFB_ERR_INVALID; }
+  return dispatch_nv(C, "sfb_rmsnorm", [&](auto nv) {
+    rmsnorm_kernel<decltype(nv)::value><<<(rows + ROW_WARPS - 1) / ROW_WARPS, ROW_WARPS * 32, 0, (cudaStream_t)stream>>>(
+        (const bf16*)x, ldx, (bf16*)y, ldy, rows, eps, (const bf16*)weight);
+    return check_cuda(cudaGetLastError(), "rmsnorm launch");
+  });
+}
+
+extern "C" int sfb_qk_norm_rope(const void* q_in, long long ldq, const void* k_in, long long ldk, const void* v_in,
+                                long long ldv, const void* wq, const void* wk, float eps, const float* cos_tab,
+                                const float* sin_tab, int tab_rows, int B, int L, int C, int head_dim, int F, int Hh,
+                                int Ww, int start_frame, void* q_out, long long q_out_row, long long q_out_batch,
+                                void* k_out, void* v_out, long long kv_out_row, long long kv_out_batch, void* stream) {
+  if (B <= 0 || L <= 0 || L != F * Hh * Ww) { set_error("sfb_qk_norm_rope: L=%d != F*H*W=%d*%d*%d", L, F, Hh, Ww); return SFB_ERR_INVALID; }
+  if (head_dim % 16 || C % head_dim) { set_error("sfb_qk_norm_rope: bad head_dim %d for C=%d", head_dim, C); return SFB_ERR_INVALID; }
+  if (start_frame < 0 || start_frame + F > tab_rows || Hh > tab_rows || Ww > tab_rows) { set_error("sfb_qk_norm_rope: position beyond the %d-row RoPE table (start_frame=%d F=%d)", tab_rows, start_frame, F); return SFB_ERR_INVALID; }
+  if ((ldq % 8) || (ldk % 8) || (ldv % 8) || (q_out_row % 8) || (kv_out_row % 8) || (q_out_batch % 8) || (kv_out_batch % 8)) { set_error("sfb_qk_norm_rope: strides must be multiples of 8"); return SFB_ERR_INVALID; }
+  RopeGeom g;
+  g.L = L; g.Hh = Hh; g.Ww = Ww; g.start_frame = start_frame;
+  const int c = head_dim / 2;
+  g.n_f = c - 2 * (c / 3);
+  g.n_h = c / 3;
+  const int rows = B * L;
+  return dispatch_nv(C, "sfb_qk_norm_rope", [&](auto nv) {
+    qk_norm_rope_kernel<decltype(nv)::value><<<(rows + ROW_WARPS - 1) / ROW_WARPS, ROW_WARPS * 32, 0, (cudaStream_t)stream>>>(
+        (const bf16*)q_in, ldq, (const bf16*)k_in, ldk, (const bf16*)v_in, ldv, (const bf16*)wq, (const bf16*)wk, eps,
+        cos_tab, sin_tab, head_dim, g, rows, (bf16*)q_out, q_out_row, q_out_batch, (bf16*)k_out, (bf16*)v_out,
+        kv_out_row, kv_out_batch);
+    return check_cuda(cudaGetLastError(), "qk_norm_rope launch");
+  });
+}
+
+extern "C" int sfb_patchify(const void* x, long long sb, long long sc, long long sf, long long sy, long long sx,
+                            void* out, int B, int Cin, int F, int H, int W, void* stream) {
+  if ((H % 2) || (W % 2) || B <= 0 || F <= 0) { set_error("sfb_patchify: H, W must be even"); return SFB_ERR_INVALID; }
+  const long long total = (long long)B * F * (H / 2) * (W / 2) * Cin * 2;
+  patchify_kernel<<<(int)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>((const bf16*)x, sb, sc, sf, sy, sx,
+                                                                              (bf16*)out, B, Cin, F, H / 2, W / 2);
+  return check_cuda(cudaGetLastError(), "patchify launch");
+}
+
+extern "C" int sfb_sinusoid(const void* t, int t_dtype, void* out, int n, int freq_dim, void* stream) {
+  if (n <= 0 || freq_dim % 2 || t_dtype < 0 || t_dtype > 3) { set_error("sfb_sinusoid: bad arguments"); return SFB_ERR_INVALID; }
+  sinusoid_kernel<<<(n * freq_dim + 255) / 256, 256, 0, (cudaStream_t)stream>>>(t, t_dtype, (bf16*)out, n, freq_dim);
+  return check_cuda(cudaGetLastError(), "sinusoid launch");
+}
+
+extern "C" int sfb_skinny_linear(const void* x, long long ldx, const void* w, long long ldw, const void* bias, void* y,
+                                 long long ldy, int M, int N, int K, int silu_in, void* stream) {
+  if (M <= 0 || N <= 0 || K <= 0 || (K % 256) || (ldw % 8)) { set_error("sfb_skinny_linear: need K %% 256 == 0 (got %d) and ldw %% 8 == 0", K); return SFB_ERR_INVALID; }
+  const size_t smem = (size_t)SKINNY_M * K * sizeof(float);
+  if (smem > 200 * 1024) { set_error("sfb_skinny_linear: K=%d too large", K); return SFB_ERR_INVALID; }
+  static size_t configured = 0;
+  if (smem > 48 * 1024 && smem > configured) {
+    if (int e = check_cuda(cudaFuncSetAttribute(skinny_linear_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), "cudaFuncSetAttribute(skinny)")) return e;
+    configured = smem;
+  }
+  dim3 grid((N + 7) / 8, (M + SKINNY_M - 1) / SKINNY_M);
+  skinny_linear_kernel<<<grid, 256, smem, (cudaStream_t)stream>>>((const bf16*)x, ldx, (const bf16*)w, ldw,
+                                                                (const bf16*)bias, (bf16*)y, ldy, M, N, K, silu_in);
+  return check_cuda(cudaGetLastError(), "skinny_linear launch");
+}
+
+extern "C" int sfb_head_finish(const void* head_out, long long ldh, const void* xt, long long xs_b, long long xs_f,
+                               long long xs_c, long long xs_y, long long xs_x, const void* timestep, int t_dtype,
+                               const float* timesteps, const float* sigmas, int n_tab, void* flow, void* x0, int B,
+                               int F, int Cout, int H, int W, void* stream) {
+  if (B <= 0 || F <= 0 || (H % 2) || (W % 2) || (x0 != nullptr && (n_tab <= 0 || !xt || !timestep || !timesteps || !sigmas))) { set_error("sfb_head_finish: bad arguments"); return SFB_ERR_INVALID; }
+  const int per_frame = Cout * H * W;
+  dim3 grid(B * F, (per_frame + 256 * 8 - 1) / (256 * 8));
+  head_finish_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>((const bf16*)head_out, ldh, (const bf16*)xt, xs_b, xs_f,
+                                                           xs_c, xs_y, xs_x, timestep, t_dtype, timesteps, sigmas, n_tab,
+                                                           (bf16*)flow, (bf16*)x0, B, F, Cout, H / 2, W / 2);
+  return check_cuda(cudaGetLastError(), "head_finish launch");
+}
+
+extern "C" int sfb_add_noise(const void* x0, const void* noise, const void* timestep, int t_dtype,
+                             const float* timesteps, const float* sigmas, int n_tab, void* out, int n_frames,
+                             int per_frame, void* stream) {
+  if (n_frames <= 0 || per_frame <= 0 || n_tab <= 0) { set_error("sfb_add_noise: bad arguments"); return SFB_ERR_INVALID; }
+  dim3 grid(n_frames, (per_frame + 256 * 8 - 1) / (256 * 8));
+  add_noise_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>((const bf16*)x0, (const bf16*)noise, timestep, t_dtype,
+                                                         timesteps, sigmas, n_tab, (bf16*)out, per_frame);
+  return check_cuda(cudaGetLastError(), "add_noise launch");
+}

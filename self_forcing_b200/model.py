@@ -1,0 +1,376 @@
+"""B200CausalWanModel -- drop-in for `CausalWanModel` on the KV-cached inference path.
+
+Same constructor arguments, `state_dict` keys and `forward(x, t=, context=, seq_len=, kv_cache=,
+crossattn_cache=, current_start=, cache_start=)` surface as wan/modules/causal_model.py:370-1128
+(reference), but `_forward_inference` (:725-893) is re-implemented as a schedule of hand-written
+sm_100a kernels (libsfb200.so, include/sfb200.h) with no PyTorch compute on the path:
+
+  per forward   patchify -> GEMM(+bias)                 patch embed            (ref :775-781)
+                sinusoid -> 3 skinny linears            time MLPs              (ref :829-832)
+                modulation tables for all layers        e = modulation + e0    (ref :310, :365)
+                [first call per prompt] text MLP + cross K/V into crossattn_cache (ref :837-842, model.py:175-180)
+  per block     LN+modulate -> QKV GEMM -> QK-RMSNorm+RoPE+KV-append -> attention over the cache window
+                -> O GEMM (+gate+residual) -> LN affine -> Q GEMM -> RMSNorm -> cross attention
+                -> O GEMM (+residual) -> LN+modulate -> FFN1 GEMM (+GELU) -> FFN2 GEMM (+gate+residual)
+  head          LN+modulate -> GEMM -> unpatchify (+ flow -> x0)               (ref :356-367, :1081-1104)
+
+The torch.nn modules below only *hold parameters* under the reference's names; nothing calls their
+forward.  The training branch of the reference (`kv_cache is None`, FlexAttention) is out of scope
+and raises.
+"""
+from __future__ import annotations
+
+import math
+from typing import Dict, List, Optional, Sequence
+
+import torch
+from torch import nn
+
+from .cache import IndexMirror, plan_cache_update
+from .ops import EPI_BIAS, EPI_GATE_RES, EPI_GELU, EPI_RESIDUAL
+
+
+def rope_tables(head_dim: int, max_pos: int = 1024, theta: float = 10000.0):
+    """cos / sin tables fp32 [max_pos, head_dim/2] of the reference's complex128 `freqs`
+    (wan/modules/model.py:29-36 concatenated at causal_model.py:482-488): three theta ladders
+    for the (frame, height, width) axes over d-4(d//6), 2(d//6), 2(d//6) real dims."""
+    d = head_dim
+    parts = []
+    for dim in (d - 4 * (d // 6), 2 * (d // 6), 2 * (d // 6)):
+        inv = 1.0 / torch.pow(theta, torch.arange(0, dim, 2, dtype=torch.float64) / dim)
+        parts.append(torch.outer(torch.arange(max_pos, dtype=torch.float64), inv))
+    ang = torch.cat(parts, dim=1)
+    return torch.cos(ang).float().contiguous(), torch.sin(ang).float().contiguous()
+
+
+class _ParamHolder(nn.Module):
+    def forward(self, *a, **k):  # pragma: no cover - never used
+        raise RuntimeError("parameter holder: the B200 path does not call torch module forwards")
+
+
+class _Linear(_ParamHolder):
+    def __init__(self, in_f: int, out_f: int):
+        super().__init__()
+        self.weight = nn.Parameter(torch.empty(out_f, in_f))
+        self.bias = nn.Parameter(torch.empty(out_f))
+
+
+class _Scale(_ParamHolder):
+    def __init__(self, dim: int, bias: bool = False):
+        super().__init__()
+        self.weight = nn.Parameter(torch.empty(dim))
+        if bias:
+            self.bias = nn.Parameter(torch.empty(dim))
+
+
+class _Attn(_ParamHolder):
+    def __init__(self, dim: int):
+        super().__init__()
+        self.q, self.k, self.v, self.o = (_Linear(dim, dim) for _ in range(4))
+        self.norm_q, self.norm_k = _Scale(dim), _Scale(dim)
+
+
+class _Block(_ParamHolder):
+    def __init__(self, dim: int, ffn_dim: int):
+        super().__init__()
+        self.self_attn = _Attn(dim)
+        self.norm3 = _Scale(dim, bias=True)
+        self.cross_attn = _Attn(dim)
+        self.ffn = nn.ModuleList([_Linear(dim, ffn_dim), _ParamHolder(), _Linear(ffn_dim, dim)])
+        self.modulation = nn.Parameter(torch.empty(1, 6, dim))
+
+
+class _Head(_ParamHolder):
+    def __init__(self, dim: int, out_features: int):
+        super().__init__()
+        self.head = _Linear(dim, out_features)
+        self.modulation = nn.Parameter(torch.empty(1, 2, dim))
+
+
+class _PatchEmbed(_ParamHolder):
+    def __init__(self, in_dim: int, dim: int, patch):
+        super().__init__()
+        self.weight = nn.Parameter(torch.empty(dim, in_dim, *patch))
+        self.bias = nn.Parameter(torch.empty(dim))
+
+
+class B200CausalWanModel(nn.Module):
+    def __init__(self, model_type="t2v", patch_size=(1, 2, 2), text_len=512, in_dim=16, dim=2048, ffn_dim=8192,
+                 freq_dim=256, text_dim=4096, out_dim=16, num_heads=16, num_layers=32, local_attn_size=-1,
+                 sink_size=0, qk_norm=True, cross_attn_norm=True, eps=1e-6, ops=None):
+        super().__init__()
+        if model_type != "t2v":
+            raise NotImplementedError("only the t2v model type runs the cached path (SURVEY.md section 9)")
+        if tuple(patch_size) != (1, 2, 2) or not qk_norm or not cross_attn_norm:
+            raise NotImplementedError("B200 path implements patch (1,2,2), qk_norm and cross_attn_norm")
+        assert dim % num_heads == 0 and (dim // num_heads) % 2 == 0
+        self.model_type, self.patch_size, self.text_len = model_type, tuple(patch_size), text_len
+        self.in_dim, self.dim, self.ffn_dim, self.freq_dim = in_dim, dim, ffn_dim, freq_dim
+        self.text_dim, self.out_dim, self.num_heads, self.num_layers = text_dim, out_dim, num_heads, num_layers
+        self.local_attn_size, self.sink_size, self.qk_norm = local_attn_size, sink_size, qk_norm
+        self.cross_attn_norm, self.eps = cross_attn_norm, eps
+        self.head_dim = dim // num_heads
+        # reference hard-codes 1560 tokens/frame here (causal_model.py:77)
+        self.max_attention_size = 32760 if local_attn_size == -1 else local_attn_size * 1560
+        self.num_frame_per_block = 1
+        self.independent_first_frame = False
+        self.block_mask = None
+
+        self.patch_embedding = _PatchEmbed(in_dim, dim, self.patch_size)
+        self.text_embedding = nn.ModuleList([_Linear(text_dim, dim), _ParamHolder(), _Linear(dim, dim)])
+        self.time_embedding = nn.ModuleList([_Linear(freq_dim, dim), _ParamHolder(), _Linear(dim, dim)])
+        self.time_projection = nn.ModuleList([_ParamHolder(), _Linear(dim, dim * 6)])
+        self.blocks = nn.ModuleList([_Block(dim, ffn_dim) for _ in range(num_layers)])
+        self.head = _Head(dim, out_dim * math.prod(self.patch_size))
+
+        self._ops = ops
+        self._packed: Optional[Dict[str, object]] = None
+        self._ws: Dict[tuple, Dict[str, torch.Tensor]] = {}
+        self._mirror = IndexMirror()
+        self._sampler_tables = None   # (timesteps fp32, sigmas fp32) on device, set by the wrapper
+        self._rope = None
+        self.register_load_state_dict_post_hook(lambda module, incompatible: module.invalidate_packed())
+        self._register_load_state_dict_pre_hook(self._drop_foreign_keys)
+
+    # ------------------------------------------------------------------ parameters
+    @staticmethod
+    def _drop_foreign_keys(state_dict, prefix, *args):
+        # upstream / fork checkpoints carry `pose_proj.*` (causal_model.py:500-503); not on this path
+        for k in [k for k in state_dict if k.startswith(prefix + "pose_proj.")]:
+            del state_dict[k]
+
+    @torch.no_grad()
+    def init_weights(self, seed: int = 0) -> None:
+        """Synthetic random init of the named architecture (no checkpoint): xavier-variance matrices as
+        causal_model.py:1111-1125, but N(0,.02) biases / head weight and 1+N(0,.02) norm affines instead
+        of the reference's zeros/ones so that every kernel does non-trivial work."""
+        g = torch.Generator(device=self.patch_embedding.weight.device).manual_seed(seed)
+        for name, p in self.named_parameters():
+            shape = p.shape
+            if name.endswith("modulation"):
+                w = torch.randn(shape, generator=g, device=p.device) / math.sqrt(self.dim)
+            elif name.endswith(".bias") or name == "head.head.weight":
+                w = torch.randn(shape, generator=g, device=p.device) * 0.02
+            elif "norm" in name:
+                w = 1.0 + torch.randn(shape, generator=g, device=p.device) * 0.02
+            else:
+                fan_in = int(math.prod(shape[1:]))
+                w = torch.randn(shape, generator=g, device=p.device) * math.sqrt(2.0 / (fan_in + shape[0]))
+            p.copy_(w.to(p.dtype))
+        self.invalidate_packed()
+
+    def invalidate_packed(self) -> None:
+        self._packed = None
+
+    def _apply(self, fn, *a, **k):
+        self.invalidate_packed()
+        self._ws.clear()
+        return super()._apply(fn, *a, **k)
+
+    def set_sampler_tables(self, timesteps: torch.Tensor, sigmas: torch.Tensor) -> None:
+        """FlowMatchScheduler tables (utils/scheduler.py:118-141) used by the fused flow->x0 epilogue."""
+        self._sampler_tables = (timesteps.detach().float().contiguous(), sigmas.detach().float().contiguous())
+
+    @property
+    def ops(self):
+        if self._ops is None:
+            from .ops import CudaOps
+            self._ops = CudaOps()
+        return self._ops
+
+    @torch.no_grad()
+    def _pack(self) -> Dict[str, object]:
+        """Concatenated / stacked weight layouts the kernels read (built once per weight load)."""
+        dev = self.patch_embedding.weight.device
+        dt = self.patch_embedding.weight.dtype
+        if dt != torch.bfloat16 and getattr(self.ops, "requires_bf16", True):
+            raise TypeError(f"B200CausalWanModel runs in bfloat16 (call .to(torch.bfloat16)); got {dt}")
+        pk: Dict[str, object] = {}
+        pk["patch_w"] = self.patch_embedding.weight.detach().flatten(1).contiguous()
+        blocks = []
+        for b in self.blocks:
+            sa, ca = b.self_attn, b.cross_attn
+            blocks.append(dict(
+                wqkv=torch.cat([sa.q.weight, sa.k.weight, sa.v.weight]).detach().contiguous(),
+                bqkv=torch.cat([sa.q.bias, sa.k.bias, sa.v.bias]).detach().contiguous(),
+                wkv_c=torch.cat([ca.k.weight, ca.v.weight]).detach().contiguous(),
+                bkv_c=torch.cat([ca.k.bias, ca.v.bias]).detach().contiguous()))
+        pk["blocks"] = blocks
+        pk["mod"] = torch.cat([b.modulation.detach() for b in self.blocks]).contiguous()       # [NL, 6, C]
+        pk["head_mod"] = self.head.modulation.detach().contiguous()                              # [1, 2, C]
+        cos, sin = rope_tables(self.head_dim)
+        pk["cos"], pk["sin"] = cos.to(dev), sin.to(dev)
+        if self._sampler_tables is not None:
+            self._sampler_tables = tuple(t.to(dev) for t in self._sampler_tables)
+        self._packed = pk
+        return pk
+
+    def _workspace(self, B: int, L: int, F_: int, dev) -> Dict[str, torch.Tensor]:
+        key = (B, L, F_, str(dev))
+        ws = self._ws.get(key)
+        if ws is None:
+            C, bf = self.dim, self.patch_embedding.weight.dtype
+            R = B * L
+
+            def e(*shape):
+                return torch.empty(*shape, dtype=bf, device=dev)
+
+            ws = dict(tok=e(R, self.in_dim * 4), x=e(R, C), h=e(R, C), q_lin=e(R, C), k_lin=e(R, C), v_lin=e(R, C),
+                      q=e(R, C), attn=e(R, C), ffn=e(R, self.ffn_dim), sin=e(B * F_, self.freq_dim),
+                      e1=e(B * F_, C), e=e(B * F_, C), e0=e(B * F_, 6 * C), mod=e(self.num_layers, B * F_, 6, C),
+                      head_mod=e(1, B * F_, 2, C), head_out=e(R, self.out_dim * 4),
+                      ctx_h=e(B * self.text_len, C), ctx=e(B * self.text_len, C), ctx_k=e(B * self.text_len, C))
+            self._ws[key] = ws
+        return ws
+
+    # ------------------------------------------------------------------ forward
+    def forward(self, *args, **kwargs):
+        if kwargs.get("kv_cache", None) is None:
+            raise NotImplementedError(
+                "B200CausalWanModel implements the KV-cached inference path only "
+                "(reference _forward_train / FlexAttention is out of scope)")
+        return self._forward_inference(*args, **kwargs)
+
+    @torch.no_grad()
+    def _forward_inference(self, x, t, context, seq_len, clip_fea=None, y=None, add_condition=None,
+                           kv_cache: List[dict] = None, crossattn_cache: List[dict] = None,
+                           current_start: int = 0, cache_start: Optional[int] = None, return_x0: bool = False,
+                           skip_output: bool = False):
+        """x [B, 16, F, H, W] (or a list of [16, F, H, W]), t [B, F], context [B, <=512, 4096] (or list)
+        -> flow [B, 16, F, H, W]  (and x0 [B, F, 16, H, W] when return_x0)."""
+        if add_condition is not None or clip_fea is not None or y is not None:
+            raise NotImplementedError("pose / image conditioning is not part of the t2v rollout hot path")
+        if isinstance(x, (list, tuple)):
+            x = torch.stack(list(x))
+        if isinstance(context, (list, tuple)):
+            context = torch.stack([torch.cat([u, u.new_zeros(self.text_len - u.size(0), u.size(1))]) for u in context])
+        ops = self.ops
+        pk = self._packed or self._pack()
+        B, Cin, F_, H, W = x.shape
+        Hh, Ww = H // 2, W // 2
+        fs = Hh * Ww
+        L = F_ * fs
+        assert L <= seq_len
+        assert Cin == self.in_dim and t.shape == (B, F_), f"timestep shape {tuple(t.shape)} != {(B, F_)}"
+        C, NL, D, NH = self.dim, self.num_layers, self.head_dim, self.num_heads
+        dev = x.device
+        ws = self._workspace(B, L, F_, dev)
+        R = B * L
+
+        # ---- embeddings -------------------------------------------------------------------
+        ops.patchify(x, ws["tok"])
+        ops.gemm(ws["tok"], pk["patch_w"], self.patch_embedding.bias, ws["x"])
+        tflat = t.reshape(-1).contiguous()
+        ops.sinusoid(tflat, ws["sin"], self.freq_dim)
+        te, tp = self.time_embedding, self.time_projection
+        ops.skinny_linear(ws["sin"], te[0].weight, te[0].bias, ws["e1"], silu_in=False)
+        ops.skinny_linear(ws["e1"], te[2].weight, te[2].bias, ws["e"], silu_in=True)
+        ops.skinny_linear(ws["e"], tp[1].weight, tp[1].bias, ws["e0"], silu_in=True)
+        ops.modulation_table(pk["mod"], ws["e0"], ws["mod"], e_row_stride=6 * C, e_group_stride=C)
+        ops.modulation_table(pk["head_mod"], ws["e"], ws["head_mod"], e_row_stride=C, e_group_stride=0)
+
+        # ---- text context: only consumed to fill the cross-attention cache ------------------
+        need_ctx = any(not c["is_init"] for c in crossattn_cache[:NL])
+        if need_ctx:
+            if context.shape[1] < self.text_len:
+                context = torch.cat([context, context.new_zeros(B, self.text_len - context.shape[1],
+                                                                context.shape[2])], dim=1)
+            ctx_in = context.reshape(B * self.text_len, self.text_dim)
+            if not ctx_in.is_contiguous():
+                ctx_in = ctx_in.contiguous()
+            tx = self.text_embedding
+            ops.gemm(ctx_in, tx[0].weight, tx[0].bias, ws["ctx_h"], epilogue=EPI_GELU)
+            ops.gemm(ws["ctx_h"], tx[2].weight, tx[2].bias, ws["ctx"])
+
+        # ---- KV-cache plans (host integers; ref causal_model.py:195-236) --------------------
+        frame_tokens = fs
+        start_frame = current_start // frame_tokens
+        sink_tokens = self.sink_size * frame_tokens
+        idx = self._mirror.read(kv_cache[:NL])
+        plans = [plan_cache_update(g, l, current_start, L, kv_cache[i]["k"].shape[1], self.local_attn_size,
+                                   sink_tokens, self.max_attention_size) for i, (g, l) in enumerate(idx)]
+        scale = 1.0 / math.sqrt(D)
+        mod = ws["mod"]
+        mstride = 6 * C   # elements between consecutive (b, f) rows of one layer's table
+
+        for i, blk in enumerate(self.blocks):
+            pb = pk["blocks"][i]
+            cache, plan = kv_cache[i], plans[i]
+            m = mod[i]   # [B*F, 6, C]
+            sa, ca = blk.self_attn, blk.cross_attn
+            # -- self attention --
+            ops.ln_modulate(ws["x"], ws["h"], shift=m[:, 0], scale=m[:, 1], mod_stride=mstride, rows_per_mod=fs,
+                            eps=self.eps)
+            kc, vc = cache["k"], cache["v"]
+            if kc.shape[0] != B or kc.shape[2] != NH or kc.shape[3] != D:
+                raise ValueError(f"kv_cache[{i}]['k'] shape {tuple(kc.shape)} does not match B={B}, H={NH}, D={D}")
+            if plan.roll:
+                for c_ in (kc, vc):
+                    c_[:, plan.roll_dst:plan.roll_dst + plan.roll_len] = \
+                        c_[:, plan.roll_src:plan.roll_src + plan.roll_len].clone()
+            k_slot = kc[:, plan.write_start:plan.write_end]
+            v_slot = vc[:, plan.write_start:plan.write_end]
+            if B == 1:   # V projection lands directly in its cache slot
+                ops.gemm(ws["h"], pb["wqkv"], pb["bqkv"], None, seg_cols=C,
+                         outs=[ws["q_lin"], ws["k_lin"], v_slot.reshape(L, C)])
+                v_src = None
+            else:
+                ops.gemm(ws["h"], pb["wqkv"], pb["bqkv"], None, seg_cols=C,
+                         outs=[ws["q_lin"], ws["k_lin"], ws["v_lin"]])
+                v_src = ws["v_lin"]
+            q4 = ws["q"].view(B, L, NH, D)
+            ops.qk_norm_rope(ws["q_lin"], ws["k_lin"], v_src, sa.norm_q.weight, sa.norm_k.weight, self.eps,
+                             pk["cos"], pk["sin"], B, L, D, (F_, Hh, Ww), start_frame,
+                             q_out=ws["q"].view(B, L, C), k_out=k_slot, v_out=v_slot)
+            if skip_output and i == NL - 1:
+                break   # cache-refresh pass: nothing after the last layer's K/V append is consumed
+            ops.attention(q4, kc[:, plan.attn_start:plan.attn_end], vc[:, plan.attn_start:plan.attn_end],
+                          ws["attn"].view(B, L, NH, D), scale)
+            ops.gemm(ws["attn"], sa.o.weight, sa.o.bias, ws["x"], epilogue=EPI_GATE_RES, residual=ws["x"],
+                     gate=m[:, 2], gate_stride=mstride, rows_per_gate=fs)
+            # -- cross attention --
+            cc = crossattn_cache[i]
+            if not cc["is_init"]:
+                ck, cv = cc["k"], cc["v"]
+                if ck.shape != (B, self.text_len, NH, D) or not ck.is_contiguous() or not cv.is_contiguous():
+                    ck = torch.empty(B, self.text_len, NH, D, dtype=ws["x"].dtype, device=dev)
+                    cv = torch.empty_like(ck)
+                    cc["k"], cc["v"] = ck, cv
+                ops.gemm(ws["ctx"], pb["wkv_c"], pb["bkv_c"], None, seg_cols=C,
+                         outs=[ws["ctx_k"], cv.view(B * self.text_len, C)])
+                ops.rmsnorm(ws["ctx_k"], ck.view(B * self.text_len, C), ca.norm_k.weight, self.eps)
+                cc["is_init"] = True
+            ops.ln_affine(ws["x"], ws["h"], blk.norm3.weight, blk.norm3.bias, self.eps)
+            ops.gemm(ws["h"], ca.q.weight, ca.q.bias, ws["q_lin"])
+            ops.rmsnorm(ws["q_lin"], ws["q"], ca.norm_q.weight, self.eps)
+            ops.attention(q4, cc["k"], cc["v"], ws["attn"].view(B, L, NH, D), scale)
+            ops.gemm(ws["attn"], ca.o.weight, ca.o.bias, ws["x"], epilogue=EPI_RESIDUAL, residual=ws["x"])
+            # -- feed forward --
+            ops.ln_modulate(ws["x"], ws["h"], shift=m[:, 3], scale=m[:, 4], mod_stride=mstride, rows_per_mod=fs,
+                            eps=self.eps)
+            ops.gemm(ws["h"], blk.ffn[0].weight, blk.ffn[0].bias, ws["ffn"], epilogue=EPI_GELU)
+            ops.gemm(ws["ffn"], blk.ffn[2].weight, blk.ffn[2].bias, ws["x"], epilogue=EPI_GATE_RES,
+                     residual=ws["x"], gate=m[:, 5], gate_stride=mstride, rows_per_gate=fs)
+
+        self._mirror.write(kv_cache[:NL], [(p.global_end, p.local_end) for p in plans])
+        if skip_output:
+            return None
+
+        # ---- head ------------------------------------------------------------------------------
+        hm = ws["head_mod"][0]   # [B*F, 2, C]
+        ops.ln_modulate(ws["x"], ws["h"], shift=hm[:, 0], scale=hm[:, 1], mod_stride=2 * C, rows_per_mod=fs,
+                        eps=self.eps)
+        ops.gemm(ws["h"], self.head.head.weight, self.head.head.bias, ws["head_out"])
+        flow = torch.empty(B, F_, self.out_dim, H, W, dtype=ws["x"].dtype, device=dev)
+        x0 = None
+        xt = x.permute(0, 2, 1, 3, 4)   # [B, F, C, H, W] view of the input
+        if return_x0:
+            if self._sampler_tables is None:
+                raise RuntimeError("return_x0 needs set_sampler_tables() (done by B200DiffusionWrapper)")
+            x0 = torch.empty_like(flow)
+            ops.head_finish(ws["head_out"], xt, t.contiguous(), self._sampler_tables[0], self._sampler_tables[1],
+                            flow, x0)
+        else:
+            ops.head_finish(ws["head_out"], xt, t.contiguous(), None, None, flow, None)
+        out = flow.permute(0, 2, 1, 3, 4)   # reference returns [B, C, F, H, W]
+        return (out, x0) if return_x0 else out

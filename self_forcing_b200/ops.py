@@ -1,0 +1,168 @@
+"""Tensor-level wrappers over the C ABI (include/sfb200.h): torch supplies device memory and the
+current stream, everything else happens in libsfb200.so.  No fallbacks."""
+from __future__ import annotations
+
+from typing import Optional, Sequence
+
+import torch
+
+from . import _lib
+
+EPI_BIAS, EPI_GELU, EPI_RESIDUAL, EPI_GATE_RES = 0, 1, 2, 3
+_T_DTYPE = {torch.float32: 0, torch.int64: 1, torch.float64: 2, torch.bfloat16: 3}
+
+
+def _ptr(t: Optional[torch.Tensor]):
+    return None if t is None else t.data_ptr()
+
+
+def _check_2d(t: torch.Tensor, name: str) -> None:
+    if t.dim() != 2 or t.stride(1) != 1 or t.dtype != torch.bfloat16 or not t.is_cuda:
+        raise ValueError(f"{name}: expected a CUDA bf16 matrix with unit column stride, got "
+                         f"{tuple(t.shape)} {t.dtype} {t.device} strides {t.stride()}")
+
+
+class CudaOps:
+    """The op set the host model is written against.  Every method enqueues exactly one kernel
+    of libsfb200.so on the current CUDA stream."""
+
+    requires_bf16 = True
+
+    def __init__(self):
+        self.lib = _lib.load()
+        if not torch.cuda.is_available():
+            raise _lib.SfbError("CUDA device required: the B200 path has no CPU fallback")
+        self.launches = 0
+
+    @staticmethod
+    def _stream():
+        return torch.cuda.current_stream().cuda_stream
+
+    # -- dense projections ---------------------------------------------------------------
+    def gemm(self, x, w, bias, out, *, epilogue=EPI_BIAS, residual=None, gate=None, gate_stride=0,
+             rows_per_gate=1, outs: Optional[Sequence[torch.Tensor]] = None, seg_cols=0, block_n=0):
+        _check_2d(x, "x"); _check_2d(w, "w")
+        M, K = x.shape
+        N = w.shape[0]
+        assert w.shape[1] == K
+        segs = list(outs) if outs is not None else [out]
+        for s in segs:
+            _check_2d(s, "out")
+        while len(segs) < 3:
+            segs.append(None)
+        if residual is not None:
+            _check_2d(residual, "residual")
+        self.launches += 1
+        _lib.check(self.lib.sfb_gemm_bf16(
+            x.data_ptr(), x.stride(0), w.data_ptr(), w.stride(0), _ptr(bias), M, N, K, epilogue,
+            _ptr(segs[0]), segs[0].stride(0), _ptr(segs[1]), segs[1].stride(0) if segs[1] is not None else 0,
+            _ptr(segs[2]), segs[2].stride(0) if segs[2] is not None else 0, seg_cols,
+            _ptr(residual), residual.stride(0) if residual is not None else 0,
+            _ptr(gate), gate_stride, rows_per_gate, block_n, self._stream()), "sfb_gemm_bf16")
+
+    # -- attention ------------------------------------------------------------------------
+    def attention(self, q, k, v, out, scale: float):
+        """q/out [B, Lq, H, D] views, k/v [B, S, H, D] views (the cache window)."""
+        B, Lq, H, D = q.shape
+        S = k.shape[1]
+        for t in (q, k, v, out):
+            assert t.stride(3) == 1 and t.stride(2) == D and t.dtype == torch.bfloat16
+        assert k.stride() == v.stride() and k.shape == v.shape
+        self.launches += 1
+        _lib.check(self.lib.sfb_attention_fwd(
+            q.data_ptr(), q.stride(1), q.stride(0), k.data_ptr(), v.data_ptr(), k.stride(1), k.stride(0),
+            out.data_ptr(), out.stride(1), out.stride(0), B, Lq, S, H, D, scale, self._stream()),
+            "sfb_attention_fwd")
+
+    # -- normalisation / modulation -------------------------------------------------------
+    def modulation_table(self, mod, e, out, e_row_stride: int, e_group_stride: int):
+        NL, G, C = mod.shape
+        R = out.shape[1]
+        assert out.shape == (NL, R, G, C) and out.is_contiguous() and mod.is_contiguous()
+        self.launches += 1
+        _lib.check(self.lib.sfb_modulation_table(mod.data_ptr(), e.data_ptr(), out.data_ptr(), NL, R, G, C,
+                                                 e_row_stride, e_group_stride, self._stream()),
+                   "sfb_modulation_table")
+
+    def ln_modulate(self, x, y, shift, scale, mod_stride: int, rows_per_mod: int, eps: float):
+        _check_2d(x, "x"); _check_2d(y, "y")
+        self.launches += 1
+        _lib.check(self.lib.sfb_ln_modulate(x.data_ptr(), x.stride(0), y.data_ptr(), y.stride(0), x.shape[0],
+                                            x.shape[1], eps, shift.data_ptr(), scale.data_ptr(), mod_stride,
+                                            rows_per_mod, self._stream()), "sfb_ln_modulate")
+
+    def ln_affine(self, x, y, weight, bias, eps: float):
+        _check_2d(x, "x"); _check_2d(y, "y")
+        self.launches += 1
+        _lib.check(self.lib.sfb_ln_affine(x.data_ptr(), x.stride(0), y.data_ptr(), y.stride(0), x.shape[0],
+                                          x.shape[1], eps, weight.data_ptr(), bias.data_ptr(), self._stream()),
+                   "sfb_ln_affine")
+
+    def rmsnorm(self, x, y, weight, eps: float):
+        _check_2d(x, "x"); _check_2d(y, "y")
+        self.launches += 1
+        _lib.check(self.lib.sfb_rmsnorm(x.data_ptr(), x.stride(0), y.data_ptr(), y.stride(0), x.shape[0],
+                                        x.shape[1], eps, weight.data_ptr(), self._stream()), "sfb_rmsnorm")
+
+    def qk_norm_rope(self, q_in, k_in, v_in, wq, wk, eps, cos_tab, sin_tab, B, L, head_dim, grid, start_frame,
+                     q_out, k_out, v_out):
+        """q_in/k_in/v_in [B*L, C]; q_out [B, L, C]-like view; k_out/v_out [B, L, H, D] cache-slot views."""
+        _check_2d(q_in, "q_in"); _check_2d(k_in, "k_in")
+        C = q_in.shape[1]
+        F_, Hh, Ww = grid
+        assert cos_tab.dtype == torch.float32 and cos_tab.is_contiguous() and sin_tab.is_contiguous()
+        assert k_out.stride() == v_out.stride()
+        self.launches += 1
+        _lib.check(self.lib.sfb_qk_norm_rope(
+            q_in.data_ptr(), q_in.stride(0), k_in.data_ptr(), k_in.stride(0), _ptr(v_in),
+            v_in.stride(0) if v_in is not None else 0, wq.data_ptr(), wk.data_ptr(), eps, cos_tab.data_ptr(),
+            sin_tab.data_ptr(), cos_tab.shape[0], B, L, C, head_dim, F_, Hh, Ww, start_frame,
+            q_out.data_ptr(), q_out.stride(1), q_out.stride(0), k_out.data_ptr(), v_out.data_ptr(),
+            k_out.stride(1), k_out.stride(0), self._stream()), "sfb_qk_norm_rope")
+
+    # -- embeddings -----------------------------------------------------------------------
+    def patchify(self, x, out):
+        """x [B, Cin, F, H, W] (any strides) -> out [B*F*(H/2)*(W/2), Cin*4]."""
+        B, Cin, F_, H, W = x.shape
+        assert out.is_contiguous() and x.dtype == torch.bfloat16
+        sb, sc, sf, sy, sx = x.stride()
+        self.launches += 1
+        _lib.check(self.lib.sfb_patchify(x.data_ptr(), sb, sc, sf, sy, sx, out.data_ptr(), B, Cin, F_, H, W,
+                                         self._stream()), "sfb_patchify")
+
+    def sinusoid(self, t, out, freq_dim: int):
+        assert t.is_contiguous() and t.dtype in _T_DTYPE
+        self.launches += 1
+        _lib.check(self.lib.sfb_sinusoid(t.data_ptr(), _T_DTYPE[t.dtype], out.data_ptr(), t.numel(), freq_dim,
+                                         self._stream()), "sfb_sinusoid")
+
+    def skinny_linear(self, x, w, bias, y, silu_in: bool):
+        _check_2d(x, "x"); _check_2d(w, "w"); _check_2d(y, "y")
+        self.launches += 1
+        _lib.check(self.lib.sfb_skinny_linear(x.data_ptr(), x.stride(0), w.data_ptr(), w.stride(0), _ptr(bias),
+                                              y.data_ptr(), y.stride(0), x.shape[0], w.shape[0], x.shape[1],
+                                              1 if silu_in else 0, self._stream()), "sfb_skinny_linear")
+
+    # -- sampler --------------------------------------------------------------------------
+    def head_finish(self, head_out, xt, timestep, timesteps, sigmas, flow, x0):
+        """head_out [B*L, 4*Cout]; xt [B, F, Cout, H, W] view; timestep [B, F]; flow/x0 contiguous outputs."""
+        B, F_, Cout, H, W = xt.shape
+        assert flow.is_contiguous() and (x0 is None or x0.is_contiguous())
+        assert timestep.is_contiguous() and timestep.dtype in _T_DTYPE
+        sb, sf, sc, sy, sx = xt.stride()
+        self.launches += 1
+        _lib.check(self.lib.sfb_head_finish(
+            head_out.data_ptr(), head_out.stride(0), xt.data_ptr(), sb, sf, sc, sy, sx, timestep.data_ptr(),
+            _T_DTYPE[timestep.dtype], _ptr(timesteps), _ptr(sigmas), 0 if timesteps is None else timesteps.numel(),
+            flow.data_ptr(), _ptr(x0), B, F_, Cout, H, W, self._stream()), "sfb_head_finish")
+
+    def add_noise(self, x0, noise, timestep, timesteps, sigmas, out):
+        """x0/noise/out [N, C, H, W] contiguous, timestep [N]."""
+        assert x0.is_contiguous() and noise.is_contiguous() and out.is_contiguous()
+        assert timestep.is_contiguous() and timestep.dtype in _T_DTYPE
+        n = x0.shape[0]
+        self.launches += 1
+        _lib.check(self.lib.sfb_add_noise(x0.data_ptr(), noise.data_ptr(), timestep.data_ptr(),
+                                          _T_DTYPE[timestep.dtype], timesteps.data_ptr(), sigmas.data_ptr(),
+                                          timesteps.numel(), out.data_ptr(), n, x0[0].numel(), self._stream()),
+                   "sfb_add_noise")

@@ -1,0 +1,113 @@
+"""B200DiffusionWrapper -- drop-in for `WanDiffusionWrapper` (utils/wan_wrapper.py:120-371) on the
+causal KV-cached path.
+
+Keeps the surface `pipeline/causal_inference.py` touches:
+`.model` (with `.local_attn_size`, `.num_frame_per_block`), `.scheduler` / `.get_scheduler()`,
+`.seq_len`, and `__call__(noisy_image_or_video=[B,F,16,H,W], conditional_dict={"prompt_embeds"},
+timestep=[B,F], kv_cache=, crossattn_cache=, current_start=) -> (flow_pred, pred_x0)`.
+The flow -> x0 conversion (wan_wrapper.py:204-228, float64) is fused into the model's last kernel.
+"""
+from __future__ import annotations
+
+import json
+import os
+from typing import List, Optional
+
+import torch
+from torch import nn
+
+from .model import B200CausalWanModel
+from .scheduler import FlowMatchScheduler
+
+WAN_T2V_1_3B = dict(model_type="t2v", patch_size=(1, 2, 2), text_len=512, in_dim=16, dim=1536, ffn_dim=8960,
+                    freq_dim=256, text_dim=4096, out_dim=16, num_heads=12, num_layers=30, qk_norm=True,
+                    cross_attn_norm=True, eps=1e-6)
+WAN_T2V_14B = dict(WAN_T2V_1_3B, dim=5120, ffn_dim=13824, num_heads=40, num_layers=40)
+
+
+class B200DiffusionWrapper(nn.Module):
+    def __init__(self, model_name: str = "Wan2.1-T2V-1.3B", model_path: Optional[str] = None,
+                 timestep_shift: float = 8.0, is_causal: bool = True, local_attn_size: int = -1, sink_size: int = 0,
+                 model_config: Optional[dict] = None, device=None, init_seed: Optional[int] = None, ops=None,
+                 dtype=torch.bfloat16, **unsupported):
+        """model_config given (or init_seed set) -> random-init weights of that architecture on `device`;
+        otherwise `config.json` + safetensors / .pth weights are read from model_path (HF layout used by
+        CausalWanModel.from_pretrained at wan_wrapper.py:139-145)."""
+        super().__init__()
+        if not is_causal:
+            raise NotImplementedError("the bidirectional WanModel is outside the rollout hot path")
+        lora = {k: v for k, v in unsupported.items() if k.startswith("lora") and v}
+        if lora.get("lora_rank"):
+            raise NotImplementedError("merge LoRA weights offline (scripts/merge_lora.py) before loading")
+        cfg = dict(model_config) if model_config is not None else None
+        state = None
+        if cfg is None:
+            path = model_path or f"wan_models/{model_name}/"
+            cfg, state = _read_checkpoint_dir(path)
+        cfg.update(local_attn_size=local_attn_size, sink_size=sink_size)
+        self.model = B200CausalWanModel(**cfg, ops=ops)
+        if device is not None:
+            self.model.to(device)
+        self.model.to(dtype)
+        if state is not None:
+            self.model.load_state_dict(state, strict=False)
+        elif init_seed is not None:
+            self.model.init_weights(init_seed)
+        self.model.eval()
+        self.uniform_timestep = False
+        self.scheduler = FlowMatchScheduler(shift=timestep_shift, sigma_min=0.0, extra_one_step=True, ops=ops)
+        self.scheduler.set_timesteps(1000, training=True)
+        self.model.set_sampler_tables(self.scheduler.timesteps, self.scheduler.sigmas)
+        self.seq_len = 32760   # [1, 21, 16, 60, 104]
+
+    def get_scheduler(self) -> FlowMatchScheduler:
+        return self.scheduler
+
+    def forward(self, noisy_image_or_video: torch.Tensor, conditional_dict: dict, timestep: torch.Tensor,
+                kv_cache: Optional[List[dict]] = None, crossattn_cache: Optional[List[dict]] = None,
+                current_start: Optional[int] = None, classify_mode: bool = False,
+                concat_time_embeddings: bool = False, clean_x=None, aug_t=None, cache_start: Optional[int] = None,
+                add_condition=None, clip_feature=None, y=None, refresh_only: bool = False):
+        if kv_cache is None:
+            raise NotImplementedError("B200DiffusionWrapper implements the KV-cached causal path only")
+        if classify_mode or clean_x is not None:
+            raise NotImplementedError("training-time modes are out of scope")
+        cond = conditional_dict
+        if add_condition is None:
+            add_condition = cond.get("add_condition")
+        if clip_feature is None:
+            clip_feature = cond.get("clip_feature")
+        if y is None:
+            y = cond.get("y")
+        out = self.model(noisy_image_or_video.permute(0, 2, 1, 3, 4), t=timestep, context=cond["prompt_embeds"],
+                         seq_len=self.seq_len, kv_cache=kv_cache, crossattn_cache=crossattn_cache,
+                         current_start=current_start, cache_start=cache_start, add_condition=add_condition,
+                         clip_fea=clip_feature, y=y, return_x0=not refresh_only, skip_output=refresh_only)
+        if refresh_only:
+            return None, None
+        flow, x0 = out
+        return flow.permute(0, 2, 1, 3, 4), x0
+
+
+def _read_checkpoint_dir(path: str):
+    cfg_file = os.path.join(path, "config.json")
+    if not os.path.isfile(cfg_file):
+        raise FileNotFoundError(f"{cfg_file} not found (pass model_config=... for random-init weights)")
+    raw = json.load(open(cfg_file))
+    keys = ("model_type", "patch_size", "text_len", "in_dim", "dim", "ffn_dim", "freq_dim", "text_dim", "out_dim",
+            "num_heads", "num_layers", "qk_norm", "cross_attn_norm", "eps")
+    cfg = {k: raw[k] for k in keys if k in raw}
+    if "patch_size" in cfg:
+        cfg["patch_size"] = tuple(cfg["patch_size"])
+    state = {}
+    files = sorted(f for f in os.listdir(path) if f.endswith(".safetensors"))
+    if files:
+        from safetensors.torch import load_file
+        for f in files:
+            state.update(load_file(os.path.join(path, f)))
+    else:
+        pth = [f for f in os.listdir(path) if f.endswith((".pth", ".pt", ".bin"))]
+        if not pth:
+            raise FileNotFoundError(f"no weights found under {path}")
+        state = torch.load(os.path.join(path, pth[0]), map_location="cpu")
+    return cfg, state

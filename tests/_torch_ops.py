@@ -1,0 +1,113 @@
+"""TEST DOUBLE (CPU): the op interface of self_forcing_b200.ops.CudaOps implemented with plain
+PyTorch in the reference's dtype/rounding order.  It exists so that the *host orchestration*
+(buffer wiring, cache slots, modulation indexing, drop-in surface) can be checked against the
+oracle on a machine without a GPU.  It is never imported by the product."""
+from __future__ import annotations
+
+import torch
+import torch.nn.functional as F
+
+from oracle import causal_wan_oracle as O
+
+EPI_BIAS, EPI_GELU, EPI_RESIDUAL, EPI_GATE_RES = 0, 1, 2, 3
+
+
+class TorchOps:
+    requires_bf16 = False
+
+    def __init__(self):
+        self.launches = 0
+        self.log = []
+
+    def gemm(self, x, w, bias, out, *, epilogue=EPI_BIAS, residual=None, gate=None, gate_stride=0,
+             rows_per_gate=1, outs=None, seg_cols=0, block_n=0):
+        self.launches += 1
+        self.log.append("gemm")
+        y = F.linear(x, w, bias)
+        if epilogue == EPI_GELU:
+            y = F.gelu(y, approximate="tanh")
+        elif epilogue == EPI_RESIDUAL:
+            y = residual + y
+        elif epilogue == EPI_GATE_RES:
+            M = x.shape[0]
+            g = gate[torch.arange(M) // rows_per_gate]          # gate is a [groups, C] strided view
+            y = residual + y * g
+        if outs is not None:
+            for i, o in enumerate(outs):
+                o.copy_(y[:, i * seg_cols:(i + 1) * seg_cols])
+        else:
+            out.copy_(y)
+
+    def attention(self, q, k, v, out, scale):
+        self.launches += 1
+        self.log.append("attention")
+        out.copy_(O.dense_attention(q, k, v))
+
+    def modulation_table(self, mod, e, out, e_row_stride, e_group_stride):
+        self.launches += 1
+        NL, G, C = mod.shape
+        R = out.shape[1]
+        ef = e.reshape(-1)
+        for r in range(R):
+            for g in range(G):
+                base = r * e_row_stride + g * e_group_stride
+                out[:, r, g] = mod[:, g] + ef[base:base + C]
+
+    def ln_modulate(self, x, y, shift, scale, mod_stride, rows_per_mod, eps):
+        self.launches += 1
+        n = F.layer_norm(x, (x.shape[1],), None, None, eps)
+        idx = torch.arange(x.shape[0]) // rows_per_mod
+        y.copy_(n * (1 + scale[idx]) + shift[idx])
+
+    def ln_affine(self, x, y, weight, bias, eps):
+        self.launches += 1
+        y.copy_(F.layer_norm(x, (x.shape[1],), weight, bias, eps))
+
+    def rmsnorm(self, x, y, weight, eps):
+        self.launches += 1
+        y.copy_(O.rms_norm(x, weight, eps))
+
+    def qk_norm_rope(self, q_in, k_in, v_in, wq, wk, eps, cos_tab, sin_tab, B, L, head_dim, grid, start_frame,
+                     q_out, k_out, v_out):
+        self.launches += 1
+        C = q_in.shape[1]
+        H = C // head_dim
+        ang = O.rope_angle_table(head_dim)
+        q = O.rms_norm(q_in, wq, eps).view(B, L, H, head_dim)
+        k = O.rms_norm(k_in, wk, eps).view(B, L, H, head_dim)
+        q_out.copy_(O.rope_rotate(q, grid, ang, start_frame).reshape(B, L, C))
+        k_out.copy_(O.rope_rotate(k, grid, ang, start_frame))
+        if v_in is not None:
+            v_out.copy_(v_in.view(B, L, H, head_dim))
+
+    def patchify(self, x, out):
+        self.launches += 1
+        B, Cin, F_, H, W = x.shape
+        t = x.reshape(B, Cin, F_, H // 2, 2, W // 2, 2).permute(0, 2, 3, 5, 1, 4, 6)
+        out.copy_(t.reshape(B * F_ * (H // 2) * (W // 2), Cin * 4))
+
+    def sinusoid(self, t, out, freq_dim):
+        self.launches += 1
+        out.copy_(O.sinusoid_embed(freq_dim, t).to(out.dtype))
+
+    def skinny_linear(self, x, w, bias, y, silu_in):
+        self.launches += 1
+        y.copy_(F.linear(F.silu(x) if silu_in else x, w, bias))
+
+    def head_finish(self, head_out, xt, timestep, timesteps, sigmas, flow, x0):
+        self.launches += 1
+        B, F_, Cout, H, W = xt.shape
+        y = head_out.reshape(B, F_, H // 2, W // 2, 1, 2, 2, Cout)
+        y = y.permute(0, 7, 1, 4, 2, 5, 3, 6).reshape(B, Cout, F_, H, W).permute(0, 2, 1, 3, 4)
+        flow.copy_(y)
+        if x0 is not None:
+            ts, sg = timesteps.double(), sigmas.double()
+            idx = torch.argmin((ts.unsqueeze(0) - timestep.flatten().double().unsqueeze(1)).abs(), dim=1)
+            s = sg[idx].reshape(B, F_, 1, 1, 1)
+            x0.copy_((xt.double() - s * flow.double()).to(flow.dtype))
+
+    def add_noise(self, x0, noise, timestep, timesteps, sigmas, out):
+        self.launches += 1
+        idx = torch.argmin((timesteps.unsqueeze(0) - timestep.unsqueeze(1)).abs(), dim=1)
+        s = sigmas[idx].reshape(-1, 1, 1, 1)
+        out.copy_(((1 - s) * x0 + s * noise).type_as(noise))
