@@ -1,0 +1,196 @@
+"""Generates tests/golden/* by running the UNMODIFIED reference (imported from /root/reference
+through oracle/ref_shim.py) on seeded synthetic inputs.  Only runnable in the build container.
+
+    python -m oracle.make_golden
+
+Fixtures (all inputs are re-creatable from seeds, so only outputs are stored):
+  scheduler_tables.pt   FlowMatchScheduler sigmas/timesteps for shift 5 and 8 + warped step lists
+  rollout_tiny.pt       CausalInferencePipeline.inference latents, 2-layer model at full width:
+                          a) 3 frames, 1 frame/block, independent_first_frame, shift 8 (configs/tiny_test.yaml)
+                          b) 6 frames, 3 frames/block (chunk-wise), shift 5 (self_forcing_dmd.yaml sampler)
+  model_rolling.pt      CausalWanModel.forward with a rolling + sink KV cache on a small grid:
+                          per-forward flow, final K/V caches, (global_end, local_end) trace
+  block_masks.pt        BlockMask tables (kv_num_blocks, kv_indices, full_*) of the three mask builders
+"""
+from __future__ import annotations
+
+import contextlib
+import io
+import os
+import types
+
+import torch
+
+from oracle import causal_wan_oracle as O
+from oracle import ref_shim
+
+GOLDEN = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests", "golden")
+
+
+class SeededNoise:
+    """Device-independent stand-in for torch.randn_like: draws on CPU from a seeded generator."""
+
+    def __init__(self, seed: int):
+        self.g = torch.Generator().manual_seed(seed)
+
+    def __call__(self, like: torch.Tensor, **kw) -> torch.Tensor:
+        return torch.randn(like.shape, generator=self.g, dtype=torch.float32).to(like.dtype).to(like.device)
+
+
+@contextlib.contextmanager
+def patched_randn_like(seed: int):
+    orig = torch.randn_like
+    torch.randn_like = SeededNoise(seed)
+    try:
+        yield
+    finally:
+        torch.randn_like = orig
+
+
+def synthetic_inputs(batch: int, frames: int, H: int = 60, W: int = 104, text_dim: int = 4096):
+    pe = torch.randn(batch, 512, text_dim, generator=torch.Generator().manual_seed(1)).to(torch.bfloat16)
+    noise = torch.randn(batch, frames, 16, H, W, generator=torch.Generator().manual_seed(2)).to(torch.bfloat16)
+    return pe, noise
+
+
+class _TextEncoder(torch.nn.Module):
+    def __init__(self, pe):
+        super().__init__()
+        self.pe = pe
+
+    def forward(self, text_prompts):
+        return {"prompt_embeds": self.pe}
+
+
+class _IdentityVAE(torch.nn.Module):
+    def decode_to_pixel(self, x, use_cache=False):
+        return x
+
+
+ROLLOUT_CASES = {
+    "tiny_test_yaml": dict(frames=3, num_frame_per_block=1, independent_first_frame=True, shift=8.0),
+    "chunkwise": dict(frames=6, num_frame_per_block=3, independent_first_frame=False, shift=5.0),
+}
+
+
+def reference_rollout(ref, case: dict, params, cfg: O.OracleConfig):
+    w = ref_shim.make_reference_wrapper(ref, cfg.reference_kwargs(), case["shift"])
+    w.model.load_state_dict(params, strict=False)
+    args = types.SimpleNamespace(denoising_step_list=[1000, 750, 500, 250], warp_denoising_step=True,
+                                 num_frame_per_block=case["num_frame_per_block"],
+                                 independent_first_frame=case["independent_first_frame"], context_noise=0,
+                                 model_kwargs={})
+    pe, noise = synthetic_inputs(1, case["frames"])
+    with contextlib.redirect_stdout(io.StringIO()):
+        pipe = ref.CausalInferencePipeline(args, "cpu", generator=w, text_encoder=_TextEncoder(pe), vae=_IdentityVAE())
+        pipe.num_transformer_blocks = cfg.num_layers
+        with torch.no_grad(), patched_randn_like(3):
+            _, lat = pipe.inference(noise, ["synthetic"], return_latents=True)
+    idx = (int(pipe.kv_cache1[0]["global_end_index"]), int(pipe.kv_cache1[0]["local_end_index"]))
+    return lat, idx
+
+
+ROLLING = dict(dim=256, ffn_dim=256, num_heads=2, num_layers=2, text_dim=512, local_attn_size=3, sink_size=1,
+               frame_hw=(8, 12), chunks=6, forwards_per_chunk=2)
+
+
+def rolling_model_inputs():
+    r = ROLLING
+    g = torch.Generator().manual_seed(11)
+    x = torch.randn(1, 16, r["chunks"], *r["frame_hw"], generator=g).to(torch.bfloat16)
+    ctx = torch.randn(1, 512, r["text_dim"], generator=g).to(torch.bfloat16)
+    return x, ctx
+
+
+def rolling_cfg() -> O.OracleConfig:
+    r = ROLLING
+    return O.OracleConfig(dim=r["dim"], ffn_dim=r["ffn_dim"], num_heads=r["num_heads"], num_layers=r["num_layers"],
+                          text_dim=r["text_dim"], local_attn_size=r["local_attn_size"], sink_size=r["sink_size"])
+
+
+def reference_rolling(ref):
+    r = ROLLING
+    cfg = rolling_cfg()
+    params = O.make_random_params(cfg, seed=5)
+    torch.manual_seed(0)
+    model = ref.CausalWanModel(**cfg.reference_kwargs())
+    model.load_state_dict(params, strict=False)
+    model = model.to(torch.bfloat16).eval()
+    x, ctx = rolling_model_inputs()
+    ft = (r["frame_hw"][0] // 2) * (r["frame_hw"][1] // 2)
+    kv = O.new_kv_cache(cfg, 1, ft, torch.bfloat16, "cpu", cache_tokens=r["local_attn_size"] * ft)
+    ca = O.new_crossattn_cache(cfg, 1, torch.bfloat16, "cpu")
+    flows, trace = [], []
+    with torch.no_grad():
+        for c in range(r["chunks"]):
+            for k in range(r["forwards_per_chunk"]):
+                t = torch.full((1, 1), 1000.0 - 300.0 * k)
+                f = model(x[:, :, c:c + 1], t=t, context=ctx, seq_len=32760, kv_cache=kv, crossattn_cache=ca,
+                          current_start=c * ft, cache_start=None)
+                flows.append(f.clone())
+                trace.append((int(kv[0]["global_end_index"]), int(kv[0]["local_end_index"])))
+    return dict(flows=torch.stack(flows), trace=trace, k=[c["k"].clone() for c in kv], v=[c["v"].clone() for c in kv])
+
+
+MASK_CASES = {
+    "causal_6f_2blk": ("causal", dict(num_frames=6, frame_seqlen=200, num_frame_per_block=2, local_attn_size=-1)),
+    "causal_6f_local2": ("causal", dict(num_frames=6, frame_seqlen=200, num_frame_per_block=1, local_attn_size=2)),
+    "causal_21f_3blk_1560": ("causal", dict(num_frames=21, frame_seqlen=1560, num_frame_per_block=3, local_attn_size=-1)),
+    "i2v_7f_3blk": ("i2v", dict(num_frames=7, frame_seqlen=200, num_frame_per_block=3, local_attn_size=-1)),
+    "tf_4f_2blk": ("tf", dict(num_frames=4, frame_seqlen=200, num_frame_per_block=2)),
+}
+
+
+def reference_masks(ref):
+    out = {}
+    M = ref.CausalWanModel
+    for name, (kind, kw) in MASK_CASES.items():
+        with contextlib.redirect_stdout(io.StringIO()):
+            if kind == "causal":
+                bm = M._prepare_blockwise_causal_attn_mask("cpu", **kw)
+            elif kind == "i2v":
+                bm = M._prepare_blockwise_causal_attn_mask_i2v("cpu", **kw)
+            else:
+                bm = M._prepare_teacher_forcing_mask("cpu", **kw)
+        out[name] = dict(kv_num_blocks=bm.kv_num_blocks[0, 0].to(torch.int32),
+                         full_kv_num_blocks=bm.full_kv_num_blocks[0, 0].to(torch.int32),
+                         kv_indices=bm.kv_indices[0, 0].to(torch.int16),
+                         full_kv_indices=bm.full_kv_indices[0, 0].to(torch.int16),
+                         sparsity=float(bm.sparsity()))
+    return out
+
+
+def main():
+    ref = ref_shim.load_reference()
+    os.makedirs(GOLDEN, exist_ok=True)
+
+    sched = {}
+    for shift in (5.0, 8.0):
+        s = ref.FlowMatchScheduler(shift=shift, sigma_min=0.0, extra_one_step=True)
+        s.set_timesteps(1000, training=True)
+        ts = torch.cat((s.timesteps.cpu(), torch.tensor([0], dtype=torch.float32)))
+        sched[shift] = dict(sigmas=s.sigmas.clone(), timesteps=s.timesteps.clone(),
+                            warped=ts[1000 - torch.tensor([1000, 750, 500, 250])].clone())
+        x0 = torch.randn(3, 16, 8, 8, generator=torch.Generator().manual_seed(7)).to(torch.bfloat16)
+        nz = torch.randn(3, 16, 8, 8, generator=torch.Generator().manual_seed(8)).to(torch.bfloat16)
+        tt = sched[shift]["warped"][1:].clone()
+        sched[shift]["add_noise_out"] = s.add_noise(x0, nz, tt)
+    torch.save(sched, os.path.join(GOLDEN, "scheduler_tables.pt"))
+
+    cfg = O.OracleConfig(**O.WAN_TINY)
+    params = O.make_random_params(cfg, seed=0)
+    roll = {}
+    for name, case in ROLLOUT_CASES.items():
+        lat, idx = reference_rollout(ref, case, params, cfg)
+        roll[name] = dict(latents=lat, final_index=idx, case=case)
+        print(name, lat.shape, idx, float(lat.float().std()))
+    torch.save(roll, os.path.join(GOLDEN, "rollout_tiny.pt"))
+
+    torch.save(reference_rolling(ref), os.path.join(GOLDEN, "model_rolling.pt"))
+    torch.save(reference_masks(ref), os.path.join(GOLDEN, "block_masks.pt"))
+    for f in sorted(os.listdir(GOLDEN)):
+        print(f, os.path.getsize(os.path.join(GOLDEN, f)))
+
+
+if __name__ == "__main__":
+    main()

@@ -263,7 +263,7 @@ __global__ void sinusoid_kernel(const void* __restrict__ t, int t_dtype, __nv_bf
   const int jj = j < half ? j : j - half;
   const double w = pow(10000.0, -((double)jj / (double)half));
   const double a = load_timestep(t, t_dtype, i) * w;
-  out[idx] = __double2bfloat16(j < half ? cos(a) : sin(a));
+  out[idx] = __float2bfloat16_rn((float)(j < half ? cos(a) : sin(a)));   // torch: double -> float -> bf16
 }
 
 // ------------------------------------------------------------------------------------
@@ -381,7 +381,8 @@ head_finish_kernel(const __nv_bfloat16* __restrict__ head_out, long long ldh, co
     const double xv = want_x0 ? (double)__bfloat162float(xt[b * xs_b + f * xs_f + c * xs_c + yh * xs_y + xw * xs_x]) : 0.0;
     const long long o = ((long long)bf * Cout + c) * H * W + (long long)yh * W + xw;
     flow[o] = fl;
-    if (want_x0) x0[o] = __double2bfloat16(xv - sigma * (double)__bfloat162float(fl));
+    if (want_x0)   // torch casts double -> float -> bf16; no fma contraction
+      x0[o] = __float2bfloat16_rn((float)__dsub_rn(xv, __dmul_rn(sigma, (double)__bfloat162float(fl))));
   }
 }
 

@@ -1,0 +1,379 @@
+"""GPU parity checks of every kernel behind the C ABI, shared by the pytest suite (`-m gpu`) and by
+`tools/gpu_report.py` (which runs each check in its own process under a timeout so one hanging
+kernel cannot hide the others' results).
+
+Each check builds seeded inputs, calls the kernel through `self_forcing_b200.ops.CudaOps` (ctypes ->
+libsfb200.so) and compares with a plain PyTorch fp32 restatement of the same op that rounds to bf16
+at the reference's rounding points.  Returns a dict of error metrics and raises AssertionError on a
+parity failure.  Tolerances: bf16 outputs may differ by one rounding (rel-L2 <= 3e-3); integer /
+copy outputs must be bit-exact.
+"""
+from __future__ import annotations
+
+import math
+import os
+import sys
+
+import torch
+import torch.nn.functional as F
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+for p in (ROOT, os.path.join(ROOT, "tests")):
+    if p not in sys.path:
+        sys.path.insert(0, p)
+
+from _torch_ops import TorchOps  # noqa: E402
+from oracle import causal_wan_oracle as O  # noqa: E402
+
+BF = torch.bfloat16
+
+
+def _ops():
+    from self_forcing_b200.ops import CudaOps
+    return CudaOps()
+
+
+def rel_l2(a: torch.Tensor, b: torch.Tensor) -> float:
+    a, b = a.double(), b.double()
+    return float((a - b).norm() / b.norm().clamp_min(1e-30))
+
+
+def _randn(*shape, seed=0, scale=1.0, dtype=BF):
+    g = torch.Generator(device="cuda").manual_seed(seed)
+    return (torch.randn(*shape, generator=g, device="cuda") * scale).to(dtype)
+
+
+def _finish(name, metrics, tol):
+    torch.cuda.synchronize()
+    bad = {k: v for k, v in metrics.items() if k.startswith("err") and not (v <= tol)}
+    metrics["tol"] = tol
+    assert not bad, f"{name}: parity failure {bad} (tol {tol}); all metrics {metrics}"
+    return metrics
+
+
+# --------------------------------------------------------------------------------------
+def check_gemm(M=300, N=256, K=192, epilogue=0, block_n=0, rows_per_gate=100, seed=0):
+    ops = _ops()
+    x = _randn(M, K, seed=seed)
+    w = _randn(N, K, seed=seed + 1, scale=1.0 / math.sqrt(K))
+    b = _randn(N, seed=seed + 2, scale=0.5)
+    res = _randn(M, N, seed=seed + 3)
+    groups = (M + rows_per_gate - 1) // rows_per_gate
+    gate_tab = _randn(groups, 3, N, seed=seed + 4)        # strided gate rows like the modulation table
+    gate = gate_tab[:, 1]
+    out = torch.full((M, N), float("nan"), device="cuda", dtype=BF)
+    kw = {}
+    if epilogue in (2, 3):
+        kw["residual"] = res
+    if epilogue == 3:
+        kw.update(gate=gate, gate_stride=gate_tab.stride(0), rows_per_gate=rows_per_gate)
+    ops.gemm(x, w, b, out, epilogue=epilogue, block_n=block_n, **kw)
+    acc = x.float() @ w.float().t() + b.float()
+    y = acc.to(BF)
+    if epilogue == 1:
+        ref = F.gelu(y.float(), approximate="tanh").to(BF)
+    elif epilogue == 2:
+        ref = (res.float() + y.float()).to(BF)
+    elif epilogue == 3:
+        g = gate[torch.arange(M, device="cuda") // rows_per_gate]
+        ref = (res.float() + (y.float() * g.float()).to(BF).float()).to(BF)
+    else:
+        ref = y
+    m = dict(err_rel_l2=rel_l2(out, ref), max_abs=float((out.float() - ref.float()).abs().max()),
+             nan=int(torch.isnan(out.float()).sum()))
+    assert m["nan"] == 0, f"gemm produced NaN / left output unwritten: {m}"
+    return _finish(f"gemm M{M} N{N} K{K} epi{epilogue} bn{block_n}", m, 3e-3)
+
+
+def check_gemm_segments(M=300, C=256, K=128, seed=0):
+    """QKV-style call: one GEMM, three destinations with different row strides (V into a cache slot)."""
+    ops = _ops()
+    x = _randn(M, K, seed=seed)
+    w = _randn(3 * C, K, seed=seed + 1, scale=1.0 / math.sqrt(K))
+    b = _randn(3 * C, seed=seed + 2, scale=0.5)
+    q = torch.zeros(M, C, device="cuda", dtype=BF)
+    k = torch.zeros(M, C + 64, device="cuda", dtype=BF)[:, :C]
+    cache = torch.zeros(M + 50, C, device="cuda", dtype=BF)
+    ops.gemm(x, w, b, None, outs=[q, k, cache[20:20 + M]], seg_cols=C)
+    ref = (x.float() @ w.float().t() + b.float()).to(BF)
+    m = dict(err_q=rel_l2(q, ref[:, :C]), err_k=rel_l2(k, ref[:, C:2 * C]), err_v=rel_l2(cache[20:20 + M], ref[:, 2 * C:]),
+             err_untouched=float(cache[:20].float().abs().max() + cache[20 + M:].float().abs().max()))
+    return _finish("gemm segments", m, 3e-3)
+
+
+def _attn_ref(q, k, v, scale):
+    qf, kf, vf = (t.float().transpose(1, 2) for t in (q, k, v))
+    s = (qf @ kf.transpose(-1, -2)) * scale
+    p = torch.softmax(s, dim=-1)
+    return (p @ vf).transpose(1, 2)
+
+
+def check_attention(B=1, Lq=300, S=520, H=2, seed=0, cache_rows=None, window_start=0, fused_q=False):
+    ops = _ops()
+    D = 128
+    cache_rows = cache_rows or (S + window_start + 7)
+    if fused_q:   # q lives inside a wider buffer (row stride > H*D)
+        qbuf = _randn(B, Lq, H * D + 256, seed=seed)
+        q = qbuf[:, :, :H * D].unflatten(2, (H, D))
+    else:
+        q = _randn(B, Lq, H, D, seed=seed)
+    kc = _randn(B, cache_rows, H, D, seed=seed + 1)
+    vc = _randn(B, cache_rows, H, D, seed=seed + 2)
+    k = kc[:, window_start:window_start + S]
+    v = vc[:, window_start:window_start + S]
+    out = torch.full((B, Lq, H, D), float("nan"), device="cuda", dtype=BF)
+    scale = 1.0 / math.sqrt(D)
+    ops.attention(q, k, v, out, scale)
+    ref = _attn_ref(q, k, v, scale)
+    m = dict(err_rel_l2=rel_l2(out, ref), max_abs=float((out.float() - ref).abs().max()),
+             nan=int(torch.isnan(out.float()).sum()))
+    assert m["nan"] == 0, f"attention produced NaN / left rows unwritten: {m}"
+    # per-head error helps localise descriptor / layout mistakes
+    m["per_head"] = [round(rel_l2(out[:, :, h], ref[:, :, h]), 5) for h in range(H)]
+    return _finish(f"attention B{B} Lq{Lq} S{S} H{H}", m, 6e-3)
+
+
+def check_attention_sharp(Lq=256, S=640, H=1, seed=3):
+    """Large-magnitude scores (row max grows late) exercise the lazy O rescale."""
+    ops = _ops()
+    D = 128
+    q = _randn(1, Lq, H, D, seed=seed, scale=3.0)
+    k = _randn(1, S, H, D, seed=seed + 1, scale=3.0)
+    k[:, S - 100:] *= 2.0        # later tiles dominate -> reference max jumps by far more than 2^8
+    v = _randn(1, S, H, D, seed=seed + 2)
+    out = torch.empty(1, Lq, H, D, device="cuda", dtype=BF)
+    ops.attention(q, k, v, out, 1.0 / math.sqrt(D))
+    ref = _attn_ref(q, k, v, 1.0 / math.sqrt(D))
+    m = dict(err_rel_l2=rel_l2(out, ref), nan=int(torch.isnan(out.float()).sum()))
+    assert m["nan"] == 0
+    return _finish("attention sharp", m, 8e-3)
+
+
+# --------------------------------------------------------------------------------------
+def _against_double(name, run, outputs, tol=3e-3, exact=()):
+    """run(ops, outs) is executed with CudaOps and with the TorchOps double; outputs compared."""
+    cu = {k: v.clone() for k, v in outputs.items()}
+    rf = {k: v.clone() for k, v in outputs.items()}
+    run(_ops(), cu)
+    run(TorchOps(), rf)
+    torch.cuda.synchronize()
+    m = {}
+    for k in outputs:
+        if k in exact:
+            m[f"err_{k}_mismatch"] = float((cu[k] != rf[k]).sum())
+        else:
+            m[f"err_{k}"] = rel_l2(cu[k], rf[k])
+            m[f"max_{k}"] = float((cu[k].float() - rf[k].float()).abs().max())
+    bad = {k: v for k, v in m.items() if k.startswith("err") and not (v <= (0 if k.endswith("mismatch") else tol))}
+    assert not bad, f"{name}: {bad}; {m}"
+    return m
+
+
+def check_ln_modulate(rows=777, C=1536, rpm=200, seed=0):
+    x = _randn(rows, C, seed=seed, scale=2.0) + 0.3
+    tab = _randn((rows + rpm - 1) // rpm, 6, C, seed=seed + 1, scale=0.5)
+
+    def run(ops, o):
+        ops.ln_modulate(x, o["y"], shift=tab[:, 3], scale=tab[:, 4], mod_stride=6 * C, rows_per_mod=rpm, eps=1e-6)
+    return _against_double("ln_modulate", run, dict(y=torch.zeros(rows, C, device="cuda", dtype=BF)))
+
+
+def check_ln_affine(rows=333, C=1536, seed=0):
+    x = _randn(rows, C, seed=seed, scale=2.0) - 0.2
+    w, b = _randn(C, seed=seed + 1) * 0.1 + 1, _randn(C, seed=seed + 2) * 0.1
+
+    def run(ops, o):
+        ops.ln_affine(x, o["y"], w, b, 1e-6)
+    return _against_double("ln_affine", run, dict(y=torch.zeros(rows, C, device="cuda", dtype=BF)))
+
+
+def check_rmsnorm(rows=333, C=1536, seed=0):
+    x = _randn(rows, C, seed=seed, scale=2.0)
+    w = _randn(C, seed=seed + 1) * 0.1 + 1
+
+    def run(ops, o):
+        ops.rmsnorm(x, o["y"], w, 1e-6)
+    return _against_double("rmsnorm", run, dict(y=torch.zeros(rows, C, device="cuda", dtype=BF)))
+
+
+def check_qk_norm_rope(B=2, F_=2, Hh=5, Ww=7, C=1536, start_frame=3, seed=0, with_v=True):
+    D = 128
+    H = C // D
+    L = F_ * Hh * Ww
+    qkv = _randn(B * L, 3 * C, seed=seed)
+    wq, wk = _randn(C, seed=seed + 1) * 0.1 + 1, _randn(C, seed=seed + 2) * 0.1 + 1
+    from self_forcing_b200.model import rope_tables
+    cos, sin = (t.cuda() for t in rope_tables(D))
+    cache_rows = L + 11
+
+    def run(ops, o):
+        ops.qk_norm_rope(qkv[:, :C], qkv[:, C:2 * C], qkv[:, 2 * C:] if with_v else None, wq, wk, 1e-6, cos, sin, B, L,
+                         D, (F_, Hh, Ww), start_frame, q_out=o["q"], k_out=o["kc"][:, 5:5 + L], v_out=o["vc"][:, 5:5 + L])
+    outs = dict(q=torch.zeros(B, L, C, device="cuda", dtype=BF),
+                kc=torch.zeros(B, cache_rows, H, D, device="cuda", dtype=BF),
+                vc=torch.zeros(B, cache_rows, H, D, device="cuda", dtype=BF))
+    return _against_double("qk_norm_rope", run, outs, exact=("vc",))
+
+
+def check_patchify(B=2, F_=3, H=12, W=20, seed=0):
+    x = _randn(B, F_, 16, H, W, seed=seed).permute(0, 2, 1, 3, 4)      # the wrapper's permuted view
+
+    def run(ops, o):
+        ops.patchify(x, o["t"])
+    return _against_double("patchify", run, dict(t=torch.zeros(B * F_ * (H // 2) * (W // 2), 64, device="cuda", dtype=BF)),
+                           exact=("t",))
+
+
+def check_sinusoid(seed=0):
+    m = {}
+    for t in (torch.tensor([1000.0, 937.5, 833.3333129882812, 625.0, 0.0, 3.0], device="cuda"),
+              torch.tensor([1000, 937, 0, 17], device="cuda", dtype=torch.int64)):
+        def run(ops, o):
+            ops.sinusoid(t, o["s"], 256)
+        r = _against_double("sinusoid", run, dict(s=torch.zeros(t.numel(), 256, device="cuda", dtype=BF)), tol=2e-3)
+        m.update({f"{k}_{t.dtype}": v for k, v in r.items()})
+    return m
+
+
+def check_skinny_linear(M=3, N=1536, K=256, silu=False, seed=0):
+    x = _randn(M, K, seed=seed)
+    w = _randn(N, K, seed=seed + 1, scale=1 / math.sqrt(K))
+    b = _randn(N, seed=seed + 2, scale=0.1)
+
+    def run(ops, o):
+        ops.skinny_linear(x, w, b, o["y"], silu_in=silu)
+    return _against_double(f"skinny M{M} N{N} K{K}", run, dict(y=torch.zeros(M, N, device="cuda", dtype=BF)))
+
+
+def check_modulation_table(NL=3, R=4, C=1536, seed=0):
+    mod = _randn(NL, 6, C, seed=seed)
+    e0 = _randn(R, 6 * C, seed=seed + 1)
+    hm = _randn(1, 2, C, seed=seed + 2)
+    e = _randn(R, C, seed=seed + 3)
+
+    def run(ops, o):
+        ops.modulation_table(mod, e0, o["a"], e_row_stride=6 * C, e_group_stride=C)
+        ops.modulation_table(hm, e, o["b"], e_row_stride=C, e_group_stride=0)
+    return _against_double("modulation_table", run, dict(a=torch.zeros(NL, R, 6, C, device="cuda", dtype=BF),
+                                                         b=torch.zeros(1, R, 2, C, device="cuda", dtype=BF)),
+                           exact=("a", "b"))
+
+
+def check_head_finish(B=2, F_=3, H=12, W=20, shift=5.0, seed=0):
+    sched = O.OracleScheduler(shift)
+    ts, sg = sched.timesteps.cuda(), sched.sigmas.cuda()
+    L = F_ * (H // 2) * (W // 2)
+    head_out = _randn(B * L, 64, seed=seed)
+    big = _randn(B, F_ + 2, 16, H, W, seed=seed + 1)
+    xt = big[:, 1:1 + F_]                                   # non-contiguous slice like noise[:, a:b]
+    m = {}
+    for timestep in (torch.tensor([[1000.0, 937.5, 833.3333129882812]] * B, device="cuda"),
+                     torch.tensor([[0, 625, 250]] * B, device="cuda", dtype=torch.int64)):
+        def run(ops, o):
+            ops.head_finish(head_out, xt, timestep, ts, sg, o["flow"], o["x0"])
+        r = _against_double("head_finish", run, dict(flow=torch.zeros(B, F_, 16, H, W, device="cuda", dtype=BF),
+                                                     x0=torch.zeros(B, F_, 16, H, W, device="cuda", dtype=BF)),
+                            exact=("flow", "x0"))
+        m.update({f"{k}_{timestep.dtype}": v for k, v in r.items()})
+    return m
+
+
+def check_add_noise(N=3, shift=5.0, seed=0):
+    sched = O.OracleScheduler(shift)
+    ts, sg = sched.timesteps.cuda(), sched.sigmas.cuda()
+    x0 = _randn(N, 16, 12, 20, seed=seed)
+    nz = _randn(N, 16, 12, 20, seed=seed + 1)
+    m = {}
+    for timestep in (torch.tensor([937.5, 833.3333129882812, 625.0], device="cuda")[:N],
+                     torch.tensor([937, 0, 250], device="cuda", dtype=torch.int64)[:N]):
+        def run(ops, o):
+            ops.add_noise(x0, nz, timestep, ts, sg, o["y"])
+        r = _against_double("add_noise", run, dict(y=torch.zeros_like(x0)), exact=("y",))
+        m.update({f"{k}_{timestep.dtype}": v for k, v in r.items()})
+    return m
+
+
+# --------------------------------------------------------------------------------------
+def _tiny_setup(num_layers=2, ffn_dim=512, shift=5.0, seed=0):
+    from self_forcing_b200.wrapper import WAN_T2V_1_3B, B200DiffusionWrapper
+    cfg = O.OracleConfig(dim=1536, ffn_dim=ffn_dim, num_heads=12, num_layers=num_layers)
+    params = O.make_random_params(cfg, seed=seed)
+    w = B200DiffusionWrapper(model_config=dict(WAN_T2V_1_3B, ffn_dim=ffn_dim, num_layers=num_layers),
+                             timestep_shift=shift, device="cuda")
+    w.model.load_state_dict(params, strict=True)
+    gpu_params = {k: v.cuda() for k, v in params.items()}
+    return cfg, gpu_params, w
+
+
+def check_model_forward(F_=1, H=60, W=104, seed=0):
+    """Two consecutive cached forwards of a 2-layer model vs the oracle run on the same GPU."""
+    cfg, params, w = _tiny_setup()
+    ow = O.OracleWrapper(params, cfg, 5.0)
+    fs = (H // 2) * (W // 2)
+    pe = _randn(1, 512, 4096, seed=1)
+    x = _randn(1, 2 * F_, 16, H, W, seed=2)
+    m = {}
+    kv_a, ca_a = O.new_kv_cache(cfg, 1, fs, BF, "cuda", cache_tokens=4 * F_ * fs), O.new_crossattn_cache(cfg, 1, BF, "cuda")
+    kv_b, ca_b = O.new_kv_cache(cfg, 1, fs, BF, "cuda", cache_tokens=4 * F_ * fs), O.new_crossattn_cache(cfg, 1, BF, "cuda")
+    for step, (t, start) in enumerate([(1000.0, 0), (0.0, 0), (937.5, F_)]):
+        xin = x[:, :F_] if start == 0 else x[:, F_:]
+        ts = torch.full((1, F_), t, device="cuda")
+        f1, x1 = w(xin, {"prompt_embeds": pe}, ts, kv_cache=kv_a, crossattn_cache=ca_a, current_start=start * fs)
+        with torch.no_grad():
+            f2, x2 = ow(xin, pe, ts, kv_b, ca_b, start * fs)
+        m[f"err_flow_{step}"] = rel_l2(f1, f2)
+        m[f"err_x0_{step}"] = rel_l2(x1, x2)
+        m[f"err_k_{step}"] = rel_l2(kv_a[1]["k"], kv_b[1]["k"])
+        m[f"err_v_{step}"] = rel_l2(kv_a[1]["v"], kv_b[1]["v"])
+        m[f"idx_{step}"] = (int(kv_a[0]["global_end_index"]), int(kv_a[0]["local_end_index"]),
+                            int(kv_b[0]["global_end_index"]), int(kv_b[0]["local_end_index"]))
+        assert m[f"idx_{step}"][:2] == m[f"idx_{step}"][2:], m
+    return _finish("model_forward", m, 1e-2)
+
+
+ALL = {
+    "gemm_small": lambda: check_gemm(),
+    "gemm_bn64": lambda: check_gemm(M=200, N=64, K=1536, block_n=64),
+    "gemm_bn128": lambda: check_gemm(M=300, N=384, K=256, block_n=128),
+    "gemm_bn256": lambda: check_gemm(M=515, N=512, K=320, block_n=256),
+    "gemm_k64": lambda: check_gemm(M=700, N=1536, K=64),
+    "gemm_gelu": lambda: check_gemm(M=300, N=512, K=256, epilogue=1),
+    "gemm_residual": lambda: check_gemm(M=300, N=256, K=256, epilogue=2),
+    "gemm_gate": lambda: check_gemm(M=300, N=256, K=256, epilogue=3, rows_per_gate=70),
+    "gemm_qkv_full": lambda: check_gemm(M=4680, N=4608, K=1536),
+    "gemm_ffn2_full": lambda: check_gemm(M=4680, N=1536, K=8960, epilogue=3, rows_per_gate=1560),
+    "gemm_segments": check_gemm_segments,
+    "attn_small": lambda: check_attention(),
+    "attn_one_tile": lambda: check_attention(Lq=128, S=128, H=1),
+    "attn_tail": lambda: check_attention(Lq=72, S=72, H=3),
+    "attn_window": lambda: check_attention(Lq=260, S=1000, H=2, window_start=37),
+    "attn_batch": lambda: check_attention(B=2, Lq=200, S=384, H=2),
+    "attn_fusedq": lambda: check_attention(Lq=300, S=520, H=2, fused_q=True),
+    "attn_cross": lambda: check_attention(Lq=1560, S=512, H=12),
+    "attn_sharp": check_attention_sharp,
+    "attn_chunk": lambda: check_attention(Lq=4680, S=4680, H=12),
+    "ln_modulate": check_ln_modulate,
+    "ln_affine": check_ln_affine,
+    "rmsnorm": check_rmsnorm,
+    "qk_norm_rope": check_qk_norm_rope,
+    "qk_norm_rope_nov": lambda: check_qk_norm_rope(B=1, with_v=False),
+    "patchify": check_patchify,
+    "sinusoid": check_sinusoid,
+    "skinny_linear": check_skinny_linear,
+    "skinny_linear_silu": lambda: check_skinny_linear(M=6, N=9216, K=1536, silu=True),
+    "modulation_table": check_modulation_table,
+    "head_finish": check_head_finish,
+    "add_noise": check_add_noise,
+    "model_forward": check_model_forward,
+}
+
+
+if __name__ == "__main__":
+    import json
+    name = sys.argv[1]
+    try:
+        res = ALL[name]()
+        print("RESULT " + json.dumps(dict(name=name, ok=True, metrics=res)))
+    except AssertionError as e:
+        print("RESULT " + json.dumps(dict(name=name, ok=False, error=str(e)[:2000])))
+        sys.exit(1)

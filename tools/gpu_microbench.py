@@ -1,0 +1,99 @@
+"""Device-time microbenchmarks of the two tensor-core kernels at the 1.3B rollout shapes.
+Writes gpurun_out/microbench.json.  CUDA events on the launching stream, L2 flushed between reps."""
+from __future__ import annotations
+
+import json
+import math
+import os
+import sys
+
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+from self_forcing_b200.ops import CudaOps  # noqa: E402
+
+BF = torch.bfloat16
+
+
+def timeit(fn, reps=10, warm=3, flush=None):
+    for _ in range(warm):
+        fn()
+    torch.cuda.synchronize()
+    ts = []
+    for _ in range(reps):
+        if flush is not None:
+            flush.zero_()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        fn()
+        b.record()
+        torch.cuda.synchronize()
+        ts.append(a.elapsed_time(b))
+    ts.sort()
+    return ts[len(ts) // 2], ts[0]
+
+
+def main():
+    ops = CudaOps()
+    flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device="cuda")
+    out = []
+    only = sys.argv[1:]
+    M = 4680
+    gemms = [("qkv", 4608, 1536, 0, 0), ("qkv_bn128", 4608, 1536, 0, 128), ("o_proj", 1536, 1536, 3, 0),
+             ("o_proj_bn256", 1536, 1536, 3, 256), ("ffn1", 8960, 1536, 1, 0), ("ffn1_bn128", 8960, 1536, 1, 128),
+             ("ffn2", 1536, 8960, 3, 0), ("ffn2_bn256", 1536, 8960, 3, 256), ("head", 64, 1536, 0, 0)]
+    for name, N, K, epi, bn in gemms:
+        if only and not any(o in "gemm_" + name for o in only):
+            continue
+        x = torch.randn(M, K, device="cuda").to(BF)
+        w = (torch.randn(N, K, device="cuda") / math.sqrt(K)).to(BF)
+        b = torch.randn(N, device="cuda").to(BF)
+        res = torch.randn(M, N, device="cuda").to(BF)
+        gate = torch.randn(3, N, device="cuda").to(BF)
+        y = torch.empty(M, N, device="cuda", dtype=BF)
+        kw = dict(epilogue=epi, block_n=bn)
+        if epi in (2, 3):
+            kw["residual"] = res
+        if epi == 3:
+            kw.update(gate=gate, gate_stride=N, rows_per_gate=1560)
+        med, best = timeit(lambda: ops.gemm(x, w, b, y, **kw), flush=flush)
+        tmed, _ = timeit(lambda: torch.nn.functional.linear(x, w, b), flush=flush)
+        fl = 2.0 * M * N * K
+        rec = dict(kernel="gemm_" + name, M=M, N=N, K=K, ms=med, ms_best=best, tflops=fl / med / 1e9,
+                   cublas_ms=tmed, cublas_tflops=fl / tmed / 1e9)
+        print(json.dumps(rec), flush=True)
+        out.append(rec)
+    for name, Lq, S, H in [("self_S4680", 4680, 4680, 12), ("self_S18720", 4680, 18720, 12),
+                           ("self_S32760", 4680, 32760, 12), ("cross_S512", 4680, 512, 12),
+                           ("frame_S32760", 1560, 32760, 12)]:
+        if only and not any(o in "attn_" + name for o in only):
+            continue
+        q = torch.randn(1, Lq, H, 128, device="cuda").to(BF)
+        k = torch.randn(1, S, H, 128, device="cuda").to(BF)
+        v = torch.randn(1, S, H, 128, device="cuda").to(BF)
+        o = torch.empty_like(q)
+        med, best = timeit(lambda: ops.attention(q, k, v, o, 1 / math.sqrt(128)), flush=flush, reps=5)
+        fl = 4.0 * Lq * S * H * 128
+        rec = dict(kernel="attn_" + name, Lq=Lq, S=S, H=H, ms=med, ms_best=best, tflops=fl / med / 1e9)
+        try:
+            tmed, _ = timeit(lambda: torch.nn.functional.scaled_dot_product_attention(
+                q.transpose(1, 2), k.transpose(1, 2), v.transpose(1, 2)), flush=flush, reps=5)
+            rec.update(sdpa_ms=tmed, sdpa_tflops=fl / tmed / 1e9)
+        except Exception as e:  # pragma: no cover
+            rec["sdpa_error"] = str(e)[:100]
+        try:
+            from flash_attn import flash_attn_func
+            tmed, _ = timeit(lambda: flash_attn_func(q, k, v), flush=flush, reps=5)
+            rec.update(fa2_ms=tmed, fa2_tflops=fl / tmed / 1e9)
+        except Exception as e:  # pragma: no cover
+            rec["fa2_error"] = str(e)[:100]
+        print(json.dumps(rec), flush=True)
+        out.append(rec)
+    os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
+    with open(os.path.join(ROOT, "gpurun_out", "microbench.json"), "w") as f:
+        json.dump(out, f, indent=1)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,50 @@
+"""Runs every GPU parity check of tests/gpu_checks.py in its own process under a timeout and writes
+gpurun_out/gpu_report.json.  One hung / crashed kernel therefore cannot hide the other results.
+
+    python tools/gpu_report.py [name-substring ...]
+"""
+from __future__ import annotations
+
+import json
+import os
+import subprocess
+import sys
+import time
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+
+def main():
+    import gpu_checks
+    names = list(gpu_checks.ALL)
+    filt = sys.argv[1:]
+    if filt:
+        names = [n for n in names if any(f in n for f in filt)]
+    os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
+    results = []
+    for n in names:
+        t0 = time.time()
+        try:
+            r = subprocess.run([sys.executable, os.path.join(ROOT, "tests", "gpu_checks.py"), n], capture_output=True,
+                               text=True, timeout=int(os.environ.get("SFB_CHECK_TIMEOUT", "150")), cwd=ROOT)
+            line = [l for l in r.stdout.splitlines() if l.startswith("RESULT ")]
+            if line:
+                rec = json.loads(line[-1][7:])
+            else:
+                rec = dict(name=n, ok=False, error="no result", stderr=r.stderr[-3000:], rc=r.returncode)
+        except subprocess.TimeoutExpired as e:
+            rec = dict(name=n, ok=False, error="TIMEOUT", stderr=(e.stderr or b"")[-2000:].decode("utf8", "replace")
+                       if isinstance(e.stderr, bytes) else str(e.stderr)[-2000:])
+        rec["seconds"] = round(time.time() - t0, 1)
+        results.append(rec)
+        print(json.dumps(rec)[:1500], flush=True)
+        with open(os.path.join(ROOT, "gpurun_out", "gpu_report.json"), "w") as f:
+            json.dump(results, f, indent=1)
+    bad = [r["name"] for r in results if not r.get("ok")]
+    print(f"SUMMARY {len(results) - len(bad)}/{len(results)} ok; failed: {bad}")
+
+
+if __name__ == "__main__":
+    main()
