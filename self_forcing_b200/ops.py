@@ -4,6 +4,8 @@ from __future__ import annotations
 
 from typing import Optional, Sequence
 
+import functools
+
 import torch
 
 from . import _lib
@@ -22,6 +24,24 @@ def _check_2d(t: torch.Tensor, name: str) -> None:
                          f"{tuple(t.shape)} {t.dtype} {t.device} strides {t.stride()}")
 
 
+def _op(fn):
+    """Counts the launch and, while profiling is on, brackets it with CUDA events on the launching stream."""
+    name = fn.__name__
+
+    @functools.wraps(fn)
+    def wrapped(self, *a, **k):
+        self.launches += 1
+        if self._prof is None:
+            return fn(self, *a, **k)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        out = fn(self, *a, **k)
+        e1.record()
+        self._prof.append((name, self._prof_tag(name, a, k), e0, e1))
+        return out
+    return wrapped
+
+
 class CudaOps:
     """The op set the host model is written against.  Every method enqueues exactly one kernel
     of libsfb200.so on the current CUDA stream."""
@@ -33,12 +53,35 @@ class CudaOps:
         if not torch.cuda.is_available():
             raise _lib.SfbError("CUDA device required: the B200 path has no CPU fallback")
         self.launches = 0
+        self._prof = None
+
+    # -- optional per-launch device timing (bench.py roofline leg) ------------------------------
+    def start_profile(self):
+        self._prof = []
+
+    def stop_profile(self):
+        """-> list of (op name, tag, milliseconds) for every launch since start_profile()."""
+        torch.cuda.synchronize()
+        out = [(n, tag, e0.elapsed_time(e1)) for n, tag, e0, e1 in (self._prof or [])]
+        self._prof = None
+        return out
+
+    @staticmethod
+    def _prof_tag(name, a, k):
+        if name == "attention":
+            q, kk = a[0], a[1]
+            return ("attention", q.shape[0], q.shape[1], kk.shape[1], q.shape[2])
+        if name == "gemm":
+            x, w = a[0], a[1]
+            return ("gemm", x.shape[0], w.shape[0], x.shape[1], k.get("epilogue", 0))
+        return (name,)
 
     @staticmethod
     def _stream():
         return torch.cuda.current_stream().cuda_stream
 
     # -- dense projections ---------------------------------------------------------------
+    @_op
     def gemm(self, x, w, bias, out, *, epilogue=EPI_BIAS, residual=None, gate=None, gate_stride=0,
              rows_per_gate=1, outs: Optional[Sequence[torch.Tensor]] = None, seg_cols=0, block_n=0):
         _check_2d(x, "x"); _check_2d(w, "w")
@@ -52,7 +95,6 @@ class CudaOps:
             segs.append(None)
         if residual is not None:
             _check_2d(residual, "residual")
-        self.launches += 1
         _lib.check(self.lib.sfb_gemm_bf16(
             x.data_ptr(), x.stride(0), w.data_ptr(), w.stride(0), _ptr(bias), M, N, K, epilogue,
             _ptr(segs[0]), segs[0].stride(0), _ptr(segs[1]), segs[1].stride(0) if segs[1] is not None else 0,
@@ -61,6 +103,7 @@ class CudaOps:
             _ptr(gate), gate_stride, rows_per_gate, block_n, self._stream()), "sfb_gemm_bf16")
 
     # -- attention ------------------------------------------------------------------------
+    @_op
     def attention(self, q, k, v, out, scale: float):
         """q/out [B, Lq, H, D] views, k/v [B, S, H, D] views (the cache window)."""
         B, Lq, H, D = q.shape
@@ -68,42 +111,42 @@ class CudaOps:
         for t in (q, k, v, out):
             assert t.stride(3) == 1 and t.stride(2) == D and t.dtype == torch.bfloat16
         assert k.stride() == v.stride() and k.shape == v.shape
-        self.launches += 1
         _lib.check(self.lib.sfb_attention_fwd(
             q.data_ptr(), q.stride(1), q.stride(0), k.data_ptr(), v.data_ptr(), k.stride(1), k.stride(0),
             out.data_ptr(), out.stride(1), out.stride(0), B, Lq, S, H, D, scale, self._stream()),
             "sfb_attention_fwd")
 
     # -- normalisation / modulation -------------------------------------------------------
+    @_op
     def modulation_table(self, mod, e, out, e_row_stride: int, e_group_stride: int):
         NL, G, C = mod.shape
         R = out.shape[1]
         assert out.shape == (NL, R, G, C) and out.is_contiguous() and mod.is_contiguous()
-        self.launches += 1
         _lib.check(self.lib.sfb_modulation_table(mod.data_ptr(), e.data_ptr(), out.data_ptr(), NL, R, G, C,
                                                  e_row_stride, e_group_stride, self._stream()),
                    "sfb_modulation_table")
 
+    @_op
     def ln_modulate(self, x, y, shift, scale, mod_stride: int, rows_per_mod: int, eps: float):
         _check_2d(x, "x"); _check_2d(y, "y")
-        self.launches += 1
         _lib.check(self.lib.sfb_ln_modulate(x.data_ptr(), x.stride(0), y.data_ptr(), y.stride(0), x.shape[0],
                                             x.shape[1], eps, shift.data_ptr(), scale.data_ptr(), mod_stride,
                                             rows_per_mod, self._stream()), "sfb_ln_modulate")
 
+    @_op
     def ln_affine(self, x, y, weight, bias, eps: float):
         _check_2d(x, "x"); _check_2d(y, "y")
-        self.launches += 1
         _lib.check(self.lib.sfb_ln_affine(x.data_ptr(), x.stride(0), y.data_ptr(), y.stride(0), x.shape[0],
                                           x.shape[1], eps, weight.data_ptr(), bias.data_ptr(), self._stream()),
                    "sfb_ln_affine")
 
+    @_op
     def rmsnorm(self, x, y, weight, eps: float):
         _check_2d(x, "x"); _check_2d(y, "y")
-        self.launches += 1
         _lib.check(self.lib.sfb_rmsnorm(x.data_ptr(), x.stride(0), y.data_ptr(), y.stride(0), x.shape[0],
                                         x.shape[1], eps, weight.data_ptr(), self._stream()), "sfb_rmsnorm")
 
+    @_op
     def qk_norm_rope(self, q_in, k_in, v_in, wq, wk, eps, cos_tab, sin_tab, B, L, head_dim, grid, start_frame,
                      q_out, k_out, v_out):
         """q_in/k_in/v_in [B*L, C]; q_out [B, L, C]-like view; k_out/v_out [B, L, H, D] cache-slot views."""
@@ -112,7 +155,6 @@ class CudaOps:
         F_, Hh, Ww = grid
         assert cos_tab.dtype == torch.float32 and cos_tab.is_contiguous() and sin_tab.is_contiguous()
         assert k_out.stride() == v_out.stride()
-        self.launches += 1
         _lib.check(self.lib.sfb_qk_norm_rope(
             q_in.data_ptr(), q_in.stride(0), k_in.data_ptr(), k_in.stride(0), _ptr(v_in),
             v_in.stride(0) if v_in is not None else 0, wq.data_ptr(), wk.data_ptr(), eps, cos_tab.data_ptr(),
@@ -121,47 +163,47 @@ class CudaOps:
             k_out.stride(1), k_out.stride(0), self._stream()), "sfb_qk_norm_rope")
 
     # -- embeddings -----------------------------------------------------------------------
+    @_op
     def patchify(self, x, out):
         """x [B, Cin, F, H, W] (any strides) -> out [B*F*(H/2)*(W/2), Cin*4]."""
         B, Cin, F_, H, W = x.shape
         assert out.is_contiguous() and x.dtype == torch.bfloat16
         sb, sc, sf, sy, sx = x.stride()
-        self.launches += 1
         _lib.check(self.lib.sfb_patchify(x.data_ptr(), sb, sc, sf, sy, sx, out.data_ptr(), B, Cin, F_, H, W,
                                          self._stream()), "sfb_patchify")
 
+    @_op
     def sinusoid(self, t, out, freq_dim: int):
         assert t.is_contiguous() and t.dtype in _T_DTYPE
-        self.launches += 1
         _lib.check(self.lib.sfb_sinusoid(t.data_ptr(), _T_DTYPE[t.dtype], out.data_ptr(), t.numel(), freq_dim,
                                          self._stream()), "sfb_sinusoid")
 
+    @_op
     def skinny_linear(self, x, w, bias, y, silu_in: bool):
         _check_2d(x, "x"); _check_2d(w, "w"); _check_2d(y, "y")
-        self.launches += 1
         _lib.check(self.lib.sfb_skinny_linear(x.data_ptr(), x.stride(0), w.data_ptr(), w.stride(0), _ptr(bias),
                                               y.data_ptr(), y.stride(0), x.shape[0], w.shape[0], x.shape[1],
                                               1 if silu_in else 0, self._stream()), "sfb_skinny_linear")
 
     # -- sampler --------------------------------------------------------------------------
+    @_op
     def head_finish(self, head_out, xt, timestep, timesteps, sigmas, flow, x0):
         """head_out [B*L, 4*Cout]; xt [B, F, Cout, H, W] view; timestep [B, F]; flow/x0 contiguous outputs."""
         B, F_, Cout, H, W = xt.shape
         assert flow.is_contiguous() and (x0 is None or x0.is_contiguous())
         assert timestep.is_contiguous() and timestep.dtype in _T_DTYPE
         sb, sf, sc, sy, sx = xt.stride()
-        self.launches += 1
         _lib.check(self.lib.sfb_head_finish(
             head_out.data_ptr(), head_out.stride(0), xt.data_ptr(), sb, sf, sc, sy, sx, timestep.data_ptr(),
             _T_DTYPE[timestep.dtype], _ptr(timesteps), _ptr(sigmas), 0 if timesteps is None else timesteps.numel(),
             flow.data_ptr(), _ptr(x0), B, F_, Cout, H, W, self._stream()), "sfb_head_finish")
 
+    @_op
     def add_noise(self, x0, noise, timestep, timesteps, sigmas, out):
         """x0/noise/out [N, C, H, W] contiguous, timestep [N]."""
         assert x0.is_contiguous() and noise.is_contiguous() and out.is_contiguous()
         assert timestep.is_contiguous() and timestep.dtype in _T_DTYPE
         n = x0.shape[0]
-        self.launches += 1
         _lib.check(self.lib.sfb_add_noise(x0.data_ptr(), noise.data_ptr(), timestep.data_ptr(),
                                           _T_DTYPE[timestep.dtype], timesteps.data_ptr(), sigmas.data_ptr(),
                                           timesteps.numel(), out.data_ptr(), n, x0[0].numel(), self._stream()),

@@ -1,0 +1,167 @@
+"""Host-side logic of the product on CPU: cache index arithmetic, scheduler tables, mask tables and the
+whole model/wrapper/pipeline orchestration driven through the TorchOps test double (tests/_torch_ops.py)
+and compared with the oracle.  No CUDA kernel runs here."""
+import numpy as np
+import pytest
+import torch
+
+from _torch_ops import TorchOps
+from helpers import ROLLOUT_CASES, golden, make_product_pipeline, patched_randn_like, rel_l2
+from oracle import causal_wan_oracle as O
+from oracle.make_golden import MASK_CASES, ROLLING, rolling_cfg, rolling_model_inputs
+from self_forcing_b200 import masks
+from self_forcing_b200.cache import IndexMirror, plan_cache_update
+from self_forcing_b200.scheduler import FlowMatchScheduler
+
+
+def test_cache_plan_matches_oracle_exhaustively():
+    """Product and oracle index arithmetic are separate restatements of causal_model.py:195-236: sweep them
+    against each other over rolling / sink / re-denoise sequences."""
+    for cache, local, sink, new in [(24, 6, 0, 12), (24, 6, 1, 12), (30, 5, 2, 6), (32760, -1, 0, 4680), (72, 3, 1, 24)]:
+        g = l = 0
+        for chunk in range(9):
+            if local == -1 and (chunk + 1) * new > cache:
+                break
+            for rep in range(3):
+                a = plan_cache_update(g, l, chunk * new, new, cache, local, sink * 4, 7 * 4)
+                b = O.plan_cache_update(g, l, chunk * new, new, cache, local, sink * 4, 7 * 4)
+                assert (a.roll, a.roll_src, a.roll_dst, a.roll_len, a.write_start, a.write_end, a.attn_start,
+                        a.attn_end, a.global_end, a.local_end) == \
+                       (b.roll, b.roll_src, b.roll_dst, b.roll_len, b.write_start, b.write_end, b.attn_start,
+                        b.attn_end, b.global_end, b.local_end)
+                g, l = a.global_end, a.local_end
+
+
+def test_cache_plan_overflow_raises():
+    with pytest.raises(ValueError):
+        plan_cache_update(32760, 32760, 32760, 4680, 32760, -1, 0, 32760)
+
+
+def test_index_mirror_tracks_rebinding():
+    kv = [dict(global_end_index=torch.tensor([0]), local_end_index=torch.tensor([0])) for _ in range(3)]
+    m = IndexMirror()
+    assert m.read(kv) == [(0, 0)] * 3
+    m.write(kv, [(12, 12)] * 3)
+    assert int(kv[1]["global_end_index"]) == 12 and m.read(kv) == [(12, 12)] * 3
+    kv[1]["global_end_index"] = torch.tensor([5])       # the pipeline resets by rebinding
+    kv[1]["local_end_index"] = torch.tensor([4])
+    assert m.read(kv) == [(12, 12), (5, 4), (12, 12)]
+
+
+def test_scheduler_tables_match_golden():
+    g = golden("scheduler_tables.pt")
+    for shift, ref in g.items():
+        s = FlowMatchScheduler(shift=shift, sigma_min=0.0, extra_one_step=True)
+        s.set_timesteps(1000, training=True)
+        assert torch.equal(s.sigmas, ref["sigmas"]) and torch.equal(s.timesteps, ref["timesteps"])
+
+
+def test_scheduler_add_noise_through_double():
+    g = golden("scheduler_tables.pt")[5.0]
+    s = FlowMatchScheduler(shift=5.0, ops=TorchOps())
+    s.set_timesteps(1000, training=True)
+    x0 = torch.randn(3, 16, 8, 8, generator=torch.Generator().manual_seed(7)).to(torch.bfloat16)
+    nz = torch.randn(3, 16, 8, 8, generator=torch.Generator().manual_seed(8)).to(torch.bfloat16)
+    assert torch.equal(s.add_noise(x0, nz, g["warped"][1:].clone()), g["add_noise_out"])
+
+
+@pytest.mark.parametrize("name", list(MASK_CASES))
+def test_mask_tables_bit_exact(name):
+    kind, kw = MASK_CASES[name]
+    ref = golden("block_masks.pt")[name]
+    r = masks.teacher_forcing_tables(**kw) if kind == "tf" else \
+        masks.blockwise_causal_tables(lone_first_frame=(kind == "i2v"), **kw)
+    for k in ("kv_num_blocks", "full_kv_num_blocks", "kv_indices", "full_kv_indices"):
+        assert np.array_equal(r[k], ref[k].numpy().astype(np.int32)), k
+    assert r["sparsity"] == pytest.approx(ref["sparsity"], abs=1e-4)
+
+
+def test_mask_known_answer_21_frames():
+    """causal 21 frames, 3 per block -> sparsity 42.52 %, full_kv_num_blocks[0] = 36."""
+    r = masks.blockwise_causal_tables(21, 1560, 3)
+    assert round(r["sparsity"], 2) == 42.52 and int(r["full_kv_num_blocks"][0]) == 36
+
+
+@pytest.mark.parametrize("name", list(ROLLOUT_CASES))
+def test_pipeline_orchestration_fp32_exact(name):
+    """fp32 on both sides removes rounding noise: any wiring mistake (wrong modulation row, cache slot,
+    frame offset, chunk order) shows up as a large error; a correct schedule reproduces the oracle."""
+    case = ROLLOUT_CASES[name]
+    ops = TorchOps()
+    pipe, cfg, params, pe, noise = make_product_pipeline(case, "cpu", ops=ops, dtype=torch.float32, hw=(16, 24))
+    with patched_randn_like(3):
+        _, lat = pipe.inference(noise, ["synthetic"], return_latents=True)
+    ow = O.OracleWrapper(params, cfg, case["shift"])
+    steps = O.warp_denoising_steps(ow.scheduler, [1000, 750, 500, 250])
+    with torch.no_grad(), patched_randn_like(3):
+        tr = O.rollout(ow, noise, pe, steps, case["num_frame_per_block"],
+                       independent_first_frame=case["independent_first_frame"])
+    assert rel_l2(lat, tr.latents) < 1e-5
+    assert (int(pipe.kv_cache1[0]["global_end_index"]), int(pipe.kv_cache1[-1]["local_end_index"])) == tr.index_trace[-1]
+    assert ops.launches > 0
+
+
+def test_pipeline_bf16_vs_reference_golden():
+    case = ROLLOUT_CASES["tiny_test_yaml"]
+    g = golden("rollout_tiny.pt")["tiny_test_yaml"]
+    pipe, *_ , noise = make_product_pipeline(case, "cpu", ops=TorchOps())
+    with patched_randn_like(3):
+        _, lat = pipe.inference(noise, ["synthetic"], return_latents=True)
+    assert rel_l2(lat, g["latents"]) <= 1e-2
+    assert (int(pipe.kv_cache1[0]["global_end_index"]), int(pipe.kv_cache1[0]["local_end_index"])) == tuple(g["final_index"])
+
+
+def test_skip_refresh_tail_is_output_neutral():
+    case = dict(ROLLOUT_CASES["tiny_test_yaml"], frames=2, independent_first_frame=False)
+    outs = []
+    for skip in (False, True):
+        pipe, *_, noise = make_product_pipeline(case, "cpu", ops=TorchOps(), dtype=torch.float32, hw=(16, 24),
+                                                skip_refresh_tail=skip)
+        with patched_randn_like(3):
+            outs.append(pipe.inference(noise, ["synthetic"], return_latents=True)[1])
+    assert torch.equal(outs[0], outs[1])
+
+
+def test_rolling_sink_model_matches_golden():
+    from self_forcing_b200.model import B200CausalWanModel
+    g = golden("model_rolling.pt")
+    r = ROLLING
+    cfg = rolling_cfg()
+    params = O.make_random_params(cfg, seed=5)
+    model = B200CausalWanModel(dim=r["dim"], ffn_dim=r["ffn_dim"], num_heads=r["num_heads"], num_layers=r["num_layers"],
+                               text_dim=r["text_dim"], local_attn_size=r["local_attn_size"], sink_size=r["sink_size"],
+                               ops=TorchOps()).to(torch.bfloat16)
+    model.load_state_dict(params, strict=True)
+    x, ctx = rolling_model_inputs()
+    ft = (r["frame_hw"][0] // 2) * (r["frame_hw"][1] // 2)
+    kv = O.new_kv_cache(cfg, 1, ft, torch.bfloat16, "cpu", cache_tokens=r["local_attn_size"] * ft)
+    ca = O.new_crossattn_cache(cfg, 1, torch.bfloat16, "cpu")
+    flows, trace = [], []
+    for c in range(r["chunks"]):
+        for k in range(r["forwards_per_chunk"]):
+            t = torch.full((1, 1), 1000.0 - 300.0 * k)
+            flows.append(model(x[:, :, c:c + 1], t=t, context=ctx, seq_len=32760, kv_cache=kv, crossattn_cache=ca,
+                               current_start=c * ft).clone())
+            trace.append((int(kv[0]["global_end_index"]), int(kv[0]["local_end_index"])))
+    assert trace == [tuple(t) for t in g["trace"]]
+    assert rel_l2(torch.stack(flows), g["flows"]) <= 1e-2
+    for i in range(cfg.num_layers):
+        assert rel_l2(kv[i]["k"], g["k"][i]) <= 1e-2 and rel_l2(kv[i]["v"], g["v"][i]) <= 1e-2
+
+
+def test_state_dict_is_reference_compatible():
+    from self_forcing_b200.model import B200CausalWanModel
+    cfg = O.OracleConfig(dim=256, ffn_dim=256, num_heads=2, num_layers=2, text_dim=512)
+    m = B200CausalWanModel(dim=256, ffn_dim=256, num_heads=2, num_layers=2, text_dim=512, ops=TorchOps())
+    assert set(m.state_dict().keys()) == set(O.parameter_shapes(cfg).keys())
+    sd = O.make_random_params(cfg)
+    sd["pose_proj.weight"] = torch.zeros(256, 5120)      # fork-specific extra keys are tolerated
+    sd["pose_proj.bias"] = torch.zeros(256)
+    m.load_state_dict(sd, strict=True)
+
+
+def test_training_path_raises():
+    from self_forcing_b200.model import B200CausalWanModel
+    m = B200CausalWanModel(dim=256, ffn_dim=256, num_heads=2, num_layers=1, text_dim=512, ops=TorchOps())
+    with pytest.raises(NotImplementedError):
+        m(torch.zeros(1, 16, 1, 8, 8), t=torch.zeros(1, 1), context=torch.zeros(1, 512, 512), seq_len=100)
