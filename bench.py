@@ -1,0 +1,432 @@
+#!/usr/bin/env python
+"""bench.py -- 480x832 frames/s of the Self-Forcing 1.3B 4-step chunk-wise rollout on B200.
+
+A *step* is one full rollout of the headline configuration (BASELINE.json configs[1]): random-init
+Wan2.1-T2V-1.3B architecture, 21 latent frames (81 pixel frames) at 60x104 latents, chunks of 3 latent
+frames, denoising steps [1000,750,500,250] warped with shift 5, context_noise 0  =  7 chunks x (4 denoise
++ 1 cache-refresh) = 35 KV-cached model forwards, 990.3 TFLOP.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W]            product arm (CUDA kernels via the C ABI)
+    python bench.py --impl reference [--gpus N] ...                reference arm: the CPU oracle port
+
+One JSON line on stdout (rank 0).  Keys follow the driver contract:
+  value        whole-job frames/s, inputs resident in HBM, CUDA events, max over ranks
+  e2e          the same through CausalInferencePipeline.inference with HOST (pinned) noise / text
+               embeddings copied in and the latents copied out inside the timed region
+  roofline     dominant kernel (tcgen05 self-attention over the KV window): algorithmic FLOPs of its
+               launches / their CUDA-event durations measured inside the timed steps, vs MEASURED_PEAKS.json
+  cpu_baseline the oracle (CPU restatement of the reference) on this box's host cores, bounded sample
+  clocks       nvidia-smi samples taken during the timed region
+N > 1 is data parallel over prompts (one rollout per rank per step, no data-path collective).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+import types
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+# ------------------------------------------------------------------------------------------------
+# workload constants
+# ------------------------------------------------------------------------------------------------
+NL, C, FFN, NH, HD, T_CTX = 30, 1536, 8960, 12, 128, 512
+LAT_FRAMES, PIX_FRAMES, LAT_H, LAT_W = 21, 81, 60, 104
+FRAME_TOKENS = (LAT_H // 2) * (LAT_W // 2)          # 1560
+DENOISE_STEPS = [1000, 750, 500, 250]
+SHIFT = 5.0
+METRIC = "480p frames/sec, 1.3B 4-step chunkwise rollout"
+UNIT = "frames/s"
+
+
+def forward_flops(L: int, S: int, layers: int = NL) -> float:
+    """Algorithmic FLOPs of one cached forward: linear + self-attn over S + cross-attn over 512."""
+    return layers * (12.0 * L * C * C + 4.0 * L * C * FFN + 4.0 * L * S * C + 4.0 * L * T_CTX * C)
+
+
+def rollout_flops(chunk_frames: int) -> float:
+    L = chunk_frames * FRAME_TOKENS
+    return sum((len(DENOISE_STEPS) + 1) * forward_flops(L, (i + 1) * L) for i in range(LAT_FRAMES // chunk_frames))
+
+
+def peaks() -> dict:
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        p = json.load(open(path))
+        return dict(burst=p["bf16_tflops"], sustained=p.get("bf16_tflops_sustained", p["bf16_tflops"]),
+                    hbm=p["hbm_gbs"], source="measured (MEASURED_PEAKS.json)")
+    return dict(burst=1590.0, sustained=1400.0, hbm=6650.0, source="fallback (B200_PROFILING.md)")
+
+
+def workload_name(chunk_frames: int) -> str:
+    kind = "chunk-wise (3 latent frames/chunk)" if chunk_frames == 3 else f"{chunk_frames} latent frame(s)/block"
+    return f"wan2.1-t2v-1.3b self-forcing dmd {kind}, 81 frames 480x832, 4 steps, batch 1 per GPU"
+
+
+# ------------------------------------------------------------------------------------------------
+# clocks: nvidia-smi sampled during the timed region
+# ------------------------------------------------------------------------------------------------
+class ClockSampler:
+    FIELDS = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+              "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+              "clocks_event_reasons.sw_power_cap")
+    NAMES = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+
+    def __init__(self, gpu_uuid=None):
+        self.rows = []
+        self.proc = None
+        cmd = ["nvidia-smi", f"--query-gpu={self.FIELDS}", "--format=csv,noheader,nounits", "-lms", "100"]
+        if gpu_uuid:
+            cmd += ["-i", gpu_uuid]
+        try:
+            self.proc = subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+        except OSError:
+            return
+        threading.Thread(target=self._pump, daemon=True).start()
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            parts = [x.strip() for x in line.split(",")]
+            if len(parts) >= 7:
+                self.rows.append(parts)
+
+    def mark(self) -> int:
+        return len(self.rows)
+
+    def stop(self, start_row: int = 0, end_row=None) -> dict:
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()            # the exact child we started
+        try:
+            self.proc.wait(timeout=5)
+        except subprocess.TimeoutExpired:
+            self.proc.kill()
+        rows = self.rows[start_row:end_row] or self.rows
+
+        def num(s):
+            try:
+                return float(s)
+            except ValueError:
+                return None
+        sm = sorted(v for v in (num(r[0]) for r in rows) if v is not None)
+        mx = [v for v in (num(r[1]) for r in rows) if v is not None]
+        pw = [v for v in (num(r[2]) for r in rows) if v is not None]
+        reasons = [n for i, n in enumerate(self.NAMES) if any(r[3 + i].lower().startswith("active") for r in rows)]
+        return {"sm_mhz": int(sm[len(sm) // 2]) if sm else None, "sm_max_mhz": int(max(mx)) if mx else None,
+                "power_w_max": max(pw) if pw else None, "samples": len(rows), "reasons": reasons}
+
+
+# ------------------------------------------------------------------------------------------------
+# CPU oracle sample (cpu_baseline leg and the --impl reference arm)
+# ------------------------------------------------------------------------------------------------
+class CpuOracleSample:
+    """One oracle forward of chunk 0 of the rollout (L = S = chunk tokens, 1.3B layer shapes, bf16, all
+    host threads) with `layers` of the 30 identical transformer layers; the rollout time is extrapolated
+    by algorithmic FLOPs.  The oracle is the CPU restatement of the reference's own PyTorch path
+    (oracle/causal_wan_oracle.py) -- the reference checkout itself cannot travel to the GPU box."""
+
+    def __init__(self, chunk_frames: int):
+        import torch
+        from oracle import causal_wan_oracle as O
+        self.torch, self.O = torch, O
+        self.threads = os.cpu_count() or 1
+        torch.set_num_threads(self.threads)
+        self.chunk_frames = chunk_frames
+        self.L = chunk_frames * FRAME_TOKENS
+        self.x = torch.randn(1, chunk_frames, 16, LAT_H, LAT_W,
+                             generator=torch.Generator().manual_seed(2)).to(torch.bfloat16)
+        self.pe = torch.randn(1, T_CTX, 4096, generator=torch.Generator().manual_seed(1)).to(torch.bfloat16)
+        self.layers = 0
+
+    def prepare(self, layers: int) -> None:
+        O, torch = self.O, self.torch
+        cfg = O.OracleConfig(dim=C, ffn_dim=FFN, num_heads=NH, num_layers=layers)
+        self.w = O.OracleWrapper(O.make_random_params(cfg, seed=0), cfg, SHIFT)
+        steps = O.warp_denoising_steps(self.w.scheduler, DENOISE_STEPS)
+        self.ts = torch.ones([1, self.chunk_frames], dtype=torch.int64) * steps[0]
+        self.kv = O.new_kv_cache(cfg, 1, FRAME_TOKENS, torch.bfloat16, "cpu", cache_tokens=self.L)
+        self.ca = O.new_crossattn_cache(cfg, 1, torch.bfloat16, "cpu")
+        self.layers = layers
+
+    def step(self) -> float:
+        with self.torch.no_grad():
+            t0 = time.perf_counter()
+            self.w(self.x, self.pe, self.ts, self.kv, self.ca, 0)   # re-denoising chunk 0 overwrites in place
+            return time.perf_counter() - t0
+
+    def calibrate(self, seconds_per_step: float) -> None:
+        self.prepare(1)
+        self.step()                      # first call also fills the cross-attention cache
+        t1 = self.step()
+        layers = max(1, min(NL, int(seconds_per_step / max(t1, 1e-3))))
+        if layers != 1:
+            self.prepare(layers)
+            self.step()
+
+    def fps(self, seconds: float) -> float:
+        scale = rollout_flops(self.chunk_frames) / forward_flops(self.L, self.L, self.layers)
+        return PIX_FRAMES / (seconds * scale)
+
+    def describe(self, seconds: float) -> str:
+        fl = forward_flops(self.L, self.L, self.layers)
+        return (f"oracle forward of chunk 0 (L=S={self.L}) with {self.layers} of {NL} layers = {fl / 1e12:.2f} TFLOP in "
+                f"{seconds:.2f} s on {self.threads} threads (bf16, SDPA); rollout extrapolated by algorithmic FLOPs "
+                f"({rollout_flops(self.chunk_frames) / 1e12:.1f} TFLOP)")
+
+
+def run_reference_arm(args) -> None:
+    """`--impl reference`: the reference's CPU path (oracle port) on this box's host cores."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    total = max(1, args.steps + args.warmup)
+    per_step = max(2.0, min(20.0, 150.0 / total))
+    s = CpuOracleSample(args.chunk_frames)
+    s.calibrate(per_step)
+    for _ in range(args.warmup):
+        s.step()
+    times = [s.step() for _ in range(args.steps)]
+    sec = sum(times) / len(times)
+    fps = s.fps(sec)
+    line = {
+        "impl": "reference", "metric": METRIC, "value": fps, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+        "config": {"workload": workload_name(args.chunk_frames), "device": "cpu", "weights": "random-init"},
+        "cpu_baseline": {"value": fps, "unit": UNIT, "cores": s.threads, "kind": "port", "sample": s.describe(sec)},
+        "e2e": {"value": fps, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------------
+# product arm
+# ------------------------------------------------------------------------------------------------
+class _HostTextEncoder:
+    """Stands in for the (out-of-scope) UMT5 encoder: the e2e leg keeps the prompt embeddings in pinned
+    host memory and copies them to the device on every call -- that is the step's H2D input traffic."""
+
+    def __init__(self, pe, device):
+        self.pe, self.device = pe, device
+
+    def __call__(self, text_prompts):
+        return {"prompt_embeds": self.pe.to(self.device, non_blocking=True)}
+
+
+class _NoVAE:
+    def decode_to_pixel(self, x, use_cache=False):   # the VAE is after the path
+        return x
+
+
+def run_product_arm(args) -> None:
+    import torch
+    import torch.distributed as dist
+    from self_forcing_b200.ops import CudaOps
+    from self_forcing_b200.pipeline import CausalInferencePipeline
+    from self_forcing_b200.wrapper import WAN_T2V_1_3B, B200DiffusionWrapper
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device (the B200 path has no CPU fallback; use --impl reference for the CPU arm)")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+    if args.gpus != world and rank == 0:
+        print(f"bench.py: --gpus {args.gpus} but WORLD_SIZE={world}; launch with torchrun for N>1", file=sys.stderr)
+
+    ops = CudaOps()
+    cf = args.chunk_frames
+    gen = B200DiffusionWrapper(model_config=dict(WAN_T2V_1_3B), timestep_shift=SHIFT, device=dev, init_seed=0, ops=ops)
+    # data-parallel over prompts: every rank owns a different prompt / noise (inference.py:45,96-100 in the reference)
+    pe_host = torch.randn(1, T_CTX, 4096, generator=torch.Generator().manual_seed(1 + rank)).to(torch.bfloat16).pin_memory()
+    noise_host = torch.randn(1, LAT_FRAMES, 16, LAT_H, LAT_W,
+                             generator=torch.Generator().manual_seed(2 + rank)).to(torch.bfloat16).pin_memory()
+    out_host = torch.empty_like(noise_host).pin_memory()
+    pe_dev, noise_dev = pe_host.to(dev), noise_host.to(dev)
+    pargs = types.SimpleNamespace(denoising_step_list=DENOISE_STEPS, warp_denoising_step=True, num_frame_per_block=cf,
+                                  independent_first_frame=False, context_noise=0, model_kwargs={},
+                                  skip_refresh_tail=args.skip_refresh_tail, use_cuda_graphs=args.cuda_graphs)
+    enc_dev = lambda text_prompts: {"prompt_embeds": pe_dev}   # noqa: E731
+    pipe = CausalInferencePipeline(pargs, dev, generator=gen, text_encoder=enc_dev, vae=_NoVAE())
+    torch.manual_seed(1234 + rank)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(x: float) -> float:
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def resident_step():
+        _, lat = pipe.inference(noise_dev, ["synthetic"], return_latents=True)
+        return lat
+
+    def host_step():
+        pipe.text_encoder = _HostTextEncoder(pe_host, dev)
+        noise = noise_host.to(dev, non_blocking=True)
+        _, lat = pipe.inference(noise, ["synthetic"], return_latents=True)
+        out_host.copy_(lat, non_blocking=True)
+        torch.cuda.synchronize()
+        pipe.text_encoder = enc_dev
+
+    uuid = None
+    try:
+        uuid = "GPU-" + str(torch.cuda.get_device_properties(dev).uuid)
+    except Exception:
+        pass
+    clocks = ClockSampler(uuid) if rank == 0 else None
+
+    if args.ncu_rollout:     # one plain rollout and nothing else: the command profiled under ncu
+        resident_step()
+        torch.cuda.synchronize()
+        if clocks:
+            clocks.stop()
+        print(json.dumps({"ncu_rollout": "ok", "gpu_launches": ops.launches}))
+        return
+
+    for _ in range(args.warmup):
+        resident_step()
+    # ---- timed region 1: inputs resident in HBM, CUDA events on the launching (current) stream ----
+    ops.start_profile(only={"attention"})      # brackets only the attention launches with events
+    barrier()
+    row0 = clocks.mark() if clocks else 0
+    launches0 = ops.launches
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        lat = resident_step()
+    e1.record()
+    barrier()
+    row1 = clocks.mark() if clocks else 0
+    ms_total = max_over_ranks(e0.elapsed_time(e1))
+    launches = ops.launches - launches0
+    attn_prof = ops.stop_profile()
+    finite = bool(torch.isfinite(lat.float()).all().item())
+
+    # ---- timed region 2: end to end with host buffers ------------------------------------------
+    host_step()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        host_step()
+    barrier()
+    e2e_s = max_over_ranks(time.perf_counter() - t0)
+    clk = clocks.stop(row0, None) if clocks else None
+
+    # ---- per-kernel breakdown of one more (untimed) rollout --------------------------------------
+    ops.start_profile()
+    resident_step()
+    prof = ops.stop_profile()
+
+    if world > 1:
+        dist.barrier()
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    pk = peaks()
+    frames = PIX_FRAMES * world * args.steps
+    value = frames / (ms_total / 1e3)
+    # roofline of the dominant kernel: self-attention launches (KV window > text length) inside the timed steps
+    self_attn = [(tag, ms) for _, tag, ms in attn_prof if tag[3] > T_CTX]
+    fl = sum(4.0 * tag[1] * tag[2] * tag[3] * tag[4] * HD for tag, _ in self_attn)
+    ms_attn = sum(ms for _, ms in self_attn)
+    achieved = fl / (ms_attn * 1e-3) / 1e12 if ms_attn > 0 else 0.0
+    groups = {}
+    for name, tag, ms in prof:
+        key = name
+        if name == "attention":
+            key = "attention_self" if tag[3] > T_CTX else "attention_cross"
+        g = groups.setdefault(key, [0, 0.0, 0.0])
+        g[0] += 1
+        g[1] += ms
+        if name == "attention":
+            g[2] += 4.0 * tag[1] * tag[2] * tag[3] * tag[4] * HD
+        elif name == "gemm":
+            g[2] += 2.0 * tag[1] * tag[2] * tag[3]
+    kernel_ms = sum(g[1] for g in groups.values())
+    breakdown = {k: {"launches": g[0], "ms": round(g[1], 3), "share": round(g[1] / kernel_ms, 4),
+                     **({"tflops": round(g[2] / g[1] / 1e9, 1)} if g[2] else {})}
+                 for k, g in sorted(groups.items(), key=lambda kv: -kv[1][1])}
+    gemm = groups.get("gemm", [0, 0.0, 0.0])
+    total_fl = rollout_flops(cf)
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "bf16", "data": "synthetic",
+        "config": {"workload": workload_name(cf), "parallelism": f"dp{world}", "weights": "random-init 1.3B architecture",
+                   "frames_per_step_per_gpu": PIX_FRAMES, "forwards_per_step": (LAT_FRAMES // cf) * 5,
+                   "l2": "inputs larger than L2 (2.8 GB weights + 6 GB KV cache stream through the 126 MB L2 every forward)",
+                   "skip_refresh_tail": bool(args.skip_refresh_tail), "cuda_graphs": bool(args.cuda_graphs)},
+        "per_gpu": value / world,
+        "model_tflops": total_fl * world * args.steps / (ms_total / 1e3) / 1e12,
+        "model_frac_of_peak": total_fl * args.steps / (ms_total / 1e3) / 1e12 / pk["sustained"],
+        "e2e": {"value": frames / e2e_s, "unit": UNIT,
+                "h2d_bytes_per_step": noise_host.numel() * 2 + pe_host.numel() * 2, "d2h_bytes_per_step": out_host.numel() * 2},
+        "gpu_launches": launches,
+        "roofline": {"kernel": "attention_fwd_kernel (self-attention over the KV window)", "bound": "tensor",
+                     "achieved": achieved, "peak": pk["sustained"], "unit": "TFLOP/s",
+                     "frac": achieved / pk["sustained"], "traffic": None,
+                     "peak_kind": "sustained bf16 cuBLAS, " + pk["source"], "frac_of_burst": achieved / pk["burst"],
+                     "launches_timed": len(self_attn), "ms_in_timed_region": ms_attn},
+        "roofline_gemm": {"kernel": "gemm_bf16_kernel (all projections)", "bound": "tensor",
+                          "achieved": gemm[2] / gemm[1] / 1e9 if gemm[1] else 0.0, "peak": pk["sustained"],
+                          "unit": "TFLOP/s", "frac": (gemm[2] / gemm[1] / 1e9 if gemm[1] else 0.0) / pk["sustained"]},
+        "breakdown": breakdown, "kernel_ms_per_step": kernel_ms, "finite": finite,
+        "clocks": clk,
+    }
+    if world == 1 and not args.no_cpu_baseline:
+        s = CpuOracleSample(cf)
+        s.calibrate(args.cpu_seconds)
+        sec = s.step()
+        line["cpu_baseline"] = {"value": s.fps(sec), "unit": UNIT, "cores": s.threads, "kind": "port",
+                                "sample": s.describe(sec)}
+    os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
+    with open(os.path.join(ROOT, "gpurun_out", f"bench_n{world}.json"), "w") as f:
+        json.dump(line, f, indent=1)
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--chunk-frames", type=int, default=3, help="latent frames per block (3 = headline, 1 = frame-wise)")
+    ap.add_argument("--skip-refresh-tail", action="store_true",
+                    help="skip the unused tail of the clean-context refresh pass (NOT the default: changes the work)")
+    ap.add_argument("--cuda-graphs", action="store_true", help="replay each forward as a CUDA graph")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--ncu-rollout", action="store_true", help="run exactly one rollout (the command captured by ncu)")
+    ap.add_argument("--cpu-seconds", type=float, default=15.0, help="CPU-oracle sample budget (seconds)")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference_arm(args)
+    else:
+        run_product_arm(args)
+
+
+if __name__ == "__main__":
+    main()

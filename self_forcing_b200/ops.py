@@ -31,7 +31,7 @@ def _op(fn):
     @functools.wraps(fn)
     def wrapped(self, *a, **k):
         self.launches += 1
-        if self._prof is None:
+        if self._prof is None or (self._prof_only is not None and name not in self._prof_only):
             return fn(self, *a, **k)
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
@@ -54,10 +54,13 @@ class CudaOps:
             raise _lib.SfbError("CUDA device required: the B200 path has no CPU fallback")
         self.launches = 0
         self._prof = None
+        self._prof_only = None
 
     # -- optional per-launch device timing (bench.py roofline leg) ------------------------------
-    def start_profile(self):
+    def start_profile(self, only=None):
+        """only: optional set of op names to bracket (the others run untouched)."""
         self._prof = []
+        self._prof_only = set(only) if only else None
 
     def stop_profile(self):
         """-> list of (op name, tag, milliseconds) for every launch since start_profile()."""
