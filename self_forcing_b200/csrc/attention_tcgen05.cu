@@ -16,6 +16,7 @@
 // pipes the other tile's PV / next QK^T MMAs run.  O is rescaled lazily (only when a row max grows
 // by more than 2^8), done by the softmax warps themselves between PV(j-1) and PV(j).
 #include <math.h>
+#include <stdlib.h>
 
 #include "common.cuh"
 
@@ -35,6 +36,7 @@ constexpr int ATT_THREADS = 320;
 constexpr int ATT_TILE_BYTES = 128 * 128 * 2;    // 32 KB: two 16 KB halves (d 0-63 | d 64-127)
 constexpr int ATT_HALF_BYTES = 128 * 64 * 2;
 constexpr int ATT_KV_STAGES = 2;
+constexpr int ATT_DEFAULT_EMU = 1;
 constexpr int ATT_SMEM_BYTES = 2 * ATT_TILE_BYTES + 2 * ATT_KV_STAGES * ATT_TILE_BYTES + 1024 + 256;
 
 __device__ __forceinline__ float fast_exp2(float x) {
@@ -43,6 +45,21 @@ __device__ __forceinline__ float fast_exp2(float x) {
   return y;
 }
 
+// 2^x on the FMA pipe (Cody-Waite range reduction + degree-3 minimax polynomial, rel. error 8.8e-5 --
+// far below the bf16 rounding of P).  MUFU.EX2 runs at 16 lanes/clk/SM, which for head_dim 128 is
+// exactly the rate the tensor pipe consumes P at; moving a fraction of the exponentials here takes
+// the softmax off the critical path.  x <= ~8 (lazy rescaling bound); clamped below for the exponent.
+__device__ __forceinline__ float poly_exp2(float x) {
+  x = fmaxf(x, -125.0f);
+  float r;
+  asm("add.rm.ftz.f32 %0, %1, %2;" : "=f"(r) : "f"(x), "f"(12582912.0f));   // 1.5 * 2^23 + floor(x)
+  const float f = x - (r - 12582912.0f);                                       // frac(x) in [0, 1)
+  const float p = fmaf(fmaf(fmaf(0.077119089663028717f, f, 0.227564394474029541f), f, 0.695146143436431885f), f, 1.0f);
+  return __int_as_float(__float_as_int(p) + (__float_as_int(r) << 23));
+}
+
+// EMU: how many of every 4 exponentials run on the FMA pipe instead of MUFU (0, 1 or 2).
+template <int EMU>
 __global__ void __launch_bounds__(ATT_THREADS, 1)
 attention_fwd_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_constant__ CUtensorMap tma_k,
                      const __grid_constant__ CUtensorMap tma_v, const AttnParams p) {
@@ -238,8 +255,11 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_con
         uint32_t pk[16];
 #pragma unroll
         for (int i = 0; i < 16; ++i) {
-          const float p0 = fast_exp2(fmaf(__uint_as_float(s[c * 32 + 2 * i]), sl2, neg_m));
-          const float p1 = fast_exp2(fmaf(__uint_as_float(s[c * 32 + 2 * i + 1]), sl2, neg_m));
+          const float x0 = fmaf(__uint_as_float(s[c * 32 + 2 * i]), sl2, neg_m);
+          const float x1 = fmaf(__uint_as_float(s[c * 32 + 2 * i + 1]), sl2, neg_m);
+          // element index within its group of four: 2*(i&1) and 2*(i&1)+1
+          const float p0 = (EMU >= 2 && (i & 1) == 0) ? poly_exp2(x0) : fast_exp2(x0);
+          const float p1 = (EMU >= 1 && (i & 1) == 1) ? poly_exp2(x1) : fast_exp2(x1);
           sum0 += p0;
           sum1 += p1;
           pk[i] = pack_bf16(p0, p1);
@@ -326,14 +346,20 @@ extern "C" int sfb_attention_fwd(const void* q, long long q_row_stride, long lon
   p.out_row_stride = out_row_stride;
   p.out_batch_stride = out_batch_stride;
 
-  static bool attr_set = false;
-  if (!attr_set) {
-    if (int e = check_cuda(cudaFuncSetAttribute(attention_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                                ATT_SMEM_BYTES), "cudaFuncSetAttribute(attention)"))
-      return e;
-    attr_set = true;
+  static int emu = -1;
+  if (emu < 0) {
+    const char* env = getenv("SFB_ATTN_EMU");   // tuning knob; the default is the measured best
+    emu = env ? atoi(env) : ATT_DEFAULT_EMU;
+    if (emu < 0 || emu > 2) emu = ATT_DEFAULT_EMU;
+    for (auto kern : {attention_fwd_kernel<0>, attention_fwd_kernel<1>, attention_fwd_kernel<2>})
+      if (int e = check_cuda(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT_SMEM_BYTES),
+                             "cudaFuncSetAttribute(attention)")) {
+        emu = -1;
+        return e;
+      }
   }
   dim3 grid((Lq + 2 * ATT_BM - 1) / (2 * ATT_BM), H, B);
-  attention_fwd_kernel<<<grid, ATT_THREADS, ATT_SMEM_BYTES, stream>>>(tq, tk, tv, p);
+  auto kern = emu == 0 ? attention_fwd_kernel<0> : (emu == 1 ? attention_fwd_kernel<1> : attention_fwd_kernel<2>);
+  kern<<<grid, ATT_THREADS, ATT_SMEM_BYTES, stream>>>(tq, tk, tv, p);
   return check_cuda(cudaGetLastError(), "attention launch");
 }

@@ -1,0 +1,183 @@
+// CTA-pair bf16 GEMM for sm_100a: one 256 x 256 output tile per cluster of two CTAs (cta_group::2).
+//
+// Why: with one CTA per tile the kernel in gemm_tcgen05.cu is bound by the L2 -> SM fill rate, not by the
+// tensor pipe (ncu, profiles/r01a: 128x256 tiles move 48 KB per 64-wide k-block and sustain ~43 B/clk/SM
+// of l1tex__m_xbar2l1tex_read_bytes, i.e. 44 % tensor-pipe utilisation).  A CTA pair shares the B tile:
+// each CTA stages its own 128 rows of A and only HALF of B (128 of the 256 columns); the UMMA reads both
+// halves.  That is 32 KB per k-block per SM for the same 512 tensor cycles -> 1.5x the arithmetic
+// intensity per byte that crosses the crossbar.
+//
+// Roles per CTA (192 threads):  warp 0 TMA producer (own A rows, own B half; completion bytes land on the
+// LEADER's mbarrier), warp 1 = MMA issuer (leader CTA only; tcgen05.mma.cta_group::2, M=256 N=256 K=16,
+// commits multicast to both CTAs), warps 2-5 epilogue of this CTA's 128 accumulator rows (TMEM double
+// buffered: 2 x 256 columns).
+#include "gemm_common.cuh"
+
+namespace sfb {
+
+constexpr int G2_ROWS = 128;           // accumulator rows per CTA (pair tile = 256 rows)
+constexpr int G2_BN = 256;             // pair tile columns; each CTA stages 128 of them
+constexpr int G2_BK = 64;
+constexpr int G2_STAGES = 6;
+constexpr int G2_A_BYTES = G2_ROWS * G2_BK * 2;
+constexpr int G2_B_BYTES = (G2_BN / 2) * G2_BK * 2;
+constexpr int G2_STAGE_BYTES = G2_A_BYTES + G2_B_BYTES;
+constexpr int G2_SMEM_BYTES = G2_STAGES * G2_STAGE_BYTES + 1024 + 256;
+constexpr int G2_THREADS = 192;
+
+template <int EPI>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(G2_THREADS, 1)
+gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b,
+                  const GemmParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + G2_STAGES * G2_STAGE_BYTES);
+  uint64_t* empty_bar = full_bar + G2_STAGES;
+  uint64_t* tmem_full = empty_bar + G2_STAGES;   // [2]
+  uint64_t* tmem_empty = tmem_full + 2;          // [2]  (only the leader's copy is waited on)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+  const bool leader = rank == 0;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tma_a);
+    tma_prefetch_desc(&tma_b);
+    for (int s = 0; s < G2_STAGES; ++s) {
+      mbar_init(&full_bar[s], 1);    // leader: one arrive.expect_tx covering both CTAs' bytes
+      mbar_init(&empty_bar[s], 1);   // one multicast commit per use
+    }
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(&tmem_full[s], 1);
+      mbar_init(&tmem_empty[s], 8);  // 4 epilogue warps x 2 CTAs arrive on the leader's barrier
+    }
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc_pair(tmem_slot, 512);
+  tc_fence_before();
+  cluster_sync_all();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  const int num_tiles = p.num_m_blocks * p.num_n_blocks;   // pair tiles
+  const int pair = blockIdx.x >> 1;
+  const int num_pairs = gridDim.x >> 1;
+
+  if (warp == 0) {
+    // ------------------------------ TMA producer (both CTAs) ------------------
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = pair; tile < num_tiles; tile += num_pairs) {
+        const int m_blk = tile % p.num_m_blocks, n_blk = tile / p.num_m_blocks;
+        const int a_row = m_blk * (2 * G2_ROWS) + rank * G2_ROWS;
+        const int b_row = n_blk * G2_BN + rank * (G2_BN / 2);
+        for (int kb = 0; kb < p.num_k_blocks; ++kb) {
+          mbar_wait(&empty_bar[stage], phase ^ 1);
+          uint8_t* a_dst = smem + stage * G2_STAGE_BYTES;
+          if (leader) mbar_expect_tx(&full_bar[stage], 2 * G2_STAGE_BYTES);
+          const uint32_t bar = mapa_cluster(smem_u32(&full_bar[stage]), 0);
+          tma_load_2d_pair(a_dst, &tma_a, bar, kb * G2_BK, a_row);
+          tma_load_2d_pair(a_dst + G2_A_BYTES, &tma_b, bar, kb * G2_BK, b_row);
+          if (++stage == G2_STAGES) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------ MMA issuer (leader only) ------------------
+    if (leader && lane == 0) {
+      constexpr uint32_t idesc = umma_idesc_bf16(2 * G2_ROWS, G2_BN, 0, 0);
+      int stage = 0;
+      uint32_t phase = 0;
+      int it = 0;
+      for (int tile = pair; tile < num_tiles; tile += num_pairs, ++it) {
+        const int acc = it & 1;
+        const uint32_t acc_phase = (it >> 1) & 1;
+        mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + acc * G2_BN;
+        for (int kb = 0; kb < p.num_k_blocks; ++kb) {
+          mbar_wait(&full_bar[stage], phase);
+          tc_fence_after();
+          const uint32_t a_addr = smem_u32(smem + stage * G2_STAGE_BYTES);
+          const uint64_t a_desc = umma_desc_sw128(a_addr, 16, 1024);
+          const uint64_t b_desc = umma_desc_sw128(a_addr + G2_A_BYTES, 16, 1024);
+#pragma unroll
+          for (int k = 0; k < G2_BK / 16; ++k)
+            umma_ss_pair(d_tmem, a_desc + 2 * k, b_desc + 2 * k, idesc, (kb | k) != 0);
+          umma_commit_pair(&empty_bar[stage], 3);   // both CTAs' smem slots are free once these retire
+          if (++stage == G2_STAGES) { stage = 0; phase ^= 1; }
+        }
+        umma_commit_pair(&tmem_full[acc], 3);
+      }
+    }
+  } else {
+    // ------------------------------ epilogue warps (both CTAs) ----------------
+    const int quarter = warp & 3;
+    const uint32_t leader_empty0 = mapa_cluster(smem_u32(&tmem_empty[0]), 0);
+    int it = 0;
+    for (int tile = pair; tile < num_tiles; tile += num_pairs, ++it) {
+      const int m_blk = tile % p.num_m_blocks, n_blk = tile / p.num_m_blocks;
+      const int acc = it & 1;
+      const uint32_t acc_phase = (it >> 1) & 1;
+      mbar_wait(&tmem_full[acc], acc_phase);
+      tc_fence_after();
+      const int row = m_blk * (2 * G2_ROWS) + rank * G2_ROWS + quarter * 32 + lane;
+      gemm_epilogue_row<G2_BN, EPI>(p, row, n_blk * G2_BN,
+                                    tmem_base + ((uint32_t)(quarter * 32) << 16) + acc * G2_BN);
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive_cluster(leader_empty0 + acc * 8);
+    }
+  }
+
+  tc_fence_before();
+  cluster_sync_all();   // the peer may still be reading this CTA's smem / TMEM through the pair MMA
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc_pair(tmem_base, 512);
+  }
+}
+
+template <int EPI>
+static int launch_gemm2(const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& p, int num_sms,
+                        cudaStream_t stream) {
+  auto kern = gemm2_bf16_kernel<EPI>;
+  static int max_clusters = 0;
+  if (max_clusters == 0) {
+    if (int e = check_cuda(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, G2_SMEM_BYTES),
+                           "cudaFuncSetAttribute(gemm2)"))
+      return e;
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(num_sms & ~1);
+    cfg.blockDim = dim3(G2_THREADS);
+    cfg.dynamicSmemBytes = G2_SMEM_BYTES;
+    int n = 0;
+    if (cudaOccupancyMaxActiveClusters(&n, kern, &cfg) != cudaSuccess || n <= 0) {
+      cudaGetLastError();
+      n = num_sms / 2;
+    }
+    max_clusters = n < num_sms / 2 ? n : num_sms / 2;
+  }
+  const int tiles = p.num_m_blocks * p.num_n_blocks;
+  const int clusters = tiles < max_clusters ? tiles : max_clusters;
+  kern<<<2 * clusters, G2_THREADS, G2_SMEM_BYTES, stream>>>(ta, tb, p);
+  return check_cuda(cudaGetLastError(), "gemm2 launch");
+}
+
+// Called by sfb_gemm_bf16 (gemm_tcgen05.cu) for N % 256 == 0 problems.  `p` carries pair-tile counts.
+int launch_gemm_pair(int epi, const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& p, int num_sms,
+                     cudaStream_t stream) {
+  switch (epi) {
+    case EPI_BIAS: return launch_gemm2<EPI_BIAS>(ta, tb, p, num_sms, stream);
+    case EPI_GELU: return launch_gemm2<EPI_GELU>(ta, tb, p, num_sms, stream);
+    case EPI_RESIDUAL: return launch_gemm2<EPI_RESIDUAL>(ta, tb, p, num_sms, stream);
+    case EPI_GATE_RES: return launch_gemm2<EPI_GATE_RES>(ta, tb, p, num_sms, stream);
+  }
+  set_error("sfb_gemm_bf16: unknown epilogue %d", epi);
+  return SFB_ERR_INVALID;
+}
+
+}  // namespace sfb

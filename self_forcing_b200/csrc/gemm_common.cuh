@@ -1,0 +1,98 @@
+// Shared pieces of the two tcgen05 GEMM kernels (1-CTA tiles in gemm_tcgen05.cu, CTA-pair tiles in
+// gemm2_tcgen05.cu): parameters, the GELU used by the reference, and the fused epilogue of one
+// accumulator row (TMEM -> registers -> bias / GELU / gate / residual -> 16-byte global stores).
+#pragma once
+#include "common.cuh"
+
+namespace sfb {
+
+enum : int { EPI_BIAS = 0, EPI_GELU = 1, EPI_RESIDUAL = 2, EPI_GATE_RES = 3 };
+
+struct GemmParams {
+  int M, N, K;
+  int num_m_blocks, num_n_blocks, num_k_blocks;
+  const __nv_bfloat16* bias;   // [N] or nullptr
+  __nv_bfloat16* out[3];       // output column segments (QKV writes three destinations)
+  long long ldo[3];            // row stride (elements) of each segment
+  int seg_cols;                // columns per segment (== N when there is a single destination)
+  const __nv_bfloat16* residual;
+  long long ldr;
+  const __nv_bfloat16* gate;   // gate vector of row r lives at gate + (r / rows_per_gate) * gate_stride
+  long long gate_stride;
+  int rows_per_gate;
+};
+
+__device__ __forceinline__ float gelu_tanh_f(float x) {
+  // 0.5 x (1 + tanh(sqrt(2/pi) (x + 0.044715 x^3))), tanh(u) = 1 - 2 / (1 + e^{2u})
+  const float kBeta = 0.7978845608028654f, kKappa = 0.044715f;
+  float u = kBeta * (x + kKappa * x * x * x);
+  float t = 1.0f - __fdividef(2.0f, 1.0f + __expf(2.0f * u));
+  return 0.5f * x * (1.0f + t);
+}
+
+
+// One thread owns accumulator row `row` (TMEM lane) of a tile that starts at column n0 and is
+// TILE_N columns wide; t_row is the TMEM address of (lane, first column).
+template <int TILE_N, int EPI>
+__device__ __forceinline__ void gemm_epilogue_row(const GemmParams& p, int row, int n0, uint32_t t_row) {
+  const bool row_ok = row < p.M;
+  const int seg = n0 / p.seg_cols;
+  __nv_bfloat16* orow = p.out[seg] + (long long)row * p.ldo[seg] + (n0 - seg * p.seg_cols);
+  const __nv_bfloat16* rrow = nullptr;
+  const __nv_bfloat16* grow = nullptr;
+  if (EPI == EPI_RESIDUAL || EPI == EPI_GATE_RES) rrow = p.residual + (long long)row * p.ldr + n0;
+  if (EPI == EPI_GATE_RES) grow = p.gate + (long long)(row_ok ? row / p.rows_per_gate : 0) * p.gate_stride + n0;
+#pragma unroll 1
+  for (int c = 0; c < TILE_N / 32; ++c) {
+    uint32_t v[32];
+    tmem_ld32(t_row + c * 32, v);
+    tmem_ld_wait();
+    if (row_ok) {
+#pragma unroll
+      for (int g = 0; g < 4; ++g) {   // 8 columns (16 bytes of bf16) per step
+        const int col = c * 32 + g * 8;
+        if (n0 + col < p.N) {
+          float f[8];
+#pragma unroll
+          for (int i = 0; i < 8; ++i) f[i] = __uint_as_float(v[g * 8 + i]);
+          if (p.bias != nullptr) {
+            const uint4 b = __ldg(reinterpret_cast<const uint4*>(p.bias + n0 + col));
+            const uint32_t bw[4] = {b.x, b.y, b.z, b.w};
+#pragma unroll
+            for (int i = 0; i < 4; ++i) { f[2 * i] += bf_lo(bw[i]); f[2 * i + 1] += bf_hi(bw[i]); }
+          }
+          if (EPI == EPI_GELU) {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) f[i] = gelu_tanh_f(bf16r(f[i]));
+          }
+          if (EPI == EPI_GATE_RES) {
+            const uint4 gq = __ldg(reinterpret_cast<const uint4*>(grow + col));
+            const uint32_t gw[4] = {gq.x, gq.y, gq.z, gq.w};
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              f[2 * i] = bf16r(bf16r(f[2 * i]) * bf_lo(gw[i]));
+              f[2 * i + 1] = bf16r(bf16r(f[2 * i + 1]) * bf_hi(gw[i]));
+            }
+          }
+          if (EPI == EPI_RESIDUAL || EPI == EPI_GATE_RES) {
+            const uint4 rq = *reinterpret_cast<const uint4*>(rrow + col);
+            const uint32_t rw[4] = {rq.x, rq.y, rq.z, rq.w};
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              f[2 * i] = bf_lo(rw[i]) + bf16r(f[2 * i]);
+              f[2 * i + 1] = bf_hi(rw[i]) + bf16r(f[2 * i + 1]);
+            }
+          }
+          uint4 o;
+          o.x = pack_bf16(f[0], f[1]);
+          o.y = pack_bf16(f[2], f[3]);
+          o.z = pack_bf16(f[4], f[5]);
+          o.w = pack_bf16(f[6], f[7]);
+          *reinterpret_cast<uint4*>(orow + col) = o;
+        }
+      }
+    }
+  }
+}
+
+}  // namespace sfb

@@ -15,25 +15,9 @@
 //   warp 1   : MMA issuer    -- tcgen05.mma cta_group::1, M=128, N=BLOCK_N, K=16, fp32 accum in TMEM
 //   warps 2-5: epilogue      -- tcgen05.ld the accumulator (double-buffered in TMEM so the next
 //                               tile's main loop overlaps), fused epilogue, 16-byte global stores
-#include "common.cuh"
+#include "gemm_common.cuh"
 
 namespace sfb {
-
-enum : int { EPI_BIAS = 0, EPI_GELU = 1, EPI_RESIDUAL = 2, EPI_GATE_RES = 3 };
-
-struct GemmParams {
-  int M, N, K;
-  int num_m_blocks, num_n_blocks, num_k_blocks;
-  const __nv_bfloat16* bias;   // [N] or nullptr
-  __nv_bfloat16* out[3];       // output column segments (QKV writes three destinations)
-  long long ldo[3];            // row stride (elements) of each segment
-  int seg_cols;                // columns per segment (== N when there is a single destination)
-  const __nv_bfloat16* residual;
-  long long ldr;
-  const __nv_bfloat16* gate;   // gate vector of row r lives at gate + (r / rows_per_gate) * gate_stride
-  long long gate_stride;
-  int rows_per_gate;
-};
 
 constexpr int BLOCK_M = 128;
 constexpr int BLOCK_K = 64;   // 64 bf16 = one 128-byte swizzle row
@@ -49,14 +33,6 @@ struct GemmCfg {
   static constexpr int TMEM_COLS = (2 * BLOCK_N < 32) ? 32 : 2 * BLOCK_N;
   static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
 };
-
-__device__ __forceinline__ float gelu_tanh_f(float x) {
-  // 0.5 x (1 + tanh(sqrt(2/pi) (x + 0.044715 x^3))), tanh(u) = 1 - 2 / (1 + e^{2u})
-  const float kBeta = 0.7978845608028654f, kKappa = 0.044715f;
-  float u = kBeta * (x + kKappa * x * x * x);
-  float t = 1.0f - __fdividef(2.0f, 1.0f + __expf(2.0f * u));
-  return 0.5f * x * (1.0f + t);
-}
 
 template <int BLOCK_N, int EPI>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
@@ -154,66 +130,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
       mbar_wait(&tmem_full[acc], acc_phase);
       tc_fence_after();
       const int row = m_blk * BLOCK_M + quarter * 32 + lane;
-      const bool row_ok = row < p.M;
-      const int n0 = n_blk * BLOCK_N;
-      const int seg = n0 / p.seg_cols;
-      __nv_bfloat16* orow = p.out[seg] + (long long)row * p.ldo[seg] + (n0 - seg * p.seg_cols);
-      const __nv_bfloat16* rrow = nullptr;
-      const __nv_bfloat16* grow = nullptr;
-      if (EPI == EPI_RESIDUAL || EPI == EPI_GATE_RES) rrow = p.residual + (long long)row * p.ldr + n0;
-      if (EPI == EPI_GATE_RES) grow = p.gate + (long long)(row_ok ? row / p.rows_per_gate : 0) * p.gate_stride + n0;
-      const uint32_t t_row = tmem_base + ((uint32_t)(quarter * 32) << 16) + acc * BLOCK_N;
-#pragma unroll 1
-      for (int c = 0; c < BLOCK_N / 32; ++c) {
-        uint32_t v[32];
-        tmem_ld32(t_row + c * 32, v);
-        tmem_ld_wait();
-        if (row_ok) {
-#pragma unroll
-          for (int g = 0; g < 4; ++g) {   // 8 columns (16 bytes of bf16) per step
-            const int col = c * 32 + g * 8;
-            if (n0 + col < p.N) {
-              float f[8];
-#pragma unroll
-              for (int i = 0; i < 8; ++i) f[i] = __uint_as_float(v[g * 8 + i]);
-              if (p.bias != nullptr) {
-                const uint4 b = __ldg(reinterpret_cast<const uint4*>(p.bias + n0 + col));
-                const uint32_t bw[4] = {b.x, b.y, b.z, b.w};
-#pragma unroll
-                for (int i = 0; i < 4; ++i) { f[2 * i] += bf_lo(bw[i]); f[2 * i + 1] += bf_hi(bw[i]); }
-              }
-              if (EPI == EPI_GELU) {
-#pragma unroll
-                for (int i = 0; i < 8; ++i) f[i] = gelu_tanh_f(bf16r(f[i]));
-              }
-              if (EPI == EPI_GATE_RES) {
-                const uint4 gq = __ldg(reinterpret_cast<const uint4*>(grow + col));
-                const uint32_t gw[4] = {gq.x, gq.y, gq.z, gq.w};
-#pragma unroll
-                for (int i = 0; i < 4; ++i) {
-                  f[2 * i] = bf16r(bf16r(f[2 * i]) * bf_lo(gw[i]));
-                  f[2 * i + 1] = bf16r(bf16r(f[2 * i + 1]) * bf_hi(gw[i]));
-                }
-              }
-              if (EPI == EPI_RESIDUAL || EPI == EPI_GATE_RES) {
-                const uint4 rq = *reinterpret_cast<const uint4*>(rrow + col);
-                const uint32_t rw[4] = {rq.x, rq.y, rq.z, rq.w};
-#pragma unroll
-                for (int i = 0; i < 4; ++i) {
-                  f[2 * i] = bf_lo(rw[i]) + bf16r(f[2 * i]);
-                  f[2 * i + 1] = bf_hi(rw[i]) + bf16r(f[2 * i + 1]);
-                }
-              }
-              uint4 o;
-              o.x = pack_bf16(f[0], f[1]);
-              o.y = pack_bf16(f[2], f[3]);
-              o.z = pack_bf16(f[4], f[5]);
-              o.w = pack_bf16(f[6], f[7]);
-              *reinterpret_cast<uint4*>(orow + col) = o;
-            }
-          }
-        }
-      }
+      gemm_epilogue_row<BLOCK_N, EPI>(p, row, n_blk * BLOCK_N, tmem_base + ((uint32_t)(quarter * 32) << 16) + acc * BLOCK_N);
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&tmem_empty[acc]);
@@ -260,6 +177,8 @@ static int dispatch_epi(int epi, const CUtensorMap& ta, const CUtensorMap& tb, c
 }
 
 int device_sm_count();
+int launch_gemm_pair(int epi, const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& p, int num_sms,
+                     cudaStream_t stream);
 
 }  // namespace sfb
 
@@ -277,19 +196,24 @@ extern "C" int sfb_gemm_bf16(const void* x, long long ldx, const void* w, long l
     return SFB_ERR_INVALID;
   }
   if (seg_cols <= 0) seg_cols = N;
+  // block_n: 0 = choose; 64 / 128 / 256 = one-CTA tiles of 128 x block_n; 512 = CTA-pair tiles of 256 x 256
+  // (tcgen05 cta_group::2, gemm2_tcgen05.cu) -- the default whenever N and the segments are multiples of 256.
+  if (block_n == 0 && N % 256 == 0 && seg_cols % 256 == 0 && M > 128) block_n = 512;
   if (block_n == 0) {
     // Tile choice: wide tiles amortise smem traffic; narrow problems take 128 so the tile count
     // fills the 148 SMs (M=4680: N=1536 -> 37x12 = 444 = 3 waves of 148).
     block_n = (N % 256 == 0 && N >= 4096) ? 256 : (N % 128 == 0 ? 128 : 64);
   }
-  if (block_n != 64 && block_n != 128 && block_n != 256) { set_error("sfb_gemm_bf16: block_n must be 64/128/256"); return SFB_ERR_INVALID; }
+  const bool pair = block_n == 512;
+  if (pair) block_n = 256;
+  if (block_n != 64 && block_n != 128 && block_n != 256) { set_error("sfb_gemm_bf16: block_n must be 64/128/256/512"); return SFB_ERR_INVALID; }
   if (seg_cols % block_n) { set_error("sfb_gemm_bf16: seg_cols=%d not a multiple of the N tile %d", seg_cols, block_n); return SFB_ERR_INVALID; }
   if ((epilogue == EPI_RESIDUAL || epilogue == EPI_GATE_RES) && residual == nullptr) { set_error("sfb_gemm_bf16: residual epilogue without residual"); return SFB_ERR_INVALID; }
   if (epilogue == EPI_GATE_RES && (gate == nullptr || rows_per_gate <= 0)) { set_error("sfb_gemm_bf16: gate epilogue without gate"); return SFB_ERR_INVALID; }
 
   GemmParams p{};
   p.M = M; p.N = N; p.K = K;
-  p.num_m_blocks = (M + BLOCK_M - 1) / BLOCK_M;
+  p.num_m_blocks = pair ? (M + 2 * BLOCK_M - 1) / (2 * BLOCK_M) : (M + BLOCK_M - 1) / BLOCK_M;
   p.num_n_blocks = (N + block_n - 1) / block_n;
   p.num_k_blocks = (K + BLOCK_K - 1) / BLOCK_K;
   p.bias = static_cast<const __nv_bfloat16*>(bias);
@@ -314,11 +238,12 @@ extern "C" int sfb_gemm_bf16(const void* x, long long ldx, const void* w, long l
   {
     uint64_t dims[2] = {(uint64_t)K, (uint64_t)N};
     uint64_t strides[1] = {(uint64_t)ldw * 2};
-    uint32_t box[2] = {BLOCK_K, (uint32_t)block_n};
+    uint32_t box[2] = {BLOCK_K, (uint32_t)(pair ? block_n / 2 : block_n)};
     if (int e = make_tmap_bf16(&tb, w, 2, dims, strides, box, true)) return e;
   }
   const int sms = device_sm_count();
   if (sms <= 0) return SFB_ERR_CUDA;
+  if (pair) return launch_gemm_pair(epilogue, ta, tb, p, sms, stream);
   switch (block_n) {
     case 64: return dispatch_epi<64>(epilogue, ta, tb, p, sms, stream);
     case 128: return dispatch_epi<128>(epilogue, ta, tb, p, sms, stream);

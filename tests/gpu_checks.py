@@ -343,6 +343,13 @@ ALL = {
     "gemm_qkv_full": lambda: check_gemm(M=4680, N=4608, K=1536),
     "gemm_ffn2_full": lambda: check_gemm(M=4680, N=1536, K=8960, epilogue=3, rows_per_gate=1560),
     "gemm_segments": check_gemm_segments,
+    "gemm_segments_1cta": lambda: check_gemm_segments(C=128),
+    "gemm_pair_small": lambda: check_gemm(M=300, N=512, K=192, block_n=512),
+    "gemm_pair_tail": lambda: check_gemm(M=130, N=256, K=64, block_n=512),
+    "gemm_pair_one_cta_empty": lambda: check_gemm(M=700, N=256, K=1536, block_n=512, epilogue=2),
+    "gemm_pair_persistent_gelu": lambda: check_gemm(M=4680, N=8960, K=256, epilogue=1, block_n=512),
+    "gemm_pair_gate": lambda: check_gemm(M=1000, N=768, K=320, epilogue=3, rows_per_gate=70, block_n=512),
+    "gemm_pair_o_proj": lambda: check_gemm(M=4680, N=1536, K=1536, epilogue=3, rows_per_gate=1560, block_n=512),
     "attn_small": lambda: check_attention(),
     "attn_one_tile": lambda: check_attention(Lq=128, S=128, H=1),
     "attn_tail": lambda: check_attention(Lq=72, S=72, H=3),

@@ -40,9 +40,9 @@ def main():
     out = []
     only = sys.argv[1:]
     M = 4680
-    gemms = [("qkv", 4608, 1536, 0, 0), ("qkv_bn128", 4608, 1536, 0, 128), ("o_proj", 1536, 1536, 3, 0),
-             ("o_proj_bn256", 1536, 1536, 3, 256), ("ffn1", 8960, 1536, 1, 0), ("ffn1_bn128", 8960, 1536, 1, 128),
-             ("ffn2", 1536, 8960, 3, 0), ("ffn2_bn256", 1536, 8960, 3, 256), ("head", 64, 1536, 0, 0)]
+    gemms = [("qkv", 4608, 1536, 0, 0), ("qkv_1cta256", 4608, 1536, 0, 256), ("o_proj", 1536, 1536, 3, 0),
+             ("o_proj_1cta128", 1536, 1536, 3, 128), ("ffn1", 8960, 1536, 1, 0), ("ffn1_1cta256", 8960, 1536, 1, 256),
+             ("ffn2", 1536, 8960, 3, 0), ("ffn2_1cta128", 1536, 8960, 3, 128), ("head", 64, 1536, 0, 0)]
     for name, N, K, epi, bn in gemms:
         if only and not any(o in "gemm_" + name for o in only):
             continue
@@ -91,7 +91,8 @@ def main():
         print(json.dumps(rec), flush=True)
         out.append(rec)
     os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
-    with open(os.path.join(ROOT, "gpurun_out", "microbench.json"), "w") as f:
+    tag = os.environ.get("SFB_MICROBENCH_TAG", "")
+    with open(os.path.join(ROOT, "gpurun_out", f"microbench{tag}.json"), "w") as f:
         json.dump(out, f, indent=1)
 
 
