@@ -11,6 +11,12 @@
 // LEADER's mbarrier), warp 1 = MMA issuer (leader CTA only; tcgen05.mma.cta_group::2, M=256 N=256 K=16,
 // commits multicast to both CTAs), warps 2-5 epilogue of this CTA's 128 accumulator rows (TMEM double
 // buffered: 2 x 256 columns).
+//
+// Epilogue: the accumulator rows are staged in shared memory (four 128 x 64 bf16 sub-tiles, 128-byte
+// swizzle) and written with TMA stores; the residual tile is prefetched into the same staging buffers with
+// TMA loads while the main loop of the tile is still running, and updated in place.  (A per-thread
+// row-strided epilogue -- 16-byte global loads/stores at a 3 KB row pitch -- measured 24 k .. 54 k cycles per
+// tile on B200, longer than the 18 k-cycle main loop of a K=1536 tile, and became the bound.)
 #include "gemm_common.cuh"
 
 namespace sfb {
@@ -18,24 +24,31 @@ namespace sfb {
 constexpr int G2_ROWS = 128;           // accumulator rows per CTA (pair tile = 256 rows)
 constexpr int G2_BN = 256;             // pair tile columns; each CTA stages 128 of them
 constexpr int G2_BK = 64;
-constexpr int G2_STAGES = 6;
+constexpr int G2_STAGES = 5;
+constexpr int G2_SUB = 64;             // staging sub-tile width (one 128-byte swizzle row of bf16)
+constexpr int G2_NSUB = G2_BN / G2_SUB;
+constexpr int G2_SUB_BYTES = G2_ROWS * G2_SUB * 2;
 constexpr int G2_A_BYTES = G2_ROWS * G2_BK * 2;
 constexpr int G2_B_BYTES = (G2_BN / 2) * G2_BK * 2;
 constexpr int G2_STAGE_BYTES = G2_A_BYTES + G2_B_BYTES;
-constexpr int G2_SMEM_BYTES = G2_STAGES * G2_STAGE_BYTES + 1024 + 256;
+constexpr int G2_SMEM_BYTES = G2_STAGES * G2_STAGE_BYTES + G2_NSUB * G2_SUB_BYTES + 1024 + 256;
 constexpr int G2_THREADS = 192;
 
 template <int EPI>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(G2_THREADS, 1)
 gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b,
+                  const __grid_constant__ CUtensorMap tma_out0, const __grid_constant__ CUtensorMap tma_out1,
+                  const __grid_constant__ CUtensorMap tma_out2, const __grid_constant__ CUtensorMap tma_res,
                   const GemmParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + G2_STAGES * G2_STAGE_BYTES);
+  uint8_t* stage_out = smem + G2_STAGES * G2_STAGE_BYTES;   // [G2_NSUB][128 rows][128 B], swizzled
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(stage_out + G2_NSUB * G2_SUB_BYTES);
   uint64_t* empty_bar = full_bar + G2_STAGES;
   uint64_t* tmem_full = empty_bar + G2_STAGES;   // [2]
   uint64_t* tmem_empty = tmem_full + 2;          // [2]  (only the leader's copy is waited on)
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+  uint64_t* res_full = tmem_empty + 2;           // [1]  residual tile landed in the staging buffers
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(res_full + 1);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -53,6 +66,7 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_consta
       mbar_init(&tmem_full[s], 1);
       mbar_init(&tmem_empty[s], 8);  // 4 epilogue warps x 2 CTAs arrive on the leader's barrier
     }
+    mbar_init(res_full, 1);
     fence_barrier_init();
   }
   if (warp == 1) tmem_alloc_pair(tmem_slot, 512);
@@ -115,22 +129,75 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_consta
     }
   } else {
     // ------------------------------ epilogue warps (both CTAs) ----------------
+    constexpr bool HAS_RES = (EPI == EPI_RESIDUAL || EPI == EPI_GATE_RES);
     const int quarter = warp & 3;
+    const int r_local = quarter * 32 + lane;                 // accumulator row (TMEM lane) of this thread
+    const bool elected = (warp == 2 && lane == 0);
     const uint32_t leader_empty0 = mapa_cluster(smem_u32(&tmem_empty[0]), 0);
+    uint8_t* my_row = stage_out + r_local * 128;
+    const int sw = r_local & 7;                              // 128-byte swizzle: 16-byte chunk index ^ (row % 8)
+    if (elected) {
+      tma_prefetch_desc(&tma_out0);
+      if (HAS_RES) tma_prefetch_desc(&tma_res);
+    }
+    uint32_t res_phase = 0;
     int it = 0;
     for (int tile = pair; tile < num_tiles; tile += num_pairs, ++it) {
       const int m_blk = tile % p.num_m_blocks, n_blk = tile / p.num_m_blocks;
       const int acc = it & 1;
       const uint32_t acc_phase = (it >> 1) & 1;
+      const int row0 = m_blk * (2 * G2_ROWS) + rank * G2_ROWS;
+      const int n0 = n_blk * G2_BN;
+      const int seg = n0 / p.seg_cols;
+      const int seg_col0 = n0 - seg * p.seg_cols;
+      const CUtensorMap* omap = seg == 0 ? &tma_out0 : (seg == 1 ? &tma_out1 : &tma_out2);
+      // staging buffers are free once the previous tile's TMA stores have read them
+      if (elected) tma_store_wait_read<0>();
+      named_barrier_sync(1, 128);
+      if (HAS_RES && elected) {
+        mbar_expect_tx(res_full, G2_NSUB * G2_SUB_BYTES);
+        for (int sb = 0; sb < G2_NSUB; ++sb)
+          tma_load_2d(stage_out + sb * G2_SUB_BYTES, &tma_res, res_full, n0 + sb * G2_SUB, row0);
+      }
       mbar_wait(&tmem_full[acc], acc_phase);
       tc_fence_after();
-      const int row = m_blk * (2 * G2_ROWS) + rank * G2_ROWS + quarter * 32 + lane;
-      gemm_epilogue_row<G2_BN, EPI>(p, row, n_blk * G2_BN,
-                                    tmem_base + ((uint32_t)(quarter * 32) << 16) + acc * G2_BN);
+      if (HAS_RES) {
+        mbar_wait(res_full, res_phase);
+        res_phase ^= 1;
+      }
+      const int row = row0 + r_local;
+      const __nv_bfloat16* grow = nullptr;
+      if (EPI == EPI_GATE_RES)
+        grow = p.gate + (long long)((row < p.M ? row : p.M - 1) / p.rows_per_gate) * p.gate_stride + n0;
+      const uint32_t t_row = tmem_base + ((uint32_t)(quarter * 32) << 16) + acc * G2_BN;
+#pragma unroll 1
+      for (int sb = 0; sb < G2_NSUB; ++sb) {
+        uint32_t v[64];
+        tmem_ld32(t_row + sb * G2_SUB, *reinterpret_cast<uint32_t(*)[32]>(&v[0]));
+        tmem_ld32(t_row + sb * G2_SUB + 32, *reinterpret_cast<uint32_t(*)[32]>(&v[32]));
+        tmem_ld_wait();
+        uint8_t* buf_row = my_row + sb * G2_SUB_BYTES;
+#pragma unroll
+        for (int c = 0; c < 8; ++c) {
+          uint4* slot = reinterpret_cast<uint4*>(buf_row + ((c ^ sw) << 4));
+          uint4 res = make_uint4(0, 0, 0, 0);
+          if (HAS_RES) res = *slot;
+          const int col = sb * G2_SUB + c * 8;
+          *slot = gemm_epilogue_chunk<EPI>(&v[c * 8], p.bias ? p.bias + n0 + col : nullptr,
+                                           EPI == EPI_GATE_RES ? grow + col : nullptr, res);
+        }
+        fence_proxy_async();
+        named_barrier_sync(2, 128);
+        if (elected) {
+          tma_store_2d(omap, stage_out + sb * G2_SUB_BYTES, seg_col0 + sb * G2_SUB, row0);
+          tma_store_commit();
+        }
+      }
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive_cluster(leader_empty0 + acc * 8);
     }
+    if (elected) tma_store_wait_read<0>();
   }
 
   tc_fence_before();
@@ -141,9 +208,14 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_consta
   }
 }
 
+struct PairMaps {
+  CUtensorMap out[3];
+  CUtensorMap res;
+};
+
 template <int EPI>
-static int launch_gemm2(const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& p, int num_sms,
-                        cudaStream_t stream) {
+static int launch_gemm2(const CUtensorMap& ta, const CUtensorMap& tb, const PairMaps& pm, const GemmParams& p,
+                        int num_sms, cudaStream_t stream) {
   auto kern = gemm2_bf16_kernel<EPI>;
   static int max_clusters = 0;
   if (max_clusters == 0) {
@@ -163,18 +235,34 @@ static int launch_gemm2(const CUtensorMap& ta, const CUtensorMap& tb, const Gemm
   }
   const int tiles = p.num_m_blocks * p.num_n_blocks;
   const int clusters = tiles < max_clusters ? tiles : max_clusters;
-  kern<<<2 * clusters, G2_THREADS, G2_SMEM_BYTES, stream>>>(ta, tb, p);
+  kern<<<2 * clusters, G2_THREADS, G2_SMEM_BYTES, stream>>>(ta, tb, pm.out[0], pm.out[1], pm.out[2], pm.res, p);
   return check_cuda(cudaGetLastError(), "gemm2 launch");
 }
 
 // Called by sfb_gemm_bf16 (gemm_tcgen05.cu) for N % 256 == 0 problems.  `p` carries pair-tile counts.
 int launch_gemm_pair(int epi, const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& p, int num_sms,
                      cudaStream_t stream) {
+  PairMaps pm;
+  const uint32_t box[2] = {G2_SUB, G2_ROWS};
+  const int nseg = (p.N + p.seg_cols - 1) / p.seg_cols;
+  for (int sgm = 0; sgm < 3; ++sgm) {
+    const int src = sgm < nseg ? sgm : 0;   // unused slots alias segment 0 (never dereferenced)
+    uint64_t dims[2] = {(uint64_t)p.seg_cols, (uint64_t)p.M};
+    uint64_t strides[1] = {(uint64_t)p.ldo[src] * 2};
+    if (int e = make_tmap_bf16(&pm.out[sgm], p.out[src], 2, dims, strides, box, true)) return e;
+  }
+  if (epi == EPI_RESIDUAL || epi == EPI_GATE_RES) {
+    uint64_t dims[2] = {(uint64_t)p.N, (uint64_t)p.M};
+    uint64_t strides[1] = {(uint64_t)p.ldr * 2};
+    if (int e = make_tmap_bf16(&pm.res, p.residual, 2, dims, strides, box, true)) return e;
+  } else {
+    pm.res = pm.out[0];
+  }
   switch (epi) {
-    case EPI_BIAS: return launch_gemm2<EPI_BIAS>(ta, tb, p, num_sms, stream);
-    case EPI_GELU: return launch_gemm2<EPI_GELU>(ta, tb, p, num_sms, stream);
-    case EPI_RESIDUAL: return launch_gemm2<EPI_RESIDUAL>(ta, tb, p, num_sms, stream);
-    case EPI_GATE_RES: return launch_gemm2<EPI_GATE_RES>(ta, tb, p, num_sms, stream);
+    case EPI_BIAS: return launch_gemm2<EPI_BIAS>(ta, tb, pm, p, num_sms, stream);
+    case EPI_GELU: return launch_gemm2<EPI_GELU>(ta, tb, pm, p, num_sms, stream);
+    case EPI_RESIDUAL: return launch_gemm2<EPI_RESIDUAL>(ta, tb, pm, p, num_sms, stream);
+    case EPI_GATE_RES: return launch_gemm2<EPI_GATE_RES>(ta, tb, pm, p, num_sms, stream);
   }
   set_error("sfb_gemm_bf16: unknown epilogue %d", epi);
   return SFB_ERR_INVALID;

@@ -31,6 +31,49 @@ __device__ __forceinline__ float gelu_tanh_f(float x) {
 }
 
 
+// Fused epilogue math on 8 consecutive accumulator columns (one 16-byte bf16 chunk), shared by both
+// store paths.  bias/gate point at the chunk's first column; res holds the residual chunk.
+template <int EPI>
+__device__ __forceinline__ uint4 gemm_epilogue_chunk(const uint32_t* acc8, const __nv_bfloat16* bias,
+                                                     const __nv_bfloat16* gate, uint4 res) {
+  float f[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) f[i] = __uint_as_float(acc8[i]);
+  if (bias != nullptr) {
+    const uint4 b = __ldg(reinterpret_cast<const uint4*>(bias));
+    const uint32_t bw[4] = {b.x, b.y, b.z, b.w};
+#pragma unroll
+    for (int i = 0; i < 4; ++i) { f[2 * i] += bf_lo(bw[i]); f[2 * i + 1] += bf_hi(bw[i]); }
+  }
+  if (EPI == EPI_GELU) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) f[i] = gelu_tanh_f(bf16r(f[i]));
+  }
+  if (EPI == EPI_GATE_RES) {
+    const uint4 gq = __ldg(reinterpret_cast<const uint4*>(gate));
+    const uint32_t gw[4] = {gq.x, gq.y, gq.z, gq.w};
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      f[2 * i] = bf16r(bf16r(f[2 * i]) * bf_lo(gw[i]));
+      f[2 * i + 1] = bf16r(bf16r(f[2 * i + 1]) * bf_hi(gw[i]));
+    }
+  }
+  if (EPI == EPI_RESIDUAL || EPI == EPI_GATE_RES) {
+    const uint32_t rw[4] = {res.x, res.y, res.z, res.w};
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      f[2 * i] = bf_lo(rw[i]) + bf16r(f[2 * i]);
+      f[2 * i + 1] = bf_hi(rw[i]) + bf16r(f[2 * i + 1]);
+    }
+  }
+  uint4 o;
+  o.x = pack_bf16(f[0], f[1]);
+  o.y = pack_bf16(f[2], f[3]);
+  o.z = pack_bf16(f[4], f[5]);
+  o.w = pack_bf16(f[6], f[7]);
+  return o;
+}
+
 // One thread owns accumulator row `row` (TMEM lane) of a tile that starts at column n0 and is
 // TILE_N columns wide; t_row is the TMEM address of (lane, first column).
 template <int TILE_N, int EPI>
