@@ -20,7 +20,7 @@
 extern "C" {
 #endif
 
-#define SFB_ABI_VERSION 1
+#define SFB_ABI_VERSION 2
 
 const char* sfb_last_error(void);
 int sfb_abi_version(void);
@@ -50,7 +50,13 @@ int sfb_gemm_bf16(const void* x, long long ldx, const void* w, long long ldw, co
 int sfb_attention_fwd(const void* q, long long q_row_stride, long long q_batch_stride,
                       const void* k, const void* v, long long kv_row_stride, long long kv_batch_stride,
                       void* out, long long out_row_stride, long long out_batch_stride,
-                      int B, int Lq, int Skv, int H, int head_dim, float softmax_scale, void* stream);
+                      int B, int Lq, int Skv, int H, int head_dim, float softmax_scale,
+                      void* workspace, long long workspace_bytes, void* stream);
+
+/* Scratch (bytes) sfb_attention_fwd uses to spread long KV windows evenly over all SMs: the (item, KV step)
+ * space is cut into one contiguous range per SM and partial (O, max, sum) results of split items are merged
+ * by a second small kernel.  The caller owns the buffer; workspace == NULL disables the split. */
+long long sfb_attention_workspace_bytes(void);
 
 /* out[l][r][g][:] = bf16(mod[l][g][:] + e[r * e_row_stride + g * e_group_stride + :])
  * adaLN tables for all layers at once: causal_model.py:310 (G=6) and :365 (head, G=2, broadcast e). */

@@ -12,11 +12,12 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "libsfb200.so")
 
 P, LL, I, F = c_void_p, c_longlong, c_int, c_float
+ABI_VERSION = 2
 
 # name -> argtypes, mirroring include/sfb200.h one to one
 SIGNATURES = {
     "sfb_gemm_bf16": [P, LL, P, LL, P, I, I, I, I, P, LL, P, LL, P, LL, I, P, LL, P, LL, I, I, P],
-    "sfb_attention_fwd": [P, LL, LL, P, P, LL, LL, P, LL, LL, I, I, I, I, I, F, P],
+    "sfb_attention_fwd": [P, LL, LL, P, P, LL, LL, P, LL, LL, I, I, I, I, I, F, P, LL, P],
     "sfb_modulation_table": [P, P, P, I, I, I, I, LL, LL, P],
     "sfb_ln_modulate": [P, LL, P, LL, I, I, F, P, P, LL, I, P],
     "sfb_ln_affine": [P, LL, P, LL, I, I, F, P, P, P],
@@ -52,10 +53,14 @@ def load(path: str | None = None) -> ctypes.CDLL:
     lib.sfb_last_error.argtypes = []
     lib.sfb_abi_version.restype = c_int
     lib.sfb_abi_version.argtypes = []
+    lib.sfb_attention_workspace_bytes.restype = c_longlong
+    lib.sfb_attention_workspace_bytes.argtypes = []
     for name, argtypes in SIGNATURES.items():
         fn = getattr(lib, name)
         fn.argtypes = argtypes
         fn.restype = c_int
+    if lib.sfb_abi_version() != ABI_VERSION:
+        raise SfbError(f"{path} has ABI version {lib.sfb_abi_version()}, this package needs {ABI_VERSION}: rebuild it")
     _lib = lib
     return lib
 

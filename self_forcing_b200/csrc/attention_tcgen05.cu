@@ -7,14 +7,28 @@
 // K and V are read in place from the cache layout [B, S, H, 128] (row stride H*128) through TMA, so
 // there is no varlen packing / cu_seqlens traffic and no copy of the window.
 //
-// One CTA per (pair of 128-row query tiles, head, batch); 320 threads:
-//   warp 0     TMA producer: Q pair once, then K / V tiles through two 2-deep rings
-//   warp 1     MMA issuer  : S_t = Q_t K^T (SS), O_t += P_t V (P from TMEM, V MN-major from smem)
-//   warps 2-5  softmax for query tile 0      warps 6-9  softmax for query tile 1
+// Work decomposition (persistent, "stream-K" over the KV axis).  A work ITEM is (batch, head, pair of
+// 128-row query tiles); it needs n_kv = ceil(S / 128) KV steps.  The B*H*ceil(Lq/256) items rarely divide
+// by the 148 SMs (Lq = 4680, H = 12: 228 items = 1.54 waves, a quarter of the GPU idle), so the item x
+// step space is linearised and cut into one CONTIGUOUS range of steps per CTA.  A CTA therefore runs a
+// few SEGMENTS (item, [j0, j1)); a segment that covers its whole item writes bf16 output directly, a
+// partial one parks (unnormalised O^T, row max, row sum) in the caller's workspace and
+// `attention_combine_kernel` merges the (at most a few) partials of each split item.  Short KV (cross
+// attention, 4 steps) is not split: CTAs take whole items.
+//
+// One CTA per SM, 384 threads = 3 warpgroups:
+//   WG0  warp 0: TMA producer (Q pair per segment; K / V tiles through two 2-deep rings)
+//        warp 1: MMA issuer   S_t = Q_t K^T (SS), O_t += P_t V (P from TMEM, V MN-major from smem)
+//   WG1 / WG2    softmax of query tile 0 / 1, one row per thread (setmaxnreg moves registers to them)
 // TMEM (512 columns): S0 | S1 | O0 | O1, P_t (bf16) aliases the first 64 columns of S_t.
-// The two query tiles ping-pong on the tensor pipe: while one tile's softmax runs on the SIMT
+// The two query tiles ping-pong on the tensor pipe: while one tile's softmax runs on the SIMT / XU
 // pipes the other tile's PV / next QK^T MMAs run.  O is rescaled lazily (only when a row max grows
-// by more than 2^8), done by the softmax warps themselves between PV(j-1) and PV(j).
+// by more than 2^8), by the softmax warps themselves between PV(j-1) and PV(j).
+//
+// Softmax arithmetic: x = s * scale_log2 - m with packed fp32x2 FMAs, 2^x on MUFU.EX2 (16 lanes/clk/SM --
+// for head_dim 128 that is exactly the rate at which the tensor pipe consumes P, so the exponentials,
+// not the MMAs, are the critical resource) with an optional share computed by a degree-3 polynomial on
+// the FMA pipe (template EMU), row sums with packed adds.
 #include <math.h>
 #include <stdlib.h>
 
@@ -26,18 +40,34 @@ struct AttnParams {
   int Lq, Skv, H, B;
   int n_kv_tiles;
   int kv_tail;            // valid columns in the last KV tile (1..128)
+  int n_qpairs;           // ceil(Lq / 256)
+  int items;              // B * H * n_qpairs
+  int split;              // 1: contiguous step ranges per CTA (partials in ws), 0: whole items per CTA
   float scale_log2;       // softmax_scale * log2(e)
   __nv_bfloat16* out;
   long long out_row_stride, out_batch_stride;   // elements
+  float* ws;              // [grid][2 slots][2 tiles][128*128 O^T + 128 m + 128 l] floats (split mode)
 };
 
 constexpr int ATT_BM = 128, ATT_BN = 128, ATT_D = 128;
-constexpr int ATT_THREADS = 320;
+constexpr int ATT_THREADS = 384;
 constexpr int ATT_TILE_BYTES = 128 * 128 * 2;    // 32 KB: two 16 KB halves (d 0-63 | d 64-127)
 constexpr int ATT_HALF_BYTES = 128 * 64 * 2;
 constexpr int ATT_KV_STAGES = 2;
-constexpr int ATT_DEFAULT_EMU = 1;
 constexpr int ATT_SMEM_BYTES = 2 * ATT_TILE_BYTES + 2 * ATT_KV_STAGES * ATT_TILE_BYTES + 1024 + 256;
+constexpr int ATT_DEFAULT_EMU = 0;
+constexpr int ATT_SLOT_FLOATS = ATT_BM * ATT_D + 2 * ATT_BM;   // one (tile, segment) partial
+constexpr int ATT_MIN_SPLIT_KV_TILES = 16;                     // shorter KV: whole items per CTA
+
+// first KV step (in the linearised item x step space) of CTA c, and the owner of a step
+__host__ __device__ __forceinline__ long long att_range_start(int c, int grid, const AttnParams& p) {
+  if (p.split) return ((long long)c * p.items * p.n_kv_tiles) / grid;
+  return (((long long)c * p.items) / grid) * p.n_kv_tiles;
+}
+__host__ __device__ __forceinline__ int att_step_owner(long long step, int grid, const AttnParams& p) {
+  const long long G = (long long)p.items * p.n_kv_tiles;
+  return (int)(((step + 1) * grid - 1) / G);   // largest c with floor(c * G / grid) <= step   (split mode)
+}
 
 __device__ __forceinline__ float fast_exp2(float x) {
   float y;
@@ -45,20 +75,35 @@ __device__ __forceinline__ float fast_exp2(float x) {
   return y;
 }
 
-// 2^x on the FMA pipe (Cody-Waite range reduction + degree-3 minimax polynomial, rel. error 8.8e-5 --
-// far below the bf16 rounding of P).  MUFU.EX2 runs at 16 lanes/clk/SM, which for head_dim 128 is
-// exactly the rate the tensor pipe consumes P at; moving a fraction of the exponentials here takes
-// the softmax off the critical path.  x <= ~8 (lazy rescaling bound); clamped below for the exponent.
-__device__ __forceinline__ float poly_exp2(float x) {
-  x = fmaxf(x, -125.0f);
-  float r;
-  asm("add.rm.ftz.f32 %0, %1, %2;" : "=f"(r) : "f"(x), "f"(12582912.0f));   // 1.5 * 2^23 + floor(x)
-  const float f = x - (r - 12582912.0f);                                       // frac(x) in [0, 1)
-  const float p = fmaf(fmaf(fmaf(0.077119089663028717f, f, 0.227564394474029541f), f, 0.695146143436431885f), f, 1.0f);
-  return __int_as_float(__float_as_int(p) + (__float_as_int(r) << 23));
+__device__ __forceinline__ unsigned long long f2_bits(float2 v) {
+  return (unsigned long long)__float_as_uint(v.x) | ((unsigned long long)__float_as_uint(v.y) << 32);
 }
 
-// EMU: how many of every 4 exponentials run on the FMA pipe instead of MUFU (0, 1 or 2).
+// 2^x for two values on the FMA pipe: Cody-Waite range reduction + degree-3 minimax polynomial
+// (rel. error 8.8e-5, far below the bf16 rounding of P).  x <= ~8 (lazy-rescale bound).
+__device__ __forceinline__ float2 poly_exp2x2(float2 x) {
+  x.x = fmaxf(x.x, -125.0f);
+  x.y = fmaxf(x.y, -125.0f);
+  unsigned long long rb;
+  asm("add.rm.ftz.f32x2 %0, %1, %2;" : "=l"(rb) : "l"(f2_bits(x)), "l"(f2_bits(make_float2(12582912.0f, 12582912.0f))));
+  const float2 r = make_float2(__uint_as_float((uint32_t)rb), __uint_as_float((uint32_t)(rb >> 32)));   // 1.5*2^23 + floor(x)
+  const float2 fl = __fadd2_rn(r, make_float2(-12582912.0f, -12582912.0f));          // floor(x)
+  const float2 f = __ffma2_rn(fl, make_float2(-1.0f, -1.0f), x);                       // frac(x) in [0, 1)
+  float2 q = __ffma2_rn(make_float2(0.077119089663028717f, 0.077119089663028717f), f,
+                        make_float2(0.227564394474029541f, 0.227564394474029541f));
+  q = __ffma2_rn(q, f, make_float2(0.695146143436431885f, 0.695146143436431885f));
+  q = __ffma2_rn(q, f, make_float2(1.0f, 1.0f));
+  q.x = __int_as_float(__float_as_int(q.x) + (__float_as_int(r.x) << 23));
+  q.y = __int_as_float(__float_as_int(q.y) + (__float_as_int(r.y) << 23));
+  return q;
+}
+
+template <int REGS>
+__device__ __forceinline__ void setmaxnreg_inc() { asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(REGS)); }
+template <int REGS>
+__device__ __forceinline__ void setmaxnreg_dec() { asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(REGS)); }
+
+// EMU: how many of every 4 exponential PAIRS run on the FMA pipe instead of MUFU (0, 1 or 2).
 template <int EMU>
 __global__ void __launch_bounds__(ATT_THREADS, 1)
 attention_fwd_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_constant__ CUtensorMap tma_k,
@@ -69,28 +114,28 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_con
   uint8_t* k_smem = smem + 2 * ATT_TILE_BYTES;               // [stages][32 KB]
   uint8_t* v_smem = k_smem + ATT_KV_STAGES * ATT_TILE_BYTES; // [stages][32 KB]
   uint64_t* bars = reinterpret_cast<uint64_t*>(v_smem + ATT_KV_STAGES * ATT_TILE_BYTES);
-  uint64_t* q_full = bars;            // [1]
-  uint64_t* k_full = bars + 1;        // [2]
-  uint64_t* k_empty = bars + 3;       // [2]
-  uint64_t* v_full = bars + 5;        // [2]
-  uint64_t* v_empty = bars + 7;       // [2]
-  uint64_t* s_full = bars + 9;        // [2] per query tile
-  uint64_t* p_full = bars + 11;       // [2]
-  uint64_t* o_final = bars + 13;      // [2]
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 15);
+  uint64_t* q_full = bars;            // [1]  per segment
+  uint64_t* q_empty = bars + 1;       // [1]  per segment
+  uint64_t* k_full = bars + 2;        // [2]  ring
+  uint64_t* k_empty = bars + 4;       // [2]
+  uint64_t* v_full = bars + 6;        // [2]
+  uint64_t* v_empty = bars + 8;       // [2]
+  uint64_t* s_full = bars + 10;       // [2] per query tile, per KV step
+  uint64_t* p_full = bars + 12;       // [2] per query tile, per KV step (128 arrivals)
+  uint64_t* o_final = bars + 14;      // [2] per query tile, per segment
+  uint64_t* o_free = bars + 16;       // [2] per query tile, per segment (128 arrivals)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 18);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  const int q_row0 = blockIdx.x * (2 * ATT_BM);
-  const int head = blockIdx.y;
-  const int batch = blockIdx.z;
-  const int n_tiles = p.n_kv_tiles;
+  const int n_kv = p.n_kv_tiles;
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tma_q);
     tma_prefetch_desc(&tma_k);
     tma_prefetch_desc(&tma_v);
     mbar_init(q_full, 1);
+    mbar_init(q_empty, 1);
     for (int s = 0; s < 2; ++s) {
       mbar_init(&k_full[s], 1);
       mbar_init(&k_empty[s], 1);
@@ -99,6 +144,7 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_con
       mbar_init(&s_full[s], 1);
       mbar_init(&p_full[s], 128);
       mbar_init(&o_final[s], 1);
+      mbar_init(&o_free[s], 128);
     }
     fence_barrier_init();
   }
@@ -108,193 +154,272 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_con
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
-  if (warp == 0) {
-    // ------------------------------ TMA producer ------------------------------
-    if (lane == 0) {
-      mbar_expect_tx(q_full, 2 * ATT_TILE_BYTES);
-      for (int t = 0; t < 2; ++t)
-        for (int hf = 0; hf < 2; ++hf)
-          tma_load_4d(q_smem + t * ATT_TILE_BYTES + hf * ATT_HALF_BYTES, &tma_q, q_full, hf * 64, head,
-                      q_row0 + t * ATT_BM, batch);
-      for (int j = 0; j < n_tiles; ++j) {
-        const int st = j & 1;
-        const uint32_t ph = (j >> 1) & 1;
-        mbar_wait(&k_empty[st], ph ^ 1);
-        mbar_expect_tx(&k_full[st], ATT_TILE_BYTES);
-        for (int hf = 0; hf < 2; ++hf)
-          tma_load_4d(k_smem + st * ATT_TILE_BYTES + hf * ATT_HALF_BYTES, &tma_k, &k_full[st], hf * 64, head,
-                      j * ATT_BN, batch);
-        mbar_wait(&v_empty[st], ph ^ 1);
-        mbar_expect_tx(&v_full[st], ATT_TILE_BYTES);
-        for (int hf = 0; hf < 2; ++hf)
-          tma_load_4d(v_smem + st * ATT_TILE_BYTES + hf * ATT_HALF_BYTES, &tma_v, &v_full[st], hf * 64, head,
-                      j * ATT_BN, batch);
-      }
-    }
-  } else if (warp == 1) {
-    // ------------------------------ MMA issuer --------------------------------
-    if (lane == 0) {
-      constexpr uint32_t idesc_qk = umma_idesc_bf16(ATT_BM, ATT_BN, 0, 0);   // A, B K-major
-      constexpr uint32_t idesc_pv = umma_idesc_bf16(ATT_BM, ATT_D, 0, 1);    // B (=V) MN-major
-      const uint32_t q_addr = smem_u32(q_smem), k_addr = smem_u32(k_smem), v_addr = smem_u32(v_smem);
+  // this CTA's contiguous range of (item, KV step) work
+  const long long range_begin = att_range_start(blockIdx.x, gridDim.x, p);
+  const long long range_end = att_range_start(blockIdx.x + 1, gridDim.x, p);
 
-      auto issue_qk = [&](int t, int kst) {
-        const uint32_t qa = q_addr + t * ATT_TILE_BYTES, ka = k_addr + kst * ATT_TILE_BYTES;
-#pragma unroll
-        for (int k = 0; k < ATT_D / 16; ++k) {
-          const uint32_t off = (k >> 2) * ATT_HALF_BYTES + (k & 3) * 32;
-          umma_ss(tmem_base + t * 128, umma_desc_sw128(qa + off, 16, 1024), umma_desc_sw128(ka + off, 16, 1024),
-                  idesc_qk, k != 0);
-        }
-      };
-      auto issue_pv = [&](int t, int vst, bool acc) {
-        const uint32_t va = v_addr + vst * ATT_TILE_BYTES;
-#pragma unroll
-        for (int k = 0; k < ATT_BN / 16; ++k) {
-          // A: P_t rows on TMEM lanes, 16 bf16 of K per 8 32-bit columns.
-          // B: V tile [kv][d], d contiguous -> MN-major; 16 kv rows = 2048 B; d halves 16 KB apart.
-          umma_ts(tmem_base + 256 + t * 128, tmem_base + t * 128 + k * 8,
-                  umma_desc_sw128(va + k * 2048, ATT_HALF_BYTES, 1024), idesc_pv, (acc || k != 0) ? 1u : 0u);
-        }
-      };
-
-      mbar_wait(q_full, 0);
-      mbar_wait(&k_full[0], 0);
-      tc_fence_after();
-      issue_qk(0, 0);
-      umma_commit(&s_full[0]);
-      issue_qk(1, 0);
-      umma_commit(&s_full[1]);
-      umma_commit(&k_empty[0]);
-      for (int j = 0; j < n_tiles; ++j) {
-        const int vst = j & 1;
-        const uint32_t vph = (j >> 1) & 1;
-        const bool has_next = (j + 1) < n_tiles;
-        const int kst = (j + 1) & 1;
-        const uint32_t kph = ((j + 1) >> 1) & 1;
-        for (int t = 0; t < 2; ++t) {
-          mbar_wait(&p_full[t], j & 1);
-          if (t == 0) mbar_wait(&v_full[vst], vph);
-          tc_fence_after();
-          issue_pv(t, vst, j > 0);
-          if (t == 1) umma_commit(&v_empty[vst]);
-          if (has_next) {
-            if (t == 0) {
-              mbar_wait(&k_full[kst], kph);
-              tc_fence_after();
-            }
-            issue_qk(t, kst);
-            umma_commit(&s_full[t]);
-            if (t == 1) umma_commit(&k_empty[kst]);
-          } else {
-            umma_commit(&o_final[t]);
+  if (warp < 4) {
+    setmaxnreg_dec<104>();
+    if (warp == 0) {
+      // ------------------------------ TMA producer ------------------------------
+      if (lane == 0) {
+        uint32_t seg = 0, g = 0;   // segment counter, ring counter (KV steps issued so far)
+        for (long long cur = range_begin; cur < range_end; ++seg) {
+          const int item = (int)(cur / n_kv);
+          const int j0 = (int)(cur - (long long)item * n_kv);
+          const int j1 = (range_end - cur) < (long long)(n_kv - j0) ? j0 + (int)(range_end - cur) : n_kv;
+          const int qp = item % p.n_qpairs, bh = item / p.n_qpairs;
+          const int head = bh % p.H, batch = bh / p.H;
+          const int q_row0 = qp * (2 * ATT_BM);
+          mbar_wait(q_empty, (seg & 1) ^ 1);           // previous segment's QK^T MMAs have retired
+          mbar_expect_tx(q_full, 2 * ATT_TILE_BYTES);
+          for (int t = 0; t < 2; ++t)
+            for (int hf = 0; hf < 2; ++hf)
+              tma_load_4d(q_smem + t * ATT_TILE_BYTES + hf * ATT_HALF_BYTES, &tma_q, q_full, hf * 64, head,
+                          q_row0 + t * ATT_BM, batch);
+          for (int j = j0; j < j1; ++j, ++g) {
+            const int st = g & 1;
+            const uint32_t ph = (g >> 1) & 1;
+            mbar_wait(&k_empty[st], ph ^ 1);
+            mbar_expect_tx(&k_full[st], ATT_TILE_BYTES);
+            for (int hf = 0; hf < 2; ++hf)
+              tma_load_4d(k_smem + st * ATT_TILE_BYTES + hf * ATT_HALF_BYTES, &tma_k, &k_full[st], hf * 64, head,
+                          j * ATT_BN, batch);
+            mbar_wait(&v_empty[st], ph ^ 1);
+            mbar_expect_tx(&v_full[st], ATT_TILE_BYTES);
+            for (int hf = 0; hf < 2; ++hf)
+              tma_load_4d(v_smem + st * ATT_TILE_BYTES + hf * ATT_HALF_BYTES, &tma_v, &v_full[st], hf * 64, head,
+                          j * ATT_BN, batch);
           }
+          cur += j1 - j0;
+        }
+      }
+    } else if (warp == 1) {
+      // ------------------------------ MMA issuer --------------------------------
+      if (lane == 0) {
+        constexpr uint32_t idesc_qk = umma_idesc_bf16(ATT_BM, ATT_BN, 0, 0);   // A, B K-major
+        constexpr uint32_t idesc_pv = umma_idesc_bf16(ATT_BM, ATT_D, 0, 1);    // B (=V) MN-major
+        const uint32_t q_addr = smem_u32(q_smem), k_addr = smem_u32(k_smem), v_addr = smem_u32(v_smem);
+
+        auto issue_qk = [&](int t, int kst) {
+          const uint32_t qa = q_addr + t * ATT_TILE_BYTES, ka = k_addr + kst * ATT_TILE_BYTES;
+#pragma unroll
+          for (int k = 0; k < ATT_D / 16; ++k) {
+            const uint32_t off = (k >> 2) * ATT_HALF_BYTES + (k & 3) * 32;
+            umma_ss(tmem_base + t * 128, umma_desc_sw128(qa + off, 16, 1024), umma_desc_sw128(ka + off, 16, 1024),
+                    idesc_qk, k != 0);
+          }
+        };
+        auto issue_pv = [&](int t, int vst, bool acc) {
+          const uint32_t va = v_addr + vst * ATT_TILE_BYTES;
+#pragma unroll
+          for (int k = 0; k < ATT_BN / 16; ++k) {
+            // A: P_t rows on TMEM lanes, 16 bf16 of K per 8 32-bit columns.
+            // B: V tile [kv][d], d contiguous -> MN-major; 16 kv rows = 2048 B; d halves 16 KB apart.
+            umma_ts(tmem_base + 256 + t * 128, tmem_base + t * 128 + k * 8,
+                    umma_desc_sw128(va + k * 2048, ATT_HALF_BYTES, 1024), idesc_pv, (acc || k != 0) ? 1u : 0u);
+          }
+        };
+
+        uint32_t seg = 0, g = 0;
+        for (long long cur = range_begin; cur < range_end; ++seg) {
+          const int item = (int)(cur / n_kv);
+          const int j0 = (int)(cur - (long long)item * n_kv);
+          const int n = (range_end - cur) < (long long)(n_kv - j0) ? (int)(range_end - cur) : (n_kv - j0);
+          mbar_wait(q_full, seg & 1);
+          mbar_wait(&k_full[g & 1], (g >> 1) & 1);
+          tc_fence_after();
+          issue_qk(0, g & 1);
+          umma_commit(&s_full[0]);
+          issue_qk(1, g & 1);
+          umma_commit(&s_full[1]);
+          umma_commit(&k_empty[g & 1]);
+          if (n == 1) umma_commit(q_empty);
+          for (int i = 0; i < n; ++i, ++g) {
+            const int vst = g & 1;
+            const uint32_t vph = (g >> 1) & 1;
+            const bool has_next = (i + 1) < n;
+            const int kst = (g + 1) & 1;
+            const uint32_t kph = ((g + 1) >> 1) & 1;
+            for (int t = 0; t < 2; ++t) {
+              mbar_wait(&p_full[t], g & 1);
+              if (t == 0) mbar_wait(&v_full[vst], vph);
+              if (i == 0) mbar_wait(&o_free[t], (seg & 1) ^ 1);   // previous segment's epilogue has read O_t
+              tc_fence_after();
+              issue_pv(t, vst, i > 0);
+              if (t == 1) umma_commit(&v_empty[vst]);
+              if (has_next) {
+                if (t == 0) {
+                  mbar_wait(&k_full[kst], kph);
+                  tc_fence_after();
+                }
+                issue_qk(t, kst);
+                umma_commit(&s_full[t]);
+                if (t == 1) {
+                  umma_commit(&k_empty[kst]);
+                  if (i + 2 == n) umma_commit(q_empty);   // that was the segment's last QK^T: Q smem reusable
+                }
+              } else {
+                umma_commit(&o_final[t]);
+              }
+            }
+          }
+          cur += n;
         }
       }
     }
   } else {
     // ------------------------------ softmax / correction / epilogue ------------
-    const int t = (warp - 2) >> 2;
+    setmaxnreg_inc<200>();
+    const int t = (warp - 4) >> 2;
     const int quarter = warp & 3;
+    const int r_local = quarter * 32 + lane;
     const uint32_t lane_base = (uint32_t)(quarter * 32) << 16;
     const uint32_t s_addr = tmem_base + lane_base + t * 128;
     const uint32_t o_addr = tmem_base + lane_base + 256 + t * 128;
     const float sl2 = p.scale_log2;
-    float m_ref = -INFINITY;   // reference max (raw score units) the stored exponentials are relative to
-    float l = 0.f;             // running sum of exponentials relative to m_ref
 
-    for (int j = 0; j < n_tiles; ++j) {
-      mbar_wait(&s_full[t], j & 1);
-      tc_fence_after();
-      uint32_t s[128];
-#pragma unroll
-      for (int c = 0; c < 4; ++c) tmem_ld32(s_addr + c * 32, *reinterpret_cast<uint32_t(*)[32]>(&s[c * 32]));
-      tmem_ld_wait();
-      if (j == n_tiles - 1 && p.kv_tail < ATT_BN) {
-#pragma unroll
-        for (int i = 0; i < 128; ++i)
-          if (i >= p.kv_tail) s[i] = 0xff800000u;   // -inf
-      }
-      float mx0 = __uint_as_float(s[0]), mx1 = __uint_as_float(s[1]), mx2 = __uint_as_float(s[2]),
-            mx3 = __uint_as_float(s[3]);
-#pragma unroll
-      for (int i = 4; i < 128; i += 4) {
-        mx0 = fmaxf(mx0, __uint_as_float(s[i]));
-        mx1 = fmaxf(mx1, __uint_as_float(s[i + 1]));
-        mx2 = fmaxf(mx2, __uint_as_float(s[i + 2]));
-        mx3 = fmaxf(mx3, __uint_as_float(s[i + 3]));
-      }
-      const float mx = fmaxf(fmaxf(mx0, mx1), fmaxf(mx2, mx3));
-      if (j == 0) {
-        m_ref = mx;
-      } else {
-        const float m_new = fmaxf(m_ref, mx);
-        const bool need = (m_new - m_ref) * sl2 > 8.0f;
-        if (__any_sync(0xffffffffu, need)) {
-          // PV(j-1) has retired (s_full(j) was committed after it), so O_t is quiescent here.
-          const float m_upd = need ? m_new : m_ref;
-          const float alpha = fast_exp2((m_ref - m_upd) * sl2);
-          l *= alpha;
-          m_ref = m_upd;
+    uint32_t seg = 0, g = 0;
+    for (long long cur = range_begin; cur < range_end; ++seg) {
+      const int item = (int)(cur / n_kv);
+      const int j0 = (int)(cur - (long long)item * n_kv);
+      const int j1 = (range_end - cur) < (long long)(n_kv - j0) ? j0 + (int)(range_end - cur) : n_kv;
+      float m_ref = -INFINITY;   // reference max (raw score units) the stored exponentials are relative to
+      float l = 0.f;             // running sum of exponentials relative to m_ref
+
+      for (int j = j0; j < j1; ++j, ++g) {
+        mbar_wait(&s_full[t], g & 1);
+        tc_fence_after();
+        if (j == n_kv - 1 && p.kv_tail < ATT_BN) {
+          // ragged last KV tile: overwrite the out-of-range score columns with -inf in TMEM (rare path,
+          // kept out of the register-resident fast path below)
 #pragma unroll 1
-          for (int c = 0; c < 4; ++c) {
-            uint32_t o[32];
-            tmem_ld32(o_addr + c * 32, o);
+          for (int c = p.kv_tail & ~15; c < ATT_BN; c += 16) {
+            uint32_t w[16];
+            asm volatile(
+                "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+                : "=r"(w[0]), "=r"(w[1]), "=r"(w[2]), "=r"(w[3]), "=r"(w[4]), "=r"(w[5]), "=r"(w[6]), "=r"(w[7]),
+                  "=r"(w[8]), "=r"(w[9]), "=r"(w[10]), "=r"(w[11]), "=r"(w[12]), "=r"(w[13]), "=r"(w[14]), "=r"(w[15])
+                : "r"(s_addr + c)
+                : "memory");
             tmem_ld_wait();
 #pragma unroll
-            for (int i = 0; i < 32; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
-            tmem_st32(o_addr + c * 32, o);
+            for (int i = 0; i < 16; ++i)
+              if (c + i >= p.kv_tail) w[i] = 0xff800000u;   // -inf
+            tmem_st16(s_addr + c, w);
           }
           tmem_st_wait();
         }
-      }
-      const float neg_m = -m_ref * sl2;
-      float sum0 = 0.f, sum1 = 0.f;
+        uint32_t s[128];
 #pragma unroll
-      for (int c = 0; c < 4; ++c) {
-        uint32_t pk[16];
+        for (int c = 0; c < 4; ++c) tmem_ld32(s_addr + c * 32, *reinterpret_cast<uint32_t(*)[32]>(&s[c * 32]));
+        tmem_ld_wait();
+        float mx0 = __uint_as_float(s[0]), mx1 = __uint_as_float(s[1]), mx2 = __uint_as_float(s[2]),
+              mx3 = __uint_as_float(s[3]);
 #pragma unroll
-        for (int i = 0; i < 16; ++i) {
-          const float x0 = fmaf(__uint_as_float(s[c * 32 + 2 * i]), sl2, neg_m);
-          const float x1 = fmaf(__uint_as_float(s[c * 32 + 2 * i + 1]), sl2, neg_m);
-          // element index within its group of four: 2*(i&1) and 2*(i&1)+1
-          const float p0 = (EMU >= 2 && (i & 1) == 0) ? poly_exp2(x0) : fast_exp2(x0);
-          const float p1 = (EMU >= 1 && (i & 1) == 1) ? poly_exp2(x1) : fast_exp2(x1);
-          sum0 += p0;
-          sum1 += p1;
-          pk[i] = pack_bf16(p0, p1);
+        for (int i = 4; i < 128; i += 4) {
+          mx0 = fmaxf(mx0, __uint_as_float(s[i]));
+          mx1 = fmaxf(mx1, __uint_as_float(s[i + 1]));
+          mx2 = fmaxf(mx2, __uint_as_float(s[i + 2]));
+          mx3 = fmaxf(mx3, __uint_as_float(s[i + 3]));
         }
-        tmem_st16(s_addr + c * 16, pk);   // P_t aliases the first 64 columns of S_t
-      }
-      l += sum0 + sum1;
-      tmem_st_wait();
-      tc_fence_before();
-      mbar_arrive(&p_full[t]);
-    }
-
-    // epilogue: O_t / l -> bf16 -> global, one query row per thread (256 contiguous bytes)
-    mbar_wait(&o_final[t], 0);
-    tc_fence_after();
-    const int row = q_row0 + t * ATT_BM + quarter * 32 + lane;
-    const float inv_l = 1.0f / l;
-    __nv_bfloat16* orow = p.out + (long long)batch * p.out_batch_stride + (long long)row * p.out_row_stride +
-                          head * ATT_D;
+        const float mx = fmaxf(fmaxf(mx0, mx1), fmaxf(mx2, mx3));
+        if (j == j0) {
+          m_ref = mx;
+        } else {
+          const float m_new = fmaxf(m_ref, mx);
+          const bool need = (m_new - m_ref) * sl2 > 8.0f;
+          if (__any_sync(0xffffffffu, need)) {
+            // PV(j-1) has retired (s_full(j) was committed after it), so O_t is quiescent here.
+            const float m_upd = need ? m_new : m_ref;
+            const float alpha = fast_exp2((m_ref - m_upd) * sl2);
+            l *= alpha;
+            m_ref = m_upd;
 #pragma unroll 1
-    for (int c = 0; c < 4; ++c) {
-      uint32_t o[32];
-      tmem_ld32(o_addr + c * 32, o);
-      tmem_ld_wait();
-      if (row < p.Lq) {
+            for (int c = 0; c < 4; ++c) {
+              uint32_t o[32];
+              tmem_ld32(o_addr + c * 32, o);
+              tmem_ld_wait();
 #pragma unroll
-        for (int g = 0; g < 4; ++g) {
-          uint4 w;
-          w.x = pack_bf16(__uint_as_float(o[g * 8 + 0]) * inv_l, __uint_as_float(o[g * 8 + 1]) * inv_l);
-          w.y = pack_bf16(__uint_as_float(o[g * 8 + 2]) * inv_l, __uint_as_float(o[g * 8 + 3]) * inv_l);
-          w.z = pack_bf16(__uint_as_float(o[g * 8 + 4]) * inv_l, __uint_as_float(o[g * 8 + 5]) * inv_l);
-          w.w = pack_bf16(__uint_as_float(o[g * 8 + 6]) * inv_l, __uint_as_float(o[g * 8 + 7]) * inv_l);
-          *reinterpret_cast<uint4*>(orow + c * 32 + g * 8) = w;
+              for (int i = 0; i < 32; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
+              tmem_st32(o_addr + c * 32, o);
+            }
+            tmem_st_wait();
+          }
         }
+        const float neg_m = -m_ref * sl2;
+        const float2 sl2v = make_float2(sl2, sl2), negv = make_float2(neg_m, neg_m);
+        float2 sum_a = make_float2(0.f, 0.f), sum_b = make_float2(0.f, 0.f);
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          uint32_t pk[16];
+#pragma unroll
+          for (int i = 0; i < 16; ++i) {
+            const float2 x = __ffma2_rn(make_float2(__uint_as_float(s[c * 32 + 2 * i]), __uint_as_float(s[c * 32 + 2 * i + 1])),
+                                        sl2v, negv);
+            float2 e;
+            if ((i & 3) < EMU) {
+              e = poly_exp2x2(x);
+            } else {
+              e.x = fast_exp2(x.x);
+              e.y = fast_exp2(x.y);
+            }
+            if (i & 1) sum_b = __fadd2_rn(sum_b, e); else sum_a = __fadd2_rn(sum_a, e);
+            pk[i] = pack_bf16(e.x, e.y);
+          }
+          tmem_st16(s_addr + c * 16, pk);   // P_t aliases the first 64 columns of S_t
+        }
+        l += (sum_a.x + sum_a.y) + (sum_b.x + sum_b.y);
+        tmem_st_wait();
+        tc_fence_before();
+        mbar_arrive(&p_full[t]);
       }
+
+      // segment epilogue
+      mbar_wait(&o_final[t], seg & 1);
+      tc_fence_after();
+      const int qp = item % p.n_qpairs, bh = item / p.n_qpairs;
+      const int head = bh % p.H, batch = bh / p.H;
+      if (j0 == 0 && j1 == n_kv) {
+        // whole item: O_t / l -> bf16 -> global, one query row per thread (256 contiguous bytes)
+        const int row = qp * (2 * ATT_BM) + t * ATT_BM + r_local;
+        const float inv_l = 1.0f / l;
+        __nv_bfloat16* orow = p.out + (long long)batch * p.out_batch_stride + (long long)row * p.out_row_stride +
+                              head * ATT_D;
+#pragma unroll 1
+        for (int c = 0; c < 4; ++c) {
+          uint32_t o[32];
+          tmem_ld32(o_addr + c * 32, o);
+          tmem_ld_wait();
+          if (row < p.Lq) {
+#pragma unroll
+            for (int gq = 0; gq < 4; ++gq) {
+              uint4 w;
+              w.x = pack_bf16(__uint_as_float(o[gq * 8 + 0]) * inv_l, __uint_as_float(o[gq * 8 + 1]) * inv_l);
+              w.y = pack_bf16(__uint_as_float(o[gq * 8 + 2]) * inv_l, __uint_as_float(o[gq * 8 + 3]) * inv_l);
+              w.z = pack_bf16(__uint_as_float(o[gq * 8 + 4]) * inv_l, __uint_as_float(o[gq * 8 + 5]) * inv_l);
+              w.w = pack_bf16(__uint_as_float(o[gq * 8 + 6]) * inv_l, __uint_as_float(o[gq * 8 + 7]) * inv_l);
+              *reinterpret_cast<uint4*>(orow + c * 32 + gq * 8) = w;
+            }
+          }
+        }
+      } else {
+        // partial item: park (O^T, m, l) in this CTA's workspace slot (first segment -> 0, last -> 1)
+        float* slot = p.ws + (((long long)blockIdx.x * 2 + (seg == 0 ? 0 : 1)) * 2 + t) * ATT_SLOT_FLOATS;
+#pragma unroll 1
+        for (int c = 0; c < 4; ++c) {
+          uint32_t o[32];
+          tmem_ld32(o_addr + c * 32, o);
+          tmem_ld_wait();
+#pragma unroll
+          for (int i = 0; i < 32; ++i) slot[(c * 32 + i) * ATT_BM + r_local] = __uint_as_float(o[i]);   // coalesced
+        }
+        slot[ATT_BM * ATT_D + r_local] = m_ref;
+        slot[ATT_BM * ATT_D + ATT_BM + r_local] = l;
+      }
+      tc_fence_before();
+      mbar_arrive(&o_free[t]);
+      cur += j1 - j0;
     }
   }
 
@@ -306,15 +431,70 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_con
   }
 }
 
+// Merges the partial segments of every split item: out = sum_s O_s 2^{(m_s - m) c} / sum_s l_s 2^{(m_s - m) c}.
+// grid (items, 2 query tiles), 128 threads = one query row each.
+__global__ void __launch_bounds__(128)
+attention_combine_kernel(const AttnParams p, int grid_fwd) {
+  const int item = blockIdx.x, t = blockIdx.y, r = threadIdx.x;
+  const int n_kv = p.n_kv_tiles;
+  const long long s0 = (long long)item * n_kv, s1 = s0 + n_kv - 1;
+  const int c0 = att_step_owner(s0, grid_fwd, p), c1 = att_step_owner(s1, grid_fwd, p);
+  if (c0 == c1) return;   // the item was computed whole by one CTA
+  const int qp = item % p.n_qpairs, bh = item / p.n_qpairs;
+  const int head = bh % p.H, batch = bh / p.H;
+  const int row = qp * (2 * ATT_BM) + t * ATT_BM + r;
+  if (row >= p.Lq) return;
+  auto slot_of = [&](int c) {
+    const int first_item = (int)(att_range_start(c, grid_fwd, p) / n_kv);
+    return p.ws + (((long long)c * 2 + (first_item == item ? 0 : 1)) * 2 + t) * ATT_SLOT_FLOATS;
+  };
+  float m = -INFINITY;
+  for (int c = c0; c <= c1; ++c) m = fmaxf(m, slot_of(c)[ATT_BM * ATT_D + r]);
+  float L = 0.f;
+  for (int c = c0; c <= c1; ++c) {
+    const float* sl = slot_of(c);
+    L += sl[ATT_BM * ATT_D + ATT_BM + r] * exp2f((sl[ATT_BM * ATT_D + r] - m) * p.scale_log2);
+  }
+  const float inv_l = 1.0f / L;
+  __nv_bfloat16* orow = p.out + (long long)batch * p.out_batch_stride + (long long)row * p.out_row_stride + head * ATT_D;
+  for (int col = 0; col < ATT_D; col += 8) {
+    float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    for (int c = c0; c <= c1; ++c) {
+      const float* sl = slot_of(c);
+      const float w = exp2f((sl[ATT_BM * ATT_D + r] - m) * p.scale_log2);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) acc[i] += sl[(col + i) * ATT_BM + r] * w;
+    }
+    uint4 o;
+    o.x = pack_bf16(acc[0] * inv_l, acc[1] * inv_l);
+    o.y = pack_bf16(acc[2] * inv_l, acc[3] * inv_l);
+    o.z = pack_bf16(acc[4] * inv_l, acc[5] * inv_l);
+    o.w = pack_bf16(acc[6] * inv_l, acc[7] * inv_l);
+    *reinterpret_cast<uint4*>(orow + col) = o;
+  }
+}
+
+int device_sm_count();
+
 }  // namespace sfb
+
+// Bytes of scratch sfb_attention_fwd needs to balance long-KV problems across all SMs (0 on error).
+extern "C" long long sfb_attention_workspace_bytes(void) {
+  const int sms = sfb::device_sm_count();
+  if (sms <= 0) return 0;
+  return (long long)sms * 2 * 2 * sfb::ATT_SLOT_FLOATS * (long long)sizeof(float);
+}
 
 // q   : [B, Lq, H, 128] view with element strides (q_row_stride between tokens, q_batch_stride)
 // k, v: cache window start (already offset to attn_start), [B, Skv, H, 128] with their strides
 // out : [B, Lq, H, 128] with out_row_stride / out_batch_stride
+// workspace: caller-owned scratch of sfb_attention_workspace_bytes() bytes (may be NULL: then long-KV problems
+//            are not split across CTAs and run with whole-item granularity)
 extern "C" int sfb_attention_fwd(const void* q, long long q_row_stride, long long q_batch_stride, const void* k,
                                  const void* v, long long kv_row_stride, long long kv_batch_stride, void* out,
                                  long long out_row_stride, long long out_batch_stride, int B, int Lq, int Skv,
-                                 int H, int head_dim, float softmax_scale, void* stream_) {
+                                 int H, int head_dim, float softmax_scale, void* workspace,
+                                 long long workspace_bytes, void* stream_) {
   using namespace sfb;
   cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
   if (head_dim != ATT_D) { set_error("sfb_attention_fwd: head_dim %d unsupported (128 only)", head_dim); return SFB_ERR_INVALID; }
@@ -337,29 +517,42 @@ extern "C" int sfb_attention_fwd(const void* q, long long q_row_stride, long lon
     if (int e = make_tmap_bf16(&tk, k, 4, dims, str, box, true)) return e;
     if (int e = make_tmap_bf16(&tv, v, 4, dims, str, box, true)) return e;
   }
+  const int sms = device_sm_count();
+  if (sms <= 0) return SFB_ERR_CUDA;
   AttnParams p{};
   p.Lq = Lq; p.Skv = Skv; p.H = H; p.B = B;
   p.n_kv_tiles = (Skv + ATT_BN - 1) / ATT_BN;
   p.kv_tail = Skv - (p.n_kv_tiles - 1) * ATT_BN;
+  p.n_qpairs = (Lq + 2 * ATT_BM - 1) / (2 * ATT_BM);
+  p.items = B * H * p.n_qpairs;
   p.scale_log2 = softmax_scale * 1.4426950408889634f;
   p.out = static_cast<__nv_bfloat16*>(out);
   p.out_row_stride = out_row_stride;
   p.out_batch_stride = out_batch_stride;
+  p.ws = static_cast<float*>(workspace);
+  const int grid = p.items < sms ? p.items : sms;
+  const long long need = (long long)grid * 2 * 2 * ATT_SLOT_FLOATS * (long long)sizeof(float);
+  const char* nosplit = getenv("SFB_ATTN_NOSPLIT");
+  p.split = (p.items % grid != 0 && p.n_kv_tiles >= ATT_MIN_SPLIT_KV_TILES && workspace != nullptr &&
+             workspace_bytes >= need && !(nosplit && nosplit[0] == '1')) ? 1 : 0;
 
   static int emu = -1;
   if (emu < 0) {
     const char* env = getenv("SFB_ATTN_EMU");   // tuning knob; the default is the measured best
-    emu = env ? atoi(env) : ATT_DEFAULT_EMU;
-    if (emu < 0 || emu > 2) emu = ATT_DEFAULT_EMU;
+    int want = env ? atoi(env) : ATT_DEFAULT_EMU;
+    if (want < 0 || want > 2) want = ATT_DEFAULT_EMU;
     for (auto kern : {attention_fwd_kernel<0>, attention_fwd_kernel<1>, attention_fwd_kernel<2>})
       if (int e = check_cuda(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT_SMEM_BYTES),
-                             "cudaFuncSetAttribute(attention)")) {
-        emu = -1;
+                             "cudaFuncSetAttribute(attention)"))
         return e;
-      }
+    emu = want;
   }
-  dim3 grid((Lq + 2 * ATT_BM - 1) / (2 * ATT_BM), H, B);
   auto kern = emu == 0 ? attention_fwd_kernel<0> : (emu == 1 ? attention_fwd_kernel<1> : attention_fwd_kernel<2>);
   kern<<<grid, ATT_THREADS, ATT_SMEM_BYTES, stream>>>(tq, tk, tv, p);
-  return check_cuda(cudaGetLastError(), "attention launch");
+  if (int e = check_cuda(cudaGetLastError(), "attention launch")) return e;
+  if (p.split) {
+    attention_combine_kernel<<<dim3(p.items, 2), 128, 0, stream>>>(p, grid);
+    return check_cuda(cudaGetLastError(), "attention combine launch");
+  }
+  return SFB_OK;
 }

@@ -55,6 +55,7 @@ class CudaOps:
         self.launches = 0
         self._prof = None
         self._prof_only = None
+        self._attn_ws = {}    # device index -> uint8 scratch for the split-KV attention schedule
 
     # -- optional per-launch device timing (bench.py roofline leg) ------------------------------
     def start_profile(self, only=None):
@@ -114,10 +115,15 @@ class CudaOps:
         for t in (q, k, v, out):
             assert t.stride(3) == 1 and t.stride(2) == D and t.dtype == torch.bfloat16
         assert k.stride() == v.stride() and k.shape == v.shape
+        ws = self._attn_ws.get(q.device.index)
+        if ws is None:
+            with torch.cuda.device(q.device):
+                ws = torch.empty(int(self.lib.sfb_attention_workspace_bytes()), dtype=torch.uint8, device=q.device)
+            self._attn_ws[q.device.index] = ws
         _lib.check(self.lib.sfb_attention_fwd(
             q.data_ptr(), q.stride(1), q.stride(0), k.data_ptr(), v.data_ptr(), k.stride(1), k.stride(0),
-            out.data_ptr(), out.stride(1), out.stride(0), B, Lq, S, H, D, scale, self._stream()),
-            "sfb_attention_fwd")
+            out.data_ptr(), out.stride(1), out.stride(0), B, Lq, S, H, D, scale, ws.data_ptr(), ws.numel(),
+            self._stream()), "sfb_attention_fwd")
 
     # -- normalisation / modulation -------------------------------------------------------
     @_op

@@ -359,6 +359,10 @@ ALL = {
     "attn_cross": lambda: check_attention(Lq=1560, S=512, H=12),
     "attn_sharp": check_attention_sharp,
     "attn_chunk": lambda: check_attention(Lq=4680, S=4680, H=12),
+    "attn_split_tail": lambda: check_attention(Lq=4000, S=5000, H=12, seed=5),
+    "attn_split_batch": lambda: check_attention(B=2, Lq=1560, S=9360, H=12, seed=6),
+    "attn_split_3way": lambda: check_attention(Lq=1300, S=40000, H=32, seed=7),
+    "attn_whole_items": lambda: check_attention(Lq=1560, S=4680, H=12, seed=8),
     "ln_modulate": check_ln_modulate,
     "ln_affine": check_ln_affine,
     "rmsnorm": check_rmsnorm,

@@ -165,3 +165,61 @@ def test_training_path_raises():
     m = B200CausalWanModel(dim=256, ffn_dim=256, num_heads=2, num_layers=1, text_dim=512, ops=TorchOps())
     with pytest.raises(NotImplementedError):
         m(torch.zeros(1, 16, 1, 8, 8), t=torch.zeros(1, 1), context=torch.zeros(1, 512, 512), seq_len=100)
+
+
+# --------------------------------------------------------------------------------------------------
+# attention work schedule (self_forcing_b200/csrc/attention_tcgen05.cu: att_range_start / att_step_owner):
+# a Python model of the integer arithmetic the forward and the combine kernel must agree on
+# --------------------------------------------------------------------------------------------------
+def _range_start(c, grid, items, n_kv, split=True):
+    return (c * items * n_kv) // grid if split else ((c * items) // grid) * n_kv
+
+
+def _owner(step, grid, items, n_kv):
+    return ((step + 1) * grid - 1) // (items * n_kv)
+
+
+def _segments(c, grid, items, n_kv, split=True):
+    cur, end, out = _range_start(c, grid, items, n_kv, split), _range_start(c + 1, grid, items, n_kv, split), []
+    while cur < end:
+        item = cur // n_kv
+        j0 = cur - item * n_kv
+        j1 = min(n_kv, j0 + (end - cur))
+        out.append((item, j0, j1))
+        cur += j1 - j0
+    return out
+
+
+@pytest.mark.parametrize("items,n_kv,grid", [(228, 37, 148), (228, 256, 148), (84, 256, 84), (336, 74, 148),
+                                             (149, 16, 148), (1000, 17, 148), (32 * 6, 313, 148), (5, 100, 5)])
+def test_attention_split_schedule_is_consistent(items, n_kv, grid):
+    covered = {}
+    for c in range(grid):
+        segs = _segments(c, grid, items, n_kv)
+        partial = [(i, s) for i, s in enumerate(segs) if not (s[1] == 0 and s[2] == n_kv)]
+        # only the first and the last segment of a CTA can be partial -> two workspace slots per CTA suffice
+        assert all(i in (0, len(segs) - 1) for i, _ in partial)
+        for i, (item, j0, j1) in enumerate(segs):
+            for j in range(j0, j1):
+                assert (item, j) not in covered
+                covered[(item, j)] = c
+                assert _owner(item * n_kv + j, grid, items, n_kv) == c
+            if (j0, j1) != (0, n_kv):
+                # slot rule of the combine kernel: slot 0 iff the CTA's range starts inside this item
+                slot_fwd = 0 if i == 0 else 1
+                slot_comb = 0 if _range_start(c, grid, items, n_kv) // n_kv == item else 1
+                assert slot_fwd == slot_comb
+    assert len(covered) == items * n_kv
+    # the load is balanced to within one KV step
+    sizes = [_range_start(c + 1, grid, items, n_kv) - _range_start(c, grid, items, n_kv) for c in range(grid)]
+    assert max(sizes) - min(sizes) <= 1
+
+
+def test_attention_whole_item_schedule_never_splits():
+    for items, n_kv, grid in [(228, 4, 148), (84, 256, 84), (7, 3, 7)]:
+        seen = []
+        for c in range(grid):
+            for item, j0, j1 in _segments(c, grid, items, n_kv, split=False):
+                assert (j0, j1) == (0, n_kv)
+                seen.append(item)
+        assert seen == list(range(items))
