@@ -30,6 +30,7 @@
 // not the MMAs, are the critical resource) with an optional share computed by a degree-3 polynomial on
 // the FMA pipe (template EMU), row sums with packed adds.
 #include <math.h>
+#include <stdio.h>
 #include <stdlib.h>
 
 #include "common.cuh"
@@ -47,6 +48,7 @@ struct AttnParams {
   __nv_bfloat16* out;
   long long out_row_stride, out_batch_stride;   // elements
   float* ws;              // [grid][2 slots][2 tiles][128*128 O^T + 128 m + 128 l] floats (split mode)
+  long long* dbg;         // diagnostic phase timers [grid][8] (SFB_ATTN_TIMING=1), else nullptr
 };
 
 constexpr int ATT_BM = 128, ATT_BN = 128, ATT_D = 128;
@@ -279,6 +281,16 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_con
     const uint32_t o_addr = tmem_base + lane_base + 256 + t * 128;
     const float sl2 = p.scale_log2;
 
+    const bool timing = p.dbg != nullptr && warp == 4 && lane == 0;
+    long long tm[6] = {0, 0, 0, 0, 0, 0};
+    long long t_prev = timing ? clock64() : 0;
+    auto stamp = [&](int k) {
+      if (timing) {
+        const long long now = clock64();
+        tm[k] += now - t_prev;
+        t_prev = now;
+      }
+    };
     uint32_t seg = 0, g = 0;
     for (long long cur = range_begin; cur < range_end; ++seg) {
       const int item = (int)(cur / n_kv);
@@ -288,8 +300,10 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_con
       float l = 0.f;             // running sum of exponentials relative to m_ref
 
       for (int j = j0; j < j1; ++j, ++g) {
+        stamp(5);
         mbar_wait(&s_full[t], g & 1);
         tc_fence_after();
+        stamp(0);
         if (j == n_kv - 1 && p.kv_tail < ATT_BN) {
           // ragged last KV tile: overwrite the out-of-range score columns with -inf in TMEM (rare path,
           // kept out of the register-resident fast path below)
@@ -314,6 +328,7 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_con
 #pragma unroll
         for (int c = 0; c < 4; ++c) tmem_ld32(s_addr + c * 32, *reinterpret_cast<uint32_t(*)[32]>(&s[c * 32]));
         tmem_ld_wait();
+        stamp(1);
         float mx0 = __uint_as_float(s[0]), mx1 = __uint_as_float(s[1]), mx2 = __uint_as_float(s[2]),
               mx3 = __uint_as_float(s[3]);
 #pragma unroll
@@ -347,6 +362,7 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_con
             tmem_st_wait();
           }
         }
+        stamp(2);
         const float neg_m = -m_ref * sl2;
         const float2 sl2v = make_float2(sl2, sl2), negv = make_float2(neg_m, neg_m);
         float2 sum_a = make_float2(0.f, 0.f), sum_b = make_float2(0.f, 0.f);
@@ -370,9 +386,11 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_con
           tmem_st16(s_addr + c * 16, pk);   // P_t aliases the first 64 columns of S_t
         }
         l += (sum_a.x + sum_a.y) + (sum_b.x + sum_b.y);
+        stamp(3);
         tmem_st_wait();
         tc_fence_before();
         mbar_arrive(&p_full[t]);
+        stamp(4);
       }
 
       // segment epilogue
@@ -420,6 +438,10 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_con
       tc_fence_before();
       mbar_arrive(&o_free[t]);
       cur += j1 - j0;
+    }
+    if (timing) {
+      for (int k = 0; k < 6; ++k) p.dbg[blockIdx.x * 8 + k] = tm[k];
+      p.dbg[blockIdx.x * 8 + 6] = g;
     }
   }
 
@@ -530,11 +552,24 @@ extern "C" int sfb_attention_fwd(const void* q, long long q_row_stride, long lon
   p.out_row_stride = out_row_stride;
   p.out_batch_stride = out_batch_stride;
   p.ws = static_cast<float*>(workspace);
-  const int grid = p.items < sms ? p.items : sms;
+  int grid = p.items < sms ? p.items : sms;
+  if (const char* cap = getenv("SFB_ATTN_GRID")) {   // diagnostic: run on fewer SMs
+    const int g = atoi(cap);
+    if (g > 0 && g < grid) grid = g;
+  }
   const long long need = (long long)grid * 2 * 2 * ATT_SLOT_FLOATS * (long long)sizeof(float);
   const char* nosplit = getenv("SFB_ATTN_NOSPLIT");
   p.split = (p.items % grid != 0 && p.n_kv_tiles >= ATT_MIN_SPLIT_KV_TILES && workspace != nullptr &&
              workspace_bytes >= need && !(nosplit && nosplit[0] == '1')) ? 1 : 0;
+
+  static long long* dbg_buf = nullptr;
+  static int timing = -1;
+  if (timing < 0) {
+    const char* env = getenv("SFB_ATTN_TIMING");
+    timing = (env && env[0] == '1') ? 1 : 0;
+    if (timing) cudaMalloc(&dbg_buf, 256 * 8 * sizeof(long long));   // diagnostic mode only
+  }
+  p.dbg = timing ? dbg_buf : nullptr;
 
   static int emu = -1;
   if (emu < 0) {
@@ -550,6 +585,16 @@ extern "C" int sfb_attention_fwd(const void* q, long long q_row_stride, long lon
   auto kern = emu == 0 ? attention_fwd_kernel<0> : (emu == 1 ? attention_fwd_kernel<1> : attention_fwd_kernel<2>);
   kern<<<grid, ATT_THREADS, ATT_SMEM_BYTES, stream>>>(tq, tk, tv, p);
   if (int e = check_cuda(cudaGetLastError(), "attention launch")) return e;
+  if (timing) {   // diagnostic: per-phase cycles of one softmax warp, averaged over CTAs, per KV step
+    long long h[256 * 8];
+    cudaStreamSynchronize(stream);
+    cudaMemcpy(h, dbg_buf, sizeof(long long) * grid * 8, cudaMemcpyDeviceToHost);
+    double acc[6] = {0, 0, 0, 0, 0, 0}, steps = 0;
+    for (int c = 0; c < grid; ++c) { for (int k = 0; k < 6; ++k) acc[k] += (double)h[c * 8 + k]; steps += (double)h[c * 8 + 6]; }
+    fprintf(stderr, "[attn timing] Lq=%d S=%d grid=%d split=%d steps/cta=%.1f | clk/step: wait_s=%.0f ld=%.0f max=%.0f exp=%.0f st+arrive=%.0f other=%.0f total=%.0f\n",
+            Lq, Skv, grid, p.split, steps / grid, acc[0] / steps, acc[1] / steps, acc[2] / steps, acc[3] / steps, acc[4] / steps,
+            acc[5] / steps, (acc[0] + acc[1] + acc[2] + acc[3] + acc[4] + acc[5]) / steps);
+  }
   if (p.split) {
     attention_combine_kernel<<<dim3(p.items, 2), 128, 0, stream>>>(p, grid);
     return check_cuda(cudaGetLastError(), "attention combine launch");
