@@ -32,6 +32,16 @@ __device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {
   return *reinterpret_cast<uint32_t*>(&t);
 }
 
+// One lane of a fully active warp (always the same one).  Role warps stay warp-uniform -- every lane runs the
+// loop control and the mbarrier waits -- and only the TMA / tcgen05 issue is predicated on this, which lets the
+// compiler keep descriptors in uniform registers instead of wrapping every UTCHMMA / UTMALDG in a per-thread
+// R2UR + ELECT loop (measured ~98 cycles per MMA issue with `if (lane == 0)` around the whole role).
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
+  return pred != 0;
+}
+
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);

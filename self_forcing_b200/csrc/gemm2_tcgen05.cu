@@ -80,8 +80,8 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_consta
   const int num_pairs = gridDim.x >> 1;
 
   if (warp == 0) {
-    // ------------------------------ TMA producer (both CTAs) ------------------
-    if (lane == 0) {
+    // ------------------------------ TMA producer (both CTAs; warp-uniform, one lane issues) ----
+    {
       int stage = 0;
       uint32_t phase = 0;
       for (int tile = pair; tile < num_tiles; tile += num_pairs) {
@@ -90,18 +90,21 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_consta
         const int b_row = n_blk * G2_BN + rank * (G2_BN / 2);
         for (int kb = 0; kb < p.num_k_blocks; ++kb) {
           mbar_wait(&empty_bar[stage], phase ^ 1);
-          uint8_t* a_dst = smem + stage * G2_STAGE_BYTES;
-          if (leader) mbar_expect_tx(&full_bar[stage], 2 * G2_STAGE_BYTES);
-          const uint32_t bar = mapa_cluster(smem_u32(&full_bar[stage]), 0);
-          tma_load_2d_pair(a_dst, &tma_a, bar, kb * G2_BK, a_row);
-          tma_load_2d_pair(a_dst + G2_A_BYTES, &tma_b, bar, kb * G2_BK, b_row);
+          if (elect_one()) {
+            uint8_t* a_dst = smem + stage * G2_STAGE_BYTES;
+            if (leader) mbar_expect_tx(&full_bar[stage], 2 * G2_STAGE_BYTES);
+            const uint32_t bar = mapa_cluster(smem_u32(&full_bar[stage]), 0);
+            tma_load_2d_pair(a_dst, &tma_a, bar, kb * G2_BK, a_row);
+            tma_load_2d_pair(a_dst + G2_A_BYTES, &tma_b, bar, kb * G2_BK, b_row);
+          }
+          __syncwarp();
           if (++stage == G2_STAGES) { stage = 0; phase ^= 1; }
         }
       }
     }
   } else if (warp == 1) {
     // ------------------------------ MMA issuer (leader only) ------------------
-    if (leader && lane == 0) {
+    if (leader) {   // warp-uniform; one lane issues
       constexpr uint32_t idesc = umma_idesc_bf16(2 * G2_ROWS, G2_BN, 0, 0);
       int stage = 0;
       uint32_t phase = 0;
@@ -115,16 +118,19 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_consta
         for (int kb = 0; kb < p.num_k_blocks; ++kb) {
           mbar_wait(&full_bar[stage], phase);
           tc_fence_after();
-          const uint32_t a_addr = smem_u32(smem + stage * G2_STAGE_BYTES);
-          const uint64_t a_desc = umma_desc_sw128(a_addr, 16, 1024);
-          const uint64_t b_desc = umma_desc_sw128(a_addr + G2_A_BYTES, 16, 1024);
+          if (elect_one()) {
+            const uint32_t a_addr = smem_u32(smem + stage * G2_STAGE_BYTES);
+            const uint64_t a_desc = umma_desc_sw128(a_addr, 16, 1024);
+            const uint64_t b_desc = umma_desc_sw128(a_addr + G2_A_BYTES, 16, 1024);
 #pragma unroll
-          for (int k = 0; k < G2_BK / 16; ++k)
-            umma_ss_pair(d_tmem, a_desc + 2 * k, b_desc + 2 * k, idesc, (kb | k) != 0);
-          umma_commit_pair(&empty_bar[stage], 3);   // both CTAs' smem slots are free once these retire
+            for (int k = 0; k < G2_BK / 16; ++k)
+              umma_ss_pair(d_tmem, a_desc + 2 * k, b_desc + 2 * k, idesc, (kb | k) != 0);
+            umma_commit_pair(&empty_bar[stage], 3);   // both CTAs' smem slots are free once these retire
+            if (kb == p.num_k_blocks - 1) umma_commit_pair(&tmem_full[acc], 3);
+          }
+          __syncwarp();
           if (++stage == G2_STAGES) { stage = 0; phase ^= 1; }
         }
-        umma_commit_pair(&tmem_full[acc], 3);
       }
     }
   } else {
@@ -132,11 +138,10 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_consta
     constexpr bool HAS_RES = (EPI == EPI_RESIDUAL || EPI == EPI_GATE_RES);
     const int quarter = warp & 3;
     const int r_local = quarter * 32 + lane;                 // accumulator row (TMEM lane) of this thread
-    const bool elected = (warp == 2 && lane == 0);
     const uint32_t leader_empty0 = mapa_cluster(smem_u32(&tmem_empty[0]), 0);
     uint8_t* my_row = stage_out + r_local * 128;
     const int sw = r_local & 7;                              // 128-byte swizzle: 16-byte chunk index ^ (row % 8)
-    if (elected) {
+    if (warp == 2 && elect_one()) {
       tma_prefetch_desc(&tma_out0);
       if (HAS_RES) tma_prefetch_desc(&tma_res);
     }
@@ -152,10 +157,11 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_consta
       const int seg_col0 = n0 - seg * p.seg_cols;
       const CUtensorMap* omap = seg == 0 ? &tma_out0 : (seg == 1 ? &tma_out1 : &tma_out2);
       // staging buffers are free once the previous tile's TMA stores have read them
-      if (elected) tma_store_wait_read<0>();
+      if (warp == 2 && elect_one()) tma_store_wait_read<0>();
       named_barrier_sync(1, 128);
-      if (HAS_RES && elected) {
+      if (HAS_RES && warp == 2 && elect_one()) {
         mbar_expect_tx(res_full, G2_NSUB * G2_SUB_BYTES);
+#pragma unroll
         for (int sb = 0; sb < G2_NSUB; ++sb)
           tma_load_2d(stage_out + sb * G2_SUB_BYTES, &tma_res, res_full, n0 + sb * G2_SUB, row0);
       }
@@ -188,7 +194,7 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_consta
         }
         fence_proxy_async();
         named_barrier_sync(2, 128);
-        if (elected) {
+        if (warp == 2 && elect_one()) {
           tma_store_2d(omap, stage_out + sb * G2_SUB_BYTES, seg_col0 + sb * G2_SUB, row0);
           tma_store_commit();
         }
@@ -197,7 +203,7 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_consta
       __syncwarp();
       if (lane == 0) mbar_arrive_cluster(leader_empty0 + acc * 8);
     }
-    if (elected) tma_store_wait_read<0>();
+    if (warp == 2 && elect_one()) tma_store_wait_read<0>();
   }
 
   tc_fence_before();

@@ -73,25 +73,28 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
   const int num_tiles = p.num_m_blocks * p.num_n_blocks;
 
   if (warp == 0) {
-    // ------------------------------ TMA producer ------------------------------
-    if (lane == 0) {
+    // ------------------------------ TMA producer (warp-uniform, one lane issues) ----
+    {
       int stage = 0;
       uint32_t phase = 0;
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
         const int m_blk = tile % p.num_m_blocks, n_blk = tile / p.num_m_blocks;
         for (int kb = 0; kb < p.num_k_blocks; ++kb) {
           mbar_wait(&empty_bar[stage], phase ^ 1);
-          uint8_t* a_dst = smem + stage * Cfg::STAGE_BYTES;
-          mbar_expect_tx(&full_bar[stage], Cfg::STAGE_BYTES);
-          tma_load_2d(a_dst, &tma_a, &full_bar[stage], kb * BLOCK_K, m_blk * BLOCK_M);
-          tma_load_2d(a_dst + Cfg::A_BYTES, &tma_b, &full_bar[stage], kb * BLOCK_K, n_blk * BLOCK_N);
+          if (elect_one()) {
+            uint8_t* a_dst = smem + stage * Cfg::STAGE_BYTES;
+            mbar_expect_tx(&full_bar[stage], Cfg::STAGE_BYTES);
+            tma_load_2d(a_dst, &tma_a, &full_bar[stage], kb * BLOCK_K, m_blk * BLOCK_M);
+            tma_load_2d(a_dst + Cfg::A_BYTES, &tma_b, &full_bar[stage], kb * BLOCK_K, n_blk * BLOCK_N);
+          }
+          __syncwarp();
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
       }
     }
   } else if (warp == 1) {
-    // ------------------------------ MMA issuer --------------------------------
-    if (lane == 0) {
+    // ------------------------------ MMA issuer (warp-uniform, one lane issues) -----
+    {
       constexpr uint32_t idesc = umma_idesc_bf16(BLOCK_M, BLOCK_N, 0, 0);
       int stage = 0;
       uint32_t phase = 0;
@@ -105,18 +108,21 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
         for (int kb = 0; kb < p.num_k_blocks; ++kb) {
           mbar_wait(&full_bar[stage], phase);
           tc_fence_after();
-          const uint32_t a_addr = smem_u32(smem + stage * Cfg::STAGE_BYTES);
-          const uint64_t a_desc = umma_desc_sw128(a_addr, 16, 1024);
-          const uint64_t b_desc = umma_desc_sw128(a_addr + Cfg::A_BYTES, 16, 1024);
+          if (elect_one()) {
+            const uint32_t a_addr = smem_u32(smem + stage * Cfg::STAGE_BYTES);
+            const uint64_t a_desc = umma_desc_sw128(a_addr, 16, 1024);
+            const uint64_t b_desc = umma_desc_sw128(a_addr + Cfg::A_BYTES, 16, 1024);
 #pragma unroll
-          for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
-            // advance 32 bytes (16 bf16) inside the 128-byte swizzle row: +2 in the >>4 address field
-            umma_ss(d_tmem, a_desc + 2 * k, b_desc + 2 * k, idesc, (kb | k) != 0);
+            for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
+              // advance 32 bytes (16 bf16) inside the 128-byte swizzle row: +2 in the >>4 address field
+              umma_ss(d_tmem, a_desc + 2 * k, b_desc + 2 * k, idesc, (kb | k) != 0);
+            }
+            umma_commit(&empty_bar[stage]);   // smem slot reusable once these MMAs retire
+            if (kb == p.num_k_blocks - 1) umma_commit(&tmem_full[acc]);
           }
-          umma_commit(&empty_bar[stage]);   // smem slot reusable once these MMAs retire
+          __syncwarp();
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
-        umma_commit(&tmem_full[acc]);
       }
     }
   } else {
