@@ -20,15 +20,10 @@
 //   WG0  warp 0: TMA producer (Q pair per segment; K / V tiles through two 2-deep rings)
 //        warp 1: MMA issuer   S_t = Q_t K^T (SS), O_t += P_t V (P from TMEM, V MN-major from smem)
 //   WG1 / WG2    softmax of query tile 0 / 1, one row per thread (setmaxnreg moves registers to them)
-// KV steps are 64 rows wide and the score tile of every query tile is DOUBLE BUFFERED in TMEM:
-//   TMEM (512 columns): O0 | O1 | S(0,0) S(0,1) | S(1,0) S(1,1)   (S(t,b): 128 x 64 fp32 = 64 columns;
-//   P (bf16) aliases the first 32 columns of its S buffer)
-// so QK^T of step j+2 is issued as soon as P(j) has been consumed and the softmax of a tile never waits
-// for the tensor pipe (it always finds the next score tile ready); the MMA warp only ever waits for P.
-// (With a single 128-wide S buffer per tile the chain softmax(j) -> PV(j) -> QK^T(j+1) -> softmax(j+1)
-// was serial: measured 3490 cycles per 128 KV rows of which each softmax warp waited 1670.)
-// O is rescaled lazily (only when a row max grows by more than 2^8) by the softmax warps themselves
-// after the previous PV has retired (o_done barrier).
+// TMEM (512 columns): S0 | S1 | O0 | O1, P_t (bf16) aliases the first 64 columns of S_t.
+// The two query tiles ping-pong on the tensor pipe: while one tile's softmax runs on the SIMT / XU
+// pipes the other tile's PV / next QK^T MMAs run.  O is rescaled lazily (only when a row max grows
+// by more than 2^8), by the softmax warps themselves between PV(j-1) and PV(j).
 //
 // Softmax arithmetic: x = s * scale_log2 - m with packed fp32x2 FMAs, 2^x on MUFU.EX2 (16 lanes/clk/SM --
 // for head_dim 128 that is exactly the rate at which the tensor pipe consumes P, so the exponentials,
@@ -56,17 +51,15 @@ struct AttnParams {
   long long* dbg;         // diagnostic phase timers [grid][8] (SFB_ATTN_TIMING=1), else nullptr
 };
 
-constexpr int ATT_BM = 128, ATT_BN = 64, ATT_D = 128;
+constexpr int ATT_BM = 128, ATT_BN = 128, ATT_D = 128;
 constexpr int ATT_THREADS = 384;
-constexpr int ATT_TILE_BYTES = 128 * 128 * 2;    // Q tile, 32 KB: two 16 KB halves (d 0-63 | d 64-127)
+constexpr int ATT_TILE_BYTES = 128 * 128 * 2;    // 32 KB: two 16 KB halves (d 0-63 | d 64-127)
 constexpr int ATT_HALF_BYTES = 128 * 64 * 2;
-constexpr int ATT_KV_BYTES = ATT_BN * 128 * 2;   // K or V step tile, 16 KB: two 8 KB halves
-constexpr int ATT_KV_HALF = ATT_BN * 64 * 2;
-constexpr int ATT_KV_STAGES = 4;
-constexpr int ATT_SMEM_BYTES = 2 * ATT_TILE_BYTES + 2 * ATT_KV_STAGES * ATT_KV_BYTES + 1024 + 512;
-constexpr int ATT_DEFAULT_EMU = 0;
+constexpr int ATT_KV_STAGES = 2;
+constexpr int ATT_SMEM_BYTES = 2 * ATT_TILE_BYTES + 2 * ATT_KV_STAGES * ATT_TILE_BYTES + 1024 + 256;
+constexpr int ATT_DEFAULT_EMU = 1;
 constexpr int ATT_SLOT_FLOATS = ATT_BM * ATT_D + 2 * ATT_BM;   // one (tile, segment) partial
-constexpr int ATT_MIN_SPLIT_KV_TILES = 32;                     // shorter KV: whole items per CTA
+constexpr int ATT_MIN_SPLIT_KV_TILES = 16;                     // shorter KV: whole items per CTA
 
 // first KV step (in the linearised item x step space) of CTA c, and the owner of a step
 __host__ __device__ __forceinline__ long long att_range_start(int c, int grid, const AttnParams& p) {
@@ -120,21 +113,20 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_con
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* q_smem = smem;                                    // [2 tiles][32 KB]
-  uint8_t* k_smem = smem + 2 * ATT_TILE_BYTES;               // [stages][16 KB]
-  uint8_t* v_smem = k_smem + ATT_KV_STAGES * ATT_KV_BYTES;   // [stages][16 KB]
-  uint64_t* bars = reinterpret_cast<uint64_t*>(v_smem + ATT_KV_STAGES * ATT_KV_BYTES);
+  uint8_t* k_smem = smem + 2 * ATT_TILE_BYTES;               // [stages][32 KB]
+  uint8_t* v_smem = k_smem + ATT_KV_STAGES * ATT_TILE_BYTES; // [stages][32 KB]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(v_smem + ATT_KV_STAGES * ATT_TILE_BYTES);
   uint64_t* q_full = bars;            // [1]  per segment
   uint64_t* q_empty = bars + 1;       // [1]  per segment
-  uint64_t* k_full = bars + 2;        // [4]  ring
-  uint64_t* k_empty = bars + 6;       // [4]
-  uint64_t* v_full = bars + 10;       // [4]
-  uint64_t* v_empty = bars + 14;      // [4]
-  uint64_t* s_full = bars + 18;       // [2 tiles][2 buffers], one phase per use of the buffer
-  uint64_t* p_full = bars + 22;       // [2 tiles][2 buffers] (128 arrivals)
-  uint64_t* o_final = bars + 26;      // [2] per query tile, per segment
-  uint64_t* o_free = bars + 28;       // [2] per query tile, per segment (128 arrivals)
-  uint64_t* o_done = bars + 30;       // [2] per query tile, one phase per PV (only the rescale path waits)
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 32);
+  uint64_t* k_full = bars + 2;        // [2]  ring
+  uint64_t* k_empty = bars + 4;       // [2]
+  uint64_t* v_full = bars + 6;        // [2]
+  uint64_t* v_empty = bars + 8;       // [2]
+  uint64_t* s_full = bars + 10;       // [2] per query tile, per KV step
+  uint64_t* p_half = bars + 18;       // [2 tiles][2 halves of the KV step], one arrival per softmax warp
+  uint64_t* o_final = bars + 14;      // [2] per query tile, per segment
+  uint64_t* o_free = bars + 16;       // [2] per query tile, per segment (128 arrivals)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 22);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -146,20 +138,16 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_con
     tma_prefetch_desc(&tma_v);
     mbar_init(q_full, 1);
     mbar_init(q_empty, 1);
-    for (int s = 0; s < ATT_KV_STAGES; ++s) {
+    for (int s = 0; s < 2; ++s) {
       mbar_init(&k_full[s], 1);
       mbar_init(&k_empty[s], 1);
       mbar_init(&v_full[s], 1);
       mbar_init(&v_empty[s], 1);
-    }
-    for (int s = 0; s < 4; ++s) {
       mbar_init(&s_full[s], 1);
-      mbar_init(&p_full[s], 128);
-    }
-    for (int s = 0; s < 2; ++s) {
+      mbar_init(&p_half[2 * s], 4);
+      mbar_init(&p_half[2 * s + 1], 4);
       mbar_init(&o_final[s], 1);
       mbar_init(&o_free[s], 128);
-      mbar_init(&o_done[s], 1);
     }
     fence_barrier_init();
   }
@@ -198,23 +186,23 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_con
           }
           __syncwarp();
           for (int j = j0; j < j1; ++j, ++g) {
-            const int st = g & (ATT_KV_STAGES - 1);
-            const uint32_t ph = (g / ATT_KV_STAGES) & 1;
+            const int st = g & 1;
+            const uint32_t ph = (g >> 1) & 1;
             mbar_wait(&k_empty[st], ph ^ 1);
             if (elect_one()) {
-              mbar_expect_tx(&k_full[st], ATT_KV_BYTES);
+              mbar_expect_tx(&k_full[st], ATT_TILE_BYTES);
 #pragma unroll
               for (int hf = 0; hf < 2; ++hf)
-                tma_load_4d(k_smem + st * ATT_KV_BYTES + hf * ATT_KV_HALF, &tma_k, &k_full[st], hf * 64, head,
+                tma_load_4d(k_smem + st * ATT_TILE_BYTES + hf * ATT_HALF_BYTES, &tma_k, &k_full[st], hf * 64, head,
                             j * ATT_BN, batch);
             }
             __syncwarp();
             mbar_wait(&v_empty[st], ph ^ 1);
             if (elect_one()) {
-              mbar_expect_tx(&v_full[st], ATT_KV_BYTES);
+              mbar_expect_tx(&v_full[st], ATT_TILE_BYTES);
 #pragma unroll
               for (int hf = 0; hf < 2; ++hf)
-                tma_load_4d(v_smem + st * ATT_KV_BYTES + hf * ATT_KV_HALF, &tma_v, &v_full[st], hf * 64, head,
+                tma_load_4d(v_smem + st * ATT_TILE_BYTES + hf * ATT_HALF_BYTES, &tma_v, &v_full[st], hf * 64, head,
                             j * ATT_BN, batch);
             }
             __syncwarp();
@@ -229,110 +217,82 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_con
         constexpr uint32_t idesc_pv = umma_idesc_bf16(ATT_BM, ATT_D, 0, 1);    // B (=V) MN-major
         const uint32_t q_addr = smem_u32(q_smem), k_addr = smem_u32(k_smem), v_addr = smem_u32(v_smem);
 
-        // S(t, b) = Q_t K^T for one 64-row KV step: M 128, N 64, K 128 (8 MMAs of K 16)
-        auto issue_qk = [&](int t, int b, int kst) {
-          const uint32_t qa = q_addr + t * ATT_TILE_BYTES, ka = k_addr + kst * ATT_KV_BYTES;
+        auto issue_qk = [&](int t, int kst) {
+          const uint32_t qa = q_addr + t * ATT_TILE_BYTES, ka = k_addr + kst * ATT_TILE_BYTES;
 #pragma unroll
           for (int k = 0; k < ATT_D / 16; ++k) {
-            const uint32_t qoff = (k >> 2) * ATT_HALF_BYTES + (k & 3) * 32;
-            const uint32_t koff = (k >> 2) * ATT_KV_HALF + (k & 3) * 32;
-            umma_ss(tmem_base + 256 + (t * 2 + b) * ATT_BN, umma_desc_sw128(qa + qoff, 16, 1024),
-                    umma_desc_sw128(ka + koff, 16, 1024), idesc_qk, k != 0);
+            const uint32_t off = (k >> 2) * ATT_HALF_BYTES + (k & 3) * 32;
+            umma_ss(tmem_base + t * 128, umma_desc_sw128(qa + off, 16, 1024), umma_desc_sw128(ka + off, 16, 1024),
+                    idesc_qk, k != 0);
           }
         };
-        // O_t += P(t, b) V: M 128, N 128 (d), K 64 (4 MMAs of K 16)
-        auto issue_pv = [&](int t, int b, int vst, bool acc) {
-          const uint32_t va = v_addr + vst * ATT_KV_BYTES;
+        auto issue_pv = [&](int t, int vst, bool acc, int half) {
+          const uint32_t va = v_addr + vst * ATT_TILE_BYTES;
 #pragma unroll
-          for (int k = 0; k < ATT_BN / 16; ++k) {
-            // A: P rows on TMEM lanes, 16 bf16 of K per 8 32-bit columns.
-            // B: V tile [kv][d], d contiguous -> MN-major; 16 kv rows = 2048 B; d halves 8 KB apart.
-            umma_ts(tmem_base + t * 128, tmem_base + 256 + (t * 2 + b) * ATT_BN + k * 8,
-                    umma_desc_sw128(va + k * 2048, ATT_KV_HALF, 1024), idesc_pv, (acc || k != 0) ? 1u : 0u);
+          for (int k = half * 4; k < half * 4 + 4; ++k) {
+            // A: P_t rows on TMEM lanes, 16 bf16 of K per 8 32-bit columns.
+            // B: V tile [kv][d], d contiguous -> MN-major; 16 kv rows = 2048 B; d halves 16 KB apart.
+            umma_ts(tmem_base + 256 + t * 128, tmem_base + t * 128 + k * 8,
+                    umma_desc_sw128(va + k * 2048, ATT_HALF_BYTES, 1024), idesc_pv, (acc || k != 0) ? 1u : 0u);
           }
         };
 
-        const bool mt = p.dbg != nullptr;
-        long long mm[5] = {0, 0, 0, 0, 0};
-        long long m_prev = mt ? clock64() : 0;
-        auto mstamp = [&](int k) {
-          if (mt) {
-            const long long now = clock64();
-            mm[k] += now - m_prev;
-            m_prev = now;
-          }
-        };
         uint32_t seg = 0, g = 0;
         for (long long cur = range_begin; cur < range_end; ++seg) {
           const int item = (int)(cur / n_kv);
           const int j0 = (int)(cur - (long long)item * n_kv);
           const int n = (range_end - cur) < (long long)(n_kv - j0) ? (int)(range_end - cur) : (n_kv - j0);
           mbar_wait(q_full, seg & 1);
-          // prologue: score tiles of the first two steps into the two S buffers of each query tile
-          for (int s0 = 0; s0 < 2 && s0 < n; ++s0) {
-            const uint32_t gs = g + s0;
-            const int ring = gs & (ATT_KV_STAGES - 1);
-            mbar_wait(&k_full[ring], (gs / ATT_KV_STAGES) & 1);
-            tc_fence_after();
-            if (elect_one()) {
-              issue_qk(0, gs & 1, ring);
-              umma_commit(&s_full[0 * 2 + (gs & 1)]);
-              issue_qk(1, gs & 1, ring);
-              umma_commit(&s_full[1 * 2 + (gs & 1)]);
-              umma_commit(&k_empty[ring]);
-              if (n <= 2 && s0 + 1 == (n < 2 ? n : 2)) umma_commit(q_empty);
-            }
-            __syncwarp();
+          mbar_wait(&k_full[g & 1], (g >> 1) & 1);
+          tc_fence_after();
+          if (elect_one()) {
+            issue_qk(0, g & 1);
+            umma_commit(&s_full[0]);
+            issue_qk(1, g & 1);
+            umma_commit(&s_full[1]);
+            umma_commit(&k_empty[g & 1]);
+            if (n == 1) umma_commit(q_empty);
           }
-          for (int i = 0; i < n; ++i) {
-            const uint32_t gi = g + i;
-            const int b = gi & 1;
-            const int vst = gi & (ATT_KV_STAGES - 1);
-            const uint32_t vph = (gi / ATT_KV_STAGES) & 1;
-            const uint32_t g2 = gi + 2;
-            const int kst = g2 & (ATT_KV_STAGES - 1);
-            const uint32_t kph = (g2 / ATT_KV_STAGES) & 1;
+          __syncwarp();
+          for (int i = 0; i < n; ++i, ++g) {
+            const int vst = g & 1;
+            const uint32_t vph = (g >> 1) & 1;
+            const bool has_next = (i + 1) < n;
+            const int kst = (g + 1) & 1;
+            const uint32_t kph = ((g + 1) >> 1) & 1;
             for (int t = 0; t < 2; ++t) {
-              mstamp(4);
-              mbar_wait(&p_full[t * 2 + b], (gi >> 1) & 1);
-              mstamp(t);
+              // P arrives in two halves (64 KV columns each): the first half's PV overlaps the softmax of the second
+              mbar_wait(&p_half[2 * t], g & 1);
               if (t == 0) mbar_wait(&v_full[vst], vph);
               if (i == 0) mbar_wait(&o_free[t], (seg & 1) ^ 1);   // previous segment's epilogue has read O_t
-              mstamp(2);
               tc_fence_after();
-              if (elect_one()) {
-                issue_pv(t, b, vst, i > 0);
-                umma_commit(&o_done[t]);
-                if (t == 1) umma_commit(&v_empty[vst]);
-              }
+              if (elect_one()) issue_pv(t, vst, i > 0, 0);
               __syncwarp();
-              if (i + 2 < n) {
-                // P(t, b) has been consumed (in order on the tensor pipe): refill the buffer with step i + 2
-                if (t == 0) {
-                  mstamp(4);
-                  mbar_wait(&k_full[kst], kph);
-                  mstamp(3);
-                  tc_fence_after();
-                }
-                if (elect_one()) {
-                  issue_qk(t, b, kst);
-                  umma_commit(&s_full[t * 2 + b]);
+              mbar_wait(&p_half[2 * t + 1], g & 1);
+              tc_fence_after();
+              if (has_next && t == 0) {
+                mbar_wait(&k_full[kst], kph);
+                tc_fence_after();
+              }
+              if (elect_one()) {
+                issue_pv(t, vst, true, 1);
+                if (t == 1) umma_commit(&v_empty[vst]);
+                if (has_next) {
+                  issue_qk(t, kst);
+                  umma_commit(&s_full[t]);
                   if (t == 1) {
                     umma_commit(&k_empty[kst]);
-                    if (i + 3 == n) umma_commit(q_empty);   // that was the segment's last QK^T: Q smem reusable
+                    if (i + 2 == n) umma_commit(q_empty);   // that was the segment's last QK^T: Q smem reusable
                   }
+                } else {
+                  umma_commit(&o_final[t]);
                 }
-                __syncwarp();
-              } else if (i + 1 == n) {
-                if (elect_one()) umma_commit(&o_final[t]);
-                __syncwarp();
               }
+              __syncwarp();
             }
           }
-          g += n;
           cur += n;
         }
-        if (mt && lane == 0) for (int k = 0; k < 5; ++k) p.dbg[(gridDim.x + blockIdx.x) * 8 + k] = mm[k];
       }
     }
   } else {
@@ -342,8 +302,8 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_con
     const int quarter = warp & 3;
     const int r_local = quarter * 32 + lane;
     const uint32_t lane_base = (uint32_t)(quarter * 32) << 16;
-    const uint32_t s_addr0 = tmem_base + lane_base + 256 + t * 2 * ATT_BN;
-    const uint32_t o_addr = tmem_base + lane_base + t * 128;
+    const uint32_t s_addr = tmem_base + lane_base + t * 128;
+    const uint32_t o_addr = tmem_base + lane_base + 256 + t * 128;
     const float sl2 = p.scale_log2;
 
     const bool timing = p.dbg != nullptr && warp == 4 && lane == 0;
@@ -366,9 +326,7 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_con
 
       for (int j = j0; j < j1; ++j, ++g) {
         stamp(5);
-        const int b = g & 1;
-        const uint32_t s_addr = s_addr0 + b * ATT_BN;
-        mbar_wait(&s_full[t * 2 + b], (g >> 1) & 1);
+        mbar_wait(&s_full[t], g & 1);
         tc_fence_after();
         stamp(0);
         if (j == n_kv - 1 && p.kv_tail < ATT_BN) {
@@ -391,15 +349,15 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_con
           }
           tmem_st_wait();
         }
-        uint32_t s[ATT_BN];
+        uint32_t s[128];
 #pragma unroll
-        for (int c = 0; c < ATT_BN / 32; ++c) tmem_ld32(s_addr + c * 32, *reinterpret_cast<uint32_t(*)[32]>(&s[c * 32]));
+        for (int c = 0; c < 4; ++c) tmem_ld32(s_addr + c * 32, *reinterpret_cast<uint32_t(*)[32]>(&s[c * 32]));
         tmem_ld_wait();
         stamp(1);
         float mx0 = __uint_as_float(s[0]), mx1 = __uint_as_float(s[1]), mx2 = __uint_as_float(s[2]),
               mx3 = __uint_as_float(s[3]);
 #pragma unroll
-        for (int i = 4; i < ATT_BN; i += 4) {
+        for (int i = 4; i < 128; i += 4) {
           mx0 = fmaxf(mx0, __uint_as_float(s[i]));
           mx1 = fmaxf(mx1, __uint_as_float(s[i + 1]));
           mx2 = fmaxf(mx2, __uint_as_float(s[i + 2]));
@@ -412,10 +370,7 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_con
           const float m_new = fmaxf(m_ref, mx);
           const bool need = (m_new - m_ref) * sl2 > 8.0f;
           if (__any_sync(0xffffffffu, need)) {
-            // O_t must be quiescent: wait until PV of the previous step (the g-th PV of this tile) has retired;
-            // PV of this step cannot start before we publish P below.
-            mbar_wait(&o_done[t], (g - 1) & 1);
-            tc_fence_after();
+            // PV(j-1) has retired (s_full(j) was committed after it), so O_t is quiescent here.
             const float m_upd = need ? m_new : m_ref;
             const float alpha = fast_exp2((m_ref - m_upd) * sl2);
             l *= alpha;
@@ -437,7 +392,7 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_con
         const float2 sl2v = make_float2(sl2, sl2), negv = make_float2(neg_m, neg_m);
         float2 sum_a = make_float2(0.f, 0.f), sum_b = make_float2(0.f, 0.f);
 #pragma unroll
-        for (int c = 0; c < ATT_BN / 32; ++c) {
+        for (int c = 0; c < 4; ++c) {
           uint32_t pk[16];
 #pragma unroll
           for (int i = 0; i < 16; ++i) {
@@ -453,13 +408,16 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_con
             if (i & 1) sum_b = __fadd2_rn(sum_b, e); else sum_a = __fadd2_rn(sum_a, e);
             pk[i] = pack_bf16(e.x, e.y);
           }
-          tmem_st16(s_addr + c * 16, pk);   // P aliases the first 32 columns of its S buffer
+          tmem_st16(s_addr + c * 16, pk);   // P_t aliases the first 64 columns of S_t
+          if (c & 1) {                      // publish this half of P (64 KV columns)
+            tmem_st_wait();
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&p_half[2 * t + (c >> 1)]);
+          }
         }
         l += (sum_a.x + sum_a.y) + (sum_b.x + sum_b.y);
         stamp(3);
-        tmem_st_wait();
-        tc_fence_before();
-        mbar_arrive(&p_full[t * 2 + b]);
         stamp(4);
       }
 
@@ -606,9 +564,8 @@ extern "C" int sfb_attention_fwd(const void* q, long long q_row_stride, long lon
   {
     uint64_t dims[4] = {128, (uint64_t)H, (uint64_t)Skv, (uint64_t)B};
     uint64_t str[3] = {128 * 2, (uint64_t)kv_row_stride * 2, (uint64_t)(B > 1 ? kv_batch_stride : kv_row_stride * Skv) * 2};
-    const uint32_t kv_box[4] = {64, 1, ATT_BN, 1};
-    if (int e = make_tmap_bf16(&tk, k, 4, dims, str, kv_box, true)) return e;
-    if (int e = make_tmap_bf16(&tv, v, 4, dims, str, kv_box, true)) return e;
+    if (int e = make_tmap_bf16(&tk, k, 4, dims, str, box, true)) return e;
+    if (int e = make_tmap_bf16(&tv, v, 4, dims, str, box, true)) return e;
   }
   const int sms = device_sm_count();
   if (sms <= 0) return SFB_ERR_CUDA;
@@ -638,7 +595,7 @@ extern "C" int sfb_attention_fwd(const void* q, long long q_row_stride, long lon
   if (timing < 0) {
     const char* env = getenv("SFB_ATTN_TIMING");
     timing = (env && env[0] == '1') ? 1 : 0;
-    if (timing) cudaMalloc(&dbg_buf, 512 * 8 * sizeof(long long));   // diagnostic mode only
+    if (timing) cudaMalloc(&dbg_buf, 256 * 8 * sizeof(long long));   // diagnostic mode only
   }
   p.dbg = timing ? dbg_buf : nullptr;
 
@@ -657,18 +614,14 @@ extern "C" int sfb_attention_fwd(const void* q, long long q_row_stride, long lon
   kern<<<grid, ATT_THREADS, ATT_SMEM_BYTES, stream>>>(tq, tk, tv, p);
   if (int e = check_cuda(cudaGetLastError(), "attention launch")) return e;
   if (timing) {   // diagnostic: per-phase cycles of one softmax warp, averaged over CTAs, per KV step
-    static long long h[512 * 8];
+    long long h[256 * 8];
     cudaStreamSynchronize(stream);
-    cudaMemcpy(h, dbg_buf, sizeof(long long) * 2 * grid * 8, cudaMemcpyDeviceToHost);
-    double ma[5] = {0, 0, 0, 0, 0};
-    for (int c = 0; c < grid; ++c) for (int k = 0; k < 5; ++k) ma[k] += (double)h[(grid + c) * 8 + k];
+    cudaMemcpy(h, dbg_buf, sizeof(long long) * grid * 8, cudaMemcpyDeviceToHost);
     double acc[6] = {0, 0, 0, 0, 0, 0}, steps = 0;
     for (int c = 0; c < grid; ++c) { for (int k = 0; k < 6; ++k) acc[k] += (double)h[c * 8 + k]; steps += (double)h[c * 8 + 6]; }
     fprintf(stderr, "[attn timing] Lq=%d S=%d grid=%d split=%d steps/cta=%.1f | clk/step: wait_s=%.0f ld=%.0f max=%.0f exp=%.0f st+arrive=%.0f other=%.0f total=%.0f\n",
             Lq, Skv, grid, p.split, steps / grid, acc[0] / steps, acc[1] / steps, acc[2] / steps, acc[3] / steps, acc[4] / steps,
             acc[5] / steps, (acc[0] + acc[1] + acc[2] + acc[3] + acc[4] + acc[5]) / steps);
-    fprintf(stderr, "[attn timing] mma warp clk/step: wait_p0=%.0f wait_p1=%.0f wait_v/o_free=%.0f wait_k=%.0f issue=%.0f\n",
-            ma[0] / steps, ma[1] / steps, ma[2] / steps, ma[3] / steps, ma[4] / steps);
   }
   if (p.split) {
     attention_combine_kernel<<<dim3(p.items, 2), 128, 0, stream>>>(p, grid);
