@@ -250,10 +250,20 @@ def run_product_arm(args) -> None:
     ops = CudaOps()
     cf = args.chunk_frames
     gen = B200DiffusionWrapper(model_config=dict(WAN_T2V_1_3B), timestep_shift=SHIFT, device=dev, init_seed=0, ops=ops)
-    # data-parallel over prompts: every rank owns a different prompt / noise (inference.py:45,96-100 in the reference)
-    pe_host = torch.randn(1, T_CTX, 4096, generator=torch.Generator().manual_seed(1 + rank)).to(torch.bfloat16).pin_memory()
+    # --mode dp (default): data parallel over prompts, every rank its own video (inference.py:45,96-100 in the
+    # reference).  --mode ulysses: ranks form head-parallel groups of `sp` GPUs that make ONE video together
+    # (self_forcing_b200/ulysses.py); groups are data parallel.  `video` = index of this rank's video.
+    sp_size = 1
+    if args.mode == "ulysses" and world > 1:
+        from self_forcing_b200.ulysses import UlyssesGroup
+        sp_size = next(p for p in (4, 2, 1) if world % p == 0 and p <= world)
+        groups = [dist.new_group(list(range(g0, g0 + sp_size))) for g0 in range(0, world, sp_size)]
+        gen.model.enable_ulysses(UlyssesGroup(groups[rank // sp_size], device=dev))
+    video = rank // sp_size
+    n_videos = world // sp_size
+    pe_host = torch.randn(1, T_CTX, 4096, generator=torch.Generator().manual_seed(1 + video)).to(torch.bfloat16).pin_memory()
     noise_host = torch.randn(1, LAT_FRAMES, 16, LAT_H, LAT_W,
-                             generator=torch.Generator().manual_seed(2 + rank)).to(torch.bfloat16).pin_memory()
+                             generator=torch.Generator().manual_seed(2 + video)).to(torch.bfloat16).pin_memory()
     out_host = torch.empty_like(noise_host).pin_memory()
     pe_dev, noise_dev = pe_host.to(dev), noise_host.to(dev)
     pargs = types.SimpleNamespace(denoising_step_list=DENOISE_STEPS, warp_denoising_step=True, num_frame_per_block=cf,
@@ -261,7 +271,7 @@ def run_product_arm(args) -> None:
                                   skip_refresh_tail=args.skip_refresh_tail, use_cuda_graphs=args.cuda_graphs)
     enc_dev = lambda text_prompts: {"prompt_embeds": pe_dev}   # noqa: E731
     pipe = CausalInferencePipeline(pargs, dev, generator=gen, text_encoder=enc_dev, vae=_NoVAE())
-    torch.manual_seed(1234 + rank)
+    torch.manual_seed(1234 + video)      # the re-noise stream must be identical on the ranks of one video
 
     def barrier():
         if world > 1:
@@ -305,7 +315,7 @@ def run_product_arm(args) -> None:
     for _ in range(args.warmup):
         resident_step()
     # ---- timed region 1: inputs resident in HBM, CUDA events on the launching (current) stream ----
-    ops.start_profile(only={"attention"})      # brackets only the attention launches with events
+    ops.start_profile(only={"attention", "attention_sp"})      # brackets only the attention launches with events
     barrier()
     row0 = clocks.mark() if clocks else 0
     launches0 = ops.launches
@@ -344,7 +354,7 @@ def run_product_arm(args) -> None:
         return
 
     pk = peaks()
-    frames = PIX_FRAMES * world * args.steps
+    frames = PIX_FRAMES * n_videos * args.steps
     value = frames / (ms_total / 1e3)
     # roofline of the dominant kernel: self-attention launches (KV window > text length) inside the timed steps
     self_attn = [(tag, ms) for _, tag, ms in attn_prof if tag[3] > T_CTX]
@@ -354,7 +364,8 @@ def run_product_arm(args) -> None:
     groups = {}
     for name, tag, ms in prof:
         key = name
-        if name == "attention":
+        if name in ("attention", "attention_sp"):
+            name = "attention"
             key = "attention_self" if tag[3] > T_CTX else "attention_cross"
         g = groups.setdefault(key, [0, 0.0, 0.0])
         g[0] += 1
@@ -371,15 +382,18 @@ def run_product_arm(args) -> None:
     total_fl = rollout_flops(cf)
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-        "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "ms_per_step": ms_total / args.steps, "higher_is_better": True,
+        "scaling": "weak" if sp_size == 1 else "strong", "vs_baseline": None,
         "dtype": "bf16", "data": "synthetic",
-        "config": {"workload": workload_name(cf), "parallelism": f"dp{world}", "weights": "random-init 1.3B architecture",
+        "config": {"workload": workload_name(cf),
+                   "parallelism": f"dp{world}" if sp_size == 1 else f"dp{n_videos} x ulysses{sp_size} (head-parallel, peer-memory all-to-all)",
+                   "weights": "random-init 1.3B architecture",
                    "frames_per_step_per_gpu": PIX_FRAMES, "forwards_per_step": (LAT_FRAMES // cf) * 5,
                    "l2": "inputs larger than L2 (2.8 GB weights + 6 GB KV cache stream through the 126 MB L2 every forward)",
                    "skip_refresh_tail": bool(args.skip_refresh_tail), "cuda_graphs": bool(args.cuda_graphs)},
         "per_gpu": value / world,
-        "model_tflops": total_fl * world * args.steps / (ms_total / 1e3) / 1e12,
-        "model_frac_of_peak": total_fl * args.steps / (ms_total / 1e3) / 1e12 / pk["sustained"],
+        "model_tflops": total_fl * n_videos * args.steps / (ms_total / 1e3) / 1e12,
+        "model_frac_of_peak": total_fl * n_videos * args.steps / (ms_total / 1e3) / 1e12 / pk["sustained"] / world,
         "e2e": {"value": frames / e2e_s, "unit": UNIT,
                 "h2d_bytes_per_step": noise_host.numel() * 2 + pe_host.numel() * 2, "d2h_bytes_per_step": out_host.numel() * 2},
         "gpu_launches": launches,
@@ -401,7 +415,7 @@ def run_product_arm(args) -> None:
         line["cpu_baseline"] = {"value": s.fps(sec), "unit": UNIT, "cores": s.threads, "kind": "port",
                                 "sample": s.describe(sec)}
     os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
-    with open(os.path.join(ROOT, "gpurun_out", f"bench_n{world}.json"), "w") as f:
+    with open(os.path.join(ROOT, "gpurun_out", f"bench_n{world}{'' if sp_size == 1 else '_ulysses'}.json"), "w") as f:
         json.dump(line, f, indent=1)
     print(json.dumps(line), flush=True)
     if world > 1:
@@ -414,6 +428,8 @@ def main():
     ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--mode", default="dp", choices=["dp", "ulysses"],
+                    help="multi-GPU mode: dp = one video per GPU (default), ulysses = one video per group of 2/4 GPUs")
     ap.add_argument("--chunk-frames", type=int, default=3, help="latent frames per block (3 = headline, 1 = frame-wise)")
     ap.add_argument("--skip-refresh-tail", action="store_true",
                     help="skip the unused tail of the clean-context refresh pass (NOT the default: changes the work)")

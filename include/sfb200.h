@@ -20,7 +20,7 @@
 extern "C" {
 #endif
 
-#define SFB_ABI_VERSION 2
+#define SFB_ABI_VERSION 3
 
 const char* sfb_last_error(void);
 int sfb_abi_version(void);
@@ -35,13 +35,15 @@ int sfb_abi_version(void);
  * Replaces nn.Linear (cuBLAS) at wan/modules/causal_model.py:112-114 (q,k,v -- one call with the
  * three weights stacked and up to three output segments of `seg_cols` columns each), :240 (o),
  * :277-279 (ffn), :351/:366 (head), :458-462 (patch/text embed); wan/modules/model.py:172,177-178,193.
- * `gate` row for output row r is gate + (r / rows_per_gate) * gate_stride (per-frame adaLN gate).
- * out may alias residual.  block_n: 0 = choose, else 64/128/256. */
+ * `gate` row for output row r is gate + ((r + gate_row_offset) / rows_per_gate) * gate_stride (per-frame adaLN
+ * gate; gate_row_offset = chunk-global index of row 0 for sequence-parallel callers that hold a slice of the rows).
+ * out may alias residual.  block_n: 0 = choose; 64/128/256 = one-CTA tiles of 128 x block_n; 512 = CTA-pair
+ * (tcgen05 cta_group::2) tiles of 256 x 256. */
 int sfb_gemm_bf16(const void* x, long long ldx, const void* w, long long ldw, const void* bias,
                   int M, int N, int K, int epilogue,
                   void* out0, long long ldo0, void* out1, long long ldo1, void* out2, long long ldo2, int seg_cols,
                   const void* residual, long long ldr,
-                  const void* gate, long long gate_stride, int rows_per_gate,
+                  const void* gate, long long gate_stride, int rows_per_gate, int gate_row_offset,
                   int block_n, void* stream);
 
 /* softmax(q k^T * scale) v without mask, head_dim 128, K/V read in place from a [B,S,H,128] cache
@@ -63,10 +65,11 @@ long long sfb_attention_workspace_bytes(void);
 int sfb_modulation_table(const void* mod, const void* e, void* out, int NL, int R, int G, int C,
                          long long e_row_stride, long long e_group_stride, void* stream);
 
-/* y = bf16(bf16(LN(x)) * bf16(1 + scale[g]) + shift[g]), g = row / rows_per_mod; LN eps, no affine.
+/* y = bf16(bf16(LN(x)) * bf16(1 + scale[g]) + shift[g]), g = (row + row_offset) / rows_per_mod; LN eps, no affine.
  * causal_model.py:315, :327-328, :366 with WanLayerNorm (model.py:89-99). */
 int sfb_ln_modulate(const void* x, long long ldx, void* y, long long ldy, int rows, int C, float eps,
-                    const void* shift, const void* scale, long long mod_stride, int rows_per_mod, void* stream);
+                    const void* shift, const void* scale, long long mod_stride, int rows_per_mod, int row_offset,
+                    void* stream);
 
 /* y = bf16(LN(x) * weight + bias)   (norm3, causal_model.py:268-270,324). */
 int sfb_ln_affine(const void* x, long long ldx, void* y, long long ldy, int rows, int C, float eps,
@@ -85,6 +88,32 @@ int sfb_qk_norm_rope(const void* q_in, long long ldq, const void* k_in, long lon
                      int tab_rows, int B, int L, int C, int head_dim, int F, int Hh, int Ww, int start_frame,
                      void* q_out, long long q_out_row, long long q_out_batch,
                      void* k_out, void* v_out, long long kv_out_row, long long kv_out_batch, void* stream);
+
+/* ---- Ulysses head-parallel attention for one long video (wan/distributed/xdit_context_parallel.py:66-192) ----
+ * Every rank holds a contiguous slice of the chunk's tokens with ALL heads for the token-wise work and ONE head
+ * group for attention.  The two all-to-alls per block are plain stores into peer-mapped memory issued by the
+ * producing kernels; sfb_peer_barrier is the only synchronisation. */
+
+/* sfb_qk_norm_rope for `rows` tokens starting at chunk token `token_offset`; head group g (C / groups columns) of
+ * every row is stored to q_dst[g] / k_dst[g] / v_dst[g] at row (token_offset + local row).  *_dst are HOST arrays of
+ * `groups` device pointers (rank g's q buffer / KV-cache write slot as mapped in this process). */
+int sfb_qk_norm_rope_sp(const void* q_in, long long ldq, const void* k_in, long long ldk, const void* v_in, long long ldv,
+                        const void* wq, const void* wk, float eps, const float* cos_tab, const float* sin_tab,
+                        int tab_rows, int rows, int C, int head_dim, int F, int Hh, int Ww, int start_frame,
+                        int token_offset, int groups, void* const* q_dst, long long q_dst_row,
+                        void* const* k_dst, void* const* v_dst, long long kv_dst_row, void* stream);
+
+/* sfb_attention_fwd for one sample and this rank's H heads over ALL Lq tokens; output rows
+ * [d * rows_per_dst, (d+1) * rows_per_dst) are stored to out_dst[d] (rank d's buffer, already offset to this head
+ * group's columns) at row (token - d * rows_per_dst). */
+int sfb_attention_fwd_sp(const void* q, long long q_row_stride, const void* k, const void* v, long long kv_row_stride,
+                         void* const* out_dst, int n_dst, int rows_per_dst, long long out_row_stride,
+                         int Lq, int Skv, int H, int head_dim, float softmax_scale,
+                         void* workspace, long long workspace_bytes, void* stream);
+
+/* All-ranks barrier over peer-mapped flag words: flag_ptrs[p] = rank p's zero-initialised int32[n] array as mapped
+ * here; `epoch` increases by one per call on every rank. */
+int sfb_peer_barrier(void* const* flag_ptrs, int rank, int n, int epoch, void* stream);
 
 /* im2col of Conv3d(k = s = (1,2,2)) (causal_model.py:775-778): x[b][c][f][y][x] with element strides
  * -> out[(b,f,y/2,x/2)][c*4 + (y%2)*2 + x%2]. */

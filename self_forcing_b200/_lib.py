@@ -12,14 +12,15 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "libsfb200.so")
 
 P, LL, I, F = c_void_p, c_longlong, c_int, c_float
-ABI_VERSION = 2
+PP = ctypes.POINTER(c_void_p)
+ABI_VERSION = 3
 
 # name -> argtypes, mirroring include/sfb200.h one to one
 SIGNATURES = {
-    "sfb_gemm_bf16": [P, LL, P, LL, P, I, I, I, I, P, LL, P, LL, P, LL, I, P, LL, P, LL, I, I, P],
+    "sfb_gemm_bf16": [P, LL, P, LL, P, I, I, I, I, P, LL, P, LL, P, LL, I, P, LL, P, LL, I, I, I, P],
     "sfb_attention_fwd": [P, LL, LL, P, P, LL, LL, P, LL, LL, I, I, I, I, I, F, P, LL, P],
     "sfb_modulation_table": [P, P, P, I, I, I, I, LL, LL, P],
-    "sfb_ln_modulate": [P, LL, P, LL, I, I, F, P, P, LL, I, P],
+    "sfb_ln_modulate": [P, LL, P, LL, I, I, F, P, P, LL, I, I, P],
     "sfb_ln_affine": [P, LL, P, LL, I, I, F, P, P, P],
     "sfb_rmsnorm": [P, LL, P, LL, I, I, F, P, P],
     "sfb_qk_norm_rope": [P, LL, P, LL, P, LL, P, P, F, P, P, I, I, I, I, I, I, I, I, I, P, LL, LL, P, P, LL, LL, P],
@@ -28,7 +29,16 @@ SIGNATURES = {
     "sfb_skinny_linear": [P, LL, P, LL, P, P, LL, I, I, I, I, P],
     "sfb_head_finish": [P, LL, P, LL, LL, LL, LL, LL, P, I, P, P, I, P, P, I, I, I, I, I, P],
     "sfb_add_noise": [P, P, P, I, P, P, I, P, I, I, P],
+    # Ulysses head-parallel path: PP = host array of device pointers (ctypes c_void_p * n)
+    "sfb_qk_norm_rope_sp": [P, LL, P, LL, P, LL, P, P, F, P, P, I, I, I, I, I, I, I, I, I, I, PP, LL, PP, PP, LL, P],
+    "sfb_attention_fwd_sp": [P, LL, P, P, LL, PP, I, I, LL, I, I, I, I, F, P, LL, P],
+    "sfb_peer_barrier": [PP, I, I, I, P],
 }
+
+
+def ptr_array(ptrs):
+    """Host array of device pointers for the PP arguments."""
+    return (c_void_p * len(ptrs))(*ptrs)
 
 
 class SfbError(RuntimeError):

@@ -44,10 +44,13 @@ struct AttnParams {
   int n_qpairs;           // ceil(Lq / 256)
   int items;              // B * H * n_qpairs
   int split;              // 1: contiguous step ranges per CTA (partials in ws), 0: whole items per CTA
+  int heads_per_group;    // (batch, head) pairs processed together; groups run one after the other so that the
+  int n_groups;           //   K/V of the heads in flight stays L2-resident (every K/V tile is read by all q tiles)
   float scale_log2;       // softmax_scale * log2(e)
-  __nv_bfloat16* out;
+  __nv_bfloat16* out[8];  // query rows [d * rows_per_dst, (d + 1) * rows_per_dst) go to out[d] (Ulysses: peer-mapped
+  int rows_per_dst;       //   buffers, the epilogue stores are the reverse all-to-all); one destination otherwise
   long long out_row_stride, out_batch_stride;   // elements
-  float* ws;              // [grid][2 slots][2 tiles][128*128 O^T + 128 m + 128 l] floats (split mode)
+  float* ws;              // [group][grid][2 slots][2 tiles][128*128 O^T + 128 m + 128 l] floats (split mode)
   long long* dbg;         // diagnostic phase timers [grid][8] (SFB_ATTN_TIMING=1), else nullptr
 };
 
@@ -60,14 +63,22 @@ constexpr int ATT_SMEM_BYTES = 2 * ATT_TILE_BYTES + 2 * ATT_KV_STAGES * ATT_TILE
 constexpr int ATT_DEFAULT_EMU = 1;
 constexpr int ATT_SLOT_FLOATS = ATT_BM * ATT_D + 2 * ATT_BM;   // one (tile, segment) partial
 constexpr int ATT_MIN_SPLIT_KV_TILES = 16;                     // shorter KV: whole items per CTA
+constexpr int ATT_MAX_GROUPS = 4;
+constexpr long long ATT_L2_BUDGET = 56ll << 20;                // K + V bytes of the heads in flight (L2 is 126 MB)
 
-// first KV step (in the linearised item x step space) of CTA c, and the owner of a step
-__host__ __device__ __forceinline__ long long att_range_start(int c, int grid, const AttnParams& p) {
-  if (p.split) return ((long long)c * p.items * p.n_kv_tiles) / grid;
-  return (((long long)c * p.items) / grid) * p.n_kv_tiles;
+// Work of one head group: items_g = (heads in the group) x n_qpairs items of n_kv steps, linearised item-major.
+__host__ __device__ __forceinline__ int att_group_items(int grp, const AttnParams& p) {
+  const int bh0 = grp * p.heads_per_group;
+  const int nbh = (p.B * p.H - bh0) < p.heads_per_group ? (p.B * p.H - bh0) : p.heads_per_group;
+  return nbh * p.n_qpairs;
 }
-__host__ __device__ __forceinline__ int att_step_owner(long long step, int grid, const AttnParams& p) {
-  const long long G = (long long)p.items * p.n_kv_tiles;
+// first KV step (in the group's linearised item x step space) of CTA c, and the owner of a step
+__host__ __device__ __forceinline__ long long att_range_start(int c, int grid, int items_g, const AttnParams& p) {
+  if (p.split) return ((long long)c * items_g * p.n_kv_tiles) / grid;
+  return (((long long)c * items_g) / grid) * p.n_kv_tiles;
+}
+__host__ __device__ __forceinline__ int att_step_owner(long long step, int grid, int items_g, const AttnParams& p) {
+  const long long G = (long long)items_g * p.n_kv_tiles;
   return (int)(((step + 1) * grid - 1) / G);   // largest c with floor(c * G / grid) <= step   (split mode)
 }
 
@@ -157,9 +168,7 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_con
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
-  // this CTA's contiguous range of (item, KV step) work
-  const long long range_begin = att_range_start(blockIdx.x, gridDim.x, p);
-  const long long range_end = att_range_start(blockIdx.x + 1, gridDim.x, p);
+  // per head group, this CTA owns one contiguous range of (item, KV step) work: see att_range_start
 
   if (warp < 4) {
     setmaxnreg_dec<104>();
@@ -167,11 +176,14 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_con
       // ------------------------------ TMA producer (warp-uniform, one lane issues) ----
       {
         uint32_t seg = 0, g = 0;   // segment counter, ring counter (KV steps issued so far)
-        for (long long cur = range_begin; cur < range_end; ++seg) {
+        for (int grp = 0; grp < p.n_groups; ++grp) {
+        const int items_g = att_group_items(grp, p);
+        const long long range_end = att_range_start(blockIdx.x + 1, gridDim.x, items_g, p);
+        for (long long cur = att_range_start(blockIdx.x, gridDim.x, items_g, p); cur < range_end; ++seg) {
           const int item = (int)(cur / n_kv);
           const int j0 = (int)(cur - (long long)item * n_kv);
           const int j1 = (range_end - cur) < (long long)(n_kv - j0) ? j0 + (int)(range_end - cur) : n_kv;
-          const int qp = item % p.n_qpairs, bh = item / p.n_qpairs;
+          const int qp = item % p.n_qpairs, bh = grp * p.heads_per_group + item / p.n_qpairs;
           const int head = bh % p.H, batch = bh / p.H;
           const int q_row0 = qp * (2 * ATT_BM);
           mbar_wait(q_empty, (seg & 1) ^ 1);           // previous segment's QK^T MMAs have retired
@@ -209,6 +221,7 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_con
           }
           cur += j1 - j0;
         }
+        }
       }
     } else if (warp == 1) {
       // ------------------------------ MMA issuer (warp-uniform, one lane issues) -----
@@ -238,7 +251,10 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_con
         };
 
         uint32_t seg = 0, g = 0;
-        for (long long cur = range_begin; cur < range_end; ++seg) {
+        for (int grp = 0; grp < p.n_groups; ++grp) {
+        const int items_g = att_group_items(grp, p);
+        const long long range_end = att_range_start(blockIdx.x + 1, gridDim.x, items_g, p);
+        for (long long cur = att_range_start(blockIdx.x, gridDim.x, items_g, p); cur < range_end; ++seg) {
           const int item = (int)(cur / n_kv);
           const int j0 = (int)(cur - (long long)item * n_kv);
           const int n = (range_end - cur) < (long long)(n_kv - j0) ? (int)(range_end - cur) : (n_kv - j0);
@@ -293,6 +309,7 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_con
           }
           cur += n;
         }
+        }
       }
     }
   } else {
@@ -317,6 +334,10 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_con
       }
     };
     uint32_t seg = 0, g = 0;
+    for (int grp = 0; grp < p.n_groups; ++grp) {
+    const int items_g = att_group_items(grp, p);
+    const long long range_begin = att_range_start(blockIdx.x, gridDim.x, items_g, p);
+    const long long range_end = att_range_start(blockIdx.x + 1, gridDim.x, items_g, p);
     for (long long cur = range_begin; cur < range_end; ++seg) {
       const int item = (int)(cur / n_kv);
       const int j0 = (int)(cur - (long long)item * n_kv);
@@ -424,14 +445,15 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_con
       // segment epilogue
       mbar_wait(&o_final[t], seg & 1);
       tc_fence_after();
-      const int qp = item % p.n_qpairs, bh = item / p.n_qpairs;
+      const int qp = item % p.n_qpairs, bh = grp * p.heads_per_group + item / p.n_qpairs;
       const int head = bh % p.H, batch = bh / p.H;
       if (j0 == 0 && j1 == n_kv) {
         // whole item: O_t / l -> bf16 -> global, one query row per thread (256 contiguous bytes)
         const int row = qp * (2 * ATT_BM) + t * ATT_BM + r_local;
         const float inv_l = 1.0f / l;
-        __nv_bfloat16* orow = p.out + (long long)batch * p.out_batch_stride + (long long)row * p.out_row_stride +
-                              head * ATT_D;
+        const int dst = row / p.rows_per_dst;
+        __nv_bfloat16* orow = p.out[dst < 8 ? dst : 0] + (long long)batch * p.out_batch_stride +
+                              (long long)(row - dst * p.rows_per_dst) * p.out_row_stride + head * ATT_D;
 #pragma unroll 1
         for (int c = 0; c < 4; ++c) {
           uint32_t o[32];
@@ -451,7 +473,8 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_con
         }
       } else {
         // partial item: park (O^T, m, l) in this CTA's workspace slot (first segment -> 0, last -> 1)
-        float* slot = p.ws + (((long long)blockIdx.x * 2 + (seg == 0 ? 0 : 1)) * 2 + t) * ATT_SLOT_FLOATS;
+        float* slot = p.ws + ((((long long)grp * gridDim.x + blockIdx.x) * 2 + (cur == range_begin ? 0 : 1)) * 2 + t) *
+                                 ATT_SLOT_FLOATS;
 #pragma unroll 1
         for (int c = 0; c < 4; ++c) {
           uint32_t o[32];
@@ -466,6 +489,7 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_con
       tc_fence_before();
       mbar_arrive(&o_free[t]);
       cur += j1 - j0;
+    }
     }
     if (timing) {
       for (int k = 0; k < 6; ++k) p.dbg[blockIdx.x * 8 + k] = tm[k];
@@ -485,18 +509,21 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_con
 // grid (items, 2 query tiles), 128 threads = one query row each.
 __global__ void __launch_bounds__(128)
 attention_combine_kernel(const AttnParams p, int grid_fwd) {
-  const int item = blockIdx.x, t = blockIdx.y, r = threadIdx.x;
+  const int t = blockIdx.y, r = threadIdx.x;
   const int n_kv = p.n_kv_tiles;
-  const long long s0 = (long long)item * n_kv, s1 = s0 + n_kv - 1;
-  const int c0 = att_step_owner(s0, grid_fwd, p), c1 = att_step_owner(s1, grid_fwd, p);
-  if (c0 == c1) return;   // the item was computed whole by one CTA
-  const int qp = item % p.n_qpairs, bh = item / p.n_qpairs;
+  const int qp = blockIdx.x % p.n_qpairs, bh = blockIdx.x / p.n_qpairs;
   const int head = bh % p.H, batch = bh / p.H;
+  const int grp = bh / p.heads_per_group;
+  const int item = (bh - grp * p.heads_per_group) * p.n_qpairs + qp;   // item index inside its head group
+  const int items_g = att_group_items(grp, p);
+  const long long s0 = (long long)item * n_kv, s1 = s0 + n_kv - 1;
+  const int c0 = att_step_owner(s0, grid_fwd, items_g, p), c1 = att_step_owner(s1, grid_fwd, items_g, p);
+  if (c0 == c1) return;   // the item was computed whole by one CTA
   const int row = qp * (2 * ATT_BM) + t * ATT_BM + r;
   if (row >= p.Lq) return;
   auto slot_of = [&](int c) {
-    const int first_item = (int)(att_range_start(c, grid_fwd, p) / n_kv);
-    return p.ws + (((long long)c * 2 + (first_item == item ? 0 : 1)) * 2 + t) * ATT_SLOT_FLOATS;
+    const int first_item = (int)(att_range_start(c, grid_fwd, items_g, p) / n_kv);
+    return p.ws + ((((long long)grp * grid_fwd + c) * 2 + (first_item == item ? 0 : 1)) * 2 + t) * ATT_SLOT_FLOATS;
   };
   float m = -INFINITY;
   for (int c = c0; c <= c1; ++c) m = fmaxf(m, slot_of(c)[ATT_BM * ATT_D + r]);
@@ -506,7 +533,9 @@ attention_combine_kernel(const AttnParams p, int grid_fwd) {
     L += sl[ATT_BM * ATT_D + ATT_BM + r] * exp2f((sl[ATT_BM * ATT_D + r] - m) * p.scale_log2);
   }
   const float inv_l = 1.0f / L;
-  __nv_bfloat16* orow = p.out + (long long)batch * p.out_batch_stride + (long long)row * p.out_row_stride + head * ATT_D;
+  const int dst = row / p.rows_per_dst;
+  __nv_bfloat16* orow = p.out[dst] + (long long)batch * p.out_batch_stride +
+                        (long long)(row - dst * p.rows_per_dst) * p.out_row_stride + head * ATT_D;
   for (int col = 0; col < ATT_D; col += 8) {
     float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
     for (int c = c0; c <= c1; ++c) {
@@ -532,26 +561,25 @@ int device_sm_count();
 extern "C" long long sfb_attention_workspace_bytes(void) {
   const int sms = sfb::device_sm_count();
   if (sms <= 0) return 0;
-  return (long long)sms * 2 * 2 * sfb::ATT_SLOT_FLOATS * (long long)sizeof(float);
+  return (long long)sfb::ATT_MAX_GROUPS * sms * 2 * 2 * sfb::ATT_SLOT_FLOATS * (long long)sizeof(float);
 }
 
-// q   : [B, Lq, H, 128] view with element strides (q_row_stride between tokens, q_batch_stride)
-// k, v: cache window start (already offset to attn_start), [B, Skv, H, 128] with their strides
-// out : [B, Lq, H, 128] with out_row_stride / out_batch_stride
-// workspace: caller-owned scratch of sfb_attention_workspace_bytes() bytes (may be NULL: then long-KV problems
-//            are not split across CTAs and run with whole-item granularity)
-extern "C" int sfb_attention_fwd(const void* q, long long q_row_stride, long long q_batch_stride, const void* k,
-                                 const void* v, long long kv_row_stride, long long kv_batch_stride, void* out,
-                                 long long out_row_stride, long long out_batch_stride, int B, int Lq, int Skv,
-                                 int H, int head_dim, float softmax_scale, void* workspace,
-                                 long long workspace_bytes, void* stream_) {
-  using namespace sfb;
-  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+namespace sfb {
+
+static int attention_launch(const void* q, long long q_row_stride, long long q_batch_stride, const void* k,
+                            const void* v, long long kv_row_stride, long long kv_batch_stride, void* const* out_dst,
+                            int n_dst, int rows_per_dst, long long out_row_stride, long long out_batch_stride, int B,
+                            int Lq, int Skv, int H, int head_dim, float softmax_scale, void* workspace,
+                            long long workspace_bytes, cudaStream_t stream) {
   if (head_dim != ATT_D) { set_error("sfb_attention_fwd: head_dim %d unsupported (128 only)", head_dim); return SFB_ERR_INVALID; }
   if (B <= 0 || Lq <= 0 || Skv <= 0 || H <= 0) { set_error("sfb_attention_fwd: empty problem B=%d Lq=%d Skv=%d H=%d", B, Lq, Skv, H); return SFB_ERR_INVALID; }
   if ((q_row_stride % 8) || (kv_row_stride % 8) || (out_row_stride % 8) || (q_batch_stride % 8) ||
       (kv_batch_stride % 8) || (out_batch_stride % 8)) {
     set_error("sfb_attention_fwd: strides must be multiples of 8 elements");
+    return SFB_ERR_INVALID;
+  }
+  if (n_dst < 1 || n_dst > 8 || rows_per_dst <= 0 || (long long)n_dst * rows_per_dst < Lq) {
+    set_error("sfb_attention_fwd: %d destinations of %d rows do not cover Lq=%d", n_dst, rows_per_dst, Lq);
     return SFB_ERR_INVALID;
   }
   CUtensorMap tq, tk, tv;
@@ -576,26 +604,46 @@ extern "C" int sfb_attention_fwd(const void* q, long long q_row_stride, long lon
   p.n_qpairs = (Lq + 2 * ATT_BM - 1) / (2 * ATT_BM);
   p.items = B * H * p.n_qpairs;
   p.scale_log2 = softmax_scale * 1.4426950408889634f;
-  p.out = static_cast<__nv_bfloat16*>(out);
+  for (int d = 0; d < 8; ++d) p.out[d] = static_cast<__nv_bfloat16*>(out_dst[d < n_dst ? d : 0]);
+  p.rows_per_dst = rows_per_dst;
   p.out_row_stride = out_row_stride;
   p.out_batch_stride = out_batch_stride;
   p.ws = static_cast<float*>(workspace);
+  // Long KV windows: one contiguous range of (item, KV step) work per SM, whatever the item count (also when there
+  // are fewer items than SMs -- head-parallel ranks and frame-wise rollouts).  Short ones: whole items per CTA.
   int grid = p.items < sms ? p.items : sms;
+  p.heads_per_group = B * H;
+  p.n_groups = 1;
+  const long long slot_bytes = (long long)sms * 2 * 2 * ATT_SLOT_FLOATS * (long long)sizeof(float);   // per group
+  const char* nosplit = getenv("SFB_ATTN_NOSPLIT");
+  p.split = (p.items % sms != 0 && p.n_kv_tiles >= ATT_MIN_SPLIT_KV_TILES && workspace != nullptr &&
+             workspace_bytes >= slot_bytes && !(nosplit && nosplit[0] == '1')) ? 1 : 0;
+  if (p.split) {
+    grid = sms;
+    // head groups: keep K + V of the (batch, head) pairs in flight within the L2 budget
+    const long long kv_bytes_per_head = 2ll * Skv * ATT_D * 2;
+    long long hg_max = ATT_L2_BUDGET / kv_bytes_per_head;
+    if (hg_max < 1) hg_max = 1;
+    int groups = (int)((B * H + hg_max - 1) / hg_max);
+    const int groups_fit = (int)(workspace_bytes / slot_bytes);
+    if (groups > ATT_MAX_GROUPS) groups = ATT_MAX_GROUPS;
+    if (groups > groups_fit) groups = groups_fit;
+    if (const char* env = getenv("SFB_ATTN_GROUPS")) { const int gq = atoi(env); if (gq >= 1 && gq <= groups_fit && gq <= ATT_MAX_GROUPS) groups = gq; }
+    p.n_groups = groups;
+    p.heads_per_group = (B * H + groups - 1) / groups;
+    p.n_groups = (B * H + p.heads_per_group - 1) / p.heads_per_group;
+  }
   if (const char* cap = getenv("SFB_ATTN_GRID")) {   // diagnostic: run on fewer SMs
     const int g = atoi(cap);
     if (g > 0 && g < grid) grid = g;
   }
-  const long long need = (long long)grid * 2 * 2 * ATT_SLOT_FLOATS * (long long)sizeof(float);
-  const char* nosplit = getenv("SFB_ATTN_NOSPLIT");
-  p.split = (p.items % grid != 0 && p.n_kv_tiles >= ATT_MIN_SPLIT_KV_TILES && workspace != nullptr &&
-             workspace_bytes >= need && !(nosplit && nosplit[0] == '1')) ? 1 : 0;
 
   static long long* dbg_buf = nullptr;
   static int timing = -1;
   if (timing < 0) {
     const char* env = getenv("SFB_ATTN_TIMING");
     timing = (env && env[0] == '1') ? 1 : 0;
-    if (timing) cudaMalloc(&dbg_buf, 256 * 8 * sizeof(long long));   // diagnostic mode only
+    if (timing) cudaMalloc(&dbg_buf, 512 * 8 * sizeof(long long));   // diagnostic mode only
   }
   p.dbg = timing ? dbg_buf : nullptr;
 
@@ -614,13 +662,13 @@ extern "C" int sfb_attention_fwd(const void* q, long long q_row_stride, long lon
   kern<<<grid, ATT_THREADS, ATT_SMEM_BYTES, stream>>>(tq, tk, tv, p);
   if (int e = check_cuda(cudaGetLastError(), "attention launch")) return e;
   if (timing) {   // diagnostic: per-phase cycles of one softmax warp, averaged over CTAs, per KV step
-    long long h[256 * 8];
+    static long long h[512 * 8];
     cudaStreamSynchronize(stream);
     cudaMemcpy(h, dbg_buf, sizeof(long long) * grid * 8, cudaMemcpyDeviceToHost);
     double acc[6] = {0, 0, 0, 0, 0, 0}, steps = 0;
-    for (int c = 0; c < grid; ++c) { for (int k = 0; k < 6; ++k) acc[k] += (double)h[c * 8 + k]; steps += (double)h[c * 8 + 6]; }
-    fprintf(stderr, "[attn timing] Lq=%d S=%d grid=%d split=%d steps/cta=%.1f | clk/step: wait_s=%.0f ld=%.0f max=%.0f exp=%.0f st+arrive=%.0f other=%.0f total=%.0f\n",
-            Lq, Skv, grid, p.split, steps / grid, acc[0] / steps, acc[1] / steps, acc[2] / steps, acc[3] / steps, acc[4] / steps,
+    for (int c = 0; c < grid; ++c) { for (int kk = 0; kk < 6; ++kk) acc[kk] += (double)h[c * 8 + kk]; steps += (double)h[c * 8 + 6]; }
+    fprintf(stderr, "[attn timing] Lq=%d S=%d H=%d grid=%d split=%d steps/cta=%.1f | clk/step: wait_s=%.0f ld=%.0f max=%.0f exp=%.0f st+arrive=%.0f other=%.0f total=%.0f\n",
+            Lq, Skv, H, grid, p.split, steps / grid, acc[0] / steps, acc[1] / steps, acc[2] / steps, acc[3] / steps, acc[4] / steps,
             acc[5] / steps, (acc[0] + acc[1] + acc[2] + acc[3] + acc[4] + acc[5]) / steps);
   }
   if (p.split) {
@@ -628,4 +676,35 @@ extern "C" int sfb_attention_fwd(const void* q, long long q_row_stride, long lon
     return check_cuda(cudaGetLastError(), "attention combine launch");
   }
   return SFB_OK;
+}
+
+}  // namespace sfb
+
+// q   : [B, Lq, H, 128] view with element strides (q_row_stride between tokens, q_batch_stride)
+// k, v: cache window start (already offset to attn_start), [B, Skv, H, 128] with their strides
+// out : [B, Lq, H, 128] with out_row_stride / out_batch_stride
+// workspace: caller-owned scratch of sfb_attention_workspace_bytes() bytes (may be NULL: then long-KV problems
+//            are not split across CTAs and run with whole-item granularity)
+extern "C" int sfb_attention_fwd(const void* q, long long q_row_stride, long long q_batch_stride, const void* k,
+                                 const void* v, long long kv_row_stride, long long kv_batch_stride, void* out,
+                                 long long out_row_stride, long long out_batch_stride, int B, int Lq, int Skv,
+                                 int H, int head_dim, float softmax_scale, void* workspace,
+                                 long long workspace_bytes, void* stream_) {
+  void* dst[1] = {out};
+  return sfb::attention_launch(q, q_row_stride, q_batch_stride, k, v, kv_row_stride, kv_batch_stride, dst, 1,
+                               Lq > 0 ? Lq : 1, out_row_stride, out_batch_stride, B, Lq, Skv, H, head_dim, softmax_scale,
+                               workspace, workspace_bytes, reinterpret_cast<cudaStream_t>(stream_));
+}
+
+// Head-parallel (Ulysses) form, one sample: this rank attends with ITS head group (H = heads per group) for ALL Lq
+// query tokens; output rows [d * rows_per_dst, (d + 1) * rows_per_dst) belong to rank d and are stored straight into
+// out_dst[d] (peer-mapped, already offset to this group's columns) at row (token - d * rows_per_dst) -- the reverse
+// all-to-all of wan/distributed/xdit_context_parallel.py:179-184 fused into the attention epilogue.
+extern "C" int sfb_attention_fwd_sp(const void* q, long long q_row_stride, const void* k, const void* v,
+                                    long long kv_row_stride, void* const* out_dst, int n_dst, int rows_per_dst,
+                                    long long out_row_stride, int Lq, int Skv, int H, int head_dim,
+                                    float softmax_scale, void* workspace, long long workspace_bytes, void* stream_) {
+  return sfb::attention_launch(q, q_row_stride, 0, k, v, kv_row_stride, 0, out_dst, n_dst, rows_per_dst, out_row_stride,
+                               0, 1, Lq, Skv, H, head_dim, softmax_scale, workspace, workspace_bytes,
+                               reinterpret_cast<cudaStream_t>(stream_));
 }

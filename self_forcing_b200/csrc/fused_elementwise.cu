@@ -64,7 +64,7 @@ template <int NV, bool AFFINE>
 __global__ void __launch_bounds__(ROW_WARPS * 32)
 ln_kernel(const __nv_bfloat16* __restrict__ x, long long ldx, __nv_bfloat16* __restrict__ y, long long ldy, int rows,
           float eps, const __nv_bfloat16* __restrict__ shift, const __nv_bfloat16* __restrict__ scale,
-          long long mod_stride, int rows_per_mod, const __nv_bfloat16* __restrict__ w,
+          long long mod_stride, int rows_per_mod, int row_offset, const __nv_bfloat16* __restrict__ w,
           const __nv_bfloat16* __restrict__ b) {
   constexpr int C = NV * 256;
   const int row = blockIdx.x * ROW_WARPS + (threadIdx.x >> 5);
@@ -85,7 +85,7 @@ ln_kernel(const __nv_bfloat16* __restrict__ x, long long ldx, __nv_bfloat16* __r
 #pragma unroll
     for (int i = 0; i < 8; ++i) { const float d = v[k][i] - mean; sq += d * d; }
   const float rstd = rsqrtf(warp_sum(sq) * (1.0f / C) + eps);
-  const long long mrow = AFFINE ? 0 : (long long)(row / rows_per_mod) * mod_stride;
+  const long long mrow = AFFINE ? 0 : (long long)((row + row_offset) / rows_per_mod) * mod_stride;
 #pragma unroll
   for (int k = 0; k < NV; ++k) {
     const int c0 = (k * 32 + lane) * 8;
@@ -111,6 +111,18 @@ ln_kernel(const __nv_bfloat16* __restrict__ x, long long ldx, __nv_bfloat16* __r
 // ------------------------------------------------------------------------------------
 // RMSNorm over the full channel width (+ optional 3-D RoPE), NV = C / 256
 // ------------------------------------------------------------------------------------
+// Destinations of the rotated q / k rows (and the V copy) when the heads of a token are dealt to several head
+// groups (Ulysses head-parallel attention: group g lives on rank g and the pointers are peer-mapped memory, so
+// this kernel's stores ARE the all-to-all).  groups == 1 is the single-GPU case.
+struct HeadScatter {
+  __nv_bfloat16* q[8];
+  __nv_bfloat16* k[8];
+  __nv_bfloat16* v[8];
+  int groups;
+  int group_cols;     // heads_per_group * head_dim
+  int token_offset;   // chunk-global token index of local row 0 (RoPE position and destination row)
+};
+
 struct RopeGeom {
   int L;            // tokens per sample in this call
   int Hh, Ww;       // token grid (height, width) of one frame
@@ -160,13 +172,12 @@ qk_norm_rope_kernel(const __nv_bfloat16* __restrict__ q_in, long long ldq, const
                     long long ldk, const __nv_bfloat16* __restrict__ v_in, long long ldv,
                     const __nv_bfloat16* __restrict__ wq, const __nv_bfloat16* __restrict__ wk, float eps,
                     const float* __restrict__ cos_tab, const float* __restrict__ sin_tab, int head_dim,
-                    RopeGeom g, int rows, __nv_bfloat16* __restrict__ q_out, long long q_out_row,
-                    long long q_out_batch, __nv_bfloat16* __restrict__ k_out, __nv_bfloat16* __restrict__ v_out,
+                    RopeGeom g, int rows, const HeadScatter hs, long long q_out_row, long long q_out_batch,
                     long long kv_out_row, long long kv_out_batch) {
   const int row = blockIdx.x * ROW_WARPS + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
   if (row >= rows) return;
-  const int b = row / g.L, n = row - b * g.L;
+  const int b = row / g.L, n = row - b * g.L + hs.token_offset;
   const int fhw = g.Hh * g.Ww;
   const int f = n / fhw, rem = n - f * fhw;
   const int hh = rem / g.Ww, ww = rem - hh * g.Ww;
@@ -188,8 +199,16 @@ qk_norm_rope_kernel(const __nv_bfloat16* __restrict__ q_in, long long ldq, const
     }
   }
   float v[NV][8];
+  // destination of this lane's k-th 16-byte vector: head group, column inside the group
+  int grp[NV], gcol[NV];
+#pragma unroll
+  for (int k = 0; k < NV; ++k) {
+    const int c0 = (k * 32 + lane) * 8;
+    grp[k] = hs.groups == 1 ? 0 : c0 / hs.group_cols;
+    gcol[k] = c0 - grp[k] * hs.group_cols;
+  }
   rms_row<NV>(q_in + row * ldq, wq, eps, lane, v);
-  __nv_bfloat16* qo = q_out + b * q_out_batch + n * q_out_row;
+  const long long q_off = b * q_out_batch + n * q_out_row;
 #pragma unroll
   for (int k = 0; k < NV; ++k) {
     float o[8];
@@ -198,10 +217,10 @@ qk_norm_rope_kernel(const __nv_bfloat16* __restrict__ q_in, long long ldq, const
       o[2 * i] = v[k][2 * i] * cs[k][i] - v[k][2 * i + 1] * sn[k][i];
       o[2 * i + 1] = v[k][2 * i] * sn[k][i] + v[k][2 * i + 1] * cs[k][i];
     }
-    *reinterpret_cast<uint4*>(qo + (k * 32 + lane) * 8) = pack8(o);
+    *reinterpret_cast<uint4*>(hs.q[grp[k]] + q_off + gcol[k]) = pack8(o);
   }
   rms_row<NV>(k_in + row * ldk, wk, eps, lane, v);
-  __nv_bfloat16* ko = k_out + b * kv_out_batch + n * kv_out_row;
+  const long long kv_off = b * kv_out_batch + n * kv_out_row;
 #pragma unroll
   for (int k = 0; k < NV; ++k) {
     float o[8];
@@ -210,13 +229,12 @@ qk_norm_rope_kernel(const __nv_bfloat16* __restrict__ q_in, long long ldq, const
       o[2 * i] = v[k][2 * i] * cs[k][i] - v[k][2 * i + 1] * sn[k][i];
       o[2 * i + 1] = v[k][2 * i] * sn[k][i] + v[k][2 * i + 1] * cs[k][i];
     }
-    *reinterpret_cast<uint4*>(ko + (k * 32 + lane) * 8) = pack8(o);
+    *reinterpret_cast<uint4*>(hs.k[grp[k]] + kv_off + gcol[k]) = pack8(o);
   }
   if (v_in != nullptr) {
-    __nv_bfloat16* vo = v_out + b * kv_out_batch + n * kv_out_row;
 #pragma unroll
     for (int k = 0; k < NV; ++k)
-      *reinterpret_cast<uint4*>(vo + (k * 32 + lane) * 8) = ldg16(v_in + row * ldv + (k * 32 + lane) * 8);
+      *reinterpret_cast<uint4*>(hs.v[grp[k]] + kv_off + gcol[k]) = ldg16(v_in + row * ldv + (k * 32 + lane) * 8);
   }
 }
 
@@ -435,12 +453,12 @@ extern "C" int sfb_modulation_table(const void* mod, const void* e, void* out, i
 
 extern "C" int sfb_ln_modulate(const void* x, long long ldx, void* y, long long ldy, int rows, int C, float eps,
                                const void* shift, const void* scale, long long mod_stride, int rows_per_mod,
-                               void* stream) {
-  if (rows <= 0 || rows_per_mod <= 0 || (ldx % 8) || (ldy % 8) || (mod_stride % 8)) { set_error("sfb_ln_modulate: bad arguments"); return SFB_ERR_INVALID; }
+                               int row_offset, void* stream) {
+  if (rows <= 0 || rows_per_mod <= 0 || row_offset < 0 || (ldx % 8) || (ldy % 8) || (mod_stride % 8)) { set_error("sfb_ln_modulate: bad arguments"); return SFB_ERR_INVALID; }
   return dispatch_nv(C, "sfb_ln_modulate", [&](auto nv) {
     ln_kernel<decltype(nv)::value, false><<<(rows + ROW_WARPS - 1) / ROW_WARPS, ROW_WARPS * 32, 0, (cudaStream_t)stream>>>(
         (const bf16*)x, ldx, (bf16*)y, ldy, rows, eps, (const bf16*)shift, (const bf16*)scale, mod_stride, rows_per_mod,
-        nullptr, nullptr);
+        row_offset, nullptr, nullptr);
     return check_cuda(cudaGetLastError(), "ln_modulate launch");
   });
 }
@@ -450,7 +468,7 @@ extern "C" int sfb_ln_affine(const void* x, long long ldx, void* y, long long ld
   if (rows <= 0 || (ldx % 8) || (ldy % 8) || !weight || !bias) { set_error("sfb_ln_affine: bad arguments"); return SFB_ERR_INVALID; }
   return dispatch_nv(C, "sfb_ln_affine", [&](auto nv) {
     ln_kernel<decltype(nv)::value, true><<<(rows + ROW_WARPS - 1) / ROW_WARPS, ROW_WARPS * 32, 0, (cudaStream_t)stream>>>(
-        (const bf16*)x, ldx, (bf16*)y, ldy, rows, eps, nullptr, nullptr, 0, 1, (const bf16*)weight, (const bf16*)bias);
+        (const bf16*)x, ldx, (bf16*)y, ldy, rows, eps, nullptr, nullptr, 0, 1, 0, (const bf16*)weight, (const bf16*)bias);
     return check_cuda(cudaGetLastError(), "ln_affine launch");
   });
 }
@@ -480,12 +498,45 @@ extern "C" int sfb_qk_norm_rope(const void* q_in, long long ldq, const void* k_i
   g.n_f = c - 2 * (c / 3);
   g.n_h = c / 3;
   const int rows = B * L;
+  HeadScatter hs{};
+  hs.q[0] = (bf16*)q_out; hs.k[0] = (bf16*)k_out; hs.v[0] = (bf16*)v_out;
+  hs.groups = 1; hs.group_cols = C; hs.token_offset = 0;
   return dispatch_nv(C, "sfb_qk_norm_rope", [&](auto nv) {
     qk_norm_rope_kernel<decltype(nv)::value><<<(rows + ROW_WARPS - 1) / ROW_WARPS, ROW_WARPS * 32, 0, (cudaStream_t)stream>>>(
         (const bf16*)q_in, ldq, (const bf16*)k_in, ldk, (const bf16*)v_in, ldv, (const bf16*)wq, (const bf16*)wk, eps,
-        cos_tab, sin_tab, head_dim, g, rows, (bf16*)q_out, q_out_row, q_out_batch, (bf16*)k_out, (bf16*)v_out,
-        kv_out_row, kv_out_batch);
+        cos_tab, sin_tab, head_dim, g, rows, hs, q_out_row, q_out_batch, kv_out_row, kv_out_batch);
     return check_cuda(cudaGetLastError(), "qk_norm_rope launch");
+  });
+}
+
+// Sequence-parallel (Ulysses) form: this rank holds `rows` consecutive tokens of the chunk starting at chunk token
+// `token_offset`, with ALL heads; head group g (C / groups columns) of every row is stored to q_dst[g] / k_dst[g] /
+// v_dst[g] at row (token_offset + local row).  With peer-mapped destination pointers the stores are the all-to-all
+// of wan/distributed/xdit_context_parallel.py:179-184 (xFuserLongContextAttention), fused into the producer.
+extern "C" int sfb_qk_norm_rope_sp(const void* q_in, long long ldq, const void* k_in, long long ldk, const void* v_in,
+                                   long long ldv, const void* wq, const void* wk, float eps, const float* cos_tab,
+                                   const float* sin_tab, int tab_rows, int rows, int C, int head_dim, int F, int Hh,
+                                   int Ww, int start_frame, int token_offset, int groups, void* const* q_dst,
+                                   long long q_dst_row, void* const* k_dst, void* const* v_dst, long long kv_dst_row,
+                                   void* stream) {
+  if (rows <= 0 || token_offset < 0 || token_offset + rows > F * Hh * Ww) { set_error("sfb_qk_norm_rope_sp: rows [%d, %d) outside the chunk of %d tokens", token_offset, token_offset + rows, F * Hh * Ww); return SFB_ERR_INVALID; }
+  if (head_dim % 16 || C % head_dim) { set_error("sfb_qk_norm_rope_sp: bad head_dim %d for C=%d", head_dim, C); return SFB_ERR_INVALID; }
+  if (groups < 1 || groups > 8 || (C / head_dim) % groups) { set_error("sfb_qk_norm_rope_sp: %d heads do not split into %d groups", C / head_dim, groups); return SFB_ERR_INVALID; }
+  if (start_frame < 0 || start_frame + F > tab_rows || Hh > tab_rows || Ww > tab_rows) { set_error("sfb_qk_norm_rope_sp: position beyond the %d-row RoPE table", tab_rows); return SFB_ERR_INVALID; }
+  if ((ldq % 8) || (ldk % 8) || (ldv % 8) || (q_dst_row % 8) || (kv_dst_row % 8)) { set_error("sfb_qk_norm_rope_sp: strides must be multiples of 8"); return SFB_ERR_INVALID; }
+  RopeGeom g;
+  g.L = F * Hh * Ww; g.Hh = Hh; g.Ww = Ww; g.start_frame = start_frame;
+  const int c = head_dim / 2;
+  g.n_f = c - 2 * (c / 3);
+  g.n_h = c / 3;
+  HeadScatter hs{};
+  for (int i = 0; i < groups; ++i) { hs.q[i] = (bf16*)q_dst[i]; hs.k[i] = (bf16*)k_dst[i]; hs.v[i] = (bf16*)v_dst[i]; }
+  hs.groups = groups; hs.group_cols = C / groups; hs.token_offset = token_offset;
+  return dispatch_nv(C, "sfb_qk_norm_rope_sp", [&](auto nv) {
+    qk_norm_rope_kernel<decltype(nv)::value><<<(rows + ROW_WARPS - 1) / ROW_WARPS, ROW_WARPS * 32, 0, (cudaStream_t)stream>>>(
+        (const bf16*)q_in, ldq, (const bf16*)k_in, ldk, (const bf16*)v_in, ldv, (const bf16*)wq, (const bf16*)wk, eps,
+        cos_tab, sin_tab, head_dim, g, rows, hs, q_dst_row, 0, kv_dst_row, 0);
+    return check_cuda(cudaGetLastError(), "qk_norm_rope_sp launch");
   });
 }
 

@@ -174,7 +174,7 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_consta
       const int row = row0 + r_local;
       const __nv_bfloat16* grow = nullptr;
       if (EPI == EPI_GATE_RES)
-        grow = p.gate + (long long)((row < p.M ? row : p.M - 1) / p.rows_per_gate) * p.gate_stride + n0;
+        grow = p.gate + (long long)(((row < p.M ? row : p.M - 1) + p.gate_row_offset) / p.rows_per_gate) * p.gate_stride + n0;
       const uint32_t t_row = tmem_base + ((uint32_t)(quarter * 32) << 16) + acc * G2_BN;
 #pragma unroll 1
       for (int sb = 0; sb < G2_NSUB; ++sb) {

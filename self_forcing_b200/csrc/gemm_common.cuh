@@ -17,9 +17,10 @@ struct GemmParams {
   int seg_cols;                // columns per segment (== N when there is a single destination)
   const __nv_bfloat16* residual;
   long long ldr;
-  const __nv_bfloat16* gate;   // gate vector of row r lives at gate + (r / rows_per_gate) * gate_stride
+  const __nv_bfloat16* gate;   // gate vector of row r lives at gate + ((r + gate_row_offset) / rows_per_gate) * gate_stride
   long long gate_stride;
   int rows_per_gate;
+  int gate_row_offset;         // chunk-global index of row 0 (sequence-parallel callers hold a slice of the rows)
 };
 
 __device__ __forceinline__ float gelu_tanh_f(float x) {
@@ -84,7 +85,7 @@ __device__ __forceinline__ void gemm_epilogue_row(const GemmParams& p, int row, 
   const __nv_bfloat16* rrow = nullptr;
   const __nv_bfloat16* grow = nullptr;
   if (EPI == EPI_RESIDUAL || EPI == EPI_GATE_RES) rrow = p.residual + (long long)row * p.ldr + n0;
-  if (EPI == EPI_GATE_RES) grow = p.gate + (long long)(row_ok ? row / p.rows_per_gate : 0) * p.gate_stride + n0;
+  if (EPI == EPI_GATE_RES) grow = p.gate + (long long)(row_ok ? (row + p.gate_row_offset) / p.rows_per_gate : 0) * p.gate_stride + n0;
 #pragma unroll 1
   for (int c = 0; c < TILE_N / 32; ++c) {
     uint32_t v[32];

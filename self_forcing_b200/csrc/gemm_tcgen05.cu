@@ -192,7 +192,7 @@ extern "C" int sfb_gemm_bf16(const void* x, long long ldx, const void* w, long l
                              int M, int N, int K, int epilogue, void* out0, long long ldo0, void* out1,
                              long long ldo1, void* out2, long long ldo2, int seg_cols, const void* residual,
                              long long ldr, const void* gate, long long gate_stride, int rows_per_gate,
-                             int block_n, void* stream_) {
+                             int gate_row_offset, int block_n, void* stream_) {
   using namespace sfb;
   cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
   if (M <= 0 || N <= 0 || K <= 0) { set_error("sfb_gemm_bf16: empty problem M=%d N=%d K=%d", M, N, K); return SFB_ERR_INVALID; }
@@ -233,6 +233,7 @@ extern "C" int sfb_gemm_bf16(const void* x, long long ldx, const void* w, long l
     if (p.out[s] == nullptr || (p.ldo[s] % 8)) { set_error("sfb_gemm_bf16: output segment %d missing or ld not multiple of 8", s); return SFB_ERR_INVALID; }
   p.residual = static_cast<const __nv_bfloat16*>(residual); p.ldr = ldr;
   p.gate = static_cast<const __nv_bfloat16*>(gate); p.gate_stride = gate_stride; p.rows_per_gate = rows_per_gate;
+  p.gate_row_offset = gate_row_offset;
 
   CUtensorMap ta, tb;
   {

@@ -28,6 +28,7 @@ from torch import nn
 
 from .cache import IndexMirror, plan_cache_update
 from .ops import EPI_BIAS, EPI_GATE_RES, EPI_GELU, EPI_RESIDUAL
+from .ulysses import UlyssesGroup, shard_rows
 
 
 def rope_tables(head_dim: int, max_pos: int = 1024, theta: float = 10000.0):
@@ -129,6 +130,9 @@ class B200CausalWanModel(nn.Module):
         self._mirror = IndexMirror()
         self._sampler_tables = None   # (timesteps fp32, sigmas fp32) on device, set by the wrapper
         self._rope = None
+        self._sp: Optional[UlyssesGroup] = None   # Ulysses head-parallel group (one long video over several GPUs)
+        self._sp_kv: Dict[int, tuple] = {}        # data_ptr of a head-sharded cache tensor -> (pool, element offset)
+        self._sp_buf: Dict[int, tuple] = {}       # chunk length -> (q buffer, attention-output buffer) peer tensors
         self.register_load_state_dict_post_hook(lambda module, incompatible: module.invalidate_packed())
         self._register_load_state_dict_pre_hook(self._drop_foreign_keys)
 
@@ -166,6 +170,52 @@ class B200CausalWanModel(nn.Module):
         self.invalidate_packed()
         self._ws.clear()
         return super()._apply(fn, *a, **k)
+
+    # ------------------------------------------------------------------ Ulysses head parallelism
+    def enable_ulysses(self, sp: UlyssesGroup) -> None:
+        """Run every forward head-parallel over the ranks of `sp` (self_forcing_b200/ulysses.py).  All ranks must
+        call forward with identical inputs; KV caches must come from allocate_kv_cache()."""
+        if self.num_heads % sp.world:
+            raise ValueError(f"{self.num_heads} heads do not split over {sp.world} ranks")
+        self._sp = sp if sp.world > 1 else None
+        self._sp_kv.clear()
+        self._sp_buf.clear()
+
+    def allocate_kv_cache(self, batch_size: int, tokens: int, dtype, device) -> List[dict]:
+        """Per-layer cache dicts like CausalInferencePipeline._initialize_kv_cache (pipeline/causal_inference.py:278-298).
+        Under Ulysses the K/V tensors are head-sharded [1, S, H/P, D] views of one peer-mapped pool, because the
+        other ranks' qk_norm_rope kernels store this rank's head group straight into it."""
+        sp = self._sp
+        heads = self.num_heads // (sp.world if sp is not None else 1)
+        if sp is None:
+            pool = torch.zeros(self.num_layers, 2, batch_size, tokens, heads, self.head_dim, dtype=dtype, device=device)
+            kv = [(pool[i, 0], pool[i, 1]) for i in range(self.num_layers)]
+        else:
+            if batch_size != 1:
+                raise ValueError("Ulysses mode runs one video (batch 1) per group")
+            peer = sp.alloc((self.num_layers, 2, tokens, heads, self.head_dim), dtype)
+            peer.local.zero_()
+            per = tokens * heads * self.head_dim
+            kv = []
+            for i in range(self.num_layers):
+                k, v = peer.local[i, 0].unsqueeze(0), peer.local[i, 1].unsqueeze(0)
+                self._sp_kv[k.data_ptr()] = (peer, (2 * i) * per)
+                self._sp_kv[v.data_ptr()] = (peer, (2 * i + 1) * per)
+                kv.append((k, v))
+            sp.sync_host()
+        return [{"k": k, "v": v,
+                 "global_end_index": torch.tensor([0], dtype=torch.long, device=device),
+                 "local_end_index": torch.tensor([0], dtype=torch.long, device=device)} for k, v in kv]
+
+    def _sp_buffers(self, L: int, dtype):
+        buf = self._sp_buf.get(L)
+        if buf is None:
+            sp = self._sp
+            hg_cols = (self.num_heads // sp.world) * self.head_dim
+            buf = (sp.alloc((L, hg_cols), dtype), sp.alloc((L // sp.world, self.dim), dtype))
+            sp.sync_host()
+            self._sp_buf[L] = buf
+        return buf
 
     def set_sampler_tables(self, timesteps: torch.Tensor, sigmas: torch.Tensor) -> None:
         """FlowMatchScheduler tables (utils/scheduler.py:118-141) used by the fused flow->x0 epilogue."""
@@ -205,8 +255,10 @@ class B200CausalWanModel(nn.Module):
         self._packed = pk
         return pk
 
-    def _workspace(self, B: int, L: int, F_: int, dev) -> Dict[str, torch.Tensor]:
-        key = (B, L, F_, str(dev))
+    def _workspace(self, B: int, L: int, F_: int, dev, L_full: Optional[int] = None) -> Dict[str, torch.Tensor]:
+        """L = token rows this rank works on per sample, L_full = tokens of the whole chunk (== L unless Ulysses)."""
+        L_full = L if L_full is None else L_full
+        key = (B, L, F_, str(dev), L_full)
         ws = self._ws.get(key)
         if ws is None:
             C, bf = self.dim, self.patch_embedding.weight.dtype
@@ -215,7 +267,7 @@ class B200CausalWanModel(nn.Module):
             def e(*shape):
                 return torch.empty(*shape, dtype=bf, device=dev)
 
-            ws = dict(tok=e(R, self.in_dim * 4), x=e(R, C), h=e(R, C), q_lin=e(R, C), k_lin=e(R, C), v_lin=e(R, C),
+            ws = dict(tok=e(B * L_full, self.in_dim * 4), head_full=e(B * L_full, self.out_dim * 4), x=e(R, C), h=e(R, C), q_lin=e(R, C), k_lin=e(R, C), v_lin=e(R, C),
                       q=e(R, C), attn=e(R, C), ffn=e(R, self.ffn_dim), sin=e(B * F_, self.freq_dim),
                       e1=e(B * F_, C), e=e(B * F_, C), e0=e(B * F_, 6 * C), mod=e(self.num_layers, B * F_, 6, C),
                       head_mod=e(1, B * F_, 2, C), head_out=e(R, self.out_dim * 4),
@@ -254,12 +306,23 @@ class B200CausalWanModel(nn.Module):
         assert Cin == self.in_dim and t.shape == (B, F_), f"timestep shape {tuple(t.shape)} != {(B, F_)}"
         C, NL, D, NH = self.dim, self.num_layers, self.head_dim, self.num_heads
         dev = x.device
-        ws = self._workspace(B, L, F_, dev)
-        R = B * L
+        sp = self._sp
+        if sp is not None:
+            # Ulysses: this rank owns token rows [off, off + Lr) of the chunk for everything but self-attention
+            if B != 1:
+                raise ValueError("Ulysses mode runs one video (batch 1) per group")
+            off, Lr = shard_rows(L, sp.world, sp.rank)
+            NHg = NH // sp.world
+            q_peer, attn_peer = self._sp_buffers(L, self.patch_embedding.weight.dtype)
+        else:
+            off, Lr, NHg = 0, L, NH
+        ws = self._workspace(B, Lr, F_, dev, L)
+        R = B * Lr
 
         # ---- embeddings -------------------------------------------------------------------
         ops.patchify(x, ws["tok"])
-        ops.gemm(ws["tok"], pk["patch_w"], self.patch_embedding.bias, ws["x"])
+        ops.gemm(ws["tok"][off:off + Lr] if sp is not None else ws["tok"], pk["patch_w"], self.patch_embedding.bias,
+                 ws["x"])
         tflat = t.reshape(-1).contiguous()
         ops.sinusoid(tflat, ws["sin"], self.freq_dim)
         te, tp = self.time_embedding, self.time_projection
@@ -300,17 +363,38 @@ class B200CausalWanModel(nn.Module):
             sa, ca = blk.self_attn, blk.cross_attn
             # -- self attention --
             ops.ln_modulate(ws["x"], ws["h"], shift=m[:, 0], scale=m[:, 1], mod_stride=mstride, rows_per_mod=fs,
-                            eps=self.eps)
+                            eps=self.eps, row_offset=off)
             kc, vc = cache["k"], cache["v"]
-            if kc.shape[0] != B or kc.shape[2] != NH or kc.shape[3] != D:
-                raise ValueError(f"kv_cache[{i}]['k'] shape {tuple(kc.shape)} does not match B={B}, H={NH}, D={D}")
+            if kc.shape[0] != B or kc.shape[2] != NHg or kc.shape[3] != D:
+                raise ValueError(f"kv_cache[{i}]['k'] shape {tuple(kc.shape)} does not match B={B}, H={NHg}, D={D}")
             if plan.roll:
                 for c_ in (kc, vc):
                     c_[:, plan.roll_dst:plan.roll_dst + plan.roll_len] = \
                         c_[:, plan.roll_src:plan.roll_src + plan.roll_len].clone()
             k_slot = kc[:, plan.write_start:plan.write_end]
             v_slot = vc[:, plan.write_start:plan.write_end]
-            if B == 1:   # V projection lands directly in its cache slot
+            if sp is not None:
+                # head-parallel self-attention: the all-to-alls are peer stores inside the two kernels below
+                ops.gemm(ws["h"], pb["wqkv"], pb["bqkv"], None, seg_cols=C,
+                         outs=[ws["q_lin"], ws["k_lin"], ws["v_lin"]])
+                try:
+                    (k_pool, k_base), (v_pool, v_base) = self._sp_kv[kc.data_ptr()], self._sp_kv[vc.data_ptr()]
+                except KeyError:
+                    raise ValueError("Ulysses mode needs KV caches from model.allocate_kv_cache()") from None
+                slot_off = plan.write_start * NHg * D
+                ops.qk_norm_rope_sp(ws["q_lin"], ws["k_lin"], ws["v_lin"], sa.norm_q.weight, sa.norm_k.weight, self.eps,
+                                    pk["cos"], pk["sin"], D, (F_, Hh, Ww), start_frame, off, sp, q_peer,
+                                    k_slot[0], v_slot[0], k_pool.ptrs_at(k_base + slot_off),
+                                    v_pool.ptrs_at(v_base + slot_off))
+                sp.barrier(ops)          # every rank's q / k / v rows have landed
+                if skip_output and i == NL - 1:
+                    break
+                ops.attention_sp(q_peer.local.view(L, NHg, D), kc[0, plan.attn_start:plan.attn_end],
+                                 vc[0, plan.attn_start:plan.attn_end], scale, sp, attn_peer, Lr)
+                sp.barrier(ops)          # every head group's output columns have landed
+                ops.gemm(attn_peer.local, sa.o.weight, sa.o.bias, ws["x"], epilogue=EPI_GATE_RES, residual=ws["x"],
+                         gate=m[:, 2], gate_stride=mstride, rows_per_gate=fs, gate_row_offset=off)
+            elif B == 1:   # V projection lands directly in its cache slot
                 ops.gemm(ws["h"], pb["wqkv"], pb["bqkv"], None, seg_cols=C,
                          outs=[ws["q_lin"], ws["k_lin"], v_slot.reshape(L, C)])
                 v_src = None
@@ -318,16 +402,17 @@ class B200CausalWanModel(nn.Module):
                 ops.gemm(ws["h"], pb["wqkv"], pb["bqkv"], None, seg_cols=C,
                          outs=[ws["q_lin"], ws["k_lin"], ws["v_lin"]])
                 v_src = ws["v_lin"]
-            q4 = ws["q"].view(B, L, NH, D)
-            ops.qk_norm_rope(ws["q_lin"], ws["k_lin"], v_src, sa.norm_q.weight, sa.norm_k.weight, self.eps,
-                             pk["cos"], pk["sin"], B, L, D, (F_, Hh, Ww), start_frame,
-                             q_out=ws["q"].view(B, L, C), k_out=k_slot, v_out=v_slot)
-            if skip_output and i == NL - 1:
-                break   # cache-refresh pass: nothing after the last layer's K/V append is consumed
-            ops.attention(q4, kc[:, plan.attn_start:plan.attn_end], vc[:, plan.attn_start:plan.attn_end],
-                          ws["attn"].view(B, L, NH, D), scale)
-            ops.gemm(ws["attn"], sa.o.weight, sa.o.bias, ws["x"], epilogue=EPI_GATE_RES, residual=ws["x"],
-                     gate=m[:, 2], gate_stride=mstride, rows_per_gate=fs)
+            q4 = ws["q"].view(B, Lr, NH, D)
+            if sp is None:
+                ops.qk_norm_rope(ws["q_lin"], ws["k_lin"], v_src, sa.norm_q.weight, sa.norm_k.weight, self.eps,
+                                 pk["cos"], pk["sin"], B, L, D, (F_, Hh, Ww), start_frame,
+                                 q_out=ws["q"].view(B, L, C), k_out=k_slot, v_out=v_slot)
+                if skip_output and i == NL - 1:
+                    break   # cache-refresh pass: nothing after the last layer's K/V append is consumed
+                ops.attention(q4, kc[:, plan.attn_start:plan.attn_end], vc[:, plan.attn_start:plan.attn_end],
+                              ws["attn"].view(B, L, NH, D), scale)
+                ops.gemm(ws["attn"], sa.o.weight, sa.o.bias, ws["x"], epilogue=EPI_GATE_RES, residual=ws["x"],
+                         gate=m[:, 2], gate_stride=mstride, rows_per_gate=fs)
             # -- cross attention --
             cc = crossattn_cache[i]
             if not cc["is_init"]:
@@ -343,14 +428,14 @@ class B200CausalWanModel(nn.Module):
             ops.ln_affine(ws["x"], ws["h"], blk.norm3.weight, blk.norm3.bias, self.eps)
             ops.gemm(ws["h"], ca.q.weight, ca.q.bias, ws["q_lin"])
             ops.rmsnorm(ws["q_lin"], ws["q"], ca.norm_q.weight, self.eps)
-            ops.attention(q4, cc["k"], cc["v"], ws["attn"].view(B, L, NH, D), scale)
+            ops.attention(q4, cc["k"], cc["v"], ws["attn"].view(B, Lr, NH, D), scale)
             ops.gemm(ws["attn"], ca.o.weight, ca.o.bias, ws["x"], epilogue=EPI_RESIDUAL, residual=ws["x"])
             # -- feed forward --
             ops.ln_modulate(ws["x"], ws["h"], shift=m[:, 3], scale=m[:, 4], mod_stride=mstride, rows_per_mod=fs,
-                            eps=self.eps)
+                            eps=self.eps, row_offset=off)
             ops.gemm(ws["h"], blk.ffn[0].weight, blk.ffn[0].bias, ws["ffn"], epilogue=EPI_GELU)
             ops.gemm(ws["ffn"], blk.ffn[2].weight, blk.ffn[2].bias, ws["x"], epilogue=EPI_GATE_RES,
-                     residual=ws["x"], gate=m[:, 5], gate_stride=mstride, rows_per_gate=fs)
+                     residual=ws["x"], gate=m[:, 5], gate_stride=mstride, rows_per_gate=fs, gate_row_offset=off)
 
         self._mirror.write(kv_cache[:NL], [(p.global_end, p.local_end) for p in plans])
         if skip_output:
@@ -359,8 +444,12 @@ class B200CausalWanModel(nn.Module):
         # ---- head ------------------------------------------------------------------------------
         hm = ws["head_mod"][0]   # [B*F, 2, C]
         ops.ln_modulate(ws["x"], ws["h"], shift=hm[:, 0], scale=hm[:, 1], mod_stride=2 * C, rows_per_mod=fs,
-                        eps=self.eps)
+                        eps=self.eps, row_offset=off)
         ops.gemm(ws["h"], self.head.head.weight, self.head.head.bias, ws["head_out"])
+        head_out = ws["head_out"]
+        if sp is not None:   # xdit_context_parallel.py:142: gather the token shards before unpatchify
+            sp.all_gather_rows(ws["head_out"], ws["head_full"])
+            head_out = ws["head_full"]
         flow = torch.empty(B, F_, self.out_dim, H, W, dtype=ws["x"].dtype, device=dev)
         x0 = None
         xt = x.permute(0, 2, 1, 3, 4)   # [B, F, C, H, W] view of the input
@@ -368,9 +457,9 @@ class B200CausalWanModel(nn.Module):
             if self._sampler_tables is None:
                 raise RuntimeError("return_x0 needs set_sampler_tables() (done by B200DiffusionWrapper)")
             x0 = torch.empty_like(flow)
-            ops.head_finish(ws["head_out"], xt, t.contiguous(), self._sampler_tables[0], self._sampler_tables[1],
+            ops.head_finish(head_out, xt, t.contiguous(), self._sampler_tables[0], self._sampler_tables[1],
                             flow, x0)
         else:
-            ops.head_finish(ws["head_out"], xt, t.contiguous(), None, None, flow, None)
+            ops.head_finish(head_out, xt, t.contiguous(), None, None, flow, None)
         out = flow.permute(0, 2, 1, 3, 4)   # reference returns [B, C, F, H, W]
         return (out, x0) if return_x0 else out

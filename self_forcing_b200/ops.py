@@ -75,6 +75,9 @@ class CudaOps:
         if name == "attention":
             q, kk = a[0], a[1]
             return ("attention", q.shape[0], q.shape[1], kk.shape[1], q.shape[2])
+        if name == "attention_sp":
+            q, kk = a[0], a[1]
+            return ("attention", 1, q.shape[0], kk.shape[0], q.shape[1])
         if name == "gemm":
             x, w = a[0], a[1]
             return ("gemm", x.shape[0], w.shape[0], x.shape[1], k.get("epilogue", 0))
@@ -87,7 +90,8 @@ class CudaOps:
     # -- dense projections ---------------------------------------------------------------
     @_op
     def gemm(self, x, w, bias, out, *, epilogue=EPI_BIAS, residual=None, gate=None, gate_stride=0,
-             rows_per_gate=1, outs: Optional[Sequence[torch.Tensor]] = None, seg_cols=0, block_n=0):
+             rows_per_gate=1, gate_row_offset=0, outs: Optional[Sequence[torch.Tensor]] = None, seg_cols=0,
+             block_n=0):
         _check_2d(x, "x"); _check_2d(w, "w")
         M, K = x.shape
         N = w.shape[0]
@@ -104,7 +108,7 @@ class CudaOps:
             _ptr(segs[0]), segs[0].stride(0), _ptr(segs[1]), segs[1].stride(0) if segs[1] is not None else 0,
             _ptr(segs[2]), segs[2].stride(0) if segs[2] is not None else 0, seg_cols,
             _ptr(residual), residual.stride(0) if residual is not None else 0,
-            _ptr(gate), gate_stride, rows_per_gate, block_n, self._stream()), "sfb_gemm_bf16")
+            _ptr(gate), gate_stride, rows_per_gate, gate_row_offset, block_n, self._stream()), "sfb_gemm_bf16")
 
     # -- attention ------------------------------------------------------------------------
     @_op
@@ -115,11 +119,7 @@ class CudaOps:
         for t in (q, k, v, out):
             assert t.stride(3) == 1 and t.stride(2) == D and t.dtype == torch.bfloat16
         assert k.stride() == v.stride() and k.shape == v.shape
-        ws = self._attn_ws.get(q.device.index)
-        if ws is None:
-            with torch.cuda.device(q.device):
-                ws = torch.empty(int(self.lib.sfb_attention_workspace_bytes()), dtype=torch.uint8, device=q.device)
-            self._attn_ws[q.device.index] = ws
+        ws = self._attn_workspace(q.device)
         _lib.check(self.lib.sfb_attention_fwd(
             q.data_ptr(), q.stride(1), q.stride(0), k.data_ptr(), v.data_ptr(), k.stride(1), k.stride(0),
             out.data_ptr(), out.stride(1), out.stride(0), B, Lq, S, H, D, scale, ws.data_ptr(), ws.numel(),
@@ -136,11 +136,11 @@ class CudaOps:
                    "sfb_modulation_table")
 
     @_op
-    def ln_modulate(self, x, y, shift, scale, mod_stride: int, rows_per_mod: int, eps: float):
+    def ln_modulate(self, x, y, shift, scale, mod_stride: int, rows_per_mod: int, eps: float, row_offset: int = 0):
         _check_2d(x, "x"); _check_2d(y, "y")
         _lib.check(self.lib.sfb_ln_modulate(x.data_ptr(), x.stride(0), y.data_ptr(), y.stride(0), x.shape[0],
                                             x.shape[1], eps, shift.data_ptr(), scale.data_ptr(), mod_stride,
-                                            rows_per_mod, self._stream()), "sfb_ln_modulate")
+                                            rows_per_mod, row_offset, self._stream()), "sfb_ln_modulate")
 
     @_op
     def ln_affine(self, x, y, weight, bias, eps: float):
@@ -170,6 +170,53 @@ class CudaOps:
             sin_tab.data_ptr(), cos_tab.shape[0], B, L, C, head_dim, F_, Hh, Ww, start_frame,
             q_out.data_ptr(), q_out.stride(1), q_out.stride(0), k_out.data_ptr(), v_out.data_ptr(),
             k_out.stride(1), k_out.stride(0), self._stream()), "sfb_qk_norm_rope")
+
+    # -- Ulysses head-parallel path (self_forcing_b200/ulysses.py) ---------------------------
+    def _attn_workspace(self, device):
+        ws = self._attn_ws.get(device.index)
+        if ws is None:
+            with torch.cuda.device(device):
+                ws = torch.empty(int(self.lib.sfb_attention_workspace_bytes()), dtype=torch.uint8, device=device)
+            self._attn_ws[device.index] = ws
+        return ws
+
+    @_op
+    def qk_norm_rope_sp(self, q_in, k_in, v_in, wq, wk, eps, cos_tab, sin_tab, head_dim, grid, start_frame,
+                        token_offset: int, sp, q_buf, k_slot_local, v_slot_local, k_slot_ptrs, v_slot_ptrs):
+        """This rank's token rows (all heads) -> head group g's rows of rank g's q buffer / KV-cache slot, stored
+        through peer-mapped pointers (the forward all-to-all).  q_buf: PeerTensor [L, H/P * D]."""
+        _check_2d(q_in, "q_in"); _check_2d(k_in, "k_in"); _check_2d(v_in, "v_in")
+        C = q_in.shape[1]
+        F_, Hh, Ww = grid
+        group_cols = C // sp.world
+        _lib.check(self.lib.sfb_qk_norm_rope_sp(
+            q_in.data_ptr(), q_in.stride(0), k_in.data_ptr(), k_in.stride(0), v_in.data_ptr(), v_in.stride(0),
+            wq.data_ptr(), wk.data_ptr(), eps, cos_tab.data_ptr(), sin_tab.data_ptr(), cos_tab.shape[0],
+            q_in.shape[0], C, head_dim, F_, Hh, Ww, start_frame, token_offset, sp.world,
+            _lib.ptr_array(q_buf.ptrs), group_cols, _lib.ptr_array(k_slot_ptrs), _lib.ptr_array(v_slot_ptrs),
+            group_cols, self._stream()), "sfb_qk_norm_rope_sp")
+
+    @_op
+    def attention_sp(self, q, k, v, scale: float, sp, out_buf, rows_per_rank: int):
+        """q [L, H/P, D] (this rank's head group, all tokens), k / v [S, H/P, D] cache window; output rows of rank d's
+        tokens are stored into rank d's out_buf (PeerTensor [L/P, C]) at this head group's columns (reverse
+        all-to-all)."""
+        Lq, Hg, D = q.shape
+        S = k.shape[0]
+        for t in (q, k, v):
+            assert t.stride(2) == 1 and t.stride(1) == D and t.dtype == torch.bfloat16
+        assert k.stride() == v.stride() and out_buf.local.stride(1) == 1
+        ws = self._attn_workspace(q.device)
+        col0 = sp.rank * Hg * D
+        _lib.check(self.lib.sfb_attention_fwd_sp(
+            q.data_ptr(), q.stride(0), k.data_ptr(), v.data_ptr(), k.stride(0), _lib.ptr_array(out_buf.ptrs_at(col0)),
+            sp.world, rows_per_rank, out_buf.local.stride(0), Lq, S, Hg, D, scale, ws.data_ptr(), ws.numel(),
+            self._stream()), "sfb_attention_fwd_sp")
+
+    @_op
+    def peer_barrier(self, sp, epoch: int):
+        _lib.check(self.lib.sfb_peer_barrier(_lib.ptr_array(sp.flags.ptrs), sp.rank, sp.world, epoch, self._stream()),
+                   "sfb_peer_barrier")
 
     # -- embeddings -----------------------------------------------------------------------
     @_op

@@ -170,6 +170,11 @@ class CausalInferencePipeline(torch.nn.Module):
             kv_cache_size = self.local_attn_size * self.frame_seq_length
         else:
             kv_cache_size = 32760
+        model = self.generator.model
+        if getattr(model, "_sp", None) is not None:
+            # Ulysses head-parallel group: head-sharded caches in peer-mapped memory (ulysses.py)
+            self.kv_cache1 = model.allocate_kv_cache(batch_size, kv_cache_size, dtype, device)
+            return
         self.kv_cache1 = [{
             "k": torch.zeros([batch_size, kv_cache_size, self.num_heads, self.head_dim], dtype=dtype, device=device),
             "v": torch.zeros([batch_size, kv_cache_size, self.num_heads, self.head_dim], dtype=dtype, device=device),

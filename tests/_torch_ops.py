@@ -20,7 +20,7 @@ class TorchOps:
         self.log = []
 
     def gemm(self, x, w, bias, out, *, epilogue=EPI_BIAS, residual=None, gate=None, gate_stride=0,
-             rows_per_gate=1, outs=None, seg_cols=0, block_n=0):
+             rows_per_gate=1, gate_row_offset=0, outs=None, seg_cols=0, block_n=0):
         self.launches += 1
         self.log.append("gemm")
         y = F.linear(x, w, bias)
@@ -30,7 +30,7 @@ class TorchOps:
             y = residual + y
         elif epilogue == EPI_GATE_RES:
             M = x.shape[0]
-            g = gate[torch.arange(M) // rows_per_gate]          # gate is a [groups, C] strided view
+            g = gate[(torch.arange(M) + gate_row_offset) // rows_per_gate]   # gate is a [groups, C] strided view
             y = residual + y * g
         if outs is not None:
             for i, o in enumerate(outs):
@@ -53,10 +53,10 @@ class TorchOps:
                 base = r * e_row_stride + g * e_group_stride
                 out[:, r, g] = mod[:, g] + ef[base:base + C]
 
-    def ln_modulate(self, x, y, shift, scale, mod_stride, rows_per_mod, eps):
+    def ln_modulate(self, x, y, shift, scale, mod_stride, rows_per_mod, eps, row_offset=0):
         self.launches += 1
         n = F.layer_norm(x, (x.shape[1],), None, None, eps)
-        idx = torch.arange(x.shape[0]) // rows_per_mod
+        idx = (torch.arange(x.shape[0]) + row_offset) // rows_per_mod
         y.copy_(n * (1 + scale[idx]) + shift[idx])
 
     def ln_affine(self, x, y, weight, bias, eps):
@@ -79,6 +79,46 @@ class TorchOps:
         k_out.copy_(O.rope_rotate(k, grid, ang, start_frame))
         if v_in is not None:
             v_out.copy_(v_in.view(B, L, H, head_dim))
+
+    # ---- Ulysses head-parallel path: the CUDA ops store into peer memory; this double exchanges with
+    # torch.distributed collectives (gloo) so the host orchestration can be tested with world_size > 1 on CPU
+    def qk_norm_rope_sp(self, q_in, k_in, v_in, wq, wk, eps, cos_tab, sin_tab, head_dim, grid, start_frame,
+                        token_offset, sp, q_buf, k_slot_local, v_slot_local, k_slot_ptrs, v_slot_ptrs):
+        import torch.distributed as dist
+        self.launches += 1
+        rows, C = q_in.shape
+        H = C // head_dim
+        Hg = H // sp.world
+        ang = O.rope_angle_table(head_dim)
+        L = grid[0] * grid[1] * grid[2]
+
+        def rot(x):   # rotate as if the rows sat at their chunk-global positions
+            full = x.new_zeros(1, L, H, head_dim)
+            full[0, token_offset:token_offset + rows] = x.view(rows, H, head_dim)
+            return O.rope_rotate(full, grid, ang, start_frame)[0, token_offset:token_offset + rows]
+
+        q = rot(O.rms_norm(q_in, wq, eps))
+        k = rot(O.rms_norm(k_in, wk, eps))
+        v = v_in.view(rows, H, head_dim)
+        for name, t, dst in (("q", q, q_buf.local.view(L, Hg, head_dim)), ("k", k, k_slot_local), ("v", v, v_slot_local)):
+            gathered = [torch.empty_like(t) for _ in range(sp.world)]
+            dist.all_gather(gathered, t.contiguous(), group=sp.group)
+            full = torch.cat(gathered, dim=0)                      # [L, H, D] in token order
+            dst.copy_(full[:, sp.rank * Hg:(sp.rank + 1) * Hg].reshape(dst.shape))
+
+    def attention_sp(self, q, k, v, scale, sp, out_buf, rows_per_rank):
+        import torch.distributed as dist
+        self.launches += 1
+        o = O.dense_attention(q.unsqueeze(0), k.unsqueeze(0), v.unsqueeze(0))[0]      # [L, Hg, D]
+        gathered = [torch.empty_like(o) for _ in range(sp.world)]
+        dist.all_gather(gathered, o.contiguous(), group=sp.group)
+        full = torch.cat(gathered, dim=1)                          # [L, H, D]
+        lo = sp.rank * rows_per_rank
+        out_buf.local.copy_(full[lo:lo + rows_per_rank].reshape(rows_per_rank, -1))
+
+    def peer_barrier(self, sp, epoch):
+        import torch.distributed as dist
+        dist.barrier(group=sp.group)
 
     def patchify(self, x, out):
         self.launches += 1

@@ -52,13 +52,13 @@ def _finish(name, metrics, tol):
 
 
 # --------------------------------------------------------------------------------------
-def check_gemm(M=300, N=256, K=192, epilogue=0, block_n=0, rows_per_gate=100, seed=0):
+def check_gemm(M=300, N=256, K=192, epilogue=0, block_n=0, rows_per_gate=100, seed=0, gate_row_offset=0):
     ops = _ops()
     x = _randn(M, K, seed=seed)
     w = _randn(N, K, seed=seed + 1, scale=1.0 / math.sqrt(K))
     b = _randn(N, seed=seed + 2, scale=0.5)
     res = _randn(M, N, seed=seed + 3)
-    groups = (M + rows_per_gate - 1) // rows_per_gate
+    groups = (M + gate_row_offset + rows_per_gate - 1) // rows_per_gate
     gate_tab = _randn(groups, 3, N, seed=seed + 4)        # strided gate rows like the modulation table
     gate = gate_tab[:, 1]
     out = torch.full((M, N), float("nan"), device="cuda", dtype=BF)
@@ -66,7 +66,7 @@ def check_gemm(M=300, N=256, K=192, epilogue=0, block_n=0, rows_per_gate=100, se
     if epilogue in (2, 3):
         kw["residual"] = res
     if epilogue == 3:
-        kw.update(gate=gate, gate_stride=gate_tab.stride(0), rows_per_gate=rows_per_gate)
+        kw.update(gate=gate, gate_stride=gate_tab.stride(0), rows_per_gate=rows_per_gate, gate_row_offset=gate_row_offset)
     ops.gemm(x, w, b, out, epilogue=epilogue, block_n=block_n, **kw)
     acc = x.float() @ w.float().t() + b.float()
     y = acc.to(BF)
@@ -75,7 +75,7 @@ def check_gemm(M=300, N=256, K=192, epilogue=0, block_n=0, rows_per_gate=100, se
     elif epilogue == 2:
         ref = (res.float() + y.float()).to(BF)
     elif epilogue == 3:
-        g = gate[torch.arange(M, device="cuda") // rows_per_gate]
+        g = gate[(torch.arange(M, device="cuda") + gate_row_offset) // rows_per_gate]
         ref = (res.float() + (y.float() * g.float()).to(BF).float()).to(BF)
     else:
         ref = y
@@ -213,6 +213,103 @@ def check_qk_norm_rope(B=2, F_=2, Hh=5, Ww=7, C=1536, start_frame=3, seed=0, wit
                 kc=torch.zeros(B, cache_rows, H, D, device="cuda", dtype=BF),
                 vc=torch.zeros(B, cache_rows, H, D, device="cuda", dtype=BF))
     return _against_double("qk_norm_rope", run, outs, exact=("vc",))
+
+
+class _FakeGroup:
+    """Stands in for UlyssesGroup in single-GPU kernel checks: `world` ranks emulated in one process."""
+    def __init__(self, world, rank):
+        self.world, self.rank = world, rank
+
+
+def check_qk_norm_rope_sp(P=2, F_=2, Hh=6, Ww=7, C=1536, start_frame=3, seed=0):
+    """The scatter form run once per emulated rank (token slice) into P per-group destinations on ONE GPU must equal
+    the plain kernel's output split by head group: bit-exact."""
+    from self_forcing_b200.model import rope_tables
+    from self_forcing_b200.ulysses import PeerTensor
+    ops = _ops()
+    D = 128
+    H = C // D
+    Hg = H // P
+    L = F_ * Hh * Ww
+    Lr = L // P
+    qkv = _randn(L, 3 * C, seed=seed)
+    wq, wk = _randn(C, seed=seed + 1) * 0.1 + 1, _randn(C, seed=seed + 2) * 0.1 + 1
+    cos, sin = (t.cuda() for t in rope_tables(D))
+    q_ref = torch.zeros(1, L, C, device="cuda", dtype=BF)
+    k_ref = torch.zeros(1, L + 9, H, D, device="cuda", dtype=BF)
+    v_ref = torch.zeros_like(k_ref)
+    ops.qk_norm_rope(qkv[:, :C], qkv[:, C:2 * C], qkv[:, 2 * C:], wq, wk, 1e-6, cos, sin, 1, L, D, (F_, Hh, Ww), start_frame,
+                     q_out=q_ref, k_out=k_ref[:, 4:4 + L], v_out=v_ref[:, 4:4 + L])
+    # per-group destinations ("rank g's" q buffer and head-sharded cache)
+    q_dst = [torch.zeros(L, Hg * D, device="cuda", dtype=BF) for _ in range(P)]
+    k_dst = [torch.zeros(L + 9, Hg, D, device="cuda", dtype=BF) for _ in range(P)]
+    v_dst = [torch.zeros(L + 9, Hg, D, device="cuda", dtype=BF) for _ in range(P)]
+    for r in range(P):
+        rows = slice(r * Lr, (r + 1) * Lr)
+        q_buf = PeerTensor(q_dst[r], [t.data_ptr() for t in q_dst])
+        ops.qk_norm_rope_sp(qkv[rows, :C], qkv[rows, C:2 * C], qkv[rows, 2 * C:], wq, wk, 1e-6, cos, sin, D, (F_, Hh, Ww),
+                            start_frame, r * Lr, _FakeGroup(P, r), q_buf, None, None,
+                            [t[4:].data_ptr() for t in k_dst], [t[4:].data_ptr() for t in v_dst])
+    torch.cuda.synchronize()
+    m = {}
+    for g in range(P):
+        cols = slice(g * Hg * D, (g + 1) * Hg * D)
+        m[f"err_q{g}_mismatch"] = float((q_dst[g] != q_ref[0][:, cols]).sum())
+        m[f"err_k{g}_mismatch"] = float((k_dst[g] != k_ref[0][:, g * Hg:(g + 1) * Hg]).sum())
+        m[f"err_v{g}_mismatch"] = float((v_dst[g] != v_ref[0][:, g * Hg:(g + 1) * Hg]).sum())
+    return _finish("qk_norm_rope_sp", m, 0.0)
+
+
+def check_attention_sp(P=2, Lq=4680, S=9360, Hg=3, seed=0):
+    """Head-parallel form: output rows scattered to P per-rank buffers at this head group's columns must equal the
+    plain kernel's output (same schedule -> bit-exact)."""
+    from self_forcing_b200.ulysses import PeerTensor
+    ops = _ops()
+    D = 128
+    q = _randn(Lq, Hg, D, seed=seed)
+    k = _randn(S, Hg, D, seed=seed + 1)
+    v = _randn(S, Hg, D, seed=seed + 2)
+    ref = torch.zeros(1, Lq, Hg, D, device="cuda", dtype=BF)
+    ops.attention(q.unsqueeze(0), k.unsqueeze(0), v.unsqueeze(0), ref, 1 / math.sqrt(D))
+    rank = 1                                       # pretend to be rank 1 of P: columns [rank*Hg*D, ...)
+    C = P * Hg * D
+    Lr = Lq // P
+    outs = [torch.full((Lr, C), float("nan"), device="cuda", dtype=BF) for _ in range(P)]
+    ops.attention_sp(q, k, v, 1 / math.sqrt(D), _FakeGroup(P, rank), PeerTensor(outs[rank], [t.data_ptr() for t in outs]), Lr)
+    torch.cuda.synchronize()
+    m = {}
+    for d in range(P):
+        got = outs[d][:, rank * Hg * D:(rank + 1) * Hg * D]
+        m[f"err_rows{d}_mismatch"] = float((got != ref[0, d * Lr:(d + 1) * Lr].reshape(Lr, Hg * D)).sum())
+        other = torch.cat([outs[d][:, :rank * Hg * D], outs[d][:, (rank + 1) * Hg * D:]], dim=1)
+        m[f"err_untouched{d}"] = float((~torch.isnan(other.float())).sum())
+    return _finish("attention_sp", m, 0.0)
+
+
+def check_peer_barrier_single():
+    """world = 1 barrier (self-signal) returns; multi-GPU behaviour is covered by tools/ulysses_gpu_check.py."""
+    from self_forcing_b200.ulysses import PeerTensor
+    ops = _ops()
+    flags = torch.zeros(2, device="cuda", dtype=torch.int32)
+
+    class G(_FakeGroup):
+        pass
+    g = G(1, 0)
+    g.flags = PeerTensor(flags, [flags.data_ptr()])
+    for e in (1, 2, 3):
+        ops.peer_barrier(g, e)
+    torch.cuda.synchronize()
+    return _finish("peer_barrier", dict(err_flag=float(abs(int(flags[0]) - 3))), 0.0)
+
+
+def check_ln_row_offset(rows=300, C=1536, seed=0):
+    x = _randn(rows, C, seed=seed)
+    tab = _randn(5, 6, C, seed=seed + 1, scale=0.3)
+
+    def run(ops, o):
+        ops.ln_modulate(x, o["y"], shift=tab[:, 0], scale=tab[:, 1], mod_stride=6 * C, rows_per_mod=130, eps=1e-6,
+                        row_offset=77)
+    return _against_double("ln_modulate row_offset", run, dict(y=torch.zeros(rows, C, device="cuda", dtype=BF)))
 
 
 def check_patchify(B=2, F_=3, H=12, W=20, seed=0):
@@ -368,6 +465,15 @@ ALL = {
     "rmsnorm": check_rmsnorm,
     "qk_norm_rope": check_qk_norm_rope,
     "qk_norm_rope_nov": lambda: check_qk_norm_rope(B=1, with_v=False),
+    "qk_norm_rope_sp": check_qk_norm_rope_sp,
+    "qk_norm_rope_sp4": lambda: check_qk_norm_rope_sp(P=4, Hh=8),
+    "attn_sp": check_attention_sp,
+    "attn_sp4": lambda: check_attention_sp(P=4, Lq=4680, S=4680, Hg=3),
+    "attn_few_items": lambda: check_attention(Lq=1560, S=32760, H=12, seed=9),
+    "peer_barrier": check_peer_barrier_single,
+    "ln_row_offset": check_ln_row_offset,
+    "gemm_gate_row_offset": lambda: check_gemm(M=700, N=512, K=256, epilogue=3, rows_per_gate=130, block_n=512, gate_row_offset=77),
+    "gemm_gate_row_offset_1cta": lambda: check_gemm(M=300, N=384, K=256, epilogue=3, rows_per_gate=70, block_n=128, gate_row_offset=33),
     "patchify": check_patchify,
     "sinusoid": check_sinusoid,
     "skinny_linear": check_skinny_linear,

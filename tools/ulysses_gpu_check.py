@@ -1,0 +1,52 @@
+"""Multi-GPU check of the Ulysses head-parallel path (run under torchrun, one rank per GPU):
+the tiny-depth chunk-wise rollout through the CUDA kernels with peer-memory exchanges must reproduce the golden
+latents made by the unmodified reference (rel-L2 <= 1e-2), give identical latents on every rank, and keep the cache
+indices bit-exact.
+
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 tools/ulysses_gpu_check.py
+"""
+import json
+import os
+import sys
+
+import torch
+import torch.distributed as dist
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+for p in (ROOT, os.path.join(ROOT, "tests")):
+    sys.path.insert(0, p)
+
+
+def main():
+    rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    dist.init_process_group("nccl", device_id=dev)
+    from helpers import golden, make_product_pipeline, patched_randn_like, rel_l2
+    from self_forcing_b200.ulysses import UlyssesGroup
+    g = golden("rollout_tiny.pt")["chunkwise"]
+    pipe, *_, noise = make_product_pipeline(g["case"], dev)
+    sp = UlyssesGroup(device=dev)
+    pipe.generator.model.enable_ulysses(sp)
+    with patched_randn_like(3):
+        _, lat = pipe.inference(noise, ["synthetic"], return_latents=True)
+    torch.cuda.synchronize()
+    err = rel_l2(lat.cpu(), g["latents"])
+    idx = (int(pipe.kv_cache1[0]["global_end_index"]), int(pipe.kv_cache1[-1]["local_end_index"]))
+    gathered = [torch.empty_like(lat) for _ in range(world)]
+    dist.all_gather(gathered, lat.contiguous())
+    same = all(torch.equal(gathered[0], t) for t in gathered)
+    with patched_randn_like(3):      # second call re-uses the peer-mapped caches
+        _, lat2 = pipe.inference(noise, ["synthetic"], return_latents=True)
+    res = dict(rank=rank, world=world, rel_l2=err, index=idx, golden_index=list(g["final_index"]), identical_across_ranks=same,
+               repeatable=bool(torch.equal(lat, lat2)), heads_per_rank=pipe.kv_cache1[0]["k"].shape[2],
+               ok=bool(err <= 1e-2 and tuple(idx) == tuple(g["final_index"]) and same and torch.equal(lat, lat2)))
+    print("ULYSSES_CHECK " + json.dumps(res), flush=True)
+    dist.barrier()
+    dist.destroy_process_group()
+    if not res["ok"]:
+        sys.exit(1)
+
+
+if __name__ == "__main__":
+    main()
