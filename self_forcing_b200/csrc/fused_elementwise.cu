@@ -25,6 +25,11 @@ __device__ __forceinline__ void unpack8(const uint4& q, float (&f)[8]) {
   f[0] = bf_lo(q.x); f[1] = bf_hi(q.x); f[2] = bf_lo(q.y); f[3] = bf_hi(q.y);
   f[4] = bf_lo(q.z); f[5] = bf_hi(q.z); f[6] = bf_lo(q.w); f[7] = bf_hi(q.w);
 }
+// Stops the compiler from keeping the unpacked fp32 copy of a packed row alive across passes (it would otherwise
+// CSE the unpacks and need 2x the registers): after this the vector has to be unpacked again.
+__device__ __forceinline__ void forget_unpacked(uint4& q) {
+  asm volatile("" : "+r"(q.x), "+r"(q.y), "+r"(q.z), "+r"(q.w));
+}
 __device__ __forceinline__ uint4 pack8(const float (&f)[8]) {
   uint4 q;
   q.x = pack_bf16(f[0], f[1]); q.y = pack_bf16(f[2], f[3]);
@@ -61,7 +66,7 @@ __global__ void modulation_table_kernel(const __nv_bfloat16* __restrict__ mod, c
 // LayerNorm (no affine) + adaLN modulation, or LayerNorm with affine.  NV = C / 256.
 // ------------------------------------------------------------------------------------
 template <int NV, bool AFFINE>
-__global__ void __launch_bounds__(ROW_WARPS * 32)
+__global__ void __launch_bounds__(ROW_WARPS * 32, 4)   // 32 rows per SM in flight: a 4680-row chunk is one wave on 148 SMs
 ln_kernel(const __nv_bfloat16* __restrict__ x, long long ldx, __nv_bfloat16* __restrict__ y, long long ldy, int rows,
           float eps, const __nv_bfloat16* __restrict__ shift, const __nv_bfloat16* __restrict__ scale,
           long long mod_stride, int rows_per_mod, int row_offset, const __nv_bfloat16* __restrict__ w,
@@ -70,39 +75,50 @@ ln_kernel(const __nv_bfloat16* __restrict__ x, long long ldx, __nv_bfloat16* __r
   const int row = blockIdx.x * ROW_WARPS + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
   if (row >= rows) return;
-  float v[NV][8];
+  // the row stays in registers as packed bf16 (NV x 16 bytes per lane) and is unpacked per pass: half the registers
+  // of an fp32 copy, which is what lets 32 rows per SM be resident
+  uint4 raw[NV];
   float sum = 0.f;
 #pragma unroll
   for (int k = 0; k < NV; ++k) {
-    unpack8(ldg16(x + row * ldx + (k * 32 + lane) * 8), v[k]);
+    raw[k] = ldg16(x + row * ldx + (k * 32 + lane) * 8);
+    float v[8];
+    unpack8(raw[k], v);
 #pragma unroll
-    for (int i = 0; i < 8; ++i) sum += v[k][i];
+    for (int i = 0; i < 8; ++i) sum += v[i];
   }
   const float mean = warp_sum(sum) * (1.0f / C);
   float sq = 0.f;
 #pragma unroll
-  for (int k = 0; k < NV; ++k)
+  for (int k = 0; k < NV; ++k) {
+    float v[8];
+    forget_unpacked(raw[k]);
+    unpack8(raw[k], v);
 #pragma unroll
-    for (int i = 0; i < 8; ++i) { const float d = v[k][i] - mean; sq += d * d; }
+    for (int i = 0; i < 8; ++i) { const float d = v[i] - mean; sq += d * d; }
+  }
   const float rstd = rsqrtf(warp_sum(sq) * (1.0f / C) + eps);
+#pragma unroll
+  for (int k = 0; k < NV; ++k) forget_unpacked(raw[k]);
   const long long mrow = AFFINE ? 0 : (long long)((row + row_offset) / rows_per_mod) * mod_stride;
 #pragma unroll
   for (int k = 0; k < NV; ++k) {
     const int c0 = (k * 32 + lane) * 8;
-    float o[8];
+    float v[8], o[8];
+    unpack8(raw[k], v);
     if (AFFINE) {
       float ww[8], bb[8];
       unpack8(ldg16(w + c0), ww);
       unpack8(ldg16(b + c0), bb);
 #pragma unroll
-      for (int i = 0; i < 8; ++i) o[i] = (v[k][i] - mean) * rstd * ww[i] + bb[i];
+      for (int i = 0; i < 8; ++i) o[i] = (v[i] - mean) * rstd * ww[i] + bb[i];
     } else {
       float sc[8], sh[8];
       unpack8(ldg16(scale + mrow + c0), sc);
       unpack8(ldg16(shift + mrow + c0), sh);
 #pragma unroll
       for (int i = 0; i < 8; ++i)
-        o[i] = bf16r(bf16r((v[k][i] - mean) * rstd) * bf16r(1.0f + sc[i])) + sh[i];
+        o[i] = bf16r(bf16r((v[i] - mean) * rstd) * bf16r(1.0f + sc[i])) + sh[i];
     }
     *reinterpret_cast<uint4*>(y + row * ldy + c0) = pack8(o);
   }
@@ -130,44 +146,55 @@ struct RopeGeom {
   int n_f, n_h;     // complex pairs on the frame / height axes (22, 21 for d=128); rest is width
 };
 
+// Loads one row as packed bf16 and returns rsqrt(mean(x^2) + eps) (full-width RMSNorm statistics).
 template <int NV>
-__device__ __forceinline__ void rms_row(const __nv_bfloat16* __restrict__ src, const __nv_bfloat16* __restrict__ w,
-                                        float eps, int lane, float (&v)[NV][8]) {
+__device__ __forceinline__ float rms_load(const __nv_bfloat16* __restrict__ src, float eps, int lane, uint4 (&raw)[NV]) {
   constexpr int C = NV * 256;
   float sq = 0.f;
 #pragma unroll
   for (int k = 0; k < NV; ++k) {
-    unpack8(ldg16(src + (k * 32 + lane) * 8), v[k]);
+    raw[k] = ldg16(src + (k * 32 + lane) * 8);
+    float v[8];
+    unpack8(raw[k], v);
 #pragma unroll
-    for (int i = 0; i < 8; ++i) sq += v[k][i] * v[k][i];
+    for (int i = 0; i < 8; ++i) sq += v[i] * v[i];
   }
-  const float rstd = rsqrtf(warp_sum(sq) * (1.0f / C) + eps);
+  return rsqrtf(warp_sum(sq) * (1.0f / C) + eps);
+}
+// k-th 16-byte vector of the normalised row: bf16(bf16(x * rstd) * w)
+template <int NV>
+__device__ __forceinline__ void rms_apply(const uint4& raw, const __nv_bfloat16* __restrict__ w, float rstd, int k, int lane,
+                                          float (&v)[8]) {
+  float ww[8];
+  uint4 r = raw;
+  forget_unpacked(r);
+  unpack8(r, v);
+  unpack8(ldg16(w + (k * 32 + lane) * 8), ww);
 #pragma unroll
-  for (int k = 0; k < NV; ++k) {
-    float ww[8];
-    unpack8(ldg16(w + (k * 32 + lane) * 8), ww);
-#pragma unroll
-    for (int i = 0; i < 8; ++i) v[k][i] = bf16r(bf16r(v[k][i] * rstd) * ww[i]);
-  }
+  for (int i = 0; i < 8; ++i) v[i] = bf16r(bf16r(v[i] * rstd) * ww[i]);
 }
 
 template <int NV>
-__global__ void __launch_bounds__(ROW_WARPS * 32)
+__global__ void __launch_bounds__(ROW_WARPS * 32, 4)
 rmsnorm_kernel(const __nv_bfloat16* __restrict__ x, long long ldx, __nv_bfloat16* __restrict__ y, long long ldy,
                int rows, float eps, const __nv_bfloat16* __restrict__ w) {
   const int row = blockIdx.x * ROW_WARPS + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
   if (row >= rows) return;
-  float v[NV][8];
-  rms_row<NV>(x + row * ldx, w, eps, lane, v);
+  uint4 raw[NV];
+  const float rstd = rms_load<NV>(x + row * ldx, eps, lane, raw);
 #pragma unroll
-  for (int k = 0; k < NV; ++k) *reinterpret_cast<uint4*>(y + row * ldy + (k * 32 + lane) * 8) = pack8(v[k]);
+  for (int k = 0; k < NV; ++k) {
+    float v[8];
+    rms_apply<NV>(raw[k], w, rstd, k, lane, v);
+    *reinterpret_cast<uint4*>(y + row * ldy + (k * 32 + lane) * 8) = pack8(v);
+  }
 }
 
 // One warp per token: q and k rows normalised + rotated; q -> q_out, k -> cache slot, v -> cache slot.
 // Rows are (sample b, token n): source row = b * L + n; destinations use their own batch strides.
 template <int NV>
-__global__ void __launch_bounds__(ROW_WARPS * 32)
+__global__ void __launch_bounds__(ROW_WARPS * 32, 4)
 qk_norm_rope_kernel(const __nv_bfloat16* __restrict__ q_in, long long ldq, const __nv_bfloat16* __restrict__ k_in,
                     long long ldk, const __nv_bfloat16* __restrict__ v_in, long long ldv,
                     const __nv_bfloat16* __restrict__ wq, const __nv_bfloat16* __restrict__ wk, float eps,
@@ -184,57 +211,42 @@ qk_norm_rope_kernel(const __nv_bfloat16* __restrict__ q_in, long long ldq, const
   const int half = head_dim / 2;
   const int pos_f = g.start_frame + f;
 
-  // rotation factors of this lane's 4 complex pairs per 16-byte vector (same for q and k)
-  float cs[NV][4], sn[NV][4];
+  // q then k: load the row (packed), full-width RMS statistics, then per 16-byte vector: normalise, rotate the 4
+  // complex pairs by the (frame | height | width) angles of this token, store to the vector's head-group destination
+  uint4 raw[NV];
+#pragma unroll 1
+  for (int which = 0; which < 2; ++which) {
+    const __nv_bfloat16* src = which == 0 ? q_in + row * ldq : k_in + row * ldk;
+    const __nv_bfloat16* wgt = which == 0 ? wq : wk;
+    const long long off = which == 0 ? b * q_out_batch + n * q_out_row : b * kv_out_batch + n * kv_out_row;
+    const float rstd = rms_load<NV>(src, eps, lane, raw);
 #pragma unroll
-  for (int k = 0; k < NV; ++k) {
-    const int c0 = (k * 32 + lane) * 8;
-    const int pair0 = (c0 % head_dim) / 2;
+    for (int k = 0; k < NV; ++k) {
+      const int c0 = (k * 32 + lane) * 8;
+      const int pair0 = (c0 % head_dim) / 2;
+      float v[8], o[8];
+      rms_apply<NV>(raw[k], wgt, rstd, k, lane, v);
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      const int pi = pair0 + i;
-      const int pos = pi < g.n_f ? pos_f : (pi < g.n_f + g.n_h ? hh : ww);
-      cs[k][i] = __ldg(cos_tab + pos * half + pi);
-      sn[k][i] = __ldg(sin_tab + pos * half + pi);
+      for (int i = 0; i < 4; ++i) {
+        const int pi = pair0 + i;
+        const int pos = pi < g.n_f ? pos_f : (pi < g.n_f + g.n_h ? hh : ww);
+        const float cs = __ldg(cos_tab + pos * half + pi), sn = __ldg(sin_tab + pos * half + pi);
+        o[2 * i] = v[2 * i] * cs - v[2 * i + 1] * sn;
+        o[2 * i + 1] = v[2 * i] * sn + v[2 * i + 1] * cs;
+      }
+      const int grp = hs.groups == 1 ? 0 : c0 / hs.group_cols;
+      __nv_bfloat16* dst = (which == 0 ? hs.q[grp] : hs.k[grp]) + off + (c0 - grp * hs.group_cols);
+      *reinterpret_cast<uint4*>(dst) = pack8(o);
     }
-  }
-  float v[NV][8];
-  // destination of this lane's k-th 16-byte vector: head group, column inside the group
-  int grp[NV], gcol[NV];
-#pragma unroll
-  for (int k = 0; k < NV; ++k) {
-    const int c0 = (k * 32 + lane) * 8;
-    grp[k] = hs.groups == 1 ? 0 : c0 / hs.group_cols;
-    gcol[k] = c0 - grp[k] * hs.group_cols;
-  }
-  rms_row<NV>(q_in + row * ldq, wq, eps, lane, v);
-  const long long q_off = b * q_out_batch + n * q_out_row;
-#pragma unroll
-  for (int k = 0; k < NV; ++k) {
-    float o[8];
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      o[2 * i] = v[k][2 * i] * cs[k][i] - v[k][2 * i + 1] * sn[k][i];
-      o[2 * i + 1] = v[k][2 * i] * sn[k][i] + v[k][2 * i + 1] * cs[k][i];
-    }
-    *reinterpret_cast<uint4*>(hs.q[grp[k]] + q_off + gcol[k]) = pack8(o);
-  }
-  rms_row<NV>(k_in + row * ldk, wk, eps, lane, v);
-  const long long kv_off = b * kv_out_batch + n * kv_out_row;
-#pragma unroll
-  for (int k = 0; k < NV; ++k) {
-    float o[8];
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      o[2 * i] = v[k][2 * i] * cs[k][i] - v[k][2 * i + 1] * sn[k][i];
-      o[2 * i + 1] = v[k][2 * i] * sn[k][i] + v[k][2 * i + 1] * cs[k][i];
-    }
-    *reinterpret_cast<uint4*>(hs.k[grp[k]] + kv_off + gcol[k]) = pack8(o);
   }
   if (v_in != nullptr) {
+    const long long kv_off = b * kv_out_batch + n * kv_out_row;
 #pragma unroll
-    for (int k = 0; k < NV; ++k)
-      *reinterpret_cast<uint4*>(hs.v[grp[k]] + kv_off + gcol[k]) = ldg16(v_in + row * ldv + (k * 32 + lane) * 8);
+    for (int k = 0; k < NV; ++k) {
+      const int c0 = (k * 32 + lane) * 8;
+      const int grp = hs.groups == 1 ? 0 : c0 / hs.group_cols;
+      *reinterpret_cast<uint4*>(hs.v[grp] + kv_off + (c0 - grp * hs.group_cols)) = ldg16(v_in + row * ldv + c0);
+    }
   }
 }
 

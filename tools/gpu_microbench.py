@@ -91,6 +91,35 @@ def main():
         print(json.dumps(rec), flush=True)
         out.append(rec)
     os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
+    if not only or any(o in "elementwise" for o in only):
+        from self_forcing_b200.model import rope_tables
+        L, C = 4680, 1536
+        x = torch.randn(L, C, device="cuda").to(BF); y = torch.empty_like(x)
+        qkv = torch.randn(L, 3 * C, device="cuda").to(BF)
+        tab = torch.randn(3, 6, C, device="cuda").to(BF)
+        w = torch.randn(C, device="cuda").to(BF); b = torch.randn(C, device="cuda").to(BF)
+        cos, sin = (t.cuda() for t in rope_tables(128))
+        qo = torch.empty(1, L, C, device="cuda", dtype=BF)
+        kc = torch.empty(1, L, 12, 128, device="cuda", dtype=BF); vc = torch.empty_like(kc)
+        cases = [
+            ("ln_modulate", 2 * L * C * 2, lambda: ops.ln_modulate(x, y, shift=tab[:, 0], scale=tab[:, 1], mod_stride=6 * C, rows_per_mod=1560, eps=1e-6)),
+            ("ln_affine", 2 * L * C * 2, lambda: ops.ln_affine(x, y, w, b, 1e-6)),
+            ("rmsnorm", 2 * L * C * 2, lambda: ops.rmsnorm(x, y, w, 1e-6)),
+            ("qk_norm_rope", 6 * L * C * 2, lambda: ops.qk_norm_rope(qkv[:, :C], qkv[:, C:2 * C], qkv[:, 2 * C:], w, w, 1e-6, cos, sin, 1, L, 128, (3, 30, 52), 0, q_out=qo, k_out=kc, v_out=vc)),
+        ]
+        for name, nbytes, fn in cases:
+            for _ in range(3): fn()
+            torch.cuda.synchronize()
+            a, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            for _ in range(50): fn()
+            e.record(); torch.cuda.synchronize()
+            us = a.elapsed_time(e) / 50 * 1e3
+            med, _ = timeit(fn, flush=flush)
+            rec = dict(kernel="ew_" + name, us_back_to_back=us, gbs_back_to_back=nbytes / us / 1e3, us_cold=med * 1e3,
+                       gbs_cold=nbytes / med / 1e6)
+            print(json.dumps(rec), flush=True)
+            out.append(rec)
     tag = os.environ.get("SFB_MICROBENCH_TAG", "")
     with open(os.path.join(ROOT, "gpurun_out", f"microbench{tag}.json"), "w") as f:
         json.dump(out, f, indent=1)
