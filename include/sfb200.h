@@ -20,7 +20,7 @@
 extern "C" {
 #endif
 
-#define SFB_ABI_VERSION 3
+#define SFB_ABI_VERSION 4
 
 const char* sfb_last_error(void);
 int sfb_abi_version(void);
@@ -44,7 +44,12 @@ int sfb_gemm_bf16(const void* x, long long ldx, const void* w, long long ldw, co
                   void* out0, long long ldo0, void* out1, long long ldo1, void* out2, long long ldo2, int seg_cols,
                   const void* residual, long long ldr,
                   const void* gate, long long gate_stride, int rows_per_gate, int gate_row_offset,
-                  int block_n, void* stream);
+                  int block_n, void* workspace, long long workspace_bytes, void* stream);
+
+/* Scratch (bytes) for the stream-K schedule of the CTA-pair GEMM (used when whole tiles would leave the last wave
+ * badly filled, e.g. 4680 x 1536 outputs = 114 tiles on 74 CTA pairs): caller-owned, zero-initialised once, one launch
+ * at a time per workspace.  workspace == NULL disables stream-K. */
+long long sfb_gemm_workspace_bytes(void);
 
 /* softmax(q k^T * scale) v without mask, head_dim 128, K/V read in place from a [B,S,H,128] cache
  * window.  Replaces wan/modules/attention.py:32-202 (flash_attn_varlen_func at :136-150) as called

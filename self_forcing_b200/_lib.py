@@ -13,11 +13,11 @@ LIB_PATH = os.path.join(HERE, "libsfb200.so")
 
 P, LL, I, F = c_void_p, c_longlong, c_int, c_float
 PP = ctypes.POINTER(c_void_p)
-ABI_VERSION = 3
+ABI_VERSION = 4
 
 # name -> argtypes, mirroring include/sfb200.h one to one
 SIGNATURES = {
-    "sfb_gemm_bf16": [P, LL, P, LL, P, I, I, I, I, P, LL, P, LL, P, LL, I, P, LL, P, LL, I, I, I, P],
+    "sfb_gemm_bf16": [P, LL, P, LL, P, I, I, I, I, P, LL, P, LL, P, LL, I, P, LL, P, LL, I, I, I, P, LL, P],
     "sfb_attention_fwd": [P, LL, LL, P, P, LL, LL, P, LL, LL, I, I, I, I, I, F, P, LL, P],
     "sfb_modulation_table": [P, P, P, I, I, I, I, LL, LL, P],
     "sfb_ln_modulate": [P, LL, P, LL, I, I, F, P, P, LL, I, I, P],
@@ -65,6 +65,8 @@ def load(path: str | None = None) -> ctypes.CDLL:
     lib.sfb_abi_version.argtypes = []
     lib.sfb_attention_workspace_bytes.restype = c_longlong
     lib.sfb_attention_workspace_bytes.argtypes = []
+    lib.sfb_gemm_workspace_bytes.restype = c_longlong
+    lib.sfb_gemm_workspace_bytes.argtypes = []
     for name, argtypes in SIGNATURES.items():
         fn = getattr(lib, name)
         fn.argtypes = argtypes

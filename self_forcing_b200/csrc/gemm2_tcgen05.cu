@@ -17,6 +17,8 @@
 // TMA loads while the main loop of the tile is still running, and updated in place.  (A per-thread
 // row-strided epilogue -- 16-byte global loads/stores at a 3 KB row pitch -- measured 24 k .. 54 k cycles per
 // tile on B200, longer than the 18 k-cycle main loop of a K=1536 tile, and became the bound.)
+#include <stdlib.h>
+
 #include "gemm_common.cuh"
 
 namespace sfb {
@@ -33,6 +35,32 @@ constexpr int G2_B_BYTES = (G2_BN / 2) * G2_BK * 2;
 constexpr int G2_STAGE_BYTES = G2_A_BYTES + G2_B_BYTES;
 constexpr int G2_SMEM_BYTES = G2_STAGES * G2_STAGE_BYTES + G2_NSUB * G2_SUB_BYTES + 1024 + 256;
 constexpr int G2_THREADS = 192;
+constexpr int G2_MAX_PAIRS = 96;       // stream-K workspace slots
+
+// This pair's contiguous range of (tile, k-block) work, walked tile by tile.  Without stream-K the range is a whole
+// number of tiles; with it the range is W / pairs k-blocks and a tile can be cut once (host guarantees tiles >= pairs).
+struct PairRange {
+  long long cur, end;
+  int kbs;
+  __device__ PairRange(const GemmParams& p, int pair, int num_pairs) : kbs(p.num_k_blocks) {
+    const long long tiles = (long long)p.num_m_blocks * p.num_n_blocks;
+    if (p.streamk) {
+      cur = tiles * kbs * pair / num_pairs;
+      end = tiles * kbs * (pair + 1) / num_pairs;
+    } else {
+      cur = (tiles * pair / num_pairs) * kbs;
+      end = (tiles * (pair + 1) / num_pairs) * kbs;
+    }
+  }
+  __device__ bool next(int& tile, int& kb0, int& kb1) {
+    if (cur >= end) return false;
+    tile = (int)(cur / kbs);
+    kb0 = (int)(cur - (long long)tile * kbs);
+    kb1 = (end - cur) < (long long)(kbs - kb0) ? kb0 + (int)(end - cur) : kbs;
+    cur += kb1 - kb0;
+    return true;
+  }
+};
 
 template <int EPI>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(G2_THREADS, 1)
@@ -75,7 +103,6 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_consta
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
-  const int num_tiles = p.num_m_blocks * p.num_n_blocks;   // pair tiles
   const int pair = blockIdx.x >> 1;
   const int num_pairs = gridDim.x >> 1;
 
@@ -84,11 +111,13 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_consta
     {
       int stage = 0;
       uint32_t phase = 0;
-      for (int tile = pair; tile < num_tiles; tile += num_pairs) {
+      PairRange range(p, pair, num_pairs);
+      int tile, kb0, kb1;
+      while (range.next(tile, kb0, kb1)) {
         const int m_blk = tile % p.num_m_blocks, n_blk = tile / p.num_m_blocks;
         const int a_row = m_blk * (2 * G2_ROWS) + rank * G2_ROWS;
         const int b_row = n_blk * G2_BN + rank * (G2_BN / 2);
-        for (int kb = 0; kb < p.num_k_blocks; ++kb) {
+        for (int kb = kb0; kb < kb1; ++kb) {
           mbar_wait(&empty_bar[stage], phase ^ 1);
           if (elect_one()) {
             uint8_t* a_dst = smem + stage * G2_STAGE_BYTES;
@@ -109,13 +138,15 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_consta
       int stage = 0;
       uint32_t phase = 0;
       int it = 0;
-      for (int tile = pair; tile < num_tiles; tile += num_pairs, ++it) {
+      PairRange range(p, pair, num_pairs);
+      int tile, kb0, kb1;
+      for (; range.next(tile, kb0, kb1); ++it) {
         const int acc = it & 1;
         const uint32_t acc_phase = (it >> 1) & 1;
         mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + acc * G2_BN;
-        for (int kb = 0; kb < p.num_k_blocks; ++kb) {
+        for (int kb = kb0; kb < kb1; ++kb) {
           mbar_wait(&full_bar[stage], phase);
           tc_fence_after();
           if (elect_one()) {
@@ -124,9 +155,9 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_consta
             const uint64_t b_desc = umma_desc_sw128(a_addr + G2_A_BYTES, 16, 1024);
 #pragma unroll
             for (int k = 0; k < G2_BK / 16; ++k)
-              umma_ss_pair(d_tmem, a_desc + 2 * k, b_desc + 2 * k, idesc, (kb | k) != 0);
+              umma_ss_pair(d_tmem, a_desc + 2 * k, b_desc + 2 * k, idesc, (kb != kb0 || k != 0) ? 1u : 0u);
             umma_commit_pair(&empty_bar[stage], 3);   // both CTAs' smem slots are free once these retire
-            if (kb == p.num_k_blocks - 1) umma_commit_pair(&tmem_full[acc], 3);
+            if (kb == kb1 - 1) umma_commit_pair(&tmem_full[acc], 3);
           }
           __syncwarp();
           if (++stage == G2_STAGES) { stage = 0; phase ^= 1; }
@@ -147,12 +178,42 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_consta
     }
     uint32_t res_phase = 0;
     int it = 0;
-    for (int tile = pair; tile < num_tiles; tile += num_pairs, ++it) {
+    PairRange range(p, pair, num_pairs);
+    int tile, kb0, kb1;
+    for (; range.next(tile, kb0, kb1); ++it) {
       const int m_blk = tile % p.num_m_blocks, n_blk = tile / p.num_m_blocks;
       const int acc = it & 1;
       const uint32_t acc_phase = (it >> 1) & 1;
       const int row0 = m_blk * (2 * G2_ROWS) + rank * G2_ROWS;
       const int n0 = n_blk * G2_BN;
+      const uint32_t t_row = tmem_base + ((uint32_t)(quarter * 32) << 16) + acc * G2_BN;
+      const bool tail_part = kb0 > 0;                        // stream-K: this pair holds k-blocks [kb0, K) of the tile
+      const bool head_part = kb0 == 0 && kb1 < p.num_k_blocks;   // ... or [0, kb1): it finishes the tile
+
+      if (tail_part) {
+        // park the fp32 partial (transposed: consecutive lanes = consecutive rows -> coalesced) for the pair that
+        // owns the head of this tile (the previous pair), then publish it
+        float* slot = p.sk_ws + ((long long)(pair - 1) * 2 + rank) * (G2_BN * G2_ROWS);
+        mbar_wait(&tmem_full[acc], acc_phase);
+        tc_fence_after();
+#pragma unroll 1
+        for (int c = 0; c < G2_BN / 32; ++c) {
+          uint32_t v[32];
+          tmem_ld32(t_row + c * 32, v);
+          tmem_ld_wait();
+#pragma unroll
+          for (int i = 0; i < 32; ++i) slot[(c * 32 + i) * G2_ROWS + r_local] = __uint_as_float(v[i]);
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive_cluster(leader_empty0 + acc * 8);
+        __threadfence();
+        named_barrier_sync(1, 128);
+        if (warp == 2 && lane == 0)
+          asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(p.sk_flags + (pair - 1) * 2 + rank), "r"(p.sk_epoch) : "memory");
+        continue;
+      }
+
       const int seg = n0 / p.seg_cols;
       const int seg_col0 = n0 - seg * p.seg_cols;
       const CUtensorMap* omap = seg == 0 ? &tma_out0 : (seg == 1 ? &tma_out1 : &tma_out2);
@@ -171,17 +232,30 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_consta
         mbar_wait(res_full, res_phase);
         res_phase ^= 1;
       }
+      const float* part = nullptr;
+      if (head_part) {   // the tail of this tile was computed by the next pair at the very start of its range
+        part = p.sk_ws + ((long long)pair * 2 + rank) * (G2_BN * G2_ROWS);
+        const int* flag = p.sk_flags + pair * 2 + rank;
+        int seen;
+        do {
+          asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(seen) : "l"(flag) : "memory");
+        } while (seen != p.sk_epoch);
+      }
       const int row = row0 + r_local;
       const __nv_bfloat16* grow = nullptr;
       if (EPI == EPI_GATE_RES)
         grow = p.gate + (long long)(((row < p.M ? row : p.M - 1) + p.gate_row_offset) / p.rows_per_gate) * p.gate_stride + n0;
-      const uint32_t t_row = tmem_base + ((uint32_t)(quarter * 32) << 16) + acc * G2_BN;
 #pragma unroll 1
       for (int sb = 0; sb < G2_NSUB; ++sb) {
         uint32_t v[64];
         tmem_ld32(t_row + sb * G2_SUB, *reinterpret_cast<uint32_t(*)[32]>(&v[0]));
         tmem_ld32(t_row + sb * G2_SUB + 32, *reinterpret_cast<uint32_t(*)[32]>(&v[32]));
         tmem_ld_wait();
+        if (part != nullptr) {
+#pragma unroll
+          for (int i = 0; i < 64; ++i)
+            v[i] = __float_as_uint(__uint_as_float(v[i]) + __ldcg(part + (sb * G2_SUB + i) * G2_ROWS + r_local));
+        }
         uint8_t* buf_row = my_row + sb * G2_SUB_BYTES;
 #pragma unroll
         for (int c = 0; c < 8; ++c) {
@@ -241,7 +315,16 @@ static int launch_gemm2(const CUtensorMap& ta, const CUtensorMap& tb, const Pair
   }
   const int tiles = p.num_m_blocks * p.num_n_blocks;
   const int clusters = tiles < max_clusters ? tiles : max_clusters;
-  kern<<<2 * clusters, G2_THREADS, G2_SMEM_BYTES, stream>>>(ta, tb, pm.out[0], pm.out[1], pm.out[2], pm.res, p);
+  GemmParams q = p;
+  // stream-K for badly filled last waves (e.g. 114 tiles on 74 pairs = 2 waves at 77 %).  OFF by default: measured on
+  // B200 it LOSES 4-8 us per GEMM (QKV 55 -> 63 us, O-proj 39 -> 47 us, FFN2 113 -> 118 us): the main loop is bound by
+  // the chip-wide L2 -> SM fill rate (~9.5 TB/s, 128 FLOP/B for 256 x 256 pair tiles), so a thinner last wave simply
+  // runs faster per tile, while the split adds an exposed partial read + epilogue at the end.  SFB_GEMM_STREAMK=1 enables.
+  const int waves = (tiles + clusters - 1) / clusters;
+  static const bool sk_off = getenv("SFB_GEMM_STREAMK") == nullptr;
+  q.streamk = (!sk_off && q.sk_ws != nullptr && tiles >= clusters && tiles % clusters != 0 && clusters <= G2_MAX_PAIRS &&
+               (double)tiles / ((double)clusters * waves) < 0.95) ? 1 : 0;
+  kern<<<2 * clusters, G2_THREADS, G2_SMEM_BYTES, stream>>>(ta, tb, pm.out[0], pm.out[1], pm.out[2], pm.res, q);
   return check_cuda(cudaGetLastError(), "gemm2 launch");
 }
 
@@ -272,6 +355,19 @@ int launch_gemm_pair(int epi, const CUtensorMap& ta, const CUtensorMap& tb, cons
   }
   set_error("sfb_gemm_bf16: unknown epilogue %d", epi);
   return SFB_ERR_INVALID;
+}
+
+long long gemm_pair_workspace_bytes() {
+  return 1024 + (long long)G2_MAX_PAIRS * 2 * (G2_BN * G2_ROWS * (long long)sizeof(float));   // flags | partial slots
+}
+// carve the caller's workspace: flags first (zero-initialised once by the caller), then the partial slots
+void gemm_pair_workspace(void* ws, long long bytes, GemmParams& p) {
+  static int epoch = 0;
+  p.sk_ws = nullptr; p.sk_flags = nullptr; p.sk_epoch = 0;
+  if (ws == nullptr || bytes < gemm_pair_workspace_bytes()) return;
+  p.sk_flags = static_cast<int*>(ws);
+  p.sk_ws = reinterpret_cast<float*>(static_cast<char*>(ws) + 1024);
+  p.sk_epoch = ++epoch;
 }
 
 }  // namespace sfb

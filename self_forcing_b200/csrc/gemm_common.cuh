@@ -21,6 +21,12 @@ struct GemmParams {
   long long gate_stride;
   int rows_per_gate;
   int gate_row_offset;         // chunk-global index of row 0 (sequence-parallel callers hold a slice of the rows)
+  // stream-K (CTA-pair kernel only): the tile x k-block space is cut into one contiguous range per CTA pair; a tile
+  // cut in two leaves its tail (fp32, transposed) in sk_ws and the owner of its head adds it before the epilogue
+  int streamk;
+  float* sk_ws;                // [pairs][2 CTAs][256 cols][128 rows] fp32
+  int* sk_flags;               // [pairs][2 CTAs], holds sk_epoch once the partial is complete
+  int sk_epoch;
 };
 
 __device__ __forceinline__ float gelu_tanh_f(float x) {

@@ -185,6 +185,8 @@ static int dispatch_epi(int epi, const CUtensorMap& ta, const CUtensorMap& tb, c
 int device_sm_count();
 int launch_gemm_pair(int epi, const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& p, int num_sms,
                      cudaStream_t stream);
+long long gemm_pair_workspace_bytes();
+void gemm_pair_workspace(void* ws, long long bytes, GemmParams& p);
 
 }  // namespace sfb
 
@@ -192,7 +194,8 @@ extern "C" int sfb_gemm_bf16(const void* x, long long ldx, const void* w, long l
                              int M, int N, int K, int epilogue, void* out0, long long ldo0, void* out1,
                              long long ldo1, void* out2, long long ldo2, int seg_cols, const void* residual,
                              long long ldr, const void* gate, long long gate_stride, int rows_per_gate,
-                             int gate_row_offset, int block_n, void* stream_) {
+                             int gate_row_offset, int block_n, void* workspace, long long workspace_bytes,
+                             void* stream_) {
   using namespace sfb;
   cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
   if (M <= 0 || N <= 0 || K <= 0) { set_error("sfb_gemm_bf16: empty problem M=%d N=%d K=%d", M, N, K); return SFB_ERR_INVALID; }
@@ -250,10 +253,17 @@ extern "C" int sfb_gemm_bf16(const void* x, long long ldx, const void* w, long l
   }
   const int sms = device_sm_count();
   if (sms <= 0) return SFB_ERR_CUDA;
-  if (pair) return launch_gemm_pair(epilogue, ta, tb, p, sms, stream);
+  if (pair) {
+    gemm_pair_workspace(workspace, workspace_bytes, p);
+    return launch_gemm_pair(epilogue, ta, tb, p, sms, stream);
+  }
   switch (block_n) {
     case 64: return dispatch_epi<64>(epilogue, ta, tb, p, sms, stream);
     case 128: return dispatch_epi<128>(epilogue, ta, tb, p, sms, stream);
     default: return dispatch_epi<256>(epilogue, ta, tb, p, sms, stream);
   }
 }
+
+// Scratch (bytes) the CTA-pair GEMM uses for stream-K partial tiles; zero-initialise it once.  One launch at a time
+// may use a given workspace (launches on one stream are fine).
+extern "C" long long sfb_gemm_workspace_bytes(void) { return sfb::gemm_pair_workspace_bytes(); }

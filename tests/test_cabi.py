@@ -30,10 +30,10 @@ def test_header_symbols_exported(lib_path):
 
 def test_binding_covers_header(lib_path):
     from self_forcing_b200 import _lib
-    declared = set(_declared()) - {"sfb_last_error", "sfb_abi_version", "sfb_attention_workspace_bytes"}
+    declared = set(_declared()) - {"sfb_last_error", "sfb_abi_version", "sfb_attention_workspace_bytes", "sfb_gemm_workspace_bytes"}
     assert declared == set(_lib.SIGNATURES), declared ^ set(_lib.SIGNATURES)
     lib = _lib.load(lib_path)
-    assert lib.sfb_abi_version() == 3
+    assert lib.sfb_abi_version() == 4
     assert isinstance(lib.sfb_last_error(), bytes)
 
 
@@ -43,7 +43,7 @@ def test_argument_errors_are_reported_without_a_gpu(lib_path):
     lib = _lib.load(lib_path)
     rc = lib.sfb_attention_fwd(None, 0, 0, None, None, 0, 0, None, 0, 0, 1, 16, 16, 1, 64, 1.0, None, 0, None)
     assert rc != 0 and b"head_dim" in lib.sfb_last_error()
-    rc = lib.sfb_gemm_bf16(None, 8, None, 8, None, 4, 10, 8, 0, None, 8, None, 0, None, 0, 0, None, 0, None, 0, 1, 0, 0, None)
+    rc = lib.sfb_gemm_bf16(None, 8, None, 8, None, 4, 10, 8, 0, None, 8, None, 0, None, 0, 0, None, 0, None, 0, 1, 0, 0, None, 0, None)
     assert rc != 0 and b"multiples of 8" in lib.sfb_last_error()
     with pytest.raises(_lib.SfbError):
         _lib.check(rc, "sfb_gemm_bf16")
