@@ -121,10 +121,11 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_consta
           mbar_wait(&empty_bar[stage], phase ^ 1);
           if (elect_one()) {
             uint8_t* a_dst = smem + stage * G2_STAGE_BYTES;
-            if (leader) mbar_expect_tx(&full_bar[stage], 2 * G2_STAGE_BYTES);
+            const bool skip_b = p.experiment_skip_b && (kb & 1);   // DIAGNOSTIC ONLY (wrong results): halves the B traffic
+            if (leader) mbar_expect_tx(&full_bar[stage], skip_b ? 2 * G2_A_BYTES : 2 * G2_STAGE_BYTES);
             const uint32_t bar = mapa_cluster(smem_u32(&full_bar[stage]), 0);
             tma_load_2d_pair(a_dst, &tma_a, bar, kb * G2_BK, a_row);
-            tma_load_2d_pair(a_dst + G2_A_BYTES, &tma_b, bar, kb * G2_BK, b_row);
+            if (!skip_b) tma_load_2d_pair(a_dst + G2_A_BYTES, &tma_b, bar, kb * G2_BK, b_row);
           }
           __syncwarp();
           if (++stage == G2_STAGES) { stage = 0; phase ^= 1; }
@@ -316,6 +317,8 @@ static int launch_gemm2(const CUtensorMap& ta, const CUtensorMap& tb, const Pair
   const int tiles = p.num_m_blocks * p.num_n_blocks;
   const int clusters = tiles < max_clusters ? tiles : max_clusters;
   GemmParams q = p;
+  static const bool exp_skip = getenv("SFB_GEMM_EXPERIMENT_SKIP_B") != nullptr;   // diagnostic: see the producer
+  q.experiment_skip_b = exp_skip ? 1 : 0;
   // stream-K for badly filled last waves (e.g. 114 tiles on 74 pairs = 2 waves at 77 %).  OFF by default: measured on
   // B200 it LOSES 4-8 us per GEMM (QKV 55 -> 63 us, O-proj 39 -> 47 us, FFN2 113 -> 118 us): the main loop is bound by
   // the chip-wide L2 -> SM fill rate (~9.5 TB/s, 128 FLOP/B for 256 x 256 pair tiles), so a thinner last wave simply
