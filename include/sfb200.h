@@ -38,7 +38,7 @@ int sfb_abi_version(void);
  * `gate` row for output row r is gate + ((r + gate_row_offset) / rows_per_gate) * gate_stride (per-frame adaLN
  * gate; gate_row_offset = chunk-global index of row 0 for sequence-parallel callers that hold a slice of the rows).
  * out may alias residual.  block_n: 0 = choose; 64/128/256 = one-CTA tiles of 128 x block_n; 512 = CTA-pair
- * (tcgen05 cta_group::2) tiles of 256 x 256. */
+ * (tcgen05 cta_group::2) tiles of 256 x 256; 513 = the same with the stream-K schedule (needs the workspace). */
 int sfb_gemm_bf16(const void* x, long long ldx, const void* w, long long ldw, const void* bias,
                   int M, int N, int K, int epilogue,
                   void* out0, long long ldo0, void* out1, long long ldo1, void* out2, long long ldo2, int seg_cols,

@@ -324,8 +324,8 @@ static int launch_gemm2(const CUtensorMap& ta, const CUtensorMap& tb, const Pair
   // the chip-wide L2 -> SM fill rate (~9.5 TB/s, 128 FLOP/B for 256 x 256 pair tiles), so a thinner last wave simply
   // runs faster per tile, while the split adds an exposed partial read + epilogue at the end.  SFB_GEMM_STREAMK=1 enables.
   const int waves = (tiles + clusters - 1) / clusters;
-  static const bool sk_off = getenv("SFB_GEMM_STREAMK") == nullptr;
-  q.streamk = (!sk_off && q.sk_ws != nullptr && tiles >= clusters && tiles % clusters != 0 && clusters <= G2_MAX_PAIRS &&
+  static const bool sk_env = getenv("SFB_GEMM_STREAMK") != nullptr;
+  q.streamk = ((sk_env || p.streamk) && q.sk_ws != nullptr && tiles >= clusters && tiles % clusters != 0 && clusters <= G2_MAX_PAIRS &&
                (double)tiles / ((double)clusters * waves) < 0.95) ? 1 : 0;
   kern<<<2 * clusters, G2_THREADS, G2_SMEM_BYTES, stream>>>(ta, tb, pm.out[0], pm.out[1], pm.out[2], pm.res, q);
   return check_cuda(cudaGetLastError(), "gemm2 launch");

@@ -213,7 +213,8 @@ extern "C" int sfb_gemm_bf16(const void* x, long long ldx, const void* w, long l
     // fills the 148 SMs (M=4680: N=1536 -> 37x12 = 444 = 3 waves of 148).
     block_n = (N % 256 == 0 && N >= 4096) ? 256 : (N % 128 == 0 ? 128 : 64);
   }
-  const bool pair = block_n == 512;
+  const bool pair = block_n == 512 || block_n == 513;   // 513: pair tiles with the stream-K schedule forced on
+  const bool force_streamk = block_n == 513;
   if (pair) block_n = 256;
   if (block_n != 64 && block_n != 128 && block_n != 256) { set_error("sfb_gemm_bf16: block_n must be 64/128/256/512"); return SFB_ERR_INVALID; }
   if (seg_cols % block_n) { set_error("sfb_gemm_bf16: seg_cols=%d not a multiple of the N tile %d", seg_cols, block_n); return SFB_ERR_INVALID; }
@@ -255,6 +256,7 @@ extern "C" int sfb_gemm_bf16(const void* x, long long ldx, const void* w, long l
   if (sms <= 0) return SFB_ERR_CUDA;
   if (pair) {
     gemm_pair_workspace(workspace, workspace_bytes, p);
+    p.streamk = force_streamk ? 1 : 0;   // request; launch_gemm_pair decides
     return launch_gemm_pair(epilogue, ta, tb, p, sms, stream);
   }
   switch (block_n) {

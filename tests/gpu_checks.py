@@ -53,7 +53,6 @@ def _finish(name, metrics, tol):
 
 # --------------------------------------------------------------------------------------
 def check_gemm(M=300, N=256, K=192, epilogue=0, block_n=0, rows_per_gate=100, seed=0, gate_row_offset=0):
-    os.environ.setdefault("SFB_GEMM_STREAMK", "1")   # parity checks also cover the (opt-in) stream-K schedule
     ops = _ops()
     x = _randn(M, K, seed=seed)
     w = _randn(N, K, seed=seed + 1, scale=1.0 / math.sqrt(K))
@@ -473,10 +472,10 @@ ALL = {
     "attn_few_items": lambda: check_attention(Lq=1560, S=32760, H=12, seed=9),
     "peer_barrier": check_peer_barrier_single,
     "ln_row_offset": check_ln_row_offset,
-    "gemm_streamk_o_proj": lambda: check_gemm(M=4680, N=1536, K=1536, epilogue=3, rows_per_gate=1560, seed=11),
-    "gemm_streamk_qkv": lambda: check_gemm(M=4680, N=4608, K=1536, seed=12),
-    "gemm_streamk_cross_o": lambda: check_gemm(M=4680, N=1536, K=1536, epilogue=2, seed=13),
-    "gemm_streamk_repeat": lambda: [check_gemm(M=4680, N=1536, K=8960, epilogue=3, rows_per_gate=1560, seed=14 + i) for i in range(3)][-1],
+    "gemm_streamk_o_proj": lambda: check_gemm(M=4680, N=1536, K=1536, epilogue=3, rows_per_gate=1560, seed=11, block_n=513),
+    "gemm_streamk_qkv": lambda: check_gemm(M=4680, N=4608, K=1536, seed=12, block_n=513),
+    "gemm_streamk_cross_o": lambda: check_gemm(M=4680, N=1536, K=1536, epilogue=2, seed=13, block_n=513),
+    "gemm_streamk_repeat": lambda: [check_gemm(M=4680, N=1536, K=8960, epilogue=3, rows_per_gate=1560, seed=14 + i, block_n=513) for i in range(3)][-1],
     "gemm_gate_row_offset": lambda: check_gemm(M=700, N=512, K=256, epilogue=3, rows_per_gate=130, block_n=512, gate_row_offset=77),
     "gemm_gate_row_offset_1cta": lambda: check_gemm(M=300, N=384, K=256, epilogue=3, rows_per_gate=70, block_n=128, gate_row_offset=33),
     "patchify": check_patchify,

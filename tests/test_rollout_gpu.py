@@ -84,3 +84,44 @@ def test_add_noise_scheduler_on_gpu():
     nz = torch.randn(3, 16, 8, 8, generator=torch.Generator().manual_seed(8)).to(torch.bfloat16).cuda()
     out = s.add_noise(x0, nz, g["warped"][1:].clone().cuda())
     assert torch.equal(out.cpu(), g["add_noise_out"])
+
+
+# --------------------------------------------------------------------------------------------------
+# Full-size (BASELINE.json configs[1]) properties: 30 layers, FFN 8960, 21 latent frames at 60x104, chunks of 3.
+# The CPU oracle cannot run this size in test time, so parity is carried by size-independent properties.
+# --------------------------------------------------------------------------------------------------
+def _sibling_pipeline(pipe, **extra):
+    """Another pipeline (own caches) around the same generator / text-encoder stub."""
+    from helpers import _IdentityVAE, pipeline_args
+    from self_forcing_b200.pipeline import CausalInferencePipeline
+    case = dict(num_frame_per_block=3, independent_first_frame=False)
+    return CausalInferencePipeline(pipeline_args(case, **extra), "cuda", generator=pipe.generator,
+                                   text_encoder=pipe.text_encoder, vae=_IdentityVAE())
+
+
+def test_full_size_rollout_properties():
+    case = dict(frames=21, num_frame_per_block=3, independent_first_frame=False, shift=5.0)
+    pipe, _, _, _, noise = make_product_pipeline(case, "cuda", num_layers=30, ffn_dim=8960)
+    with patched_randn_like(3):
+        _, lat = pipe.inference(noise, ["synthetic"], return_latents=True)
+    assert lat.shape == (1, 21, 16, 60, 104) and bool(torch.isfinite(lat.float()).all())
+    # cache indices after 7 chunks x 5 forwards (bit-exact integer arithmetic, reference causal_model.py:195-236)
+    for c in (pipe.kv_cache1[0], pipe.kv_cache1[29]):
+        assert (int(c["global_end_index"]), int(c["local_end_index"])) == (32760, 32760)
+    # determinism: the same call again reproduces every bit (fixed stream-K / split schedules, no atomics)
+    with patched_randn_like(3):
+        _, lat2 = pipe.inference(noise, ["synthetic"], return_latents=True)
+    assert torch.equal(lat, lat2)
+    # causality: the first two chunks of the 7-chunk video equal a 2-chunk rollout of the same noise prefix
+    pipe2 = _sibling_pipeline(pipe)
+    with patched_randn_like(3):
+        _, lat_prefix = pipe2.inference(noise[:, :6].contiguous(), ["synthetic"], return_latents=True)
+    assert torch.equal(lat[:, :6], lat_prefix)
+    # skipping the unused tail of the clean-context refresh pass (last layer's attention/FFN + head) changes nothing
+    pipe3 = _sibling_pipeline(pipe, skip_refresh_tail=True)
+    with patched_randn_like(3):
+        _, lat_skip = pipe3.inference(noise, ["synthetic"], return_latents=True)
+    assert torch.equal(lat, lat_skip)
+    # every kernel of the product path is ours: the launch counter moved and the library is mapped
+    assert pipe.generator.model.ops.launches > 35 * 400
+    assert "libsfb200.so" in open("/proc/self/maps").read()

@@ -11,7 +11,7 @@ timeout 900 python bench.py --steps 3 --warmup 3 > $OUT/${TAG}_bench.log 2> $OUT
 tail -c 3000 $OUT/${TAG}_bench.log; tail -5 $OUT/${TAG}_bench.err
 if [ "${SKIP_NCU:-0}" != "1" ]; then
 timeout 600 python bench.py --ncu-rollout > $OUT/${TAG}_plain.log 2>&1 &&
-timeout 1500 ncu --metrics gpu__time_duration.sum --clock-control none -c 20000 --csv --log-file $OUT/${TAG}_launches.csv \
+timeout 1500 ncu --metrics gpu__time_duration.sum --clock-control none -c 1500 --csv --log-file $OUT/${TAG}_launches.csv \
     python bench.py --ncu-rollout > $OUT/${TAG}_ncu_launches.log 2>&1; echo "ncu launches rc=$?"
 timeout 900 ncu --set full --clock-control none --import-source on -k regex:attention_fwd -s 300 -c 2 -f -o $OUT/${TAG}_attn \
     python bench.py --ncu-rollout > $OUT/${TAG}_ncu_attn.log 2>&1; echo "ncu attn rc=$?"
