@@ -65,6 +65,22 @@ def peaks() -> dict:
     return dict(burst=1590.0, sustained=1400.0, hbm=6650.0, source="fallback (B200_PROFILING.md)")
 
 
+def ncu_traffic():
+    """dram__bytes_read.sum + dram__bytes_write.sum of one attention launch from the committed ncu --set full capture
+    (profiles/, Lq 4680 x S 18720 x 12 heads: 144 MB algorithmic Q + K + V + O) -- or None if no capture is committed."""
+    path = os.path.join(ROOT, "profiles", "r01e_ncu_tensor_kernels.json")
+    try:
+        k = next(iter(json.load(open(path))["r01e_attn"].values()))
+        unit = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+        tot = 0.0
+        for key in ("dram__bytes_read.sum", "dram__bytes_write.sum"):
+            val, u = k[key].split()
+            tot += float(val) * unit[u]
+        return tot
+    except Exception:
+        return None
+
+
 def workload_name(chunk_frames: int) -> str:
     kind = "chunk-wise (3 latent frames/chunk)" if chunk_frames == 3 else f"{chunk_frames} latent frame(s)/block"
     return f"wan2.1-t2v-1.3b self-forcing dmd {kind}, 81 frames 480x832, 4 steps, batch 1 per GPU"
@@ -399,7 +415,10 @@ def run_product_arm(args) -> None:
         "gpu_launches": launches,
         "roofline": {"kernel": "attention_fwd_kernel (self-attention over the KV window)", "bound": "tensor",
                      "achieved": achieved, "peak": pk["sustained"], "unit": "TFLOP/s",
-                     "frac": achieved / pk["sustained"], "traffic": None,
+                     "frac": achieved / pk["sustained"], "traffic": ncu_traffic(),
+                     "traffic_note": "bytes of ONE launch (Lq 4680, S 18720, H 12; algorithmic Q+K+V+O = 144 MB) from the "
+                                     "committed ncu capture profiles/r01e_ncu_tensor_kernels.json; `achieved` sums all "
+                                     "self-attention launches of the timed steps (S = 4680 .. 32760)",
                      "peak_kind": "sustained bf16 cuBLAS, " + pk["source"], "frac_of_burst": achieved / pk["burst"],
                      "launches_timed": len(self_attn), "ms_in_timed_region": ms_attn},
         "roofline_gemm": {"kernel": "gemm_bf16_kernel (all projections)", "bound": "tensor",

@@ -25,6 +25,16 @@ __device__ __forceinline__ void unpack8(const uint4& q, float (&f)[8]) {
   f[0] = bf_lo(q.x); f[1] = bf_hi(q.x); f[2] = bf_lo(q.y); f[3] = bf_hi(q.y);
   f[4] = bf_lo(q.z); f[5] = bf_hi(q.z); f[6] = bf_lo(q.w); f[7] = bf_hi(q.w);
 }
+// Packed bf16 helpers.  cvt.rn.bf16x2.f32 rounds TWO values per instruction and the conversion pipe is the scarce
+// resource of these kernels (3-4 roundings per element in the reference's op-by-op bf16 chain), so roundings are done
+// pairwise; a bf16 x bf16 product is exact in fp32, hence HMUL2.BF16 (one rounding) equals torch's fp32-multiply-
+// then-round and is used for the multiplies.  Adds stay in fp32 + round (a fused bf16 add rounds once, torch twice).
+__device__ __forceinline__ uint32_t round_pair(float a, float b) { return pack_bf16(a, b); }
+__device__ __forceinline__ uint32_t mul_bf16x2(uint32_t a, uint32_t b) {
+  __nv_bfloat162 r = __hmul2(*reinterpret_cast<__nv_bfloat162*>(&a), *reinterpret_cast<__nv_bfloat162*>(&b));
+  return *reinterpret_cast<uint32_t*>(&r);
+}
+
 // Stops the compiler from keeping the unpacked fp32 copy of a packed row alive across passes (it would otherwise
 // CSE the unpacks and need 2x the registers): after this the vector has to be unpacked again.
 __device__ __forceinline__ void forget_unpacked(uint4& q) {
@@ -113,12 +123,17 @@ ln_kernel(const __nv_bfloat16* __restrict__ x, long long ldx, __nv_bfloat16* __r
 #pragma unroll
       for (int i = 0; i < 8; ++i) o[i] = (v[i] - mean) * rstd * ww[i] + bb[i];
     } else {
-      float sc[8], sh[8];
-      unpack8(ldg16(scale + mrow + c0), sc);
-      unpack8(ldg16(shift + mrow + c0), sh);
+      const uint4 scq = ldg16(scale + mrow + c0), shq = ldg16(shift + mrow + c0);
+      const uint32_t scw[4] = {scq.x, scq.y, scq.z, scq.w}, shw[4] = {shq.x, shq.y, shq.z, shq.w};
 #pragma unroll
-      for (int i = 0; i < 8; ++i)
-        o[i] = bf16r(bf16r((v[i] - mean) * rstd) * bf16r(1.0f + sc[i])) + sh[i];
+      for (int i = 0; i < 4; ++i) {
+        // bf16(bf16(LN(x)) * bf16(1 + scale)) + shift, two elements at a time
+        const uint32_t n2 = round_pair((v[2 * i] - mean) * rstd, (v[2 * i + 1] - mean) * rstd);
+        const uint32_t s2 = round_pair(1.0f + bf_lo(scw[i]), 1.0f + bf_hi(scw[i]));
+        const uint32_t p2 = mul_bf16x2(n2, s2);
+        o[2 * i] = bf_lo(p2) + bf_lo(shw[i]);
+        o[2 * i + 1] = bf_hi(p2) + bf_hi(shw[i]);
+      }
     }
     *reinterpret_cast<uint4*>(y + row * ldy + c0) = pack8(o);
   }
@@ -165,13 +180,17 @@ __device__ __forceinline__ float rms_load(const __nv_bfloat16* __restrict__ src,
 template <int NV>
 __device__ __forceinline__ void rms_apply(const uint4& raw, const __nv_bfloat16* __restrict__ w, float rstd, int k, int lane,
                                           float (&v)[8]) {
-  float ww[8];
   uint4 r = raw;
   forget_unpacked(r);
   unpack8(r, v);
-  unpack8(ldg16(w + (k * 32 + lane) * 8), ww);
+  const uint4 wq4 = ldg16(w + (k * 32 + lane) * 8);
+  const uint32_t ww[4] = {wq4.x, wq4.y, wq4.z, wq4.w};
 #pragma unroll
-  for (int i = 0; i < 8; ++i) v[i] = bf16r(bf16r(v[i] * rstd) * ww[i]);
+  for (int i = 0; i < 4; ++i) {
+    const uint32_t p2 = mul_bf16x2(round_pair(v[2 * i] * rstd, v[2 * i + 1] * rstd), ww[i]);   // bf16(bf16(x * rstd) * w)
+    v[2 * i] = bf_lo(p2);
+    v[2 * i + 1] = bf_hi(p2);
+  }
 }
 
 template <int NV>

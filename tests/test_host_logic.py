@@ -1,6 +1,7 @@
 """Host-side logic of the product on CPU: cache index arithmetic, scheduler tables, mask tables and the
 whole model/wrapper/pipeline orchestration driven through the TorchOps test double (tests/_torch_ops.py)
 and compared with the oracle.  No CUDA kernel runs here."""
+import os
 import numpy as np
 import pytest
 import torch
@@ -223,3 +224,25 @@ def test_attention_whole_item_schedule_never_splits():
                 assert (j0, j1) == (0, n_kv)
                 seen.append(item)
         assert seen == list(range(items))
+
+
+def test_reference_arm_runs_on_rank0_only():
+    """Under torchrun the CPU reference arm is rank 0's job; other ranks exit 0 without work or output."""
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    env = dict(os.environ, RANK="1", WORLD_SIZE="2", LOCAL_RANK="1")
+    r = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--impl", "reference", "--gpus", "2",
+                        "--steps", "1", "--warmup", "0"], env=env, capture_output=True, text=True, timeout=120)
+    assert r.returncode == 0 and r.stdout.strip() == ""
+
+
+def test_bench_flop_model_matches_survey():
+    """bench.py's algorithmic FLOP count is the SURVEY.md section 8d figure (990.3 TFLOP chunk-wise, 943.2 frame-wise)."""
+    import importlib.util
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    spec = importlib.util.spec_from_file_location("bench_mod", os.path.join(root, "bench.py"))
+    b = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(b)
+    assert abs(b.rollout_flops(3) / 1e12 - 990.3) < 0.5
+    assert abs(b.rollout_flops(1) / 1e12 - 943.2) < 0.5
