@@ -60,7 +60,8 @@ constexpr int ATT_TILE_BYTES = 128 * 128 * 2;    // 32 KB: two 16 KB halves (d 0
 constexpr int ATT_HALF_BYTES = 128 * 64 * 2;
 constexpr int ATT_KV_STAGES = 2;
 constexpr int ATT_SMEM_BYTES = 2 * ATT_TILE_BYTES + 2 * ATT_KV_STAGES * ATT_TILE_BYTES + 1024 + 256;
-constexpr int ATT_DEFAULT_EMU = 1;
+constexpr int ATT_DEFAULT_EMU = 0;   // measured: 0 -> 1166, 1 -> 1115, 2 -> 1063 TFLOP/s at Lq 4680 x S 32760 (the softmax is issue-bound)
+constexpr bool ATT_DEFAULT_ALU_PACK = false;
 constexpr int ATT_SLOT_FLOATS = ATT_BM * ATT_D + 2 * ATT_BM;   // one (tile, segment) partial
 constexpr int ATT_MIN_SPLIT_KV_TILES = 16;                     // shorter KV: whole items per CTA
 constexpr int ATT_MAX_GROUPS = 4;
@@ -111,13 +112,23 @@ __device__ __forceinline__ float2 poly_exp2x2(float2 x) {
   return q;
 }
 
+// fp32 pair -> packed bf16 (round to nearest even) with integer ALU ops instead of F2FP: conversions execute on the
+// same XU pipe as MUFU.EX2 (16 lanes/clk/SM), which is the scarcest resource of the softmax.  Inputs are finite, >= 0.
+__device__ __forceinline__ uint32_t pack_bf16_alu(float a, float b) {
+  uint32_t ua = __float_as_uint(a), ub = __float_as_uint(b);
+  ua += 0x7FFFu + ((ua >> 16) & 1u);
+  ub += 0x7FFFu + ((ub >> 16) & 1u);
+  return __byte_perm(ua, ub, 0x7632);
+}
+
 template <int REGS>
 __device__ __forceinline__ void setmaxnreg_inc() { asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(REGS)); }
 template <int REGS>
 __device__ __forceinline__ void setmaxnreg_dec() { asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(REGS)); }
 
 // EMU: how many of every 4 exponential PAIRS run on the FMA pipe instead of MUFU (0, 1 or 2).
-template <int EMU>
+// ALU_PACK: round P to bf16 with integer ops instead of F2FP (XU pipe).
+template <int EMU, bool ALU_PACK>
 __global__ void __launch_bounds__(ATT_THREADS, 1)
 attention_fwd_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_constant__ CUtensorMap tma_k,
                      const __grid_constant__ CUtensorMap tma_v, const AttnParams p) {
@@ -427,7 +438,7 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_con
               e.y = fast_exp2(x.y);
             }
             if (i & 1) sum_b = __fadd2_rn(sum_b, e); else sum_a = __fadd2_rn(sum_a, e);
-            pk[i] = pack_bf16(e.x, e.y);
+            pk[i] = ALU_PACK ? pack_bf16_alu(e.x, e.y) : pack_bf16(e.x, e.y);
           }
           tmem_st16(s_addr + c * 16, pk);   // P_t aliases the first 64 columns of S_t
           if (c & 1) {                      // publish this half of P (64 KV columns)
@@ -648,17 +659,22 @@ static int attention_launch(const void* q, long long q_row_stride, long long q_b
   p.dbg = timing ? dbg_buf : nullptr;
 
   static int emu = -1;
+  static bool alu_pack = false;
   if (emu < 0) {
     const char* env = getenv("SFB_ATTN_EMU");   // tuning knob; the default is the measured best
     int want = env ? atoi(env) : ATT_DEFAULT_EMU;
     if (want < 0 || want > 2) want = ATT_DEFAULT_EMU;
-    for (auto kern : {attention_fwd_kernel<0>, attention_fwd_kernel<1>, attention_fwd_kernel<2>})
+    for (auto kern : {attention_fwd_kernel<0, false>, attention_fwd_kernel<1, false>, attention_fwd_kernel<2, false>,
+                      attention_fwd_kernel<0, true>, attention_fwd_kernel<1, true>, attention_fwd_kernel<2, true>})
       if (int e = check_cuda(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT_SMEM_BYTES),
                              "cudaFuncSetAttribute(attention)"))
         return e;
+    const char* ap = getenv("SFB_ATTN_ALU_PACK");
+    alu_pack = ap ? (ap[0] == '1') : ATT_DEFAULT_ALU_PACK;
     emu = want;
   }
-  auto kern = emu == 0 ? attention_fwd_kernel<0> : (emu == 1 ? attention_fwd_kernel<1> : attention_fwd_kernel<2>);
+  auto kern = alu_pack ? (emu == 0 ? attention_fwd_kernel<0, true> : (emu == 1 ? attention_fwd_kernel<1, true> : attention_fwd_kernel<2, true>))
+                       : (emu == 0 ? attention_fwd_kernel<0, false> : (emu == 1 ? attention_fwd_kernel<1, false> : attention_fwd_kernel<2, false>));
   kern<<<grid, ATT_THREADS, ATT_SMEM_BYTES, stream>>>(tq, tk, tv, p);
   if (int e = check_cuda(cudaGetLastError(), "attention launch")) return e;
   if (timing) {   // diagnostic: per-phase cycles of one softmax warp, averaged over CTAs, per KV step
