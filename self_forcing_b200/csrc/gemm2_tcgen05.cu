@@ -76,7 +76,8 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_consta
   uint64_t* tmem_full = empty_bar + G2_STAGES;   // [2]
   uint64_t* tmem_empty = tmem_full + 2;          // [2]  (only the leader's copy is waited on)
   uint64_t* res_full = tmem_empty + 2;           // [1]  residual tile landed in the staging buffers
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(res_full + 1);
+  uint64_t* acc_init = res_full + 1;             // [1]  stream-K: the head tile's accumulator was preloaded (leader's copy)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_init + 1);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -95,6 +96,7 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_consta
       mbar_init(&tmem_empty[s], 8);  // 4 epilogue warps x 2 CTAs arrive on the leader's barrier
     }
     mbar_init(res_full, 1);
+    mbar_init(acc_init, 8);        // 4 epilogue warps x 2 CTAs
     fence_barrier_init();
   }
   if (warp == 1) tmem_alloc_pair(tmem_slot, 512);
@@ -121,11 +123,10 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_consta
           mbar_wait(&empty_bar[stage], phase ^ 1);
           if (elect_one()) {
             uint8_t* a_dst = smem + stage * G2_STAGE_BYTES;
-            const bool skip_b = p.experiment_skip_b && (kb & 1);   // DIAGNOSTIC ONLY (wrong results): halves the B traffic
-            if (leader) mbar_expect_tx(&full_bar[stage], skip_b ? 2 * G2_A_BYTES : 2 * G2_STAGE_BYTES);
+            if (leader) mbar_expect_tx(&full_bar[stage], 2 * G2_STAGE_BYTES);
             const uint32_t bar = mapa_cluster(smem_u32(&full_bar[stage]), 0);
             tma_load_2d_pair(a_dst, &tma_a, bar, kb * G2_BK, a_row);
-            if (!skip_b) tma_load_2d_pair(a_dst + G2_A_BYTES, &tma_b, bar, kb * G2_BK, b_row);
+            tma_load_2d_pair(a_dst + G2_A_BYTES, &tma_b, bar, kb * G2_BK, b_row);
           }
           __syncwarp();
           if (++stage == G2_STAGES) { stage = 0; phase ^= 1; }
@@ -145,6 +146,10 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_consta
         const int acc = it & 1;
         const uint32_t acc_phase = (it >> 1) & 1;
         mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
+        // stream-K head piece [0, kb1) of a tile whose tail another pair computed: the epilogue warps have preloaded
+        // that fp32 partial into this accumulator, so every MMA accumulates
+        const bool preloaded = p.streamk && kb0 == 0 && kb1 < p.num_k_blocks;
+        if (preloaded) mbar_wait(acc_init, 0);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + acc * G2_BN;
         for (int kb = kb0; kb < kb1; ++kb) {
@@ -156,7 +161,7 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_consta
             const uint64_t b_desc = umma_desc_sw128(a_addr + G2_A_BYTES, 16, 1024);
 #pragma unroll
             for (int k = 0; k < G2_BK / 16; ++k)
-              umma_ss_pair(d_tmem, a_desc + 2 * k, b_desc + 2 * k, idesc, (kb != kb0 || k != 0) ? 1u : 0u);
+              umma_ss_pair(d_tmem, a_desc + 2 * k, b_desc + 2 * k, idesc, (preloaded || kb != kb0 || k != 0) ? 1u : 0u);
             umma_commit_pair(&empty_bar[stage], 3);   // both CTAs' smem slots are free once these retire
             if (kb == kb1 - 1) umma_commit_pair(&tmem_full[acc], 3);
           }
@@ -180,6 +185,7 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_consta
     uint32_t res_phase = 0;
     int it = 0;
     PairRange range(p, pair, num_pairs);
+    const uint32_t leader_acc_init = mapa_cluster(smem_u32(acc_init), 0);
     int tile, kb0, kb1;
     for (; range.next(tile, kb0, kb1); ++it) {
       const int m_blk = tile % p.num_m_blocks, n_blk = tile / p.num_m_blocks;
@@ -189,7 +195,6 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_consta
       const int n0 = n_blk * G2_BN;
       const uint32_t t_row = tmem_base + ((uint32_t)(quarter * 32) << 16) + acc * G2_BN;
       const bool tail_part = kb0 > 0;                        // stream-K: this pair holds k-blocks [kb0, K) of the tile
-      const bool head_part = kb0 == 0 && kb1 < p.num_k_blocks;   // ... or [0, kb1): it finishes the tile
 
       if (tail_part) {
         // park the fp32 partial (transposed: consecutive lanes = consecutive rows -> coalesced) for the pair that
@@ -212,8 +217,39 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_consta
         named_barrier_sync(1, 128);
         if (warp == 2 && lane == 0)
           asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(p.sk_flags + (pair - 1) * 2 + rank), "r"(p.sk_epoch) : "memory");
-        continue;
       }
+
+      // Look ahead: if the NEXT (= last) segment of this pair is the head piece of a split tile, preload the tail
+      // partial (computed by the next pair at the very start of its range) into that segment's accumulator now,
+      // while the MMAs of the current segment are still running.  The other accumulator buffer is free: its
+      // previous user's epilogue finished in the previous iteration.  (After this pair's own tail partial has been
+      // published, so that waiting for the neighbour's flag never delays a flag somebody else waits for.)
+      if (p.streamk) {
+        PairRange peek = range;
+        int t2, a2, b2;
+        if (peek.next(t2, a2, b2) && a2 == 0 && b2 < p.num_k_blocks) {
+          const float* part = p.sk_ws + ((long long)pair * 2 + rank) * (G2_BN * G2_ROWS);
+          const int* flag = p.sk_flags + pair * 2 + rank;
+          int seen;
+          do {
+            asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(seen) : "l"(flag) : "memory");
+          } while (seen != p.sk_epoch);
+          const uint32_t t_next = tmem_base + ((uint32_t)(quarter * 32) << 16) + ((it + 1) & 1) * G2_BN;
+#pragma unroll 1
+          for (int c = 0; c < G2_BN / 32; ++c) {
+            uint32_t v[32];
+#pragma unroll
+            for (int i = 0; i < 32; ++i) v[i] = __float_as_uint(__ldcg(part + (c * 32 + i) * G2_ROWS + r_local));
+            tmem_st32(t_next + c * 32, v);
+          }
+          tmem_st_wait();
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive_cluster(leader_acc_init);
+        }
+      }
+
+      if (tail_part) continue;
 
       const int seg = n0 / p.seg_cols;
       const int seg_col0 = n0 - seg * p.seg_cols;
@@ -233,15 +269,6 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_consta
         mbar_wait(res_full, res_phase);
         res_phase ^= 1;
       }
-      const float* part = nullptr;
-      if (head_part) {   // the tail of this tile was computed by the next pair at the very start of its range
-        part = p.sk_ws + ((long long)pair * 2 + rank) * (G2_BN * G2_ROWS);
-        const int* flag = p.sk_flags + pair * 2 + rank;
-        int seen;
-        do {
-          asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(seen) : "l"(flag) : "memory");
-        } while (seen != p.sk_epoch);
-      }
       const int row = row0 + r_local;
       const __nv_bfloat16* grow = nullptr;
       if (EPI == EPI_GATE_RES)
@@ -252,11 +279,6 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_consta
         tmem_ld32(t_row + sb * G2_SUB, *reinterpret_cast<uint32_t(*)[32]>(&v[0]));
         tmem_ld32(t_row + sb * G2_SUB + 32, *reinterpret_cast<uint32_t(*)[32]>(&v[32]));
         tmem_ld_wait();
-        if (part != nullptr) {
-#pragma unroll
-          for (int i = 0; i < 64; ++i)
-            v[i] = __float_as_uint(__uint_as_float(v[i]) + __ldcg(part + (sb * G2_SUB + i) * G2_ROWS + r_local));
-        }
         uint8_t* buf_row = my_row + sb * G2_SUB_BYTES;
 #pragma unroll
         for (int c = 0; c < 8; ++c) {
@@ -317,12 +339,11 @@ static int launch_gemm2(const CUtensorMap& ta, const CUtensorMap& tb, const Pair
   const int tiles = p.num_m_blocks * p.num_n_blocks;
   const int clusters = tiles < max_clusters ? tiles : max_clusters;
   GemmParams q = p;
-  static const bool exp_skip = getenv("SFB_GEMM_EXPERIMENT_SKIP_B") != nullptr;   // diagnostic: see the producer
-  q.experiment_skip_b = exp_skip ? 1 : 0;
   // stream-K for badly filled last waves (e.g. 114 tiles on 74 pairs = 2 waves at 77 %).  OFF by default: measured on
-  // B200 it LOSES 4-8 us per GEMM (QKV 55 -> 63 us, O-proj 39 -> 47 us, FFN2 113 -> 118 us): the main loop is bound by
-  // the chip-wide L2 -> SM fill rate (~9.5 TB/s, 128 FLOP/B for 256 x 256 pair tiles), so a thinner last wave simply
-  // runs faster per tile, while the split adds an exposed partial read + epilogue at the end.  SFB_GEMM_STREAMK=1 enables.
+  // B200 (profiles/, tools/gpu_microbench.py *_streamk) it does not win -- QKV 56.4 -> 58.3 us, O-proj 39.8 -> 46.0 us,
+  // FFN2 112.7 -> 112.6 us even with the tail partial preloaded into TMEM ahead of time: a thinner last wave runs
+  // faster per tile (shared L2 / power budget), and each split adds a partial hand-off plus one more epilogue.
+  // block_n = 513 or SFB_GEMM_STREAMK=1 enables it.
   const int waves = (tiles + clusters - 1) / clusters;
   static const bool sk_env = getenv("SFB_GEMM_STREAMK") != nullptr;
   q.streamk = ((sk_env || p.streamk) && q.sk_ws != nullptr && tiles >= clusters && tiles % clusters != 0 && clusters <= G2_MAX_PAIRS &&

@@ -27,7 +27,6 @@ struct GemmParams {
   float* sk_ws;                // [pairs][2 CTAs][256 cols][128 rows] fp32
   int* sk_flags;               // [pairs][2 CTAs], holds sk_epoch once the partial is complete
   int sk_epoch;
-  int experiment_skip_b;       // diagnostic only: skip every other B load to probe whether the main loop is fill-bound
 };
 
 __device__ __forceinline__ float gelu_tanh_f(float x) {
