@@ -20,7 +20,7 @@
 extern "C" {
 #endif
 
-#define SFB_ABI_VERSION 4
+#define SFB_ABI_VERSION 5
 
 const char* sfb_last_error(void);
 int sfb_abi_version(void);
@@ -116,9 +116,10 @@ int sfb_attention_fwd_sp(const void* q, long long q_row_stride, const void* k, c
                          int Lq, int Skv, int H, int head_dim, float softmax_scale,
                          void* workspace, long long workspace_bytes, void* stream);
 
-/* All-ranks barrier over peer-mapped flag words: flag_ptrs[p] = rank p's zero-initialised int32[n] array as mapped
- * here; `epoch` increases by one per call on every rank. */
-int sfb_peer_barrier(void* const* flag_ptrs, int rank, int n, int epoch, void* stream);
+/* All-ranks barrier over peer-mapped flag words: flag_ptrs[p] = rank p's zero-initialised int32[n + 1] array as
+ * mapped here (slot [n] = the rank's own call counter, advanced by the kernel, so the launch is CUDA-graph
+ * replayable); every rank must call it the same number of times. */
+int sfb_peer_barrier(void* const* flag_ptrs, int rank, int n, void* stream);
 
 /* im2col of Conv3d(k = s = (1,2,2)) (causal_model.py:775-778): x[b][c][f][y][x] with element strides
  * -> out[(b,f,y/2,x/2)][c*4 + (y%2)*2 + x%2]. */

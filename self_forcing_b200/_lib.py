@@ -13,7 +13,7 @@ LIB_PATH = os.path.join(HERE, "libsfb200.so")
 
 P, LL, I, F = c_void_p, c_longlong, c_int, c_float
 PP = ctypes.POINTER(c_void_p)
-ABI_VERSION = 4
+ABI_VERSION = 5
 
 # name -> argtypes, mirroring include/sfb200.h one to one
 SIGNATURES = {
@@ -32,7 +32,7 @@ SIGNATURES = {
     # Ulysses head-parallel path: PP = host array of device pointers (ctypes c_void_p * n)
     "sfb_qk_norm_rope_sp": [P, LL, P, LL, P, LL, P, P, F, P, P, I, I, I, I, I, I, I, I, I, I, PP, LL, PP, PP, LL, P],
     "sfb_attention_fwd_sp": [P, LL, P, P, LL, PP, I, I, LL, I, I, I, I, F, P, LL, P],
-    "sfb_peer_barrier": [PP, I, I, I, P],
+    "sfb_peer_barrier": [PP, I, I, P],
 }
 
 

@@ -13,7 +13,13 @@ struct PeerFlags {
   int* flags[8];   // flags[p]: rank p's array of n ints, mapped into this process; slot [r] is written by rank r
 };
 
-__global__ void peer_barrier_kernel(PeerFlags pf, int rank, int n, int epoch) {
+// The epoch lives in device memory (slot [n] of this rank's own flag array) and is advanced by the kernel itself, so
+// the launch has no per-call argument and can be replayed inside a CUDA graph.
+__global__ void peer_barrier_kernel(PeerFlags pf, int rank, int n) {
+  __shared__ int next_epoch;
+  if (threadIdx.x == 0) next_epoch = ++pf.flags[rank][n];
+  __syncthreads();
+  const int epoch = next_epoch;
   const int p = threadIdx.x;
   if (p >= n) return;
   __threadfence_system();   // order this GPU's earlier peer stores before the flag
@@ -26,13 +32,13 @@ __global__ void peer_barrier_kernel(PeerFlags pf, int rank, int n, int epoch) {
 
 }  // namespace sfb
 
-// flag_ptrs[p] = device pointer (as mapped in THIS process) of rank p's flag array of n int32, zero-initialised.
-// Epochs must increase by one per call on every rank.
-extern "C" int sfb_peer_barrier(void* const* flag_ptrs, int rank, int n, int epoch, void* stream) {
+// flag_ptrs[p] = device pointer (as mapped in THIS process) of rank p's flag array of n + 1 int32, zero-initialised
+// (slot [n] is the rank's own call counter).  Every rank must call it the same number of times.
+extern "C" int sfb_peer_barrier(void* const* flag_ptrs, int rank, int n, void* stream) {
   using namespace sfb;
   if (n < 1 || n > 8 || rank < 0 || rank >= n) { set_error("sfb_peer_barrier: bad rank %d of %d", rank, n); return SFB_ERR_INVALID; }
   PeerFlags pf{};
   for (int i = 0; i < n; ++i) pf.flags[i] = static_cast<int*>(flag_ptrs[i]);
-  peer_barrier_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(pf, rank, n, epoch);
+  peer_barrier_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(pf, rank, n);
   return check_cuda(cudaGetLastError(), "peer_barrier launch");
 }

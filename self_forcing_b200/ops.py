@@ -47,6 +47,7 @@ class CudaOps:
     of libsfb200.so on the current CUDA stream."""
 
     requires_bf16 = True
+    supports_cuda_graphs = True   # every op only enqueues kernels on the current stream (no host sync, no allocation)
 
     def __init__(self):
         self.lib = _lib.load()
@@ -221,8 +222,8 @@ class CudaOps:
             self._stream()), "sfb_attention_fwd_sp")
 
     @_op
-    def peer_barrier(self, sp, epoch: int):
-        _lib.check(self.lib.sfb_peer_barrier(_lib.ptr_array(sp.flags.ptrs), sp.rank, sp.world, epoch, self._stream()),
+    def peer_barrier(self, sp):
+        _lib.check(self.lib.sfb_peer_barrier(_lib.ptr_array(sp.flags.ptrs), sp.rank, sp.world, self._stream()),
                    "sfb_peer_barrier")
 
     # -- embeddings -----------------------------------------------------------------------

@@ -50,8 +50,7 @@ class UlyssesGroup:
         if not 1 <= self.world <= 8:
             raise ValueError("Ulysses group size must be 1..8 (one NVSwitch box)")
         self.device = torch.device(device) if device is not None else torch.device("cpu")
-        self.epoch = 0
-        self.flags = self.alloc((max(self.world, 2),), torch.int32)
+        self.flags = self.alloc((self.world + 1,), torch.int32)   # [p] written by rank p, [world] = own call counter
         self.flags.local.zero_()
         self.sync_host()
 
@@ -80,8 +79,7 @@ class UlyssesGroup:
     def barrier(self, ops) -> None:
         """Device-side barrier on the current stream: all peer stores issued before it on any rank are visible to
         kernels launched after it on every rank."""
-        self.epoch += 1
-        ops.peer_barrier(self, self.epoch)
+        ops.peer_barrier(self)
 
     def all_gather_rows(self, local: torch.Tensor, out: torch.Tensor) -> None:
         dist.all_gather_into_tensor(out, local, group=self.group)

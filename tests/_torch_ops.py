@@ -116,7 +116,7 @@ class TorchOps:
         lo = sp.rank * rows_per_rank
         out_buf.local.copy_(full[lo:lo + rows_per_rank].reshape(rows_per_rank, -1))
 
-    def peer_barrier(self, sp, epoch):
+    def peer_barrier(self, sp):
         import torch.distributed as dist
         dist.barrier(group=sp.group)
 

@@ -296,10 +296,10 @@ def check_peer_barrier_single():
         pass
     g = G(1, 0)
     g.flags = PeerTensor(flags, [flags.data_ptr()])
-    for e in (1, 2, 3):
-        ops.peer_barrier(g, e)
+    for _ in range(3):
+        ops.peer_barrier(g)
     torch.cuda.synchronize()
-    return _finish("peer_barrier", dict(err_flag=float(abs(int(flags[0]) - 3))), 0.0)
+    return _finish("peer_barrier", dict(err_flag=float(abs(int(flags[0]) - 3)), err_count=float(abs(int(flags[1]) - 3))), 0.0)
 
 
 def check_ln_row_offset(rows=300, C=1536, seed=0):

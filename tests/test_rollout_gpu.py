@@ -122,6 +122,15 @@ def test_full_size_rollout_properties():
     with patched_randn_like(3):
         _, lat_skip = pipe3.inference(noise, ["synthetic"], return_latents=True)
     assert torch.equal(lat, lat_skip)
+    # CUDA-graph replay (default) and eager launching give the same bits
+    model = pipe.generator.model
+    assert sum(1 for g in model._graphs.values() if g != "seen") >= 7      # one graph per chunk position at least
+    model.use_cuda_graphs = False
+    pipe4 = _sibling_pipeline(pipe)
+    with patched_randn_like(3):
+        _, lat_eager = pipe4.inference(noise, ["synthetic"], return_latents=True)
+    model.use_cuda_graphs = True
+    assert torch.equal(lat, lat_eager)
     # every kernel of the product path is ours: the launch counter moved and the library is mapped
     assert pipe.generator.model.ops.launches > 35 * 400
     assert "libsfb200.so" in open("/proc/self/maps").read()
