@@ -371,11 +371,24 @@ def run_product_arm(args) -> None:
     resident_step()
     prof = ops.stop_profile()
 
+    def shutdown():
+        """Tear the process group down; never let a stuck teardown turn a finished measurement into a hang."""
+        if world == 1:
+            return
+        sys.stdout.flush()
+        watchdog = threading.Timer(45.0, lambda: os._exit(0))
+        watchdog.daemon = True
+        watchdog.start()
+        gen.model._graphs.clear()
+        torch.cuda.synchronize()
+        dist.barrier()
+        dist.destroy_process_group()
+        watchdog.cancel()
+
     if world > 1:
         dist.barrier()
     if rank != 0:
-        if world > 1:
-            dist.destroy_process_group()
+        shutdown()
         return
 
     pk = peaks()
@@ -447,8 +460,7 @@ def run_product_arm(args) -> None:
     with open(os.path.join(ROOT, "gpurun_out", f"bench_n{world}{'' if sp_size == 1 else '_ulysses'}.json"), "w") as f:
         json.dump(line, f, indent=1)
     print(json.dumps(line), flush=True)
-    if world > 1:
-        dist.destroy_process_group()
+    shutdown()
 
 
 def main():

@@ -367,6 +367,8 @@ class B200CausalWanModel(nn.Module):
         if ent is None:                       # first occurrence: run eagerly (also warms every lazy initialisation)
             self._graphs[key] = "seen"
             return self._device_forward(x, t, context, env)
+        if sp is not None:
+            env = dict(env, defer_gather=True)   # keep the NCCL collective out of the captured graph
         if ent == "seen":                     # second occurrence: capture
             xs = torch.empty(x.shape, dtype=x.dtype, device=dev)
             ts = torch.empty(t.shape, dtype=t.dtype, device=dev)
@@ -384,6 +386,8 @@ class B200CausalWanModel(nn.Module):
         ops.launches += n_launches
         if outs is None:
             return None
+        if outs == "gather":
+            return self._head_tail(xs, ts, env)
         return tuple(o.clone() if o is not None else None for o in outs)
 
     def _device_forward(self, x, t, context, env):
@@ -514,14 +518,23 @@ class B200CausalWanModel(nn.Module):
         ops.ln_modulate(ws["x"], ws["h"], shift=hm[:, 0], scale=hm[:, 1], mod_stride=2 * C, rows_per_mod=fs,
                         eps=self.eps, row_offset=off)
         ops.gemm(ws["h"], self.head.head.weight, self.head.head.bias, ws["head_out"])
+        if env.get("defer_gather"):
+            return "gather"          # Ulysses under graph capture: the NCCL gather + unpatchify run outside the graph
+        return self._head_tail(x, t, env)
+
+    def _head_tail(self, x, t, env):
+        """[Ulysses: all-gather the token shards of the head output (xdit_context_parallel.py:142)] -> unpatchify
+        (+ flow -> x0)."""
+        ops, ws, sp, dev = env["ops"], env["ws"], env["sp"], env["dev"]
+        B, F_, H, W = env["B"], env["F_"], env["H"], env["W"]
         head_out = ws["head_out"]
-        if sp is not None:   # xdit_context_parallel.py:142: gather the token shards before unpatchify
+        if sp is not None:
             sp.all_gather_rows(ws["head_out"], ws["head_full"])
             head_out = ws["head_full"]
         flow = torch.empty(B, F_, self.out_dim, H, W, dtype=ws["x"].dtype, device=dev)
         x0 = None
         xt = x.permute(0, 2, 1, 3, 4)   # [B, F, C, H, W] view of the input
-        if return_x0:
+        if env["return_x0"]:
             x0 = torch.empty_like(flow)
             ops.head_finish(head_out, xt, t.contiguous(), self._sampler_tables[0], self._sampler_tables[1],
                             flow, x0)

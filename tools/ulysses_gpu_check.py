@@ -42,10 +42,14 @@ def main():
                repeatable=bool(torch.equal(lat, lat2)), heads_per_rank=pipe.kv_cache1[0]["k"].shape[2],
                ok=bool(err <= 1e-2 and tuple(idx) == tuple(g["final_index"]) and same and torch.equal(lat, lat2)))
     print("ULYSSES_CHECK " + json.dumps(res), flush=True)
+    import threading
+    code = 0 if res["ok"] else 1
+    threading.Timer(30.0, lambda: os._exit(code)).start()     # a stuck teardown must not hang the box
+    pipe.generator.model._graphs.clear()
+    torch.cuda.synchronize()
     dist.barrier()
     dist.destroy_process_group()
-    if not res["ok"]:
-        sys.exit(1)
+    os._exit(code)
 
 
 if __name__ == "__main__":
