@@ -134,3 +134,33 @@ def test_full_size_rollout_properties():
     # every kernel of the product path is ours: the launch counter moved and the library is mapped
     assert pipe.generator.model.ops.launches > 35 * 400
     assert "libsfb200.so" in open("/proc/self/maps").read()
+
+
+def test_rolling_sink_cache_on_gpu_matches_reference_golden():
+    """local_attn_size = 3 frames with a 1-frame sink, 6 chunks x 2 forwards: the roll (evict oldest after the sink,
+    shift, append) runs on the GPU caches; flows, K/V contents and the (global, local) index trace must match the
+    unmodified reference (golden made on CPU)."""
+    from oracle.make_golden import ROLLING, rolling_cfg, rolling_model_inputs
+    from self_forcing_b200.model import B200CausalWanModel
+    g = golden("model_rolling.pt")
+    r = ROLLING
+    cfg = rolling_cfg()
+    model = B200CausalWanModel(dim=r["dim"], ffn_dim=r["ffn_dim"], num_heads=r["num_heads"], num_layers=r["num_layers"],
+                               text_dim=r["text_dim"], local_attn_size=r["local_attn_size"], sink_size=r["sink_size"])
+    model = model.to("cuda").to(torch.bfloat16)
+    model.load_state_dict(O.make_random_params(cfg, seed=5), strict=True)
+    x, ctx = (t.cuda() for t in rolling_model_inputs())
+    ft = (r["frame_hw"][0] // 2) * (r["frame_hw"][1] // 2)
+    kv = O.new_kv_cache(cfg, 1, ft, torch.bfloat16, "cuda", cache_tokens=r["local_attn_size"] * ft)
+    ca = O.new_crossattn_cache(cfg, 1, torch.bfloat16, "cuda")
+    flows, trace = [], []
+    for c in range(r["chunks"]):
+        for k in range(r["forwards_per_chunk"]):
+            t = torch.full((1, 1), 1000.0 - 300.0 * k, device="cuda")
+            flows.append(model(x[:, :, c:c + 1], t=t, context=ctx, seq_len=32760, kv_cache=kv, crossattn_cache=ca,
+                               current_start=c * ft).clone())
+            trace.append((int(kv[0]["global_end_index"]), int(kv[0]["local_end_index"])))
+    assert trace == [tuple(t) for t in g["trace"]]
+    assert rel_l2(torch.stack(flows).cpu(), g["flows"]) <= TOL
+    for i in range(cfg.num_layers):
+        assert rel_l2(kv[i]["k"].cpu(), g["k"][i]) <= TOL and rel_l2(kv[i]["v"].cpu(), g["v"][i]) <= TOL
