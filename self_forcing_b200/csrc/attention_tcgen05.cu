@@ -65,7 +65,7 @@ constexpr bool ATT_DEFAULT_ALU_PACK = false;
 constexpr int ATT_SLOT_FLOATS = ATT_BM * ATT_D + 2 * ATT_BM;   // one (tile, segment) partial
 constexpr int ATT_MIN_SPLIT_KV_TILES = 16;                     // shorter KV: whole items per CTA
 constexpr int ATT_MAX_GROUPS = 4;
-constexpr long long ATT_L2_BUDGET = 56ll << 20;                // K + V bytes of the heads in flight (L2 is 126 MB)
+constexpr long long ATT_L2_BUDGET = 72ll << 20;                // K + V bytes of the heads in flight (L2 is 126 MB; measured: 3 groups of 4 heads beat 4 x 3 and 6 x 2 at S = 32760)
 
 // Work of one head group: items_g = (heads in the group) x n_qpairs items of n_kv steps, linearised item-major.
 __host__ __device__ __forceinline__ int att_group_items(int grp, const AttnParams& p) {
