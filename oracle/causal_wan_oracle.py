@@ -358,6 +358,20 @@ def model_forward(p: Dict[str, Tensor], cfg: OracleConfig, x: Tensor, t: Tensor,
     return y
 
 
+def bidirectional_forward(p: Dict[str, Tensor], cfg: OracleConfig, x: Tensor, t: Tensor, context: Tensor) -> Tensor:
+    """WanModel._forward for t2v (wan/modules/model.py:637-771; blocks :275-354, head :439-466) for samples of
+    exactly seq_len tokens: one timestep per SAMPLE (`e0 [B, 6, C]` :697-700), every token attends to the whole
+    sequence, RoPE from frame 0 (rope_apply :40-67).  That is the cached forward above with a single timestep group
+    and an empty cache, so it is restated as exactly that.  x [B, 16, F, H, W], t [B] -> [B, 16, F, H, W]."""
+    B, _, nf, Hh, Ww = x.shape
+    ft = (Hh // cfg.patch_size[1]) * (Ww // cfg.patch_size[2])
+    kv = new_kv_cache(cfg, B, ft, x.dtype, x.device, cache_tokens=nf * ft)
+    ca = new_crossattn_cache(cfg, B, x.dtype, x.device)
+    for c in ca:                       # WanT2VCrossAttention without a cache recomputes K/V (model.py:175-180)
+        c["is_init"] = False
+    return model_forward(p, cfg, x, t.reshape(B, 1), context, kv, ca, 0)
+
+
 # --------------------------------------------------------------------------------------
 # scheduler / wrapper / rollout
 # --------------------------------------------------------------------------------------

@@ -132,6 +132,43 @@ def reference_rolling(ref):
     return dict(flows=torch.stack(flows), trace=trace, k=[c["k"].clone() for c in kv], v=[c["v"].clone() for c in kv])
 
 
+BIDIR = dict(dim=256, ffn_dim=256, num_heads=2, num_layers=2, text_dim=512, frames=2, frame_hw=(8, 12), batch=2)
+
+
+def bidirectional_inputs():
+    r = BIDIR
+    g = torch.Generator().manual_seed(21)
+    x = torch.randn(r["batch"], 16, r["frames"], *r["frame_hw"], generator=g).to(torch.bfloat16)
+    ctx = torch.randn(r["batch"], 512, r["text_dim"], generator=g).to(torch.bfloat16)
+    t = torch.tensor([937.5, 250.0])
+    return x, t, ctx
+
+
+def bidirectional_cfg() -> O.OracleConfig:
+    r = BIDIR
+    return O.OracleConfig(dim=r["dim"], ffn_dim=r["ffn_dim"], num_heads=r["num_heads"], num_layers=r["num_layers"],
+                          text_dim=r["text_dim"])
+
+
+def reference_bidirectional(ref):
+    """The unmodified bidirectional WanModel (wan/modules/model.py:497-771) on a tiny config, two samples with
+    different timesteps."""
+    cfg = bidirectional_cfg()
+    params = O.make_random_params(cfg, seed=9)
+    torch.manual_seed(0)
+    kw = cfg.reference_kwargs()
+    kw.pop("local_attn_size"), kw.pop("sink_size")
+    model = ref.WanModel(**kw)
+    missing = model.load_state_dict(params, strict=False)
+    assert not [k for k in missing.missing_keys if not k.startswith("pose_proj")], missing
+    model = model.to(torch.bfloat16).eval()
+    x, t, ctx = bidirectional_inputs()
+    L = x.shape[2] * (x.shape[3] // 2) * (x.shape[4] // 2)
+    with torch.no_grad():
+        out = model(list(x), t=t, context=list(ctx), seq_len=L)
+    return dict(flow=out.clone(), seq_len=L)
+
+
 MASK_CASES = {
     "causal_6f_2blk": ("causal", dict(num_frames=6, frame_seqlen=200, num_frame_per_block=2, local_attn_size=-1)),
     "causal_6f_local2": ("causal", dict(num_frames=6, frame_seqlen=200, num_frame_per_block=1, local_attn_size=2)),
@@ -188,6 +225,7 @@ def main():
 
     torch.save(reference_rolling(ref), os.path.join(GOLDEN, "model_rolling.pt"))
     torch.save(reference_masks(ref), os.path.join(GOLDEN, "block_masks.pt"))
+    torch.save(reference_bidirectional(ref), os.path.join(GOLDEN, "bidirectional_tiny.pt"))
     for f in sorted(os.listdir(GOLDEN)):
         print(f, os.path.getsize(os.path.join(GOLDEN, f)))
 

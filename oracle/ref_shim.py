@@ -132,6 +132,7 @@ def load_reference(root: str = REF_ROOT, force_sdpa: bool | None = None):
         attention=attention, model=model, causal_model=causal_model, scheduler=scheduler,
         wan_wrapper=wan_wrapper, causal_inference=causal_inference,
         CausalWanModel=causal_model.CausalWanModel,
+        WanModel=model.WanModel,
         WanDiffusionWrapper=wan_wrapper.WanDiffusionWrapper,
         FlowMatchScheduler=scheduler.FlowMatchScheduler,
         CausalInferencePipeline=causal_inference.CausalInferencePipeline,

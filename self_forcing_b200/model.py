@@ -188,23 +188,24 @@ class B200CausalWanModel(nn.Module):
         self._sp_kv.clear()
         self._sp_buf.clear()
 
-    def allocate_kv_cache(self, batch_size: int, tokens: int, dtype, device) -> List[dict]:
+    def allocate_kv_cache(self, batch_size: int, tokens: int, dtype, device, layers: Optional[int] = None) -> List[dict]:
         """Per-layer cache dicts like CausalInferencePipeline._initialize_kv_cache (pipeline/causal_inference.py:278-298).
         Under Ulysses the K/V tensors are head-sharded [1, S, H/P, D] views of one peer-mapped pool, because the
         other ranks' qk_norm_rope kernels store this rank's head group straight into it."""
         sp = self._sp
         heads = self.num_heads // (sp.world if sp is not None else 1)
+        nl = self.num_layers if layers is None else layers
         if sp is None:
-            pool = torch.zeros(self.num_layers, 2, batch_size, tokens, heads, self.head_dim, dtype=dtype, device=device)
-            kv = [(pool[i, 0], pool[i, 1]) for i in range(self.num_layers)]
+            pool = torch.zeros(nl, 2, batch_size, tokens, heads, self.head_dim, dtype=dtype, device=device)
+            kv = [(pool[i, 0], pool[i, 1]) for i in range(nl)]
         else:
             if batch_size != 1:
                 raise ValueError("Ulysses mode runs one video (batch 1) per group")
-            peer = sp.alloc((self.num_layers, 2, tokens, heads, self.head_dim), dtype)
+            peer = sp.alloc((nl, 2, tokens, heads, self.head_dim), dtype)
             peer.local.zero_()
             per = tokens * heads * self.head_dim
             kv = []
-            for i in range(self.num_layers):
+            for i in range(nl):
                 k, v = peer.local[i, 0].unsqueeze(0), peer.local[i, 1].unsqueeze(0)
                 self._sp_kv[k.data_ptr()] = (peer, (2 * i) * per)
                 self._sp_kv[v.data_ptr()] = (peer, (2 * i + 1) * per)
@@ -310,7 +311,11 @@ class B200CausalWanModel(nn.Module):
         fs = Hh * Ww
         L = F_ * fs
         assert L <= seq_len
-        assert Cin == self.in_dim and t.shape == (B, F_), f"timestep shape {tuple(t.shape)} != {(B, F_)}"
+        # one timestep per group of frames: [B, F] per-frame (causal rollout) ... [B, 1] per sample (bidirectional teacher)
+        assert Cin == self.in_dim and t.dim() == 2 and t.shape[0] == B and F_ % t.shape[1] == 0, \
+            f"timestep shape {tuple(t.shape)} does not divide the {F_} frames of a batch of {B}"
+        Fm = t.shape[1]
+        mod_rows = (F_ // Fm) * fs        # token rows that share one adaLN modulation vector
         C, NL, D, NH = self.dim, self.num_layers, self.head_dim, self.num_heads
         dev = x.device
         sp = self._sp
@@ -323,7 +328,7 @@ class B200CausalWanModel(nn.Module):
             q_peer, attn_peer = self._sp_buffers(L, self.patch_embedding.weight.dtype)
         else:
             off, Lr, NHg = 0, L, NH
-        ws = self._workspace(B, Lr, F_, dev, L)
+        ws = self._workspace(B, Lr, Fm, dev, L)
         R = B * Lr
 
         # ---- host prelude: what this call has to do (no device work yet) ----------------------
@@ -337,7 +342,7 @@ class B200CausalWanModel(nn.Module):
         if return_x0 and self._sampler_tables is None:
             raise RuntimeError("return_x0 needs set_sampler_tables() (done by B200DiffusionWrapper)")
 
-        env = dict(ops=ops, pk=pk, ws=ws, sp=sp, dev=dev, B=B, F_=F_, H=H, W=W, Hh=Hh, Ww=Ww, fs=fs, L=L, Lr=Lr, off=off, R=R,
+        env = dict(ops=ops, pk=pk, ws=ws, sp=sp, dev=dev, mod_rows=mod_rows, Fm=Fm, B=B, F_=F_, H=H, W=W, Hh=Hh, Ww=Ww, fs=fs, L=L, Lr=Lr, off=off, R=R,
                    C=C, NL=NL, D=D, NH=NH, NHg=NHg, kv_cache=kv_cache, crossattn_cache=crossattn_cache, plans=plans,
                    need_ctx=need_ctx, start_frame=start_frame, current_start=current_start, skip_output=skip_output,
                    return_x0=return_x0)
@@ -397,6 +402,7 @@ class B200CausalWanModel(nn.Module):
         C, NL, D, NH, NHg, dev = (env[k] for k in ("C", "NL", "D", "NH", "NHg", "dev"))
         kv_cache, crossattn_cache, plans = env["kv_cache"], env["crossattn_cache"], env["plans"]
         need_ctx, start_frame, skip_output, return_x0 = env["need_ctx"], env["start_frame"], env["skip_output"], env["return_x0"]
+        mod_rows = env["mod_rows"]
         if sp is not None:
             q_peer, attn_peer = env["q_peer"], env["attn_peer"]
 
@@ -435,7 +441,7 @@ class B200CausalWanModel(nn.Module):
             m = mod[i]   # [B*F, 6, C]
             sa, ca = blk.self_attn, blk.cross_attn
             # -- self attention --
-            ops.ln_modulate(ws["x"], ws["h"], shift=m[:, 0], scale=m[:, 1], mod_stride=mstride, rows_per_mod=fs,
+            ops.ln_modulate(ws["x"], ws["h"], shift=m[:, 0], scale=m[:, 1], mod_stride=mstride, rows_per_mod=mod_rows,
                             eps=self.eps, row_offset=off)
             kc, vc = cache["k"], cache["v"]
             if kc.shape[0] != B or kc.shape[2] != NHg or kc.shape[3] != D:
@@ -466,7 +472,7 @@ class B200CausalWanModel(nn.Module):
                                  vc[0, plan.attn_start:plan.attn_end], scale, sp, attn_peer, Lr)
                 sp.barrier(ops)          # every head group's output columns have landed
                 ops.gemm(attn_peer.local, sa.o.weight, sa.o.bias, ws["x"], epilogue=EPI_GATE_RES, residual=ws["x"],
-                         gate=m[:, 2], gate_stride=mstride, rows_per_gate=fs, gate_row_offset=off)
+                         gate=m[:, 2], gate_stride=mstride, rows_per_gate=mod_rows, gate_row_offset=off)
             elif B == 1:   # V projection lands directly in its cache slot
                 ops.gemm(ws["h"], pb["wqkv"], pb["bqkv"], None, seg_cols=C,
                          outs=[ws["q_lin"], ws["k_lin"], v_slot.reshape(L, C)])
@@ -485,7 +491,7 @@ class B200CausalWanModel(nn.Module):
                 ops.attention(q4, kc[:, plan.attn_start:plan.attn_end], vc[:, plan.attn_start:plan.attn_end],
                               ws["attn"].view(B, L, NH, D), scale)
                 ops.gemm(ws["attn"], sa.o.weight, sa.o.bias, ws["x"], epilogue=EPI_GATE_RES, residual=ws["x"],
-                         gate=m[:, 2], gate_stride=mstride, rows_per_gate=fs)
+                         gate=m[:, 2], gate_stride=mstride, rows_per_gate=mod_rows)
             # -- cross attention --
             cc = crossattn_cache[i]
             if not cc["is_init"]:
@@ -504,18 +510,18 @@ class B200CausalWanModel(nn.Module):
             ops.attention(q4, cc["k"], cc["v"], ws["attn"].view(B, Lr, NH, D), scale)
             ops.gemm(ws["attn"], ca.o.weight, ca.o.bias, ws["x"], epilogue=EPI_RESIDUAL, residual=ws["x"])
             # -- feed forward --
-            ops.ln_modulate(ws["x"], ws["h"], shift=m[:, 3], scale=m[:, 4], mod_stride=mstride, rows_per_mod=fs,
+            ops.ln_modulate(ws["x"], ws["h"], shift=m[:, 3], scale=m[:, 4], mod_stride=mstride, rows_per_mod=mod_rows,
                             eps=self.eps, row_offset=off)
             ops.gemm(ws["h"], blk.ffn[0].weight, blk.ffn[0].bias, ws["ffn"], epilogue=EPI_GELU)
             ops.gemm(ws["ffn"], blk.ffn[2].weight, blk.ffn[2].bias, ws["x"], epilogue=EPI_GATE_RES,
-                     residual=ws["x"], gate=m[:, 5], gate_stride=mstride, rows_per_gate=fs, gate_row_offset=off)
+                     residual=ws["x"], gate=m[:, 5], gate_stride=mstride, rows_per_gate=mod_rows, gate_row_offset=off)
 
         if skip_output:
             return None
 
         # ---- head ------------------------------------------------------------------------------
         hm = ws["head_mod"][0]   # [B*F, 2, C]
-        ops.ln_modulate(ws["x"], ws["h"], shift=hm[:, 0], scale=hm[:, 1], mod_stride=2 * C, rows_per_mod=fs,
+        ops.ln_modulate(ws["x"], ws["h"], shift=hm[:, 0], scale=hm[:, 1], mod_stride=2 * C, rows_per_mod=mod_rows,
                         eps=self.eps, row_offset=off)
         ops.gemm(ws["h"], self.head.head.weight, self.head.head.bias, ws["head_out"])
         if env.get("defer_gather"):
@@ -534,6 +540,8 @@ class B200CausalWanModel(nn.Module):
         flow = torch.empty(B, F_, self.out_dim, H, W, dtype=ws["x"].dtype, device=dev)
         x0 = None
         xt = x.permute(0, 2, 1, 3, 4)   # [B, F, C, H, W] view of the input
+        if env["Fm"] != F_:             # the flow -> x0 kernel wants one timestep per frame
+            t = t.repeat_interleave(F_ // env["Fm"], dim=1)
         if env["return_x0"]:
             x0 = torch.empty_like(flow)
             ops.head_finish(head_out, xt, t.contiguous(), self._sampler_tables[0], self._sampler_tables[1],
@@ -541,3 +549,50 @@ class B200CausalWanModel(nn.Module):
         else:
             ops.head_finish(head_out, xt, t.contiguous(), None, None, flow, None)
         return flow, x0
+
+
+class B200WanModel(B200CausalWanModel):
+    """Drop-in for the bidirectional `WanModel` forward (wan/modules/model.py:497-771, t2v, no GAN/classify branch):
+    the teacher / ODE-pair generator of BASELINE config 5.
+
+    A bidirectional forward is the cached causal forward with ONE timestep per sample and an empty cache: every
+    token attends to all tokens written by this very call, RoPE starts at frame 0, adaLN vectors are per sample
+    (`e [B, 6, C]`, model.py:697-700) and the text K/V are recomputed per call.  So this class only supplies scratch
+    K/V (one buffer shared by all layers -- nothing persists) and forwards to the same kernel schedule; under
+    `enable_ulysses` it is the head-parallel forward of wan/distributed/xdit_context_parallel.py:66-192.
+    Limitation: all samples must have exactly `seq_len` tokens (no padded sequences / k_lens masking)."""
+
+    def __init__(self, *args, **kwargs):
+        kwargs.pop("local_attn_size", None)
+        kwargs.pop("sink_size", None)
+        super().__init__(*args, **kwargs)
+        self._scratch: Dict[tuple, tuple] = {}
+
+    def _apply(self, fn, *a, **k):
+        self._scratch.clear()
+        return super()._apply(fn, *a, **k)
+
+    def forward(self, x, t, context, seq_len, clip_fea=None, y=None, return_x0: bool = False, **unsupported):
+        if any(v is not None and v is not False for v in unsupported.values()):
+            raise NotImplementedError(f"B200WanModel: unsupported arguments {sorted(unsupported)} (t2v forward only)")
+        if isinstance(x, (list, tuple)):
+            x = torch.stack(list(x))
+        B, _, F_, H, W = x.shape
+        L = F_ * (H // 2) * (W // 2)
+        if L != seq_len:
+            raise NotImplementedError(f"B200WanModel needs full-length samples: {L} tokens != seq_len {seq_len}")
+        dev, dt = x.device, self.patch_embedding.weight.dtype
+        key = (B, L, str(dev))
+        if key not in self._scratch:
+            kv = self.allocate_kv_cache(B, L, dt, dev, layers=1)[0]
+            ck = torch.zeros(B, self.text_len, self.num_heads, self.head_dim, dtype=dt, device=dev)
+            self._scratch[key] = (kv["k"], kv["v"], ck, torch.zeros_like(ck))
+        k, v, ck, cv = self._scratch[key]
+        zero = torch.zeros(1, dtype=torch.long, device=dev)
+        kv_cache = [dict(k=k, v=v, global_end_index=zero.clone(), local_end_index=zero.clone())
+                    for _ in range(self.num_layers)]
+        ca_cache = [dict(k=ck, v=cv, is_init=False) for _ in range(self.num_layers)]
+        if y is not None or clip_fea is not None:
+            raise NotImplementedError("image conditioning (i2v) is not supported")
+        return self._forward_inference(x, t.reshape(B, 1), context, seq_len, kv_cache=kv_cache, crossattn_cache=ca_cache,
+                                       current_start=0, return_x0=return_x0)

@@ -16,7 +16,7 @@ from typing import List, Optional
 import torch
 from torch import nn
 
-from .model import B200CausalWanModel
+from .model import B200CausalWanModel, B200WanModel
 from .scheduler import FlowMatchScheduler
 
 WAN_T2V_1_3B = dict(model_type="t2v", patch_size=(1, 2, 2), text_len=512, in_dim=16, dim=1536, ffn_dim=8960,
@@ -34,8 +34,6 @@ class B200DiffusionWrapper(nn.Module):
         otherwise `config.json` + safetensors / .pth weights are read from model_path (HF layout used by
         CausalWanModel.from_pretrained at wan_wrapper.py:139-145)."""
         super().__init__()
-        if not is_causal:
-            raise NotImplementedError("the bidirectional WanModel is outside the rollout hot path")
         lora = {k: v for k, v in unsupported.items() if k.startswith("lora") and v}
         if lora.get("lora_rank"):
             raise NotImplementedError("merge LoRA weights offline (scripts/merge_lora.py) before loading")
@@ -44,8 +42,11 @@ class B200DiffusionWrapper(nn.Module):
         if cfg is None:
             path = model_path or f"wan_models/{model_name}/"
             cfg, state = _read_checkpoint_dir(path)
-        cfg.update(local_attn_size=local_attn_size, sink_size=sink_size)
-        self.model = B200CausalWanModel(**cfg, ops=ops)
+        if is_causal:
+            cfg.update(local_attn_size=local_attn_size, sink_size=sink_size)
+            self.model = B200CausalWanModel(**cfg, ops=ops)
+        else:   # bidirectional teacher (wan_wrapper.py:146 `WanModel.from_pretrained`); one timestep per sample
+            self.model = B200WanModel(**cfg, ops=ops)
         if device is not None:
             self.model.to(device)
         self.model.to(dtype)
@@ -54,7 +55,7 @@ class B200DiffusionWrapper(nn.Module):
         elif init_seed is not None:
             self.model.init_weights(init_seed)
         self.model.eval()
-        self.uniform_timestep = False
+        self.uniform_timestep = not is_causal      # wan_wrapper.py:170
         self.scheduler = FlowMatchScheduler(shift=timestep_shift, sigma_min=0.0, extra_one_step=True, ops=ops)
         self.scheduler.set_timesteps(1000, training=True)
         self.model.set_sampler_tables(self.scheduler.timesteps, self.scheduler.sigmas)
@@ -68,10 +69,18 @@ class B200DiffusionWrapper(nn.Module):
                 current_start: Optional[int] = None, classify_mode: bool = False,
                 concat_time_embeddings: bool = False, clean_x=None, aug_t=None, cache_start: Optional[int] = None,
                 add_condition=None, clip_feature=None, y=None, refresh_only: bool = False):
-        if kv_cache is None:
-            raise NotImplementedError("B200DiffusionWrapper implements the KV-cached causal path only")
         if classify_mode or clean_x is not None:
-            raise NotImplementedError("training-time modes are out of scope")
+            raise NotImplementedError("training-time modes (GAN classify branch, teacher forcing) are out of scope")
+        if kv_cache is None:
+            # bidirectional forward (wan_wrapper.py:329-337): [B, F] timesteps must be uniform per sample (:282-283)
+            if not isinstance(self.model, B200WanModel):
+                raise NotImplementedError("the causal model without a KV cache is the training forward (out of scope)")
+            t0 = timestep[:, 0]
+            if not bool((timestep == t0[:, None]).all()):
+                raise ValueError("the bidirectional model takes one timestep per sample")
+            flow, x0 = self.model(noisy_image_or_video.permute(0, 2, 1, 3, 4), t=t0,
+                                  context=conditional_dict["prompt_embeds"], seq_len=self.seq_len, return_x0=True)
+            return flow.permute(0, 2, 1, 3, 4), x0
         cond = conditional_dict
         if add_condition is None:
             add_condition = cond.get("add_condition")

@@ -246,3 +246,46 @@ def test_bench_flop_model_matches_survey():
     spec.loader.exec_module(b)
     assert abs(b.rollout_flops(3) / 1e12 - 990.3) < 0.5
     assert abs(b.rollout_flops(1) / 1e12 - 943.2) < 0.5
+
+
+def test_bidirectional_model_matches_reference_golden():
+    """B200WanModel (host orchestration, CPU test double for the kernels): per-sample timesteps, scratch K/V shared by
+    all layers, text K/V recomputed per call -> equals the reference WanModel golden."""
+    from oracle.make_golden import BIDIR, bidirectional_cfg, bidirectional_inputs
+    from self_forcing_b200.model import B200WanModel
+    g = golden("bidirectional_tiny.pt")
+    r = BIDIR
+    model = B200WanModel(dim=r["dim"], ffn_dim=r["ffn_dim"], num_heads=r["num_heads"], num_layers=r["num_layers"],
+                         text_dim=r["text_dim"], ops=TorchOps()).to(torch.bfloat16)
+    model.load_state_dict(O.make_random_params(bidirectional_cfg(), seed=9), strict=True)
+    x, t, ctx = bidirectional_inputs()
+    out = model(list(x), t=t, context=list(ctx), seq_len=g["seq_len"])
+    assert out.shape == g["flow"].shape and rel_l2(out, g["flow"]) <= 1e-2
+    out2 = model(x, t=t, context=ctx, seq_len=g["seq_len"])        # scratch buffers are reusable
+    assert torch.equal(out, out2)
+    with pytest.raises(NotImplementedError):
+        model(x, t=t, context=ctx, seq_len=g["seq_len"] + 8)      # padded sequences are not supported
+
+
+def test_bidirectional_wrapper_surface():
+    """WanDiffusionWrapper(is_causal=False) surface (utils/wan_wrapper.py:253-349 without kv_cache): [B, F] uniform
+    timesteps -> (flow_pred, pred_x0) with x0 = x_t - sigma_t * flow in float64."""
+    from oracle.make_golden import BIDIR, bidirectional_cfg, bidirectional_inputs
+    from self_forcing_b200.wrapper import WAN_T2V_1_3B, B200DiffusionWrapper
+    g = golden("bidirectional_tiny.pt")
+    r = BIDIR
+    cfgd = dict(WAN_T2V_1_3B, dim=r["dim"], ffn_dim=r["ffn_dim"], num_heads=r["num_heads"], num_layers=r["num_layers"],
+                text_dim=r["text_dim"])
+    w = B200DiffusionWrapper(model_config=cfgd, timestep_shift=5.0, is_causal=False, ops=TorchOps())
+    w.model.load_state_dict(O.make_random_params(bidirectional_cfg(), seed=9), strict=True)
+    w.seq_len = g["seq_len"]
+    x, t, ctx = bidirectional_inputs()
+    xt = x.permute(0, 2, 1, 3, 4)                                     # the wrapper takes [B, F, C, H, W]
+    tt = t[:, None].expand(-1, xt.shape[1]).contiguous()
+    flow, x0 = w(xt, {"prompt_embeds": ctx}, tt)
+    assert rel_l2(flow.permute(0, 2, 1, 3, 4), g["flow"]) <= 1e-2
+    sched = O.OracleScheduler(5.0)
+    ref_x0 = O.flow_to_x0(sched, flow.flatten(0, 1), xt.flatten(0, 1), tt.flatten(0, 1)).unflatten(0, flow.shape[:2])
+    assert torch.equal(x0, ref_x0)
+    with pytest.raises(ValueError):
+        w(xt, {"prompt_embeds": ctx}, torch.tensor([[937.5, 250.0], [250.0, 250.0]]))

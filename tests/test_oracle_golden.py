@@ -102,3 +102,15 @@ def test_cache_plan_known_answers():
                 if chunk == 2 and sink == 1 and p.roll:
                     assert (p.roll_src, p.roll_dst, p.roll_len) == (16, 4, 8)
         assert trace == [(12, 12), (12, 12), (24, 24), (24, 24), (36, 24), (36, 24), (48, 24), (48, 24), (60, 24), (60, 24)]
+
+
+def test_bidirectional_forward_matches_reference_golden():
+    """BASELINE config 5 (teacher forward): the oracle's bidirectional restatement equals the unmodified reference
+    WanModel bit for bit."""
+    from oracle.make_golden import bidirectional_cfg, bidirectional_inputs
+    g = golden("bidirectional_tiny.pt")
+    x, t, ctx = bidirectional_inputs()
+    cfg = bidirectional_cfg()
+    with torch.no_grad():
+        out = O.bidirectional_forward(O.make_random_params(cfg, seed=9), cfg, x, t, ctx)
+    assert torch.equal(out, g["flow"])

@@ -42,3 +42,19 @@ def test_reference_sdpa_vs_fp32_softmax():
     s = torch.einsum("blhd,bshd->bhls", q.float(), k.float()) / 128 ** 0.5
     ref = torch.einsum("bhls,bshd->blhd", torch.softmax(s, -1), v.float())
     assert float((o - ref).norm() / ref.norm()) < 1e-2
+
+
+def test_bidirectional_reference_equals_golden_and_oracle():
+    """Container only: re-run the unmodified bidirectional WanModel and compare with the committed golden + oracle."""
+    import torch
+    from helpers import golden
+    from oracle import causal_wan_oracle as O
+    from oracle import make_golden as G
+    ref = ref_shim.load_reference()
+    fresh = G.reference_bidirectional(ref)
+    g = golden("bidirectional_tiny.pt")
+    assert torch.equal(fresh["flow"], g["flow"])
+    x, t, ctx = G.bidirectional_inputs()
+    cfg = G.bidirectional_cfg()
+    with torch.no_grad():
+        assert torch.equal(O.bidirectional_forward(O.make_random_params(cfg, seed=9), cfg, x, t, ctx), g["flow"])

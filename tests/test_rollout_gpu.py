@@ -164,3 +164,18 @@ def test_rolling_sink_cache_on_gpu_matches_reference_golden():
     assert rel_l2(torch.stack(flows).cpu(), g["flows"]) <= TOL
     for i in range(cfg.num_layers):
         assert rel_l2(kv[i]["k"].cpu(), g["k"][i]) <= TOL and rel_l2(kv[i]["v"].cpu(), g["v"][i]) <= TOL
+
+
+def test_bidirectional_teacher_forward_on_gpu_matches_reference_golden():
+    """BASELINE config 5 at tiny size: B200WanModel through the CUDA kernels vs the unmodified reference WanModel."""
+    from oracle.make_golden import BIDIR, bidirectional_cfg, bidirectional_inputs
+    from self_forcing_b200.model import B200WanModel
+    g = golden("bidirectional_tiny.pt")
+    r = BIDIR
+    model = B200WanModel(dim=r["dim"], ffn_dim=r["ffn_dim"], num_heads=r["num_heads"], num_layers=r["num_layers"],
+                         text_dim=r["text_dim"]).to("cuda").to(torch.bfloat16)
+    model.load_state_dict(O.make_random_params(bidirectional_cfg(), seed=9), strict=True)
+    x, t, ctx = (v.cuda() for v in bidirectional_inputs())
+    out = model(list(x), t=t, context=list(ctx), seq_len=g["seq_len"])
+    assert rel_l2(out.cpu(), g["flow"]) <= TOL
+    assert torch.equal(out, model(x, t=t, context=ctx, seq_len=g["seq_len"]))

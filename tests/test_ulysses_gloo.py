@@ -45,6 +45,20 @@ def _worker(rank: int, world: int, port: int, out_dir: str):
                    head_nonzero=float(kc[:, :9360].float().abs().max()))
         torch.save(res, os.path.join(out_dir, f"rank{rank}.pt"))
         torch.save(lat, os.path.join(out_dir, f"lat{rank}.pt"))
+
+        # bidirectional teacher forward (BASELINE config 5) head-parallel: sample 0 of the reference golden
+        from oracle import causal_wan_oracle as O
+        from oracle.make_golden import BIDIR, bidirectional_cfg, bidirectional_inputs
+        from self_forcing_b200.model import B200WanModel
+        gb = golden("bidirectional_tiny.pt")
+        r = BIDIR
+        teacher = B200WanModel(dim=r["dim"], ffn_dim=r["ffn_dim"], num_heads=r["num_heads"], num_layers=r["num_layers"],
+                               text_dim=r["text_dim"], ops=TorchOps()).to(torch.bfloat16)
+        teacher.load_state_dict(O.make_random_params(bidirectional_cfg(), seed=9), strict=True)
+        teacher.enable_ulysses(sp)
+        xb, tb, cb = bidirectional_inputs()
+        out = teacher(xb[:1], t=tb[:1], context=cb[:1], seq_len=gb["seq_len"])
+        torch.save(dict(err=rel_l2(out, gb["flow"][:1])), os.path.join(out_dir, f"bidir{rank}.pt"))
     finally:
         dist.destroy_process_group()
 
@@ -61,3 +75,5 @@ def test_ulysses_rollout_world2_matches_reference_golden(tmp_path):
         assert r["index"] == r["final_index"]                  # index arithmetic unchanged (bit-exact)
         assert r["tail_zero"] == 0.0 and r["head_nonzero"] > 0
         assert r["err"] <= 1e-2, r["err"]
+    for rk in range(world):
+        assert torch.load(tmp_path / f"bidir{rk}.pt")["err"] <= 1e-2
