@@ -41,6 +41,22 @@ def main():
     res = dict(rank=rank, world=world, rel_l2=err, index=idx, golden_index=list(g["final_index"]), identical_across_ranks=same,
                repeatable=bool(torch.equal(lat, lat2)), heads_per_rank=pipe.kv_cache1[0]["k"].shape[2],
                ok=bool(err <= 1e-2 and tuple(idx) == tuple(g["final_index"]) and same and torch.equal(lat, lat2)))
+    # bidirectional teacher forward (BASELINE config 5) head-parallel, tiny size, vs the reference WanModel golden
+    from oracle import causal_wan_oracle as O
+    from oracle.make_golden import BIDIR, bidirectional_cfg, bidirectional_inputs
+    from self_forcing_b200.model import B200WanModel
+    gb = golden("bidirectional_tiny.pt")
+    r = BIDIR
+    if r["num_heads"] % world == 0 and gb["seq_len"] % world == 0:
+        teacher = B200WanModel(dim=r["dim"], ffn_dim=r["ffn_dim"], num_heads=r["num_heads"], num_layers=r["num_layers"],
+                               text_dim=r["text_dim"]).to(dev).to(torch.bfloat16)
+        teacher.load_state_dict(O.make_random_params(bidirectional_cfg(), seed=9), strict=True)
+        teacher.enable_ulysses(sp)
+        xb, tb, cb = (v.to(dev) for v in bidirectional_inputs())
+        outb = teacher(xb[:1], t=tb[:1], context=cb[:1], seq_len=gb["seq_len"])
+        torch.cuda.synchronize()
+        res["bidirectional_rel_l2"] = rel_l2(outb.cpu(), gb["flow"][:1])
+        res["ok"] = bool(res["ok"] and res["bidirectional_rel_l2"] <= 1e-2)
     print("ULYSSES_CHECK " + json.dumps(res), flush=True)
     import threading
     code = 0 if res["ok"] else 1
