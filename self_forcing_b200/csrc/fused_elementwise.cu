@@ -75,8 +75,11 @@ __global__ void modulation_table_kernel(const __nv_bfloat16* __restrict__ mod, c
 // ------------------------------------------------------------------------------------
 // LayerNorm (no affine) + adaLN modulation, or LayerNorm with affine.  NV = C / 256.
 // ------------------------------------------------------------------------------------
+// resident blocks per SM asked of the compiler: 4 (64 registers) while a packed row fits, 1 (255 registers) for wide rows (C = 5120)
+constexpr int row_kernel_blocks(int nv) { return nv <= 8 ? 4 : 1; }
+
 template <int NV, bool AFFINE>
-__global__ void __launch_bounds__(ROW_WARPS * 32, 4)   // 32 rows per SM in flight: a 4680-row chunk is one wave on 148 SMs
+__global__ void __launch_bounds__(ROW_WARPS * 32, row_kernel_blocks(NV))   // NV <= 8: 32 rows per SM in flight, a 4680-row chunk is one wave
 ln_kernel(const __nv_bfloat16* __restrict__ x, long long ldx, __nv_bfloat16* __restrict__ y, long long ldy, int rows,
           float eps, const __nv_bfloat16* __restrict__ shift, const __nv_bfloat16* __restrict__ scale,
           long long mod_stride, int rows_per_mod, int row_offset, const __nv_bfloat16* __restrict__ w,
@@ -194,7 +197,7 @@ __device__ __forceinline__ void rms_apply(const uint4& raw, const __nv_bfloat16*
 }
 
 template <int NV>
-__global__ void __launch_bounds__(ROW_WARPS * 32, 4)
+__global__ void __launch_bounds__(ROW_WARPS * 32, row_kernel_blocks(NV))
 rmsnorm_kernel(const __nv_bfloat16* __restrict__ x, long long ldx, __nv_bfloat16* __restrict__ y, long long ldy,
                int rows, float eps, const __nv_bfloat16* __restrict__ w) {
   const int row = blockIdx.x * ROW_WARPS + (threadIdx.x >> 5);
@@ -213,7 +216,7 @@ rmsnorm_kernel(const __nv_bfloat16* __restrict__ x, long long ldx, __nv_bfloat16
 // One warp per token: q and k rows normalised + rotated; q -> q_out, k -> cache slot, v -> cache slot.
 // Rows are (sample b, token n): source row = b * L + n; destinations use their own batch strides.
 template <int NV>
-__global__ void __launch_bounds__(ROW_WARPS * 32, 4)
+__global__ void __launch_bounds__(ROW_WARPS * 32, row_kernel_blocks(NV))
 qk_norm_rope_kernel(const __nv_bfloat16* __restrict__ q_in, long long ldq, const __nv_bfloat16* __restrict__ k_in,
                     long long ldk, const __nv_bfloat16* __restrict__ v_in, long long ldv,
                     const __nv_bfloat16* __restrict__ wq, const __nv_bfloat16* __restrict__ wk, float eps,

@@ -17,6 +17,11 @@ sm_100a kernels (libsfb200.so, include/sfb200.h) with no PyTorch compute on the 
 The torch.nn modules below only *hold parameters* under the reference's names; nothing calls their
 forward.  The training branch of the reference (`kv_cache is None`, FlexAttention) is out of scope
 and raises.
+
+Execution: every forward is split into a host prelude (cache plan + index mirror: integers only) and
+`_device_forward` (all kernels, no host sync); `_device_forward` is replayed as ONE CUDA graph per static signature
+(captured on its second occurrence).  `enable_ulysses` switches self-attention to head-parallel execution over several
+GPUs (ulysses.py).  `B200WanModel` (bottom of this file) is the bidirectional teacher forward on the same schedule.
 """
 from __future__ import annotations
 

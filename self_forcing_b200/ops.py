@@ -43,8 +43,9 @@ def _op(fn):
 
 
 class CudaOps:
-    """The op set the host model is written against.  Every method enqueues exactly one kernel
-    of libsfb200.so on the current CUDA stream."""
+    """The op set the host model is written against.  Every method enqueues one kernel of libsfb200.so on the
+    current CUDA stream (attention: plus the small partial-merge kernel when a long KV window is split across SMs);
+    nothing synchronises with the host, so a whole forward can be captured into a CUDA graph."""
 
     requires_bf16 = True
     supports_cuda_graphs = True   # every op only enqueues kernels on the current stream (no host sync, no allocation)

@@ -472,6 +472,8 @@ ALL = {
     "attn_few_items": lambda: check_attention(Lq=1560, S=32760, H=12, seed=9),
     "peer_barrier": check_peer_barrier_single,
     "ln_row_offset": check_ln_row_offset,
+    "ln_row_offset_c5120": lambda: check_ln_row_offset(rows=200, C=5120, seed=3),
+    "qk_norm_rope_c5120": lambda: check_qk_norm_rope(B=1, F_=2, Hh=4, Ww=6, C=5120, start_frame=0, seed=4),
     "gemm_streamk_o_proj": lambda: check_gemm(M=4680, N=1536, K=1536, epilogue=3, rows_per_gate=1560, seed=11, block_n=513),
     "gemm_streamk_qkv": lambda: check_gemm(M=4680, N=4608, K=1536, seed=12, block_n=513),
     "gemm_streamk_cross_o": lambda: check_gemm(M=4680, N=1536, K=1536, epilogue=2, seed=13, block_n=513),
