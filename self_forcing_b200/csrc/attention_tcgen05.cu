@@ -627,7 +627,9 @@ static int attention_launch(const void* q, long long q_row_stride, long long q_b
   p.n_groups = 1;
   const long long slot_bytes = (long long)sms * 2 * 2 * ATT_SLOT_FLOATS * (long long)sizeof(float);   // per group
   const char* nosplit = getenv("SFB_ATTN_NOSPLIT");
-  p.split = (p.items % sms != 0 && p.n_kv_tiles >= ATT_MIN_SPLIT_KV_TILES && workspace != nullptr &&
+  // (with >= 8 items per SM whole items already balance to within a few per cent, and consecutive CTAs walk the same
+  // head's K/V together -- no partials, natural L2 locality: the 14B teacher has 5120 items)
+  p.split = (p.items % sms != 0 && p.items < 8 * sms && p.n_kv_tiles >= ATT_MIN_SPLIT_KV_TILES && workspace != nullptr &&
              workspace_bytes >= slot_bytes && !(nosplit && nosplit[0] == '1')) ? 1 : 0;
   if (p.split) {
     grid = sms;
