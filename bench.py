@@ -81,6 +81,23 @@ def ncu_traffic():
         return None
 
 
+def ncu_tensor_pipe():
+    """sm__pipe_tensor_cycles_active (% of active cycles) of the tensor-core kernels from the committed ncu --set full
+    captures (profiles/r01e_ncu_tensor_kernels.json) -- evidence quoted next to the live numbers, not measured here."""
+    path = os.path.join(ROOT, "profiles", "r01e_ncu_tensor_kernels.json")
+    key = "sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active"
+    try:
+        d = json.load(open(path))
+        out = {}
+        for group in ("r01e_attn", "r01e_gemm"):
+            for name, k in d[group].items():
+                out[name.replace("void ", "")] = float(k[key].split()[0])
+        out["source"] = "profiles/r01e_ncu_tensor_kernels.json (ncu --set full --clock-control none; gemm2<0> = QKV bias epilogue, gemm2<3> = N=1536 gate+residual)"
+        return out
+    except Exception:
+        return None
+
+
 def workload_name(chunk_frames: int) -> str:
     kind = "chunk-wise (3 latent frames/chunk)" if chunk_frames == 3 else f"{chunk_frames} latent frame(s)/block"
     return f"wan2.1-t2v-1.3b self-forcing dmd {kind}, 81 frames 480x832, 4 steps, batch 1 per GPU"
@@ -417,6 +434,17 @@ def run_product_arm(args) -> None:
                      **({"tflops": round(g[2] / g[1] / 1e9, 1)} if g[2] else {})}
                  for k, g in sorted(groups.items(), key=lambda kv: -kv[1][1])}
     gemm = groups.get("gemm", [0, 0.0, 0.0])
+    # HBM-bound kernels: algorithmic bytes (rows read + written, SURVEY.md 8d / DESIGN.md 4) over the event-timed launches
+    Lrows = cf * FRAME_TOKENS // sp_size
+    hbm_lines = []
+    for kname, passes in (("qk_norm_rope", 6), ("qk_norm_rope_sp", 6), ("ln_modulate", 2), ("ln_affine", 2), ("rmsnorm", 2)):
+        gk = groups.get(kname)
+        if gk and gk[1] > 0:
+            nbytes = passes * Lrows * C * 2.0 * gk[0]
+            gbs = nbytes / (gk[1] * 1e-3) / 1e9
+            hbm_lines.append({"kernel": kname, "bound": "hbm", "achieved": gbs, "peak": pk["hbm"], "unit": "GB/s",
+                              "frac": gbs / pk["hbm"], "bytes_per_launch": passes * Lrows * C * 2.0,
+                              "note": "per-launch CUDA events of the eager breakdown pass (includes launch gaps of ~10 us kernels)"})
     total_fl = rollout_flops(cf)
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
@@ -447,6 +475,7 @@ def run_product_arm(args) -> None:
         "roofline_gemm": {"kernel": "gemm_bf16_kernel (all projections)", "bound": "tensor",
                           "achieved": gemm[2] / gemm[1] / 1e9 if gemm[1] else 0.0, "peak": pk["sustained"],
                           "unit": "TFLOP/s", "frac": (gemm[2] / gemm[1] / 1e9 if gemm[1] else 0.0) / pk["sustained"]},
+        "roofline_hbm": hbm_lines, "ncu_tensor_pipe_pct": ncu_tensor_pipe(),
         "breakdown": breakdown, "kernel_ms_per_step": kernel_ms, "finite": finite,
         "clocks": clk,
     }

@@ -63,7 +63,7 @@ constexpr int ATT_SMEM_BYTES = 2 * ATT_TILE_BYTES + 2 * ATT_KV_STAGES * ATT_TILE
 constexpr int ATT_DEFAULT_EMU = 0;   // measured: 0 -> 1166, 1 -> 1115, 2 -> 1063 TFLOP/s at Lq 4680 x S 32760 (the softmax is issue-bound)
 constexpr bool ATT_DEFAULT_ALU_PACK = false;
 constexpr int ATT_SLOT_FLOATS = ATT_BM * ATT_D + 2 * ATT_BM;   // one (tile, segment) partial
-constexpr int ATT_MIN_SPLIT_KV_TILES = 16;                     // shorter KV: whole items per CTA
+constexpr int ATT_MIN_SPLIT_KV_TILES = 48;                     // shorter KV (measured: S = 4680 is better whole, S >= 9360 split): whole items per CTA
 constexpr int ATT_MAX_GROUPS = 4;
 constexpr long long ATT_L2_BUDGET = 72ll << 20;                // K + V bytes of the heads in flight (L2 is 126 MB; measured: 3 groups of 4 heads beat 4 x 3 and 6 x 2 at S = 32760)
 
@@ -536,12 +536,25 @@ attention_combine_kernel(const AttnParams p, int grid_fwd) {
     const int first_item = (int)(att_range_start(c, grid_fwd, items_g, p) / n_kv);
     return p.ws + ((((long long)grp * grid_fwd + c) * 2 + (first_item == item ? 0 : 1)) * 2 + t) * ATT_SLOT_FLOATS;
   };
+  // an item is cut by at most a few CTA boundaries: keep the segment pointers and weights in registers
+  constexpr int MAX_SEG = 8;
+  const int nseg = (c1 - c0 + 1) < MAX_SEG ? (c1 - c0 + 1) : MAX_SEG;
+  const float* seg_ptr[MAX_SEG];
+  float w[MAX_SEG];
   float m = -INFINITY;
-  for (int c = c0; c <= c1; ++c) m = fmaxf(m, slot_of(c)[ATT_BM * ATT_D + r]);
+#pragma unroll
+  for (int i = 0; i < MAX_SEG; ++i) {
+    seg_ptr[i] = i < nseg ? slot_of(c0 + i) : nullptr;
+    if (i < nseg) m = fmaxf(m, seg_ptr[i][ATT_BM * ATT_D + r]);
+  }
   float L = 0.f;
-  for (int c = c0; c <= c1; ++c) {
-    const float* sl = slot_of(c);
-    L += sl[ATT_BM * ATT_D + ATT_BM + r] * exp2f((sl[ATT_BM * ATT_D + r] - m) * p.scale_log2);
+#pragma unroll
+  for (int i = 0; i < MAX_SEG; ++i) {
+    w[i] = 0.f;
+    if (i < nseg) {
+      w[i] = exp2f((seg_ptr[i][ATT_BM * ATT_D + r] - m) * p.scale_log2);
+      L += seg_ptr[i][ATT_BM * ATT_D + ATT_BM + r] * w[i];
+    }
   }
   const float inv_l = 1.0f / L;
   const int dst = row / p.rows_per_dst;
@@ -549,11 +562,12 @@ attention_combine_kernel(const AttnParams p, int grid_fwd) {
                         (long long)(row - dst * p.rows_per_dst) * p.out_row_stride + head * ATT_D;
   for (int col = 0; col < ATT_D; col += 8) {
     float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-    for (int c = c0; c <= c1; ++c) {
-      const float* sl = slot_of(c);
-      const float w = exp2f((sl[ATT_BM * ATT_D + r] - m) * p.scale_log2);
 #pragma unroll
-      for (int i = 0; i < 8; ++i) acc[i] += sl[(col + i) * ATT_BM + r] * w;
+    for (int i = 0; i < MAX_SEG; ++i) {
+      if (i < nseg) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[j] += seg_ptr[i][(col + j) * ATT_BM + r] * w[i];
+      }
     }
     uint4 o;
     o.x = pack_bf16(acc[0] * inv_l, acc[1] * inv_l);
@@ -645,6 +659,10 @@ static int attention_launch(const void* q, long long q_row_stride, long long q_b
     p.n_groups = groups;
     p.heads_per_group = (B * H + groups - 1) / groups;
     p.n_groups = (B * H + p.heads_per_group - 1) / p.heads_per_group;
+    // the merge kernel keeps at most 8 segments of an item in registers: never cut an item into more pieces
+    const int last_heads = B * H - (p.n_groups - 1) * p.heads_per_group;
+    const int min_items = last_heads * p.n_qpairs;
+    if ((grid + min_items - 1) / min_items + 1 > 8) grid = min_items * 6;
   }
   if (const char* cap = getenv("SFB_ATTN_GRID")) {   // diagnostic: run on fewer SMs
     const int g = atoi(cap);

@@ -470,6 +470,7 @@ ALL = {
     "attn_sp": check_attention_sp,
     "attn_sp4": lambda: check_attention_sp(P=4, Lq=4680, S=4680, Hg=3),
     "attn_few_items": lambda: check_attention(Lq=1560, S=32760, H=12, seed=9),
+    "attn_very_few_items": lambda: check_attention(Lq=300, S=20000, H=2, seed=10),
     "peer_barrier": check_peer_barrier_single,
     "ln_row_offset": check_ln_row_offset,
     "ln_row_offset_c5120": lambda: check_ln_row_offset(rows=200, C=5120, seed=3),
