@@ -11,7 +11,8 @@
  *   - every pointer is a device pointer that the caller owns (no allocation inside, no state
  *     kept between calls); rows must be 16-byte aligned (strides multiples of 8 elements);
  *   - `stream` is a cudaStream_t (CUstream) cast to void*; work is enqueued asynchronously;
- *   - return value 0 = success, non-zero = error with text in sfb_last_error() (thread-local).
+ *   - return value 0 = success, non-zero = error with text in sfb_last_error() (thread-local);
+ *   - one process drives one GPU (torchrun style): kernel attributes are configured once per process on first use.
  */
 #ifndef SFB200_H_
 #define SFB200_H_
