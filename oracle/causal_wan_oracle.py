@@ -453,7 +453,7 @@ class RolloutTrace:
 def rollout(wrapper: OracleWrapper, noise: Tensor, prompt_embeds: Tensor, denoising_steps: Tensor,
             num_frame_per_block: int, context_noise: float = 0, independent_first_frame: bool = False,
             kv_cache=None, crossattn_cache=None, cache_tokens=None, max_chunks: Optional[int] = None,
-            noise_fn=None) -> RolloutTrace:
+            noise_fn=None, initial_latent: Optional[Tensor] = None) -> RolloutTrace:
     """CausalInferencePipeline.inference without T5/VAE (causal_inference.py:72-246), t2v only.
 
     noise [B, F, 16, H, W].  `noise_fn(like)` supplies the re-noise sample (default
@@ -463,7 +463,8 @@ def rollout(wrapper: OracleWrapper, noise: Tensor, prompt_embeds: Tensor, denois
     ft = (Hh // cfg.patch_size[1]) * (Ww // cfg.patch_size[2])
     if noise_fn is None:
         noise_fn = torch.randn_like
-    if independent_first_frame:
+    n_in = 0 if initial_latent is None else initial_latent.shape[1]
+    if independent_first_frame and initial_latent is None:
         assert (nfr - 1) % num_frame_per_block == 0
         chunks = [1] + [num_frame_per_block] * ((nfr - 1) // num_frame_per_block)
     else:
@@ -473,7 +474,7 @@ def rollout(wrapper: OracleWrapper, noise: Tensor, prompt_embeds: Tensor, denois
         kv_cache = new_kv_cache(cfg, B, ft, noise.dtype, noise.device, cache_tokens)
     if crossattn_cache is None:
         crossattn_cache = new_crossattn_cache(cfg, B, noise.dtype, noise.device)
-    out = torch.zeros_like(noise)
+    out = torch.zeros(B, n_in + nfr, *noise.shape[2:], dtype=noise.dtype, device=noise.device)
     trace = RolloutTrace(latents=out)
 
     def note():
@@ -481,10 +482,28 @@ def rollout(wrapper: OracleWrapper, noise: Tensor, prompt_embeds: Tensor, denois
                                   int(kv_cache[0]["local_end_index"].item())))
 
     start = 0
+    if initial_latent is not None:
+        # causal_inference.py:135-169: the conditioning frames are written to the output and pushed through the model
+        # at timestep 0 only to fill the KV cache (one lone first frame if independent_first_frame, then whole blocks)
+        groups = []
+        if independent_first_frame:
+            assert (n_in - 1) % num_frame_per_block == 0
+            groups.append(1)
+            groups += [num_frame_per_block] * ((n_in - 1) // num_frame_per_block)
+        else:
+            assert n_in % num_frame_per_block == 0
+            groups = [num_frame_per_block] * (n_in // num_frame_per_block)
+        for n in groups:
+            ref = initial_latent[:, start:start + n]
+            out[:, start:start + n] = ref
+            wrapper(ref, prompt_embeds, torch.zeros([B, n], device=noise.device, dtype=torch.int64), kv_cache,
+                    crossattn_cache, start * ft)
+            note()
+            start += n
     for ci, n in enumerate(chunks):
         if max_chunks is not None and ci >= max_chunks:
             break
-        x = noise[:, start:start + n]
+        x = noise[:, start - n_in:start - n_in + n]
         for si, ts in enumerate(denoising_steps):
             timestep = torch.ones([B, n], device=noise.device, dtype=torch.int64) * ts   # :191-194
             _, x0 = wrapper(x, prompt_embeds, timestep, kv_cache, crossattn_cache, start * ft)

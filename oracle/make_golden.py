@@ -70,7 +70,16 @@ class _IdentityVAE(torch.nn.Module):
 ROLLOUT_CASES = {
     "tiny_test_yaml": dict(frames=3, num_frame_per_block=1, independent_first_frame=True, shift=8.0),
     "chunkwise": dict(frames=6, num_frame_per_block=3, independent_first_frame=False, shift=5.0),
+    # video continuation: 3 given latent frames are cached at t = 0 (causal_inference.py:135-169), 3 more are generated
+    "continuation": dict(frames=3, num_frame_per_block=3, independent_first_frame=False, shift=5.0, initial_frames=3),
 }
+
+
+def initial_latent_for(case: dict, H: int = 60, W: int = 104):
+    n = case.get("initial_frames", 0)
+    if not n:
+        return None
+    return torch.randn(1, n, 16, H, W, generator=torch.Generator().manual_seed(4)).to(torch.bfloat16)
 
 
 def reference_rollout(ref, case: dict, params, cfg: O.OracleConfig):
@@ -85,7 +94,7 @@ def reference_rollout(ref, case: dict, params, cfg: O.OracleConfig):
         pipe = ref.CausalInferencePipeline(args, "cpu", generator=w, text_encoder=_TextEncoder(pe), vae=_IdentityVAE())
         pipe.num_transformer_blocks = cfg.num_layers
         with torch.no_grad(), patched_randn_like(3):
-            _, lat = pipe.inference(noise, ["synthetic"], return_latents=True)
+            _, lat = pipe.inference(noise, ["synthetic"], return_latents=True, initial_latent=initial_latent_for(case))
     idx = (int(pipe.kv_cache1[0]["global_end_index"]), int(pipe.kv_cache1[0]["local_end_index"]))
     return lat, idx
 

@@ -7,8 +7,8 @@ import types
 import torch
 
 from oracle import causal_wan_oracle as O
-from oracle.make_golden import (ROLLOUT_CASES, SeededNoise, _IdentityVAE, _TextEncoder, patched_randn_like,
-                                synthetic_inputs)
+from oracle.make_golden import (ROLLOUT_CASES, SeededNoise, _IdentityVAE, _TextEncoder, initial_latent_for,
+                                patched_randn_like, synthetic_inputs)
 
 GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 
@@ -23,6 +23,7 @@ def rel_l2(a, b) -> float:
 
 
 def pipeline_args(case: dict, **extra):
+    extra = {k: v for k, v in extra.items() if k != "initial_frames"}
     return types.SimpleNamespace(denoising_step_list=[1000, 750, 500, 250], warp_denoising_step=True,
                                  num_frame_per_block=case["num_frame_per_block"],
                                  independent_first_frame=case["independent_first_frame"], context_noise=0,

@@ -7,7 +7,7 @@ import pytest
 import torch
 
 from _torch_ops import TorchOps
-from helpers import ROLLOUT_CASES, golden, make_product_pipeline, patched_randn_like, rel_l2
+from helpers import ROLLOUT_CASES, golden, initial_latent_for, make_product_pipeline, patched_randn_like, rel_l2
 from oracle import causal_wan_oracle as O
 from oracle.make_golden import MASK_CASES, ROLLING, rolling_cfg, rolling_model_inputs
 from self_forcing_b200 import masks
@@ -90,13 +90,15 @@ def test_pipeline_orchestration_fp32_exact(name):
     case = ROLLOUT_CASES[name]
     ops = TorchOps()
     pipe, cfg, params, pe, noise = make_product_pipeline(case, "cpu", ops=ops, dtype=torch.float32, hw=(16, 24))
+    init = initial_latent_for(case, 16, 24)
+    init = None if init is None else init.float()
     with patched_randn_like(3):
-        _, lat = pipe.inference(noise, ["synthetic"], return_latents=True)
+        _, lat = pipe.inference(noise, ["synthetic"], return_latents=True, initial_latent=init)
     ow = O.OracleWrapper(params, cfg, case["shift"])
     steps = O.warp_denoising_steps(ow.scheduler, [1000, 750, 500, 250])
     with torch.no_grad(), patched_randn_like(3):
         tr = O.rollout(ow, noise, pe, steps, case["num_frame_per_block"],
-                       independent_first_frame=case["independent_first_frame"])
+                       independent_first_frame=case["independent_first_frame"], initial_latent=init)
     assert rel_l2(lat, tr.latents) < 1e-5
     assert (int(pipe.kv_cache1[0]["global_end_index"]), int(pipe.kv_cache1[-1]["local_end_index"])) == tr.index_trace[-1]
     assert ops.launches > 0

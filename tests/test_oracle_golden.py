@@ -4,7 +4,7 @@ import numpy as np
 import pytest
 import torch
 
-from helpers import ROLLOUT_CASES, golden, patched_randn_like, rel_l2, synthetic_inputs
+from helpers import ROLLOUT_CASES, golden, initial_latent_for, patched_randn_like, rel_l2, synthetic_inputs
 from oracle import causal_wan_oracle as O
 from oracle.make_golden import MASK_CASES, ROLLING, rolling_cfg, rolling_model_inputs
 
@@ -41,7 +41,7 @@ def test_rollout_matches_reference_golden(name):
     steps = O.warp_denoising_steps(ow.scheduler, [1000, 750, 500, 250])
     with torch.no_grad(), patched_randn_like(3):
         tr = O.rollout(ow, noise, pe, steps, case["num_frame_per_block"],
-                       independent_first_frame=case["independent_first_frame"])
+                       independent_first_frame=case["independent_first_frame"], initial_latent=initial_latent_for(case))
     assert tr.index_trace[-1] == tuple(g["final_index"])          # integers: bit-exact
     assert rel_l2(tr.latents, g["latents"]) <= TOL
 

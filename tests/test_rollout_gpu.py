@@ -5,7 +5,7 @@ rollout; cache indices bit-exact."""
 import pytest
 import torch
 
-from helpers import ROLLOUT_CASES, golden, make_product_pipeline, patched_randn_like, rel_l2, synthetic_inputs
+from helpers import ROLLOUT_CASES, golden, initial_latent_for, make_product_pipeline, patched_randn_like, rel_l2, synthetic_inputs
 from oracle import causal_wan_oracle as O
 
 pytestmark = pytest.mark.gpu
@@ -16,14 +16,16 @@ TOL = 1e-2
 def test_tiny_rollout_vs_reference_golden(name):
     g = golden("rollout_tiny.pt")[name]
     pipe, *_, noise = make_product_pipeline(g["case"], "cuda")
+    init = initial_latent_for(g["case"])
+    init = None if init is None else init.cuda()
     with patched_randn_like(3):
-        _, lat = pipe.inference(noise, ["synthetic"], return_latents=True)
+        _, lat = pipe.inference(noise, ["synthetic"], return_latents=True, initial_latent=init)
     assert (int(pipe.kv_cache1[0]["global_end_index"]), int(pipe.kv_cache1[-1]["local_end_index"])) == tuple(g["final_index"])
     err = rel_l2(lat.cpu(), g["latents"])
     assert err <= TOL, err
     # second call re-uses the allocated caches (reset by rebinding) and must reproduce the first
     with patched_randn_like(3):
-        _, lat2 = pipe.inference(noise, ["synthetic"], return_latents=True)
+        _, lat2 = pipe.inference(noise, ["synthetic"], return_latents=True, initial_latent=init)
     assert torch.equal(lat, lat2)
 
 
