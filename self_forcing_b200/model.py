@@ -26,13 +26,13 @@ GPUs (ulysses.py).  `B200WanModel` (bottom of this file) is the bidirectional te
 from __future__ import annotations
 
 import math
-from typing import Dict, List, Optional, Sequence
+from typing import Dict, List, Optional
 
 import torch
 from torch import nn
 
 from .cache import IndexMirror, plan_cache_update
-from .ops import EPI_BIAS, EPI_GATE_RES, EPI_GELU, EPI_RESIDUAL
+from .ops import EPI_GATE_RES, EPI_GELU, EPI_RESIDUAL
 from .ulysses import UlyssesGroup, shard_rows
 
 

@@ -8,7 +8,7 @@ the shifted sigma / timestep tables and `add_noise`, which runs as one fused sm_
 """
 from __future__ import annotations
 
-from typing import Dict, Optional
+from typing import Dict
 
 import torch
 

@@ -291,3 +291,23 @@ def test_bidirectional_wrapper_surface():
     assert torch.equal(x0, ref_x0)
     with pytest.raises(ValueError):
         w(xt, {"prompt_embeds": ctx}, torch.tensor([[937.5, 250.0], [250.0, 250.0]]))
+
+
+def test_wrapper_loads_a_checkpoint_directory(tmp_path):
+    """HF-style directory (config.json + weights) like CausalWanModel.from_pretrained (utils/wan_wrapper.py:139-145);
+    fork-specific `pose_proj.*` keys are tolerated."""
+    import json
+    from self_forcing_b200.wrapper import B200DiffusionWrapper
+    cfg = O.OracleConfig(dim=256, ffn_dim=256, num_heads=2, num_layers=1, text_dim=512)
+    sd = O.make_random_params(cfg, seed=3)
+    sd["pose_proj.weight"] = torch.zeros(256, 5120, dtype=torch.bfloat16)
+    json.dump(dict(model_type="t2v", patch_size=[1, 2, 2], text_len=512, in_dim=16, dim=256, ffn_dim=256, freq_dim=256,
+                   text_dim=512, out_dim=16, num_heads=2, num_layers=1, qk_norm=True, cross_attn_norm=True, eps=1e-6,
+                   _class_name="CausalWanModel"), open(tmp_path / "config.json", "w"))
+    torch.save(sd, tmp_path / "diffusion_pytorch_model.pth")
+    w = B200DiffusionWrapper(model_path=str(tmp_path), timestep_shift=5.0, ops=TorchOps())
+    got = w.model.state_dict()
+    assert all(torch.equal(got[k], v) for k, v in sd.items() if not k.startswith("pose_proj"))
+    assert w.model.num_layers == 1 and w.scheduler.shift == 5.0 and w.seq_len == 32760
+    with pytest.raises(FileNotFoundError):
+        B200DiffusionWrapper(model_path=str(tmp_path / "missing"), ops=TorchOps())

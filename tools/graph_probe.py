@@ -1,6 +1,6 @@
 """Diagnostic: how much of a forward is inter-kernel gap?  Times one full-depth cached forward (chunk 3 of the rollout,
 KV window 18720) launched eagerly vs replayed as a CUDA graph."""
-import os, sys, time
+import os, sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 import torch
