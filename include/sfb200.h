@@ -21,7 +21,7 @@
 extern "C" {
 #endif
 
-#define SFB_ABI_VERSION 5
+#define SFB_ABI_VERSION 6
 
 const char* sfb_last_error(void);
 int sfb_abi_version(void);
@@ -146,6 +146,21 @@ int sfb_head_finish(const void* head_out, long long ldh,
 int sfb_add_noise(const void* x0, const void* noise, const void* timestep, int t_dtype,
                   const float* timesteps, const float* sigmas, int n_tab, void* out, int n_frames, int per_frame,
                   void* stream);
+
+/* One step of the 50-step sampler in one launch (pipeline/causal_diffusion_inference.py:420-428 +
+ * wan/utils/fm_solvers_unipc.py:320-323 flow->x0, :549-626 UniC corrector, :404-484 UniP predictor), with the
+ * reference's bf16 rounding after every tensor op:
+ *   flow   = flow_uncond + g * (flow_cond - flow_uncond)          (flow_uncond NULL: flow = flow_cond, no guidance)
+ *   m_out  = sample - sigma * flow                                (x0 prediction of this step)
+ *   sample_out = corrector(last_sample, m0, m1, m_out)            (corrector_order 0: copy of `sample`)
+ *   prev_out   = predictor(sample_out, m_out, m0)                 (the next latents)
+ * All tensors bf16, contiguous, n elements, 16-byte aligned; m0 / m1 = x0 predictions of the previous two steps.
+ * m_out may alias m1 and sample_out may alias last_sample.  coef: HOST array of 12 floats
+ *   {g, sigma, c_x, c_m0, c_b, 1/c_rk, c_rho0, c_rho_last, p_x, p_m0, p_b, 1/p_rk}
+ * where x = sigma_t/sigma_s, m0 = alpha_t*h_phi_1, b = alpha_t*B_h for the corrector (c_) and predictor (p_). */
+int sfb_cfg_unipc_step(const void* flow_cond, const void* flow_uncond, const void* sample, const void* last_sample,
+                       const void* m0, const void* m1, void* m_out, void* sample_out, void* prev_out, long long n,
+                       const float* coef, int corrector_order, int predictor_order, void* stream);
 
 #ifdef __cplusplus
 }

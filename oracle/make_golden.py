@@ -178,6 +178,74 @@ def reference_bidirectional(ref):
     return dict(flow=out.clone(), seq_len=L)
 
 
+# 50-step sampler: CFG + UniPC on the same cached forward, separate pos / neg caches.
+# `sampling_steps` is the reference pipeline's own attribute (hard-wired to 50 in its constructor,
+# causal_diffusion_inference.py:66); the fixture lowers it on the instance so the CPU run stays short -- the solver
+# still goes through warm-up (order 1), order-2 predictor + corrector and the lower-order final step.
+DIFFUSION_CASES = {
+    "cfg_unipc": dict(frames=2, num_frame_per_block=1, independent_first_frame=False, shift=5.0, sampling_steps=6,
+                      guidance_scale=3.0),
+}
+NEGATIVE_PROMPT = "synthetic negative"
+UNIPC_TRACE = dict(shape=(1, 2, 16, 8, 8), steps=50, shift=5.0)
+
+
+class _TextEncoder2(torch.nn.Module):
+    """prompt_embeds for the prompt, a second tensor for the negative prompt."""
+
+    def __init__(self, pe, pe_neg):
+        super().__init__()
+        self.pe, self.pe_neg = pe, pe_neg
+
+    def forward(self, text_prompts):
+        return {"prompt_embeds": self.pe_neg if text_prompts[0] == NEGATIVE_PROMPT else self.pe}
+
+
+def negative_embeds(batch: int = 1, text_dim: int = 4096):
+    return torch.randn(batch, 512, text_dim, generator=torch.Generator().manual_seed(6)).to(torch.bfloat16)
+
+
+def diffusion_args(case: dict, **extra):
+    return types.SimpleNamespace(num_train_timestep=1000, timestep_shift=case["shift"],
+                                 guidance_scale=case["guidance_scale"], negative_prompt=NEGATIVE_PROMPT,
+                                 num_frame_per_block=case["num_frame_per_block"],
+                                 independent_first_frame=case["independent_first_frame"], model_kwargs={}, **extra)
+
+
+def reference_diffusion(ref, case: dict, params, cfg: O.OracleConfig):
+    w = ref_shim.make_reference_wrapper(ref, cfg.reference_kwargs(), case["shift"])
+    w.model.load_state_dict(params, strict=False)
+    pe, noise = synthetic_inputs(1, case["frames"])
+    with contextlib.redirect_stdout(io.StringIO()), contextlib.redirect_stderr(io.StringIO()):
+        pipe = ref.CausalDiffusionInferencePipeline(diffusion_args(case), "cpu", generator=w,
+                                                    text_encoder=_TextEncoder2(pe, negative_embeds()),
+                                                    vae=_IdentityVAE(), image_encoder=object())
+        pipe.num_transformer_blocks = cfg.num_layers
+        pipe.sampling_steps = case["sampling_steps"]
+        with torch.no_grad():
+            _, lat = pipe.inference(noise, ["synthetic"], None, None, None, return_latents=True)
+    idx = tuple(int(c[0][k]) for c in (pipe.kv_cache_pos, pipe.kv_cache_neg) for k in ("global_end_index", "local_end_index"))
+    return lat, idx
+
+
+def unipc_trace_flow(sample: torch.Tensor, step: int) -> torch.Tensor:
+    """Deterministic stand-in for the model: a seeded draw mixed with the current sample."""
+    g = torch.Generator().manual_seed(100 + step)
+    return (torch.randn(sample.shape, generator=g) + 0.5 * sample.float()).to(sample.dtype)
+
+
+def reference_unipc_trace(ref, dtype):
+    u = UNIPC_TRACE
+    s = ref.FlowUniPCMultistepScheduler(num_train_timesteps=1000, shift=1, use_dynamic_shifting=False)
+    s.set_timesteps(u["steps"], device="cpu", shift=u["shift"])
+    x = torch.randn(u["shape"], generator=torch.Generator().manual_seed(99)).to(dtype)
+    xs = []
+    for i, t in enumerate(s.timesteps):
+        x = s.step(unipc_trace_flow(x, i), t, x, return_dict=False)[0]
+        xs.append(x.clone())
+    return dict(timesteps=s.timesteps.clone(), sigmas=s.sigmas.clone(), samples=torch.stack(xs))
+
+
 MASK_CASES = {
     "causal_6f_2blk": ("causal", dict(num_frames=6, frame_seqlen=200, num_frame_per_block=2, local_attn_size=-1)),
     "causal_6f_local2": ("causal", dict(num_frames=6, frame_seqlen=200, num_frame_per_block=1, local_attn_size=2)),
@@ -235,6 +303,14 @@ def main():
     torch.save(reference_rolling(ref), os.path.join(GOLDEN, "model_rolling.pt"))
     torch.save(reference_masks(ref), os.path.join(GOLDEN, "block_masks.pt"))
     torch.save(reference_bidirectional(ref), os.path.join(GOLDEN, "bidirectional_tiny.pt"))
+
+    diff = {"unipc_trace_bf16": reference_unipc_trace(ref, torch.bfloat16),
+            "unipc_trace_fp32": reference_unipc_trace(ref, torch.float32)}
+    for name, case in DIFFUSION_CASES.items():
+        lat, idx = reference_diffusion(ref, case, params, cfg)
+        diff[name] = dict(latents=lat, final_index=idx, case=case)
+        print(name, lat.shape, idx, float(lat.float().std()))
+    torch.save(diff, os.path.join(GOLDEN, "diffusion_tiny.pt"))
     for f in sorted(os.listdir(GOLDEN)):
         print(f, os.path.getsize(os.path.join(GOLDEN, f)))
 

@@ -16,6 +16,11 @@ that are not in this image (diffusers, ftfy, easydict ...) and evaluates
      `__path__` pointing into the checkout (bypasses their heavy `__init__`s)
   3. stubs for `ftfy`, `wan.modules.t5`, `wan.modules.vae`, `wan.modules.tokenizers`,
      `demo_utils.memory`, `utils.lora`
+  3b. for the 50-step sampler (`pipeline/causal_diffusion_inference.py`, `wan/utils/fm_solvers_unipc.py`):
+     `diffusers.schedulers.scheduling_utils.{SchedulerMixin,SchedulerOutput,KarrasDiffusionSchedulers}`,
+     `diffusers.utils.{deprecate,is_scipy_available}`, `diffusers.utils.torch_utils.randn_tensor`, a
+     `register_to_config` that records the constructor arguments in `self.config` (the solver reads
+     `self.config.solver_order` etc.), and a `wan.modules.clip` stub (needs torchvision + xlm_roberta)
   4. CPU only: cross-attention calls `flash_attention` directly (model.py:189), which asserts
      CUDA before reaching its own SDPA fallback (attention.py:62 vs :68) -> rebind to
      `attention.attention` with the FA flags cleared.
@@ -58,7 +63,19 @@ def _install_stubs(root: str) -> None:
         pass
 
     def register_to_config(fn):
-        return fn
+        """Like diffusers': bind the constructor arguments (defaults included) to `self.config`."""
+        import functools
+        import inspect
+        sig = inspect.signature(fn)
+
+        @functools.wraps(fn)
+        def init(self, *args, **kwargs):
+            bound = sig.bind(self, *args, **kwargs)
+            bound.apply_defaults()
+            cfg = {k: v for k, v in bound.arguments.items() if k != "self"}
+            fn(self, *args, **kwargs)
+            object.__setattr__(self, "config", types.SimpleNamespace(**cfg))
+        return init
 
     cu.ConfigMixin = ConfigMixin
     cu.register_to_config = register_to_config
@@ -73,10 +90,32 @@ def _install_stubs(root: str) -> None:
     diffusers.configuration_utils = cu
     diffusers.models = models
     models.modeling_utils = mu
+    # (3b) scheduler base classes of the UniPC / DPM++ flow solvers
+    sched = _shell("diffusers.schedulers", None)
+    sched.__path__ = []
+    su = _shell("diffusers.schedulers.scheduling_utils", None)
+
+    class SchedulerMixin:
+        pass
+
+    class SchedulerOutput:
+        def __init__(self, prev_sample):
+            self.prev_sample = prev_sample
+
+    su.SchedulerMixin, su.SchedulerOutput, su.KarrasDiffusionSchedulers = SchedulerMixin, SchedulerOutput, []
+    du = _shell("diffusers.utils", None)
+    du.__path__ = []
+    du.deprecate = lambda *a, **k: None
+    du.is_scipy_available = lambda: False
+    tu = _shell("diffusers.utils.torch_utils", None)
+    tu.randn_tensor = lambda shape, generator=None, device=None, dtype=None: torch.randn(
+        shape, generator=generator, device=device, dtype=dtype)
+    diffusers.schedulers, sched.scheduling_utils, diffusers.utils, du.torch_utils = sched, su, du, tu
 
     # (2) package shells
     _shell("wan", os.path.join(root, "wan"))
     _shell("wan.modules", os.path.join(root, "wan", "modules"))
+    _shell("wan.utils", os.path.join(root, "wan", "utils"))
     _shell("pipeline", os.path.join(root, "pipeline"))
     _shell("utils", os.path.join(root, "utils"))
     _shell("demo_utils", os.path.join(root, "demo_utils"))
@@ -87,6 +126,8 @@ def _install_stubs(root: str) -> None:
     t5.umt5_xxl = lambda *a, **k: (_ for _ in ()).throw(RuntimeError("t5 stub"))
     vae = _shell("wan.modules.vae", None)
     vae._video_vae = lambda *a, **k: (_ for _ in ()).throw(RuntimeError("vae stub"))
+    clip = _shell("wan.modules.clip", None)
+    clip.CLIPModel = object
     tok = _shell("wan.modules.tokenizers", None)
     tok.HuggingfaceTokenizer = object
     mem = _shell("demo_utils.memory", None)
@@ -127,6 +168,8 @@ def load_reference(root: str = REF_ROOT, force_sdpa: bool | None = None):
     scheduler = importlib.import_module("utils.scheduler")
     wan_wrapper = importlib.import_module("utils.wan_wrapper")
     causal_inference = importlib.import_module("pipeline.causal_inference")
+    unipc = importlib.import_module("wan.utils.fm_solvers_unipc")
+    causal_diffusion = importlib.import_module("pipeline.causal_diffusion_inference")
 
     ns = types.SimpleNamespace(
         attention=attention, model=model, causal_model=causal_model, scheduler=scheduler,
@@ -136,6 +179,8 @@ def load_reference(root: str = REF_ROOT, force_sdpa: bool | None = None):
         WanDiffusionWrapper=wan_wrapper.WanDiffusionWrapper,
         FlowMatchScheduler=scheduler.FlowMatchScheduler,
         CausalInferencePipeline=causal_inference.CausalInferencePipeline,
+        FlowUniPCMultistepScheduler=unipc.FlowUniPCMultistepScheduler,
+        CausalDiffusionInferencePipeline=causal_diffusion.CausalDiffusionInferencePipeline,
     )
     _LOADED = ns
     return ns

@@ -13,7 +13,8 @@ LIB_PATH = os.path.join(HERE, "libsfb200.so")
 
 P, LL, I, F = c_void_p, c_longlong, c_int, c_float
 PP = ctypes.POINTER(c_void_p)
-ABI_VERSION = 5
+FP = ctypes.POINTER(c_float)   # host array of floats
+ABI_VERSION = 6
 
 # name -> argtypes, mirroring include/sfb200.h one to one
 SIGNATURES = {
@@ -29,6 +30,7 @@ SIGNATURES = {
     "sfb_skinny_linear": [P, LL, P, LL, P, P, LL, I, I, I, I, P],
     "sfb_head_finish": [P, LL, P, LL, LL, LL, LL, LL, P, I, P, P, I, P, P, I, I, I, I, I, P],
     "sfb_add_noise": [P, P, P, I, P, P, I, P, I, I, P],
+    "sfb_cfg_unipc_step": [P, P, P, P, P, P, P, P, P, LL, FP, I, I, P],
     # Ulysses head-parallel path: PP = host array of device pointers (ctypes c_void_p * n)
     "sfb_qk_norm_rope_sp": [P, LL, P, LL, P, LL, P, P, F, P, P, I, I, I, I, I, I, I, I, I, I, PP, LL, PP, PP, LL, P],
     "sfb_attention_fwd_sp": [P, LL, P, P, LL, PP, I, I, LL, I, I, I, I, F, P, LL, P],

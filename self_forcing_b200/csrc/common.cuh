@@ -42,6 +42,17 @@ __device__ __forceinline__ bool elect_one() {
   return pred != 0;
 }
 
+// Packed bf16 helpers.  cvt.rn.bf16x2.f32 rounds TWO values per instruction and conversions share the XU pipe with
+// MUFU (16 lanes/clk/SM), which the reference's op-by-op bf16 chains stress (3-4 roundings per element), so roundings
+// are done pairwise.  A bf16 x bf16 product is exact in fp32, hence HMUL2.BF16 (one rounding) equals torch's
+// fp32-multiply-then-round and is used for the multiplies.  Adds stay fp32 + round (a fused bf16 add rounds once,
+// torch rounds twice).
+__device__ __forceinline__ uint32_t round_pair(float a, float b) { return pack_bf16(a, b); }
+__device__ __forceinline__ uint32_t mul_bf16x2(uint32_t a, uint32_t b) {
+  __nv_bfloat162 r = __hmul2(*reinterpret_cast<__nv_bfloat162*>(&a), *reinterpret_cast<__nv_bfloat162*>(&b));
+  return *reinterpret_cast<uint32_t*>(&r);
+}
+
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);

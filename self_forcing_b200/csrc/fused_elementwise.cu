@@ -25,16 +25,6 @@ __device__ __forceinline__ void unpack8(const uint4& q, float (&f)[8]) {
   f[0] = bf_lo(q.x); f[1] = bf_hi(q.x); f[2] = bf_lo(q.y); f[3] = bf_hi(q.y);
   f[4] = bf_lo(q.z); f[5] = bf_hi(q.z); f[6] = bf_lo(q.w); f[7] = bf_hi(q.w);
 }
-// Packed bf16 helpers.  cvt.rn.bf16x2.f32 rounds TWO values per instruction and the conversion pipe is the scarce
-// resource of these kernels (3-4 roundings per element in the reference's op-by-op bf16 chain), so roundings are done
-// pairwise; a bf16 x bf16 product is exact in fp32, hence HMUL2.BF16 (one rounding) equals torch's fp32-multiply-
-// then-round and is used for the multiplies.  Adds stay in fp32 + round (a fused bf16 add rounds once, torch twice).
-__device__ __forceinline__ uint32_t round_pair(float a, float b) { return pack_bf16(a, b); }
-__device__ __forceinline__ uint32_t mul_bf16x2(uint32_t a, uint32_t b) {
-  __nv_bfloat162 r = __hmul2(*reinterpret_cast<__nv_bfloat162*>(&a), *reinterpret_cast<__nv_bfloat162*>(&b));
-  return *reinterpret_cast<uint32_t*>(&r);
-}
-
 // Stops the compiler from keeping the unpacked fp32 copy of a packed row alive across passes (it would otherwise
 // CSE the unpacks and need 2x the registers): after this the vector has to be unpacked again.
 __device__ __forceinline__ void forget_unpacked(uint4& q) {

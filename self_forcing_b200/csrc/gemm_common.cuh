@@ -52,25 +52,33 @@ __device__ __forceinline__ uint4 gemm_epilogue_chunk(const uint32_t* acc8, const
 #pragma unroll
     for (int i = 0; i < 4; ++i) { f[2 * i] += bf_lo(bw[i]); f[2 * i + 1] += bf_hi(bw[i]); }
   }
+  // the Linear output is rounded to bf16 first (pairwise: one conversion per two values), then the fused op runs
   if (EPI == EPI_GELU) {
 #pragma unroll
-    for (int i = 0; i < 8; ++i) f[i] = gelu_tanh_f(bf16r(f[i]));
+    for (int i = 0; i < 4; ++i) {
+      const uint32_t y2 = round_pair(f[2 * i], f[2 * i + 1]);
+      f[2 * i] = gelu_tanh_f(bf_lo(y2));
+      f[2 * i + 1] = gelu_tanh_f(bf_hi(y2));
+    }
   }
   if (EPI == EPI_GATE_RES) {
     const uint4 gq = __ldg(reinterpret_cast<const uint4*>(gate));
     const uint32_t gw[4] = {gq.x, gq.y, gq.z, gq.w};
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      f[2 * i] = bf16r(bf16r(f[2 * i]) * bf_lo(gw[i]));
-      f[2 * i + 1] = bf16r(bf16r(f[2 * i + 1]) * bf_hi(gw[i]));
-    }
-  }
-  if (EPI == EPI_RESIDUAL || EPI == EPI_GATE_RES) {
     const uint32_t rw[4] = {res.x, res.y, res.z, res.w};
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
-      f[2 * i] = bf_lo(rw[i]) + bf16r(f[2 * i]);
-      f[2 * i + 1] = bf_hi(rw[i]) + bf16r(f[2 * i + 1]);
+      const uint32_t p2 = mul_bf16x2(round_pair(f[2 * i], f[2 * i + 1]), gw[i]);   // bf16(bf16(y) * gate), exact
+      f[2 * i] = bf_lo(rw[i]) + bf_lo(p2);
+      f[2 * i + 1] = bf_hi(rw[i]) + bf_hi(p2);
+    }
+  }
+  if (EPI == EPI_RESIDUAL) {
+    const uint32_t rw[4] = {res.x, res.y, res.z, res.w};
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const uint32_t y2 = round_pair(f[2 * i], f[2 * i + 1]);
+      f[2 * i] = bf_lo(rw[i]) + bf_lo(y2);
+      f[2 * i + 1] = bf_hi(rw[i]) + bf_hi(y2);
     }
   }
   uint4 o;
@@ -102,42 +110,10 @@ __device__ __forceinline__ void gemm_epilogue_row(const GemmParams& p, int row, 
       for (int g = 0; g < 4; ++g) {   // 8 columns (16 bytes of bf16) per step
         const int col = c * 32 + g * 8;
         if (n0 + col < p.N) {
-          float f[8];
-#pragma unroll
-          for (int i = 0; i < 8; ++i) f[i] = __uint_as_float(v[g * 8 + i]);
-          if (p.bias != nullptr) {
-            const uint4 b = __ldg(reinterpret_cast<const uint4*>(p.bias + n0 + col));
-            const uint32_t bw[4] = {b.x, b.y, b.z, b.w};
-#pragma unroll
-            for (int i = 0; i < 4; ++i) { f[2 * i] += bf_lo(bw[i]); f[2 * i + 1] += bf_hi(bw[i]); }
-          }
-          if (EPI == EPI_GELU) {
-#pragma unroll
-            for (int i = 0; i < 8; ++i) f[i] = gelu_tanh_f(bf16r(f[i]));
-          }
-          if (EPI == EPI_GATE_RES) {
-            const uint4 gq = __ldg(reinterpret_cast<const uint4*>(grow + col));
-            const uint32_t gw[4] = {gq.x, gq.y, gq.z, gq.w};
-#pragma unroll
-            for (int i = 0; i < 4; ++i) {
-              f[2 * i] = bf16r(bf16r(f[2 * i]) * bf_lo(gw[i]));
-              f[2 * i + 1] = bf16r(bf16r(f[2 * i + 1]) * bf_hi(gw[i]));
-            }
-          }
-          if (EPI == EPI_RESIDUAL || EPI == EPI_GATE_RES) {
-            const uint4 rq = *reinterpret_cast<const uint4*>(rrow + col);
-            const uint32_t rw[4] = {rq.x, rq.y, rq.z, rq.w};
-#pragma unroll
-            for (int i = 0; i < 4; ++i) {
-              f[2 * i] = bf_lo(rw[i]) + bf16r(f[2 * i]);
-              f[2 * i + 1] = bf_hi(rw[i]) + bf16r(f[2 * i + 1]);
-            }
-          }
-          uint4 o;
-          o.x = pack_bf16(f[0], f[1]);
-          o.y = pack_bf16(f[2], f[3]);
-          o.z = pack_bf16(f[4], f[5]);
-          o.w = pack_bf16(f[6], f[7]);
+          uint4 rq = make_uint4(0u, 0u, 0u, 0u);
+          if (EPI == EPI_RESIDUAL || EPI == EPI_GATE_RES) rq = *reinterpret_cast<const uint4*>(rrow + col);
+          const uint4 o = gemm_epilogue_chunk<EPI>(v + g * 8, p.bias != nullptr ? p.bias + n0 + col : nullptr,
+                                                   EPI == EPI_GATE_RES ? grow + col : nullptr, rq);
           *reinterpret_cast<uint4*>(orow + col) = o;
         }
       }

@@ -2,9 +2,9 @@
 current stream, everything else happens in libsfb200.so.  No fallbacks."""
 from __future__ import annotations
 
-from typing import Optional, Sequence
-
+import ctypes
 import functools
+from typing import Optional, Sequence
 
 import torch
 
@@ -273,3 +273,20 @@ class CudaOps:
                                           _T_DTYPE[timestep.dtype], timesteps.data_ptr(), sigmas.data_ptr(),
                                           timesteps.numel(), out.data_ptr(), n, x0[0].numel(), self._stream()),
                    "sfb_add_noise")
+
+    @_op
+    def cfg_unipc_step(self, flow_cond, flow_uncond, sample, last_sample, m0, m1, m_out, sample_out, prev_out, coef,
+                       corrector_order: int, predictor_order: int):
+        """One fused CFG + UniPC step (sfb200.h).  Tensors bf16 contiguous with the same numel; `flow_uncond`,
+        `last_sample`, `m0`, `m1` may be None where the step does not use them; coef = 12 python floats."""
+        tensors = [t for t in (flow_cond, flow_uncond, sample, last_sample, m0, m1, m_out, sample_out, prev_out)
+                   if t is not None]
+        n = sample.numel()
+        for t in tensors:
+            assert t.dtype == torch.bfloat16 and t.is_contiguous() and t.numel() == n
+        ptr = _ptr
+        host = (ctypes.c_float * 12)(*[float(c) for c in coef])
+        _lib.check(self.lib.sfb_cfg_unipc_step(ptr(flow_cond), ptr(flow_uncond), ptr(sample), ptr(last_sample), ptr(m0),
+                                               ptr(m1), ptr(m_out), ptr(sample_out), ptr(prev_out), n, host,
+                                               int(corrector_order), int(predictor_order), self._stream()),
+                   "sfb_cfg_unipc_step")

@@ -151,3 +151,25 @@ class TorchOps:
         idx = torch.argmin((timesteps.unsqueeze(0) - timestep.unsqueeze(1)).abs(), dim=1)
         s = sigmas[idx].reshape(-1, 1, 1, 1)
         out.copy_(((1 - s) * x0 + s * noise).type_as(noise))
+
+    def cfg_unipc_step(self, flow_cond, flow_uncond, sample, last_sample, m0, m1, m_out, sample_out, prev_out, coef,
+                       corrector_order, predictor_order):
+        """Op-by-op tensor chain of the reference (causal_diffusion_inference.py:420-421,
+        fm_solvers_unipc.py:320-323, :606-624, :465-482); python-float scalars stay fp32 against bf16 tensors."""
+        self.launches += 1
+        g, sigma, cx, cm0, cb, cirk, crho0, crho1, px, pm0, pb, pirk = [float(c) for c in coef]
+        flow = flow_cond if flow_uncond is None else flow_uncond + g * (flow_cond - flow_uncond)
+        mt = sample - sigma * flow
+        xc = sample.clone()
+        if corrector_order > 0:
+            base = cx * last_sample - cm0 * m0
+            inner = crho1 * (mt - m0)
+            if corrector_order == 2:
+                inner = crho0 * ((m1 - m0) * cirk) + inner
+            xc = base - cb * inner
+        nxt = px * xc - pm0 * mt
+        if predictor_order == 2:
+            nxt = nxt - pb * (0.5 * ((m0 - mt) * pirk))
+        m_out.copy_(mt)
+        sample_out.copy_(xc)
+        prev_out.copy_(nxt)

@@ -390,6 +390,65 @@ def check_add_noise(N=3, shift=5.0, seed=0):
     return m
 
 
+def check_cfg_unipc_step(corr=2, pred=2, cfg=True, n=3 * 16 * 60 * 104, seed=0):
+    """The fused sampler step against the op-by-op torch chain on the same GPU (bit-exact: same rounding points)."""
+    t = [_randn(n, seed=seed + i) for i in range(6)]
+    fc, fu, x, xl, m0, m1 = t
+    coef = [3.0, 0.9375, 0.9957, -0.0043, 0.0042, -1.37, 0.3125, 0.4375, 0.9915, -0.0085, 0.0084, -0.93]
+
+    def run(ops, o):
+        ops.cfg_unipc_step(fc, fu if cfg else None, x, xl if corr else None, m0 if (corr or pred == 2) else None,
+                           m1 if corr == 2 else None, o["m"], o["xc"], o["xn"], coef, corr, pred)
+    z = torch.zeros(n, device="cuda", dtype=BF)
+    return _against_double("cfg_unipc_step", run, dict(m=z, xc=z.clone(), xn=z.clone()), exact=("m", "xc", "xn"))
+
+
+def check_cfg_unipc_alias(n=2 * 16 * 60 * 104, seed=3):
+    """m_out aliasing m1 and sample_out aliasing last_sample (the scheduler's history ring) give the same result."""
+    fc, fu, x, xl, m0, m1 = [_randn(n, seed=seed + i) for i in range(6)]
+    coef = [7.5, 0.5, 0.98, -0.02, 0.019, -1.1, 0.25, 0.5, 0.97, -0.03, 0.029, -0.9]
+    ops = _ops()
+    m, xc, xn = (torch.zeros(n, device="cuda", dtype=BF) for _ in range(3))
+    ops.cfg_unipc_step(fc, fu, x, xl, m0, m1, m, xc, xn, coef, 2, 2)
+    m1a, xla, xn2 = m1.clone(), xl.clone(), torch.zeros_like(xn)
+    ops.cfg_unipc_step(fc, fu, x, xla, m0, m1a, m1a, xla, xn2, coef, 2, 2)
+    torch.cuda.synchronize()
+    assert torch.equal(m, m1a) and torch.equal(xc, xla) and torch.equal(xn, xn2)
+    return dict(err_alias_mismatch=0.0)
+
+
+def check_unipc_reference_semantics(steps=50, shift=5.0):
+    """50 solver steps on the GPU: host coefficients + fused kernel against the oracle's op-by-op chain run on CUDA
+    tensors with 0-dim CPU scalar tensors, i.e. exactly what the reference executes on a GPU.  Also reports which
+    scalar-rounding mode of unipc.py matches it."""
+    from oracle import unipc_oracle as U
+    from oracle.make_golden import UNIPC_TRACE, unipc_trace_flow
+    from self_forcing_b200.unipc import FlowUniPCMultistepScheduler
+    x0 = torch.randn(UNIPC_TRACE["shape"], generator=torch.Generator().manual_seed(99)).to(BF).cuda()
+    out = {}
+    ref = U.OracleUniPC()
+    ref.set_timesteps(steps, shift)
+    xr, ref_xs = x0, []
+    for i, t in enumerate(ref.timesteps):
+        xr = ref.step(unipc_trace_flow(xr.cpu(), i).cuda(), t, xr)
+        ref_xs.append(xr)
+    for mode in ("fp32", "bf16"):
+        s = FlowUniPCMultistepScheduler(shift=1, ops=_ops(), scalar_rounding=mode)
+        s.set_timesteps(steps, device="cuda", shift=shift)
+        x, worst, n_bad = x0, 0.0, 0
+        for i, t in enumerate(s.timesteps):
+            # feed both chains the SAME flow (derived from the reference chain's sample) so that errors do not compound
+            flow = unipc_trace_flow((ref_xs[i - 1] if i else x0).cpu(), i).cuda()
+            x = s.step(flow, t, ref_xs[i - 1] if i else x0, return_dict=False)[0]
+            worst = max(worst, rel_l2(x, ref_xs[i]))
+            n_bad += int((x != ref_xs[i]).sum())
+        out[f"worst_rel_l2_{mode}"] = worst
+        out[f"mismatches_{mode}"] = float(n_bad)
+    torch.cuda.synchronize()
+    assert out["worst_rel_l2_fp32"] <= 2e-3, out
+    return out
+
+
 # --------------------------------------------------------------------------------------
 def _tiny_setup(num_layers=2, ffn_dim=512, shift=5.0, seed=0):
     from self_forcing_b200.wrapper import WAN_T2V_1_3B, B200DiffusionWrapper
@@ -488,6 +547,13 @@ ALL = {
     "modulation_table": check_modulation_table,
     "head_finish": check_head_finish,
     "add_noise": check_add_noise,
+    "cfg_unipc_step": check_cfg_unipc_step,
+    "cfg_unipc_first_step": lambda: check_cfg_unipc_step(corr=0, pred=1, seed=10),
+    "cfg_unipc_warmup": lambda: check_cfg_unipc_step(corr=1, pred=2, seed=11),
+    "cfg_unipc_last_step": lambda: check_cfg_unipc_step(corr=2, pred=1, seed=12),
+    "unipc_no_guidance_ragged": lambda: check_cfg_unipc_step(corr=2, pred=2, cfg=False, n=8 * 1001 + 5, seed=13),
+    "cfg_unipc_alias": check_cfg_unipc_alias,
+    "unipc_reference_semantics": check_unipc_reference_semantics,
     "model_forward": check_model_forward,
 }
 

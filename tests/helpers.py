@@ -7,7 +7,8 @@ import types
 import torch
 
 from oracle import causal_wan_oracle as O
-from oracle.make_golden import (ROLLOUT_CASES, SeededNoise, _IdentityVAE, _TextEncoder, initial_latent_for,
+from oracle.make_golden import (DIFFUSION_CASES, NEGATIVE_PROMPT, ROLLOUT_CASES, SeededNoise, _IdentityVAE,
+                                _TextEncoder, _TextEncoder2, diffusion_args, initial_latent_for, negative_embeds,
                                 patched_randn_like, synthetic_inputs)
 
 GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
@@ -45,3 +46,24 @@ def make_product_pipeline(case: dict, device, ops=None, num_layers=2, ffn_dim=51
     pipe = CausalInferencePipeline(pipeline_args(case, **extra), device, generator=w, text_encoder=_TextEncoder(pe),
                                    vae=_IdentityVAE())
     return pipe, cfg, params, pe, noise
+
+
+def make_product_diffusion_pipeline(case: dict, device, ops=None, num_layers=2, ffn_dim=512, dtype=torch.bfloat16, seed=0,
+                                    scalar_rounding="bf16"):
+    """B200DiffusionWrapper + product CausalDiffusionInferencePipeline (CFG + UniPC) for a tiny-depth model.
+    scalar_rounding "bf16" = how the CPU run of the reference treats the solver's 0-dim tensor scalars, i.e. what
+    the golden vectors contain (self_forcing_b200/unipc.py)."""
+    from self_forcing_b200.diffusion_pipeline import CausalDiffusionInferencePipeline
+    from self_forcing_b200.wrapper import WAN_T2V_1_3B, B200DiffusionWrapper
+    cfg = O.OracleConfig(dim=1536, ffn_dim=ffn_dim, num_heads=12, num_layers=num_layers)
+    params = O.make_random_params(cfg, seed=seed, dtype=dtype)
+    w = B200DiffusionWrapper(model_config=dict(WAN_T2V_1_3B, ffn_dim=ffn_dim, num_layers=num_layers),
+                             timestep_shift=case["shift"], device=device, ops=ops, dtype=dtype)
+    w.model.load_state_dict(params, strict=True)
+    pe, noise = synthetic_inputs(1, case["frames"])
+    pe, noise = pe.to(device=device, dtype=dtype), noise.to(device=device, dtype=dtype)
+    neg = negative_embeds().to(device=device, dtype=dtype)
+    args = diffusion_args(case, sampling_steps=case["sampling_steps"], unipc_scalar_rounding=scalar_rounding)
+    pipe = CausalDiffusionInferencePipeline(args, device, generator=w, text_encoder=_TextEncoder2(pe, neg),
+                                            vae=_IdentityVAE())
+    return pipe, cfg, params, pe, neg, noise

@@ -33,7 +33,7 @@ def test_binding_covers_header(lib_path):
     declared = set(_declared()) - {"sfb_last_error", "sfb_abi_version", "sfb_attention_workspace_bytes", "sfb_gemm_workspace_bytes"}
     assert declared == set(_lib.SIGNATURES), declared ^ set(_lib.SIGNATURES)
     lib = _lib.load(lib_path)
-    assert lib.sfb_abi_version() == 5
+    assert lib.sfb_abi_version() == 6
     assert isinstance(lib.sfb_last_error(), bytes)
 
 

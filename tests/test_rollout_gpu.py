@@ -181,3 +181,22 @@ def test_bidirectional_teacher_forward_on_gpu_matches_reference_golden():
     out = model(list(x), t=t, context=list(ctx), seq_len=g["seq_len"])
     assert rel_l2(out.cpu(), g["flow"]) <= TOL
     assert torch.equal(out, model(x, t=t, context=ctx, seq_len=g["seq_len"]))
+
+
+def test_cfg_unipc_pipeline_matches_reference_golden():
+    """the 50-step sampler (here 6 steps, like the fixture) -- batched cond/uncond
+    forward on the B200 kernels + fused CFG/UniPC step -- against the latents of the unmodified reference pipeline.
+    Guidance scale 3 amplifies forward differences by up to 2g - 1 = 5x before the solver integrates them, hence the
+    wider latent tolerance than the few-step rollout; the cache indices are integers and must match exactly."""
+    from helpers import make_product_diffusion_pipeline
+    g = golden("diffusion_tiny.pt")["cfg_unipc"]
+    pipe, *_ , noise = make_product_diffusion_pipeline(g["case"], "cuda")
+    _, lat = pipe.inference(noise, ["synthetic"], None, None, None, return_latents=True)
+    idx = tuple(int(c[0][k]) for c in (pipe.kv_cache_pos, pipe.kv_cache_neg) for k in ("global_end_index", "local_end_index"))
+    assert idx == tuple(g["final_index"])
+    err = rel_l2(lat.cpu(), g["latents"])
+    print("cfg_unipc rel_l2", err)
+    assert err <= 3e-2, err
+    # second call: caches reset by rebinding, CUDA graphs replayed -> identical latents
+    _, lat2 = pipe.inference(noise, ["synthetic"], None, None, None, return_latents=True)
+    assert torch.equal(lat, lat2)
