@@ -21,7 +21,7 @@
 extern "C" {
 #endif
 
-#define SFB_ABI_VERSION 6
+#define SFB_ABI_VERSION 7
 
 const char* sfb_last_error(void);
 int sfb_abi_version(void);
@@ -31,6 +31,8 @@ int sfb_abi_version(void);
 #define SFB_EPI_GELU 1      /* y = bf16(gelu_tanh(bf16(acc + bias)))        causal_model.py:278        */
 #define SFB_EPI_RESIDUAL 2  /* y = bf16(res + bf16(acc + bias))             causal_model.py:324        */
 #define SFB_EPI_GATE_RES 3  /* y = bf16(res + bf16(bf16(acc+bias) * gate))  causal_model.py:320,331-332 */
+#define SFB_EPI_F32 4       /* y = acc (+ bias) as FLOAT: out0 is a float matrix, ldo0 in floats, one segment,
+                               one-CTA tiles (attention logits of the VAE's single-head attention)             */
 
 /* Y[M,N] = epilogue(X[M,K] . W[N,K]^T + bias): tcgen05 GEMM, TMA-fed, fp32 accumulate in TMEM.
  * Replaces nn.Linear (cuBLAS) at wan/modules/causal_model.py:112-114 (q,k,v -- one call with the
@@ -161,6 +163,45 @@ int sfb_add_noise(const void* x0, const void* noise, const void* timestep, int t
 int sfb_cfg_unipc_step(const void* flow_cond, const void* flow_uncond, const void* sample, const void* last_sample,
                        const void* m0, const void* m1, void* m_out, void* sample_out, void* prev_out, long long n,
                        const float* coef, int corrector_order, int predictor_order, void* stream);
+
+/* ---- Wan VAE decoder (the step right after the rollout: utils/wan_wrapper.py:94-117 -> wan/modules/vae.py:545-593).
+ * Activations are CHANNELS-LAST [T, H, W, C] bf16: one voxel = one row of C channels. ---- */
+
+/* Latents in: out[v][:] = conv2_1x1x1(bf16(bf16(z[:, v] / inv_std) + mean)) for the `voxels` positions of one latent
+ * frame (wan_wrapper.py:101-102, vae.py:548-554).  z is channels-first with `z_channel_stride` elements between
+ * channels; w [16,16], bias/mean/inv_std [16]; out [voxels, 16]. */
+int sfb_vae_latent_in(const void* z, long long z_channel_stride, const void* mean, const void* inv_std,
+                      const void* w, const void* bias, void* out, int voxels, void* stream);
+
+/* RMS_norm over the channels of every voxel (vae.py:39-54: F.normalize * sqrt(C) * gamma) with the reference's bf16
+ * rounding after each op, optionally followed by SiLU (vae.py:195-198).  C multiple of 4, <= 512. */
+int sfb_vae_norm_silu(const void* x, long long ldx, const void* gamma, void* y, long long ldy, long long rows, int C,
+                      int silu, void* stream);
+
+/* CausalConv3d (vae.py:17-36) and the resample Conv2d (+ nearest 2x upsampling in front, vae.py:75-83) on
+ * channels-last frames: x [t_in, H, W, Cin] holds the cached frames followed by the new ones, `t_zero_pad` virtual
+ * zero frames stand in front (causal padding not covered by the cache); kernel (kt, ks, ks) with kt in 1..3,
+ * ks in {1,3}, "same" spatial zero padding.  w is packed [Cout, kt*ks*ks*Cin] with K order (dt, dh, dw, c).
+ * y = bf16(acc + bias) or, with `residual`, bf16(residual + bf16(acc + bias)) (ResidualBlock, vae.py:220).
+ * Output rows = (t_in + t_zero_pad - kt + 1) * Ho * Wo voxels; columns [0, seg_cols) go to y0 and, if Cout is
+ * 2 * seg_cols, columns [seg_cols, 2 seg_cols) to y1 (the time_conv whose channel halves are alternate frames,
+ * vae.py:141-144); seg_cols 0 = Cout.  The gathered operand is staged in `workspace` in row chunks (any size >=
+ * 128 rows works; sfb_causal_conv3d_workspace_bytes(rows, ...) = one chunk).  1x1x1 needs no workspace. */
+int sfb_causal_conv3d_cl(const void* x, int t_in, int H, int W, int Cin, int t_zero_pad, int upsample2x,
+                         const void* w, const void* bias, int Cout, int kt, int ks,
+                         const void* residual, long long ldr, void* y0, void* y1, long long ldo, int seg_cols,
+                         void* workspace, long long workspace_bytes, void* stream);
+long long sfb_causal_conv3d_workspace_bytes(long long rows, int Cin, int kt, int ks);
+
+/* p[r][:] = bf16(softmax(scale * s[r][:])) for fp32 score rows s (written by sfb_gemm_bf16 with SFB_EPI_F32, so the
+ * logits are never rounded to bf16 -- the single-head attention of vae.py:251-255 is two GEMMs around this kernel). */
+int sfb_softmax_rows(const void* s, long long lds, void* p, long long ldp, int rows, int cols, float scale, void* stream);
+
+/* out[c][r] = in[r][c] for a bf16 matrix (V^T for the attention's second GEMM). */
+int sfb_transpose_bf16(const void* in, long long ldi, void* out, long long ldo, int R, int C, void* stream);
+
+/* Decoder output [T*HW, ldy >= 3] bf16 (channels-last RGB) -> fp32 [T, 3, HW] clamped to [-1, 1] (wan_wrapper.py:110). */
+int sfb_vae_pixel_out(const void* y, int ldy, void* out, int T, long long HW, void* stream);
 
 #ifdef __cplusplus
 }

@@ -246,6 +246,39 @@ def reference_unipc_trace(ref, dtype):
     return dict(timesteps=s.timesteps.clone(), sigmas=s.sigmas.clone(), samples=torch.stack(xs))
 
 
+# VAE decode: full-width decoder (96 base channels), tiny latent grid
+VAE_CASE = dict(frames=3, hw=(4, 6), batch=1, seed=21)
+
+
+def vae_latents(case=VAE_CASE, frames=None, seed_offset=0):
+    f = frames or case["frames"]
+    g = torch.Generator().manual_seed(31 + seed_offset)
+    return torch.randn(case["batch"], f, 16, *case["hw"], generator=g).to(torch.bfloat16)
+
+
+def reference_vae_decode(case=VAE_CASE):
+    from . import vae_oracle as V
+    rv = ref_shim.load_reference_vae()
+    cfg = V.VaeConfig()
+    params = V.make_random_vae_params(cfg, seed=case["seed"])
+    model = rv.WanVAE_(dim=96, z_dim=16, dim_mult=[1, 2, 4, 4], num_res_blocks=2, attn_scales=[],
+                       temperal_downsample=[False, True, True], dropout=0.0)
+    missing, unexpected = model.load_state_dict(params, strict=False)
+    assert not unexpected and all(k.startswith(("encoder.", "conv1.")) for k in missing), (missing, unexpected)
+    model = model.to(torch.bfloat16).eval()
+    lat = vae_latents(case)
+    scale = [torch.tensor(V.LATENT_MEAN).to(torch.bfloat16), 1.0 / torch.tensor(V.LATENT_STD).to(torch.bfloat16)]
+    with torch.no_grad():
+        zs = lat.permute(0, 2, 1, 3, 4)
+        full = model.decode(zs, scale)                                     # clears the cache before and after
+        first = model.cached_decode(zs[:, :, :2], scale)                   # streaming: 2 frames, then 1 more
+        second = model.cached_decode(zs[:, :, 2:], scale)
+        model.clear_cache()
+        # the same weights evaluated in fp32: the yardstick for "how far apart may two bf16 evaluations be"
+        exact = model.float().decode(zs.float(), [torch.tensor(V.LATENT_MEAN), 1.0 / torch.tensor(V.LATENT_STD)])
+    return dict(case=case, pixels=full, streamed=torch.cat([first, second], dim=2), pixels_fp32=exact)
+
+
 MASK_CASES = {
     "causal_6f_2blk": ("causal", dict(num_frames=6, frame_seqlen=200, num_frame_per_block=2, local_attn_size=-1)),
     "causal_6f_local2": ("causal", dict(num_frames=6, frame_seqlen=200, num_frame_per_block=1, local_attn_size=2)),
@@ -311,6 +344,7 @@ def main():
         diff[name] = dict(latents=lat, final_index=idx, case=case)
         print(name, lat.shape, idx, float(lat.float().std()))
     torch.save(diff, os.path.join(GOLDEN, "diffusion_tiny.pt"))
+    torch.save(reference_vae_decode(), os.path.join(GOLDEN, "vae_decode_tiny.pt"))
     for f in sorted(os.listdir(GOLDEN)):
         print(f, os.path.getsize(os.path.join(GOLDEN, f)))
 

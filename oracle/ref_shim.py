@@ -186,6 +186,20 @@ def load_reference(root: str = REF_ROOT, force_sdpa: bool | None = None):
     return ns
 
 
+def load_reference_vae(root: str = REF_ROOT):
+    """The reference's real `wan/modules/vae.py` (torch + einops only), loaded under a private module name because
+    `wan.modules.vae` itself is stubbed above for the wrapper import."""
+    import importlib.util
+    name = "_sfb_reference_vae"
+    if name in sys.modules:
+        return sys.modules[name]
+    spec = importlib.util.spec_from_file_location(name, os.path.join(root, "wan", "modules", "vae.py"))
+    mod = importlib.util.module_from_spec(spec)
+    sys.modules[name] = mod
+    spec.loader.exec_module(mod)
+    return mod
+
+
 def make_reference_wrapper(ref, model_cfg: dict, timestep_shift: float, seed: int = 0,
                            dtype=torch.bfloat16):
     """Random-init `WanDiffusionWrapper` without `from_pretrained` (wan_wrapper.py:139-147).

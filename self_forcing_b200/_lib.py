@@ -14,7 +14,7 @@ LIB_PATH = os.path.join(HERE, "libsfb200.so")
 P, LL, I, F = c_void_p, c_longlong, c_int, c_float
 PP = ctypes.POINTER(c_void_p)
 FP = ctypes.POINTER(c_float)   # host array of floats
-ABI_VERSION = 6
+ABI_VERSION = 7
 
 # name -> argtypes, mirroring include/sfb200.h one to one
 SIGNATURES = {
@@ -31,6 +31,13 @@ SIGNATURES = {
     "sfb_head_finish": [P, LL, P, LL, LL, LL, LL, LL, P, I, P, P, I, P, P, I, I, I, I, I, P],
     "sfb_add_noise": [P, P, P, I, P, P, I, P, I, I, P],
     "sfb_cfg_unipc_step": [P, P, P, P, P, P, P, P, P, LL, FP, I, I, P],
+    # VAE decoder
+    "sfb_vae_latent_in": [P, LL, P, P, P, P, P, I, P],
+    "sfb_vae_norm_silu": [P, LL, P, P, LL, LL, I, I, P],
+    "sfb_causal_conv3d_cl": [P, I, I, I, I, I, I, P, P, I, I, I, P, LL, P, P, LL, I, P, LL, P],
+    "sfb_softmax_rows": [P, LL, P, LL, I, I, F, P],
+    "sfb_transpose_bf16": [P, LL, P, LL, I, I, P],
+    "sfb_vae_pixel_out": [P, I, P, I, LL, P],
     # Ulysses head-parallel path: PP = host array of device pointers (ctypes c_void_p * n)
     "sfb_qk_norm_rope_sp": [P, LL, P, LL, P, LL, P, P, F, P, P, I, I, I, I, I, I, I, I, I, I, PP, LL, PP, PP, LL, P],
     "sfb_attention_fwd_sp": [P, LL, P, P, LL, PP, I, I, LL, I, I, I, I, F, P, LL, P],
@@ -69,6 +76,8 @@ def load(path: str | None = None) -> ctypes.CDLL:
     lib.sfb_attention_workspace_bytes.argtypes = []
     lib.sfb_gemm_workspace_bytes.restype = c_longlong
     lib.sfb_gemm_workspace_bytes.argtypes = []
+    lib.sfb_causal_conv3d_workspace_bytes.restype = c_longlong
+    lib.sfb_causal_conv3d_workspace_bytes.argtypes = [c_longlong, c_int, c_int, c_int]
     for name, argtypes in SIGNATURES.items():
         fn = getattr(lib, name)
         fn.argtypes = argtypes

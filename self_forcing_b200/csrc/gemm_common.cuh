@@ -6,7 +6,7 @@
 
 namespace sfb {
 
-enum : int { EPI_BIAS = 0, EPI_GELU = 1, EPI_RESIDUAL = 2, EPI_GATE_RES = 3 };
+enum : int { EPI_BIAS = 0, EPI_GELU = 1, EPI_RESIDUAL = 2, EPI_GATE_RES = 3, EPI_F32 = 4 };
 
 struct GemmParams {
   int M, N, K;
@@ -94,6 +94,32 @@ __device__ __forceinline__ uint4 gemm_epilogue_chunk(const uint32_t* acc8, const
 template <int TILE_N, int EPI>
 __device__ __forceinline__ void gemm_epilogue_row(const GemmParams& p, int row, int n0, uint32_t t_row) {
   const bool row_ok = row < p.M;
+  if (EPI == EPI_F32) {
+    // fp32 result (attention scores): out[0] is a float matrix, ldo[0] counted in floats; one segment only
+    float* frow = reinterpret_cast<float*>(p.out[0]) + (long long)row * p.ldo[0] + n0;
+#pragma unroll 1
+    for (int c = 0; c < TILE_N / 32; ++c) {
+      uint32_t v[32];
+      tmem_ld32(t_row + c * 32, v);
+      tmem_ld_wait();
+      if (row_ok) {
+#pragma unroll
+        for (int g = 0; g < 8; ++g) {   // 4 columns (16 bytes of fp32) per step
+          const int col = c * 32 + g * 4;
+          if (n0 + col < p.N) {
+            float4 o = make_float4(__uint_as_float(v[g * 4]), __uint_as_float(v[g * 4 + 1]), __uint_as_float(v[g * 4 + 2]),
+                                   __uint_as_float(v[g * 4 + 3]));
+            if (p.bias != nullptr) {
+              const uint2 b = __ldg(reinterpret_cast<const uint2*>(p.bias + n0 + col));
+              o.x += bf_lo(b.x); o.y += bf_hi(b.x); o.z += bf_lo(b.y); o.w += bf_hi(b.y);
+            }
+            *reinterpret_cast<float4*>(frow + col) = o;
+          }
+        }
+      }
+    }
+    return;
+  }
   const int seg = n0 / p.seg_cols;
   __nv_bfloat16* orow = p.out[seg] + (long long)row * p.ldo[seg] + (n0 - seg * p.seg_cols);
   const __nv_bfloat16* rrow = nullptr;

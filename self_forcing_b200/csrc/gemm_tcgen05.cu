@@ -177,6 +177,7 @@ static int dispatch_epi(int epi, const CUtensorMap& ta, const CUtensorMap& tb, c
     case EPI_GELU: return launch_gemm<BLOCK_N, EPI_GELU>(ta, tb, p, num_sms, stream);
     case EPI_RESIDUAL: return launch_gemm<BLOCK_N, EPI_RESIDUAL>(ta, tb, p, num_sms, stream);
     case EPI_GATE_RES: return launch_gemm<BLOCK_N, EPI_GATE_RES>(ta, tb, p, num_sms, stream);
+    case EPI_F32: return launch_gemm<BLOCK_N, EPI_F32>(ta, tb, p, num_sms, stream);
   }
   set_error("sfb_gemm_bf16: unknown epilogue %d", epi);
   return SFB_ERR_INVALID;
@@ -207,7 +208,7 @@ extern "C" int sfb_gemm_bf16(const void* x, long long ldx, const void* w, long l
   if (seg_cols <= 0) seg_cols = N;
   // block_n: 0 = choose; 64 / 128 / 256 = one-CTA tiles of 128 x block_n; 512 = CTA-pair tiles of 256 x 256
   // (tcgen05 cta_group::2, gemm2_tcgen05.cu) -- the default whenever N and the segments are multiples of 256.
-  if (block_n == 0 && N % 256 == 0 && seg_cols % 256 == 0 && M > 128) block_n = 512;
+  if (block_n == 0 && N % 256 == 0 && seg_cols % 256 == 0 && M > 128 && epilogue != EPI_F32) block_n = 512;
   if (block_n == 0) {
     // Tile choice: wide tiles amortise smem traffic; narrow problems take 128 so the tile count
     // fills the 148 SMs (M=4680: N=1536 -> 37x12 = 444 = 3 waves of 148).
@@ -217,7 +218,8 @@ extern "C" int sfb_gemm_bf16(const void* x, long long ldx, const void* w, long l
   const bool force_streamk = block_n == 513;
   if (pair) block_n = 256;
   if (block_n != 64 && block_n != 128 && block_n != 256) { set_error("sfb_gemm_bf16: block_n must be 64/128/256/512"); return SFB_ERR_INVALID; }
-  if (seg_cols % block_n) { set_error("sfb_gemm_bf16: seg_cols=%d not a multiple of the N tile %d", seg_cols, block_n); return SFB_ERR_INVALID; }
+  if (epilogue == EPI_F32 && (pair || seg_cols != N)) { set_error("sfb_gemm_bf16: the fp32-output epilogue takes one-CTA tiles and one output segment"); return SFB_ERR_INVALID; }
+  if (seg_cols % block_n && seg_cols != N) { set_error("sfb_gemm_bf16: seg_cols=%d not a multiple of the N tile %d", seg_cols, block_n); return SFB_ERR_INVALID; }
   if ((epilogue == EPI_RESIDUAL || epilogue == EPI_GATE_RES) && residual == nullptr) { set_error("sfb_gemm_bf16: residual epilogue without residual"); return SFB_ERR_INVALID; }
   if (epilogue == EPI_GATE_RES && (gate == nullptr || rows_per_gate <= 0)) { set_error("sfb_gemm_bf16: gate epilogue without gate"); return SFB_ERR_INVALID; }
 

@@ -10,7 +10,7 @@ import torch
 
 from . import _lib
 
-EPI_BIAS, EPI_GELU, EPI_RESIDUAL, EPI_GATE_RES = 0, 1, 2, 3
+EPI_BIAS, EPI_GELU, EPI_RESIDUAL, EPI_GATE_RES, EPI_F32 = 0, 1, 2, 3, 4
 _T_DTYPE = {torch.float32: 0, torch.int64: 1, torch.float64: 2, torch.bfloat16: 3}
 
 
@@ -59,6 +59,8 @@ class CudaOps:
         self._prof_only = None
         self._attn_ws = {}    # device index -> uint8 scratch for the split-KV attention schedule
         self._gemm_ws = {}    # device index -> zero-initialised scratch for the stream-K GEMM schedule
+        self._conv_ws = {}    # device index -> staging buffer of the VAE convolutions' gathered operand
+        self.conv_workspace_bytes = 1 << 30
 
     # -- optional per-launch device timing (bench.py roofline leg) ------------------------------
     def start_profile(self, only=None):
@@ -101,7 +103,10 @@ class CudaOps:
         assert w.shape[1] == K
         segs = list(outs) if outs is not None else [out]
         for s in segs:
-            _check_2d(s, "out")
+            if epilogue == EPI_F32:      # fp32 result (one segment): strides are counted in floats
+                assert s.dtype == torch.float32 and s.dim() == 2 and s.stride(1) == 1 and len(segs) == 1
+            else:
+                _check_2d(s, "out")
         while len(segs) < 3:
             segs.append(None)
         if residual is not None:
@@ -290,3 +295,69 @@ class CudaOps:
                                                ptr(m1), ptr(m_out), ptr(sample_out), ptr(prev_out), n, host,
                                                int(corrector_order), int(predictor_order), self._stream()),
                    "sfb_cfg_unipc_step")
+
+    # -- Wan VAE decoder (channels-last frames [T, H, W, C]) --------------------------------
+    @_op
+    def vae_latent_in(self, z_frame, mean, inv_std, w, bias, out):
+        """z_frame [16, h, w] (any channel stride, contiguous h*w), out [h*w, 16]."""
+        assert z_frame.dtype == torch.bfloat16 and z_frame.stride(2) == 1 and z_frame.stride(1) == z_frame.shape[2]
+        assert out.is_contiguous() and w.is_contiguous()
+        _lib.check(self.lib.sfb_vae_latent_in(z_frame.data_ptr(), z_frame.stride(0), mean.data_ptr(), inv_std.data_ptr(),
+                                              w.data_ptr(), bias.data_ptr(), out.data_ptr(), out.shape[0], self._stream()),
+                   "sfb_vae_latent_in")
+
+    @_op
+    def vae_norm_silu(self, x, gamma, y, silu: bool):
+        """x, y [rows, C] (unit column stride), gamma [C]."""
+        _check_2d(x, "x"); _check_2d(y, "y")
+        _lib.check(self.lib.sfb_vae_norm_silu(x.data_ptr(), x.stride(0), gamma.data_ptr(), y.data_ptr(), y.stride(0),
+                                              x.shape[0], x.shape[1], int(silu), self._stream()), "sfb_vae_norm_silu")
+
+    @_op
+    def causal_conv3d(self, x, t_zero_pad: int, w, bias, kt: int, ks: int, y0, y1=None, *, upsample=False,
+                      residual=None, seg_cols=0):
+        """x [t_in, H, W, Cin] contiguous (cached frames first); w packed [Cout, kt*ks*ks*Cin]; y0 (/y1) [rows, seg]
+        with a common row stride; residual [rows, Cout]."""
+        assert x.is_contiguous() and w.is_contiguous() and x.dtype == torch.bfloat16
+        t_in, H, W, Cin = x.shape
+        _check_2d(y0, "y0")
+        if y1 is not None:
+            _check_2d(y1, "y1")
+            assert y1.stride(0) == y0.stride(0)
+        if residual is not None:
+            _check_2d(residual, "residual")
+        ws = self._conv_ws.get(x.device.index)
+        if ws is None:
+            with torch.cuda.device(x.device):
+                ws = torch.empty(self.conv_workspace_bytes, dtype=torch.uint8, device=x.device)
+            self._conv_ws[x.device.index] = ws
+        _lib.check(self.lib.sfb_causal_conv3d_cl(
+            x.data_ptr(), t_in, H, W, Cin, t_zero_pad, int(upsample), w.data_ptr(), _ptr(bias), w.shape[0], kt, ks,
+            _ptr(residual), residual.stride(0) if residual is not None else 0, y0.data_ptr(), _ptr(y1), y0.stride(0),
+            seg_cols, ws.data_ptr(), ws.numel(), self._stream()), "sfb_causal_conv3d_cl")
+
+    @_op
+    def softmax_rows(self, s, p, scale: float):
+        """s fp32 [rows, cols] -> p bf16 [rows, cols] = softmax(scale * s)."""
+        _check_2d(p, "p")
+        assert s.dtype == torch.float32 and s.stride(1) == 1 and s.shape == p.shape
+        _lib.check(self.lib.sfb_softmax_rows(s.data_ptr(), s.stride(0), p.data_ptr(), p.stride(0), s.shape[0], s.shape[1],
+                                             scale, self._stream()), "sfb_softmax_rows")
+
+    @_op
+    def transpose(self, x, out):
+        _check_2d(x, "x"); _check_2d(out, "out")
+        assert out.shape == (x.shape[1], x.shape[0])
+        _lib.check(self.lib.sfb_transpose_bf16(x.data_ptr(), x.stride(0), out.data_ptr(), out.stride(0), x.shape[0],
+                                               x.shape[1], self._stream()), "sfb_transpose_bf16")
+
+    @_op
+    def vae_pixel_out(self, y, out):
+        """y [T*H*W, ld >= 3] bf16, out fp32 [T, 3, H, W] contiguous."""
+        _check_2d(y, "y")
+        assert out.dtype == torch.float32 and out.is_contiguous() and out.shape[1] == 3
+        T = out.shape[0]
+        hw = out.shape[2] * out.shape[3]
+        assert y.shape[0] == T * hw
+        _lib.check(self.lib.sfb_vae_pixel_out(y.data_ptr(), y.stride(0), out.data_ptr(), T, hw, self._stream()),
+                   "sfb_vae_pixel_out")

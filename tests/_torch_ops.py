@@ -9,7 +9,7 @@ import torch.nn.functional as F
 
 from oracle import causal_wan_oracle as O
 
-EPI_BIAS, EPI_GELU, EPI_RESIDUAL, EPI_GATE_RES = 0, 1, 2, 3
+EPI_BIAS, EPI_GELU, EPI_RESIDUAL, EPI_GATE_RES, EPI_F32 = 0, 1, 2, 3, 4
 
 
 class TorchOps:
@@ -23,6 +23,9 @@ class TorchOps:
              rows_per_gate=1, gate_row_offset=0, outs=None, seg_cols=0, block_n=0):
         self.launches += 1
         self.log.append("gemm")
+        if epilogue == EPI_F32:
+            out.copy_(F.linear(x.float(), w.float(), None if bias is None else bias.float()))
+            return
         y = F.linear(x, w, bias)
         if epilogue == EPI_GELU:
             y = F.gelu(y, approximate="tanh")
@@ -173,3 +176,47 @@ class TorchOps:
         m_out.copy_(mt)
         sample_out.copy_(xc)
         prev_out.copy_(nxt)
+
+    # ---- Wan VAE decoder ops (channels-last in, channels-first torch inside) -----------------------------------
+    def vae_latent_in(self, z_frame, mean, inv_std, w, bias, out):
+        self.launches += 1
+        x = z_frame / inv_std.view(16, 1, 1) + mean.view(16, 1, 1)
+        y = F.conv3d(x.unsqueeze(0).unsqueeze(2), w.view(16, 16, 1, 1, 1), bias)          # [1, 16, 1, h, w]
+        out.copy_(y[0, :, 0].permute(1, 2, 0).reshape(-1, 16))
+
+    def vae_norm_silu(self, x, gamma, y, silu):
+        self.launches += 1
+        n = F.normalize(x, dim=1) * x.shape[1] ** 0.5 * gamma
+        y.copy_(F.silu(n) if silu else n)
+
+    def causal_conv3d(self, x, t_zero_pad, w, bias, kt, ks, y0, y1=None, *, upsample=False, residual=None, seg_cols=0):
+        self.launches += 1
+        t_in, H, W, Cin = x.shape
+        cout = w.shape[0]
+        xc = x.permute(3, 0, 1, 2).unsqueeze(0)                                          # [1, Cin, T, H, W]
+        if upsample:
+            xc = F.interpolate(xc[0].permute(1, 0, 2, 3).float(), scale_factor=(2.0, 2.0), mode="nearest").type_as(x)
+            xc = xc.permute(1, 0, 2, 3).unsqueeze(0)
+        xc = F.pad(xc, (ks // 2, ks // 2, ks // 2, ks // 2, t_zero_pad, 0))
+        w5 = w.view(cout, kt, ks, ks, Cin).permute(0, 4, 1, 2, 3)
+        y = F.conv3d(xc, w5, bias)[0].permute(1, 2, 3, 0).reshape(-1, cout)
+        if residual is not None:
+            y = residual + y
+        if y1 is None:
+            y0.copy_(y)
+        else:
+            y0.copy_(y[:, :seg_cols])
+            y1.copy_(y[:, seg_cols:2 * seg_cols])
+
+    def softmax_rows(self, s, p, scale):
+        self.launches += 1
+        p.copy_(torch.softmax(s * scale, dim=1).to(p.dtype))
+
+    def transpose(self, x, out):
+        self.launches += 1
+        out.copy_(x.t())
+
+    def vae_pixel_out(self, y, out):
+        self.launches += 1
+        T, _, H, W = out.shape
+        out.copy_(y[:, :3].float().clamp(-1, 1).reshape(T, H, W, 3).permute(0, 3, 1, 2))

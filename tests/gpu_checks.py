@@ -449,6 +449,114 @@ def check_unipc_reference_semantics(steps=50, shift=5.0):
     return out
 
 
+# ---- VAE decoder kernels ---------------------------------
+def check_vae_latent_in(h=12, w=20, seed=0):
+    z = _randn(16, h, w, seed=seed, scale=2.0)
+    mean, inv = _randn(16, seed=seed + 1), (_randn(16, seed=seed + 2).abs() + 0.3)
+    wt, b = _randn(16, 16, seed=seed + 3, scale=0.25), _randn(16, seed=seed + 4, scale=0.1)
+
+    def run(ops, o):
+        ops.vae_latent_in(z, mean, inv, wt, b, o["y"])
+    return _against_double("vae_latent_in", run, dict(y=torch.zeros(h * w, 16, device="cuda", dtype=BF)))
+
+
+def check_vae_norm_silu(rows=1000, C=96, silu=True, seed=0):
+    x = _randn(rows, C, seed=seed, scale=1.5)
+    x[3] = 0                                                     # an all-zero voxel exercises the eps clamp
+    g = _randn(C, seed=seed + 1) * 0.1 + 1
+
+    def run(ops, o):
+        ops.vae_norm_silu(x, g, o["y"], silu)
+    return _against_double("vae_norm_silu", run, dict(y=torch.zeros(rows, C, device="cuda", dtype=BF)))
+
+
+def check_causal_conv3d(t_in=1, H=8, W=12, Cin=16, Cout=384, kt=3, ks=3, pad=2, upsample=False, residual=False,
+                        segments=False, ws_bytes=None, seed=0):
+    """Gather + tcgen05 GEMM against F.conv3d on the same GPU (fp32 accumulation on both sides)."""
+    x = _randn(t_in, H, W, Cin, seed=seed)
+    K = kt * ks * ks * Cin
+    w = _randn(Cout, K, seed=seed + 1, scale=K ** -0.5)
+    b = _randn(Cout, seed=seed + 2, scale=0.1)
+    t_out = t_in + pad - (kt - 1)
+    Ho, Wo = (2 * H, 2 * W) if upsample else (H, W)
+    rows = t_out * Ho * Wo
+    res = _randn(rows, Cout, seed=seed + 3) if residual else None
+    cu = _ops()
+    saved = cu.conv_workspace_bytes
+    if ws_bytes is not None:
+        cu.conv_workspace_bytes = ws_bytes
+    if segments:
+        y0, y1 = (torch.zeros(rows, Cout // 2, device="cuda", dtype=BF) for _ in range(2))
+    else:
+        y0, y1 = torch.zeros(rows, Cout, device="cuda", dtype=BF), None
+    cu.causal_conv3d(x, pad, w, b, kt, ks, y0, y1, upsample=upsample, residual=res, seg_cols=Cout // 2 if segments else 0)
+    got = y0 if y1 is None else torch.cat([y0, y1], dim=1)
+    # reference: the same convolution in fp32 (F.conv3d through the test double), rounded where the reference rounds:
+    # bf16(conv + bias), then bf16(residual + that)
+    exact = torch.zeros(rows, Cout, device="cuda", dtype=torch.float32)
+    torch.backends.cudnn.allow_tf32 = False
+    TorchOps().causal_conv3d(x.float(), pad, w.float(), b.float(), kt, ks, exact, upsample=upsample)
+    ref = exact.to(BF)
+    if residual:
+        ref = res + ref
+    torch.cuda.synchronize()
+    cu.conv_workspace_bytes = saved
+    return _finish("causal_conv3d", dict(err=rel_l2(got, ref), max=float((got.float() - ref.float()).abs().max()),
+                                         err_vs_fp32=rel_l2(got, exact + (res.float() if residual else 0))), 3e-3)
+
+
+def check_gemm_f32(M=300, N=312, K=384, seed=0):
+    x, w = _randn(M, K, seed=seed), _randn(N, K, seed=seed + 1)
+    out = torch.zeros(M, N, device="cuda", dtype=torch.float32)
+    _ops().gemm(x, w, None, out, epilogue=4)
+    ref = x.float() @ w.float().t()
+    torch.cuda.synchronize()
+    return _finish("gemm_f32", dict(err=rel_l2(out, ref)), 1e-5)
+
+
+def check_softmax_transpose(rows=300, cols=312, seed=0):
+    s = _randn(rows, cols, seed=seed, dtype=torch.float32) * 30
+    p = torch.zeros(rows, cols, device="cuda", dtype=BF)
+    _ops().softmax_rows(s, p, 0.051)
+    ref = torch.softmax(s * 0.051, dim=1)
+    x = _randn(rows, cols, seed=seed + 1)
+    xt = torch.zeros(cols, rows, device="cuda", dtype=BF)
+    _ops().transpose(x[:, 8:], xt[:cols - 8])                     # strided source view
+    torch.cuda.synchronize()
+    assert torch.equal(xt[:cols - 8], x[:, 8:].t())
+    return _finish("softmax_rows", dict(err=rel_l2(p, ref), err_rowsum=float((p.float().sum(1) - 1).abs().max())), 1e-2)
+
+
+def check_vae_pixel_out(T=3, H=16, W=24, seed=0):
+    y = _randn(T * H * W, 8, seed=seed, scale=0.8)
+
+    def run(ops, o):
+        ops.vae_pixel_out(y, o["px"])
+    return _against_double("vae_pixel_out", run, dict(px=torch.zeros(T, 3, H, W, device="cuda")), exact=("px",))
+
+
+def check_vae_decoder(frames=None):
+    """Whole decoder on the B200 against the pixels of the unmodified reference (CPU, bf16) and its fp32 run."""
+    from helpers import golden
+    from oracle import vae_oracle as V
+    from oracle.make_golden import VAE_CASE, vae_latents
+    from self_forcing_b200.vae import B200VAEWrapper
+    g = golden("vae_decode_tiny.pt")
+    w = B200VAEWrapper(state_dict=V.make_random_vae_params(V.VaeConfig(), seed=VAE_CASE["seed"]), device="cuda", ops=_ops())
+    lat = vae_latents().cuda()
+    out = w.decode_to_pixel(lat)
+    a = w.decode_to_pixel(lat[:, :2], use_cache=True)
+    b = w.decode_to_pixel(lat[:, 2:], use_cache=True)
+    torch.cuda.synchronize()
+    ref = g["pixels"].float().clamp(-1, 1).permute(0, 2, 1, 3, 4)
+    exact = g["pixels_fp32"].clamp(-1, 1).permute(0, 2, 1, 3, 4)
+    m = dict(err_vs_ref_bf16=rel_l2(out.cpu(), ref), vs_fp32=rel_l2(out.cpu(), exact), ref_noise_floor=rel_l2(ref, exact),
+             err_stream_mismatch=float((torch.cat([a, b], dim=1) != out).sum()))
+    assert m["vs_fp32"] <= 1.25 * m["ref_noise_floor"], m
+    assert m["err_stream_mismatch"] == 0, m
+    return _finish("vae_decoder", m, 2.5e-2)
+
+
 # --------------------------------------------------------------------------------------
 def _tiny_setup(num_layers=2, ffn_dim=512, shift=5.0, seed=0):
     from self_forcing_b200.wrapper import WAN_T2V_1_3B, B200DiffusionWrapper
@@ -554,6 +662,22 @@ ALL = {
     "unipc_no_guidance_ragged": lambda: check_cfg_unipc_step(corr=2, pred=2, cfg=False, n=8 * 1001 + 5, seed=13),
     "cfg_unipc_alias": check_cfg_unipc_alias,
     "unipc_reference_semantics": check_unipc_reference_semantics,
+    "vae_latent_in": check_vae_latent_in,
+    "vae_norm_silu_c96": check_vae_norm_silu,
+    "vae_norm_c192": lambda: check_vae_norm_silu(rows=333, C=192, silu=False, seed=1),
+    "vae_norm_silu_c384": lambda: check_vae_norm_silu(rows=777, C=384, seed=2),
+    "conv3d_first_frame_k432": check_causal_conv3d,
+    "conv3d_cached_residual": lambda: check_causal_conv3d(t_in=4, H=10, W=14, Cin=96, Cout=96, pad=0, residual=True, seed=1),
+    "conv3d_one_cached_frame": lambda: check_causal_conv3d(t_in=2, H=6, W=10, Cin=192, Cout=384, pad=1, seed=2),
+    "conv2d_upsample": lambda: check_causal_conv3d(t_in=2, H=6, W=10, Cin=192, Cout=96, kt=1, pad=0, upsample=True, seed=3),
+    "time_conv_two_frames": lambda: check_causal_conv3d(t_in=3, H=6, W=10, Cin=384, Cout=768, ks=1, pad=0, segments=True, seed=4),
+    "conv_shortcut_1x1x1": lambda: check_causal_conv3d(t_in=2, H=6, W=10, Cin=192, Cout=384, kt=1, ks=1, pad=0, seed=5),
+    "conv3d_head_8_channels": lambda: check_causal_conv3d(t_in=3, H=16, W=24, Cin=96, Cout=8, pad=0, seed=6),
+    "conv3d_chunked_workspace": lambda: check_causal_conv3d(t_in=3, H=16, W=24, Cin=96, Cout=96, pad=0, ws_bytes=200 * 2592 * 2, seed=7),
+    "gemm_f32_logits": check_gemm_f32,
+    "softmax_rows_transpose": check_softmax_transpose,
+    "vae_pixel_out": check_vae_pixel_out,
+    "vae_decoder": check_vae_decoder,
     "model_forward": check_model_forward,
 }
 

@@ -30,10 +30,11 @@ def test_header_symbols_exported(lib_path):
 
 def test_binding_covers_header(lib_path):
     from self_forcing_b200 import _lib
-    declared = set(_declared()) - {"sfb_last_error", "sfb_abi_version", "sfb_attention_workspace_bytes", "sfb_gemm_workspace_bytes"}
+    declared = set(_declared()) - {"sfb_last_error", "sfb_abi_version", "sfb_attention_workspace_bytes", "sfb_gemm_workspace_bytes",
+                                   "sfb_causal_conv3d_workspace_bytes"}
     assert declared == set(_lib.SIGNATURES), declared ^ set(_lib.SIGNATURES)
     lib = _lib.load(lib_path)
-    assert lib.sfb_abi_version() == 6
+    assert lib.sfb_abi_version() == 7
     assert isinstance(lib.sfb_last_error(), bytes)
 
 
