@@ -174,7 +174,7 @@ int sfb_vae_latent_in(const void* z, long long z_channel_stride, const void* mea
                       const void* w, const void* bias, void* out, int voxels, void* stream);
 
 /* RMS_norm over the channels of every voxel (vae.py:39-54: F.normalize * sqrt(C) * gamma) with the reference's bf16
- * rounding after each op, optionally followed by SiLU (vae.py:195-198).  C multiple of 4, <= 512. */
+ * rounding after each op, optionally followed by SiLU (vae.py:195-198).  C multiple of 8, <= 512. */
 int sfb_vae_norm_silu(const void* x, long long ldx, const void* gamma, void* y, long long ldy, long long rows, int C,
                       int silu, void* stream);
 
@@ -186,12 +186,17 @@ int sfb_vae_norm_silu(const void* x, long long ldx, const void* gamma, void* y, 
  * Output rows = (t_in + t_zero_pad - kt + 1) * Ho * Wo voxels; columns [0, seg_cols) go to y0 and, if Cout is
  * 2 * seg_cols, columns [seg_cols, 2 seg_cols) to y1 (the time_conv whose channel halves are alternate frames,
  * vae.py:141-144); seg_cols 0 = Cout.  The gathered operand is staged in `workspace` in row chunks (any size >=
- * 128 rows works; sfb_causal_conv3d_workspace_bytes(rows, ...) = one chunk).  1x1x1 needs no workspace. */
+ * 128 rows works; sfb_causal_conv3d_workspace_bytes(rows, ...) = one chunk).  1x1x1 needs no workspace.
+ * workspace == NULL selects the implicit-GEMM kernel (ks = 3, upsample2x = 0, one segment, Cin % 16 == 0): the shifted
+ * input boxes go from global memory straight into the tensor-core pipeline by TMA, nothing is staged. */
 int sfb_causal_conv3d_cl(const void* x, int t_in, int H, int W, int Cin, int t_zero_pad, int upsample2x,
                          const void* w, const void* bias, int Cout, int kt, int ks,
                          const void* residual, long long ldr, void* y0, void* y1, long long ldo, int seg_cols,
                          void* workspace, long long workspace_bytes, void* stream);
 long long sfb_causal_conv3d_workspace_bytes(long long rows, int Cin, int kt, int ks);
+
+/* Nearest-neighbour 2x upsampling of H and W (vae.py:57-63), channels-last: x [T, H, W, C] -> y [T, 2H, 2W, C]. */
+int sfb_upsample2x_cl(const void* x, void* y, int T, int H, int W, int C, void* stream);
 
 /* p[r][:] = bf16(softmax(scale * s[r][:])) for fp32 score rows s (written by sfb_gemm_bf16 with SFB_EPI_F32, so the
  * logits are never rounded to bf16 -- the single-head attention of vae.py:251-255 is two GEMMs around this kernel). */

@@ -35,6 +35,7 @@ SIGNATURES = {
     "sfb_vae_latent_in": [P, LL, P, P, P, P, P, I, P],
     "sfb_vae_norm_silu": [P, LL, P, P, LL, LL, I, I, P],
     "sfb_causal_conv3d_cl": [P, I, I, I, I, I, I, P, P, I, I, I, P, LL, P, P, LL, I, P, LL, P],
+    "sfb_upsample2x_cl": [P, P, I, I, I, I, P],
     "sfb_softmax_rows": [P, LL, P, LL, I, I, F, P],
     "sfb_transpose_bf16": [P, LL, P, LL, I, I, P],
     "sfb_vae_pixel_out": [P, I, P, I, LL, P],

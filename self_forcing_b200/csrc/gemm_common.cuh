@@ -91,12 +91,13 @@ __device__ __forceinline__ uint4 gemm_epilogue_chunk(const uint32_t* acc8, const
 
 // One thread owns accumulator row `row` (TMEM lane) of a tile that starts at column n0 and is
 // TILE_N columns wide; t_row is the TMEM address of (lane, first column).
+// `row` is the output row the thread writes (for the GEMM the accumulator row itself, for the implicit-GEMM
+// convolution the voxel index of the accumulator row); row_ok = false only drains TMEM.
 template <int TILE_N, int EPI>
-__device__ __forceinline__ void gemm_epilogue_row(const GemmParams& p, int row, int n0, uint32_t t_row) {
-  const bool row_ok = row < p.M;
+__device__ __forceinline__ void gemm_epilogue_row_at(const GemmParams& p, long long row, bool row_ok, int n0, uint32_t t_row) {
   if (EPI == EPI_F32) {
     // fp32 result (attention scores): out[0] is a float matrix, ldo[0] counted in floats; one segment only
-    float* frow = reinterpret_cast<float*>(p.out[0]) + (long long)row * p.ldo[0] + n0;
+    float* frow = reinterpret_cast<float*>(p.out[0]) + row * p.ldo[0] + n0;
 #pragma unroll 1
     for (int c = 0; c < TILE_N / 32; ++c) {
       uint32_t v[32];
@@ -121,11 +122,11 @@ __device__ __forceinline__ void gemm_epilogue_row(const GemmParams& p, int row, 
     return;
   }
   const int seg = n0 / p.seg_cols;
-  __nv_bfloat16* orow = p.out[seg] + (long long)row * p.ldo[seg] + (n0 - seg * p.seg_cols);
+  __nv_bfloat16* orow = p.out[seg] + row * p.ldo[seg] + (n0 - seg * p.seg_cols);
   const __nv_bfloat16* rrow = nullptr;
   const __nv_bfloat16* grow = nullptr;
-  if (EPI == EPI_RESIDUAL || EPI == EPI_GATE_RES) rrow = p.residual + (long long)row * p.ldr + n0;
-  if (EPI == EPI_GATE_RES) grow = p.gate + (long long)(row_ok ? (row + p.gate_row_offset) / p.rows_per_gate : 0) * p.gate_stride + n0;
+  if (EPI == EPI_RESIDUAL || EPI == EPI_GATE_RES) rrow = p.residual + row * p.ldr + n0;
+  if (EPI == EPI_GATE_RES) grow = p.gate + (long long)(row_ok ? ((int)row + p.gate_row_offset) / p.rows_per_gate : 0) * p.gate_stride + n0;
 #pragma unroll 1
   for (int c = 0; c < TILE_N / 32; ++c) {
     uint32_t v[32];
@@ -145,6 +146,11 @@ __device__ __forceinline__ void gemm_epilogue_row(const GemmParams& p, int row, 
       }
     }
   }
+}
+
+template <int TILE_N, int EPI>
+__device__ __forceinline__ void gemm_epilogue_row(const GemmParams& p, int row, int n0, uint32_t t_row) {
+  gemm_epilogue_row_at<TILE_N, EPI>(p, row, row < p.M, n0, t_row);
 }
 
 }  // namespace sfb

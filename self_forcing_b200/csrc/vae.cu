@@ -26,6 +26,25 @@ extern "C" int sfb_gemm_bf16(const void* x, long long ldx, const void* w, long l
 
 namespace sfb {
 
+// conv_tcgen05.cu: implicit-GEMM 3x3 convolution (no gathered operand)
+int launch_conv3_implicit(const void* x, int t_in, int H, int W, int Cin, int t_zero_pad, const void* w, const void* bias,
+                          int Cout, int kt, const void* residual, long long ldr, void* y, long long ldo,
+                          cudaStream_t stream);
+
+// nearest-neighbour 2x upsampling of H and W, channels-last (vae.py:57-63)
+__global__ void __launch_bounds__(256)
+upsample2x_kernel(const uint4* __restrict__ x, uint4* __restrict__ y, int T, int H, int W, int cvec) {
+  const long long total = (long long)T * 2 * H * 2 * W * cvec;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int cv = (int)(i % cvec);
+    long long v = i / cvec;
+    const int wo = (int)(v % (2 * W)); v /= 2 * W;
+    const int ho = (int)(v % (2 * H));
+    const int t = (int)(v / (2 * H));
+    y[i] = __ldg(x + (((long long)t * H + (ho >> 1)) * W + (wo >> 1)) * cvec + cv);
+  }
+}
+
 // ------------------------------------------------------------------------------------
 // latents in: out[v][o] = bf16(b[o] + sum_c w[o][c] * bf16(bf16(z[c][v] / inv_std[c]) + mean[c]))
 // ------------------------------------------------------------------------------------
@@ -61,45 +80,63 @@ vae_latent_in_kernel(const __nv_bfloat16* __restrict__ z, long long z_cstride, c
 }
 
 // ------------------------------------------------------------------------------------
-// RMS_norm (+SiLU): one warp per voxel row.  Reference chain on bf16 tensors:
+// RMS_norm (+SiLU): half a warp per voxel row, 16-byte vectors.  Reference chain on bf16 tensors:
 //   d = bf16(sqrt(sum x^2)) clamped to 1e-12;  a = bf16(x / d);  b = bf16(a * sqrt(C));  c = bf16(b * gamma);
-//   y = bf16(c * sigmoid(c))
+//   y = bf16(c / (1 + exp(-c)))
+// The kernel is instruction-bound before it is HBM-bound (three IEEE divisions + an expf per element cost more issue
+// slots than the 4 bytes of traffic), so x / d is one reciprocal per row plus a Newton correction per element
+// (correctly rounded except in rare double-rounding cases) and the sigmoid uses ex2.approx + rcp; against the
+// op-by-op chain the output differs in < 1e-4 of the elements, by one bf16 ulp.
 // ------------------------------------------------------------------------------------
-template <int NV>   // uint2 (4 x bf16) vectors per lane: C = 128 * NV ... C / 4 <= 32 * NV
+template <int NV>   // uint4 (8 x bf16) vectors per lane: C / 8 <= 16 * NV
 __global__ void __launch_bounds__(256)
 vae_norm_silu_kernel(const __nv_bfloat16* __restrict__ x, long long ldx, const __nv_bfloat16* __restrict__ gamma,
                      __nv_bfloat16* __restrict__ y, long long ldy, long long rows, int C, float sqrt_c, int silu) {
-  const int lane = threadIdx.x & 31;
-  const long long row = blockIdx.x * (long long)(blockDim.x >> 5) + (threadIdx.x >> 5);
-  if (row >= rows) return;
-  const int nvec = C >> 2;
-  uint2 raw[NV];
+  const int lane = threadIdx.x & 15;
+  const long long row = blockIdx.x * (long long)(blockDim.x >> 4) + (threadIdx.x >> 4);
+  const bool live = row < rows;
+  const int nvec = C >> 3;
+  uint4 raw[NV];
   float ss = 0.f;
 #pragma unroll
   for (int i = 0; i < NV; ++i) {
-    const int v = lane + 32 * i;
-    raw[i] = make_uint2(0u, 0u);
-    if (v < nvec) raw[i] = __ldg(reinterpret_cast<const uint2*>(x + row * ldx) + v);
-    const float a = bf_lo(raw[i].x), b = bf_hi(raw[i].x), c = bf_lo(raw[i].y), d = bf_hi(raw[i].y);
-    ss = fmaf(a, a, ss); ss = fmaf(b, b, ss); ss = fmaf(c, c, ss); ss = fmaf(d, d, ss);
+    const int v = lane + 16 * i;
+    raw[i] = make_uint4(0u, 0u, 0u, 0u);
+    if (live && v < nvec) raw[i] = __ldg(reinterpret_cast<const uint4*>(x + row * ldx) + v);
+    const uint32_t w[4] = {raw[i].x, raw[i].y, raw[i].z, raw[i].w};
+#pragma unroll
+    for (int j = 0; j < 4; ++j) { const float a = bf_lo(w[j]), b = bf_hi(w[j]); ss = fmaf(a, a, ss); ss = fmaf(b, b, ss); }
   }
-  ss = warp_sum(ss);
+#pragma unroll
+  for (int o = 8; o > 0; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);   // the 16 lanes of this row
+  if (!live) return;
   const float denom = fmaxf(bf16r(sqrtf(ss)), 1e-12f);
+  const float rinv = __frcp_rn(denom);
 #pragma unroll
   for (int i = 0; i < NV; ++i) {
-    const int v = lane + 32 * i;
+    const int v = lane + 16 * i;
     if (v >= nvec) continue;
-    const uint2 gq = __ldg(reinterpret_cast<const uint2*>(gamma) + v);
-    const float in[4] = {bf_lo(raw[i].x), bf_hi(raw[i].x), bf_lo(raw[i].y), bf_hi(raw[i].y)};
-    const float g[4] = {bf_lo(gq.x), bf_hi(gq.x), bf_lo(gq.y), bf_hi(gq.y)};
-    float o[4];
+    const uint4 gq = __ldg(reinterpret_cast<const uint4*>(gamma) + v);
+    const uint32_t w[4] = {raw[i].x, raw[i].y, raw[i].z, raw[i].w};
+    const uint32_t g[4] = {gq.x, gq.y, gq.z, gq.w};
+    uint32_t o[4];
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
-      float c = bf16r(__fmul_rn(bf16r(__fmul_rn(bf16r(__fdiv_rn(in[j], denom)), sqrt_c)), g[j]));
-      if (silu) c = __fdiv_rn(c, __fadd_rn(1.0f, expf(-c)));
-      o[j] = c;
+      float e[2] = {bf_lo(w[j]), bf_hi(w[j])};
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        const float q0 = e[h] * rinv;
+        e[h] = fmaf(fmaf(-q0, denom, e[h]), rinv, q0);          // x / d
+      }
+      float c0 = bf16r(__fmul_rn(bf16r(__fmul_rn(bf16r(e[0]), sqrt_c)), bf_lo(g[j])));
+      float c1 = bf16r(__fmul_rn(bf16r(__fmul_rn(bf16r(e[1]), sqrt_c)), bf_hi(g[j])));
+      if (silu) {
+        c0 = c0 * __frcp_rn(1.0f + __expf(-c0));
+        c1 = c1 * __frcp_rn(1.0f + __expf(-c1));
+      }
+      o[j] = pack_bf16(c0, c1);
     }
-    reinterpret_cast<uint2*>(y + row * ldy)[v] = make_uint2(pack_bf16(o[0], o[1]), pack_bf16(o[2], o[3]));
+    reinterpret_cast<uint4*>(y + row * ldy)[v] = make_uint4(o[0], o[1], o[2], o[3]);
   }
 }
 
@@ -233,11 +270,11 @@ extern "C" int sfb_vae_latent_in(const void* z, long long z_channel_stride, cons
 
 extern "C" int sfb_vae_norm_silu(const void* x, long long ldx, const void* gamma, void* y, long long ldy, long long rows,
                                  int C, int silu, void* stream) {
-  if (rows <= 0 || C <= 0 || (C % 4) || C > 512 || (ldx % 4) || (ldy % 4)) {
-    set_error("sfb_vae_norm_silu: C=%d must be a multiple of 4 up to 512, row strides multiples of 4", C);
+  if (rows <= 0 || C <= 0 || (C % 8) || C > 512 || (ldx % 8) || (ldy % 8)) {
+    set_error("sfb_vae_norm_silu: C=%d must be a multiple of 8 up to 512, row strides multiples of 8", C);
     return SFB_ERR_INVALID;
   }
-  const long long blocks = (rows + 7) / 8;
+  const long long blocks = (rows + 15) / 16;
   if (blocks > 0x7fffffffLL) { set_error("sfb_vae_norm_silu: too many rows"); return SFB_ERR_INVALID; }
   const float sc = sqrtf((float)C);
   cudaStream_t st = (cudaStream_t)stream;
@@ -269,6 +306,12 @@ extern "C" int sfb_causal_conv3d_cl(const void* x, int t_in, int H, int W, int C
   if (nseg > 2 || (nseg == 2 && !y1)) { set_error("sfb_causal_conv3d_cl: at most two output segments"); return SFB_ERR_INVALID; }
   void* outs[2] = {y0, y1};
   const bool direct = (kt == 1 && ks == 1 && !upsample2x);      // 1x1x1: the activations are the operand
+  if (!direct && workspace == nullptr) {
+    // no staging buffer: implicit GEMM (conv_tcgen05.cu) -- 3x3 spatial kernels on un-upsampled input, one segment
+    if (ks != 3 || upsample2x || nseg != 1) { set_error("sfb_causal_conv3d_cl: without a workspace only ks=3, no upsampling, one output segment"); return SFB_ERR_INVALID; }
+    if (Cin % 16) { set_error("sfb_causal_conv3d_cl: implicit path needs Cin %% 16 == 0"); return SFB_ERR_INVALID; }
+    return launch_conv3_implicit(x, t_in, H, W, Cin, t_zero_pad, w, bias, Cout, kt, residual, ldr, y0, ldo, (cudaStream_t)stream);
+  }
   long long chunk = rows;
   if (!direct) {
     if (!workspace || workspace_bytes < (long long)K * 2 * 128) { set_error("sfb_causal_conv3d_cl: workspace missing or smaller than 128 gathered rows"); return SFB_ERR_INVALID; }
@@ -305,6 +348,13 @@ extern "C" int sfb_causal_conv3d_cl(const void* x, int t_in, int H, int W, int C
       return e;
   }
   return SFB_OK;
+}
+
+extern "C" int sfb_upsample2x_cl(const void* x, void* y, int T, int H, int W, int C, void* stream) {
+  if (!x || !y || T <= 0 || H <= 0 || W <= 0 || C <= 0 || (C % 8)) { set_error("sfb_upsample2x_cl: bad arguments (C must be a multiple of 8)"); return SFB_ERR_INVALID; }
+  const long long total = (long long)T * 4 * H * W * (C / 8);
+  upsample2x_kernel<<<grid_for(total, 256 * 4), 256, 0, (cudaStream_t)stream>>>((const uint4*)x, (uint4*)y, T, H, W, C / 8);
+  return check_cuda(cudaGetLastError(), "upsample2x launch");
 }
 
 extern "C" int sfb_softmax_rows(const void* s, long long lds, void* p, long long ldp, int rows, int cols, float scale,

@@ -86,6 +86,10 @@ class CudaOps:
         if name == "gemm":
             x, w = a[0], a[1]
             return ("gemm", x.shape[0], w.shape[0], x.shape[1], k.get("epilogue", 0))
+        if name == "causal_conv3d":
+            x, w = a[0], a[2]
+            return ("conv", x.shape[1], x.shape[2], x.shape[3], w.shape[0], f"k{a[4]}{a[5]}", "up" if k.get("upsample") else "",
+                    "implicit" if k.get("implicit") else "gather")
         return (name,)
 
     @staticmethod
@@ -315,7 +319,7 @@ class CudaOps:
 
     @_op
     def causal_conv3d(self, x, t_zero_pad: int, w, bias, kt: int, ks: int, y0, y1=None, *, upsample=False,
-                      residual=None, seg_cols=0):
+                      residual=None, seg_cols=0, implicit=False):
         """x [t_in, H, W, Cin] contiguous (cached frames first); w packed [Cout, kt*ks*ks*Cin]; y0 (/y1) [rows, seg]
         with a common row stride; residual [rows, Cout]."""
         assert x.is_contiguous() and w.is_contiguous() and x.dtype == torch.bfloat16
@@ -326,15 +330,23 @@ class CudaOps:
             assert y1.stride(0) == y0.stride(0)
         if residual is not None:
             _check_2d(residual, "residual")
-        ws = self._conv_ws.get(x.device.index)
-        if ws is None:
+        ws = None if implicit else self._conv_ws.get(x.device.index)
+        if ws is None and not implicit:
             with torch.cuda.device(x.device):
                 ws = torch.empty(self.conv_workspace_bytes, dtype=torch.uint8, device=x.device)
             self._conv_ws[x.device.index] = ws
         _lib.check(self.lib.sfb_causal_conv3d_cl(
             x.data_ptr(), t_in, H, W, Cin, t_zero_pad, int(upsample), w.data_ptr(), _ptr(bias), w.shape[0], kt, ks,
             _ptr(residual), residual.stride(0) if residual is not None else 0, y0.data_ptr(), _ptr(y1), y0.stride(0),
-            seg_cols, ws.data_ptr(), ws.numel(), self._stream()), "sfb_causal_conv3d_cl")
+            seg_cols, _ptr(ws), ws.numel() if ws is not None else 0, self._stream()), "sfb_causal_conv3d_cl")
+
+    @_op
+    def upsample2x(self, x, y):
+        """x [T, H, W, C] -> y [T, 2H, 2W, C], nearest."""
+        assert x.is_contiguous() and y.is_contiguous() and x.dtype == torch.bfloat16
+        T, H, W, C = x.shape
+        assert y.shape == (T, 2 * H, 2 * W, C)
+        _lib.check(self.lib.sfb_upsample2x_cl(x.data_ptr(), y.data_ptr(), T, H, W, C, self._stream()), "sfb_upsample2x_cl")
 
     @_op
     def softmax_rows(self, s, p, scale: float):

@@ -59,6 +59,8 @@ class B200VAEDecoder:
         self.w: Dict[str, torch.Tensor] = {}         # packed GEMM operands / gammas / biases
         self.geom: Dict[str, Tuple[int, int]] = {}   # conv name -> (kt, ks)
         self.cache: Optional[List] = None            # persistent feature cache of `cached_decode`
+        # 3x3 convolutions as implicit GEMM (shifted TMA boxes, nothing staged); False = gather + GEMM for all
+        self.implicit_conv = True
 
     @property
     def ops(self):
@@ -141,10 +143,15 @@ class B200VAEDecoder:
         kt, ks = self.geom[name]
         w, b = self.w[name + ".weight"], self.w[name + ".bias"]
         t_out = x.shape[0] + t_zero_pad - (kt - 1)
+        implicit = self.implicit_conv and ks == 3 and x.shape[3] % 16 == 0
+        if implicit and upsample:                      # the TMA boxes need the upsampled frames in memory
+            up = torch.empty(x.shape[0], 2 * x.shape[1], 2 * x.shape[2], x.shape[3], dtype=x.dtype, device=x.device)
+            self.ops.upsample2x(x, up)
+            x, upsample = up, False
         H, W = (2 * x.shape[1], 2 * x.shape[2]) if upsample else (x.shape[1], x.shape[2])
         y = torch.empty(t_out, H, W, w.shape[0], dtype=x.dtype, device=x.device)
         self.ops.causal_conv3d(x, t_zero_pad, w, b, kt, ks, y.view(-1, w.shape[0]), upsample=upsample,
-                               residual=None if residual is None else residual.reshape(-1, w.shape[0]))
+                               residual=None if residual is None else residual.reshape(-1, w.shape[0]), implicit=implicit)
         return y
 
     def _cached_conv(self, name: str, x: torch.Tensor, cache: List, idx: List[int], residual=None) -> torch.Tensor:

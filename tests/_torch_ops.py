@@ -189,7 +189,12 @@ class TorchOps:
         n = F.normalize(x, dim=1) * x.shape[1] ** 0.5 * gamma
         y.copy_(F.silu(n) if silu else n)
 
-    def causal_conv3d(self, x, t_zero_pad, w, bias, kt, ks, y0, y1=None, *, upsample=False, residual=None, seg_cols=0):
+    def upsample2x(self, x, y):
+        self.launches += 1
+        y.copy_(x.repeat_interleave(2, dim=1).repeat_interleave(2, dim=2))
+
+    def causal_conv3d(self, x, t_zero_pad, w, bias, kt, ks, y0, y1=None, *, upsample=False, residual=None, seg_cols=0,
+                      implicit=False):
         self.launches += 1
         t_in, H, W, Cin = x.shape
         cout = w.shape[0]

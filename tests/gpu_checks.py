@@ -471,7 +471,7 @@ def check_vae_norm_silu(rows=1000, C=96, silu=True, seed=0):
 
 
 def check_causal_conv3d(t_in=1, H=8, W=12, Cin=16, Cout=384, kt=3, ks=3, pad=2, upsample=False, residual=False,
-                        segments=False, ws_bytes=None, seed=0):
+                        segments=False, ws_bytes=None, seed=0, implicit=False):
     """Gather + tcgen05 GEMM against F.conv3d on the same GPU (fp32 accumulation on both sides)."""
     x = _randn(t_in, H, W, Cin, seed=seed)
     K = kt * ks * ks * Cin
@@ -489,7 +489,8 @@ def check_causal_conv3d(t_in=1, H=8, W=12, Cin=16, Cout=384, kt=3, ks=3, pad=2, 
         y0, y1 = (torch.zeros(rows, Cout // 2, device="cuda", dtype=BF) for _ in range(2))
     else:
         y0, y1 = torch.zeros(rows, Cout, device="cuda", dtype=BF), None
-    cu.causal_conv3d(x, pad, w, b, kt, ks, y0, y1, upsample=upsample, residual=res, seg_cols=Cout // 2 if segments else 0)
+    cu.causal_conv3d(x, pad, w, b, kt, ks, y0, y1, upsample=upsample, residual=res, seg_cols=Cout // 2 if segments else 0,
+                     implicit=implicit)
     got = y0 if y1 is None else torch.cat([y0, y1], dim=1)
     # reference: the same convolution in fp32 (F.conv3d through the test double), rounded where the reference rounds:
     # bf16(conv + bias), then bf16(residual + that)
@@ -503,6 +504,14 @@ def check_causal_conv3d(t_in=1, H=8, W=12, Cin=16, Cout=384, kt=3, ks=3, pad=2, 
     cu.conv_workspace_bytes = saved
     return _finish("causal_conv3d", dict(err=rel_l2(got, ref), max=float((got.float() - ref.float()).abs().max()),
                                          err_vs_fp32=rel_l2(got, exact + (res.float() if residual else 0))), 3e-3)
+
+
+def check_upsample2x(T=2, H=5, W=7, C=96, seed=0):
+    x = _randn(T, H, W, C, seed=seed)
+
+    def run(ops, o):
+        ops.upsample2x(x, o["y"])
+    return _against_double("upsample2x", run, dict(y=torch.zeros(T, 2 * H, 2 * W, C, device="cuda", dtype=BF)), exact=("y",))
 
 
 def check_gemm_f32(M=300, N=312, K=384, seed=0):
@@ -535,7 +544,7 @@ def check_vae_pixel_out(T=3, H=16, W=24, seed=0):
     return _against_double("vae_pixel_out", run, dict(px=torch.zeros(T, 3, H, W, device="cuda")), exact=("px",))
 
 
-def check_vae_decoder(frames=None):
+def check_vae_decoder(implicit=False):
     """Whole decoder on the B200 against the pixels of the unmodified reference (CPU, bf16) and its fp32 run."""
     from helpers import golden
     from oracle import vae_oracle as V
@@ -543,6 +552,7 @@ def check_vae_decoder(frames=None):
     from self_forcing_b200.vae import B200VAEWrapper
     g = golden("vae_decode_tiny.pt")
     w = B200VAEWrapper(state_dict=V.make_random_vae_params(V.VaeConfig(), seed=VAE_CASE["seed"]), device="cuda", ops=_ops())
+    w.model.implicit_conv = implicit
     lat = vae_latents().cuda()
     out = w.decode_to_pixel(lat)
     a = w.decode_to_pixel(lat[:, :2], use_cache=True)
@@ -674,10 +684,19 @@ ALL = {
     "conv_shortcut_1x1x1": lambda: check_causal_conv3d(t_in=2, H=6, W=10, Cin=192, Cout=384, kt=1, ks=1, pad=0, seed=5),
     "conv3d_head_8_channels": lambda: check_causal_conv3d(t_in=3, H=16, W=24, Cin=96, Cout=8, pad=0, seed=6),
     "conv3d_chunked_workspace": lambda: check_causal_conv3d(t_in=3, H=16, W=24, Cin=96, Cout=96, pad=0, ws_bytes=200 * 2592 * 2, seed=7),
+    "conv3d_implicit_first_frame": lambda: check_causal_conv3d(implicit=True, seed=20),
+    "conv3d_implicit_cached_residual": lambda: check_causal_conv3d(t_in=4, H=10, W=14, Cin=96, Cout=96, pad=0, residual=True, implicit=True, seed=21),
+    "conv3d_implicit_one_cached_frame": lambda: check_causal_conv3d(t_in=2, H=6, W=10, Cin=192, Cout=384, pad=1, implicit=True, seed=22),
+    "conv2d_implicit": lambda: check_causal_conv3d(t_in=2, H=12, W=20, Cin=192, Cout=96, kt=1, pad=0, implicit=True, seed=23),
+    "conv3d_implicit_head_8_channels": lambda: check_causal_conv3d(t_in=3, H=16, W=24, Cin=96, Cout=8, pad=0, implicit=True, seed=24),
+    "conv3d_implicit_wide_rows": lambda: check_causal_conv3d(t_in=3, H=9, W=136, Cin=96, Cout=192, pad=0, residual=True, implicit=True, seed=25),
+    "conv3d_implicit_many_tiles": lambda: check_causal_conv3d(t_in=5, H=40, W=72, Cin=384, Cout=384, pad=0, implicit=True, seed=26),
+    "upsample2x": check_upsample2x,
+    "vae_decoder_implicit": lambda: check_vae_decoder(implicit=True),
     "gemm_f32_logits": check_gemm_f32,
     "softmax_rows_transpose": check_softmax_transpose,
     "vae_pixel_out": check_vae_pixel_out,
-    "vae_decoder": check_vae_decoder,
+    "vae_decoder_gather": check_vae_decoder,
     "model_forward": check_model_forward,
 }
 

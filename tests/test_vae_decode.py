@@ -67,6 +67,10 @@ def test_host_decoder_matches_reference_golden():
     b = w.decode_to_pixel(lat[:, 2:], use_cache=True)
     assert a.shape[1] == 5 and b.shape[1] == 4
     assert torch.equal(torch.cat([a, b], dim=1), out)
+    # the implicit-GEMM switch only changes which kernels run (upsampled frames are materialised for the TMA boxes)
+    w.model.implicit_conv = not w.model.implicit_conv
+    assert torch.equal(w.decode_to_pixel(lat), out)
+    w.model.implicit_conv = not w.model.implicit_conv
     # without the cache every call starts a new video: its first frame skips the temporal upsampling
     assert w.decode_to_pixel(lat[:, 2:]).shape[1] == 1
 
