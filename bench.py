@@ -17,6 +17,7 @@ One JSON line on stdout (rank 0).  Keys follow the driver contract:
                launches / their CUDA-event durations measured inside the timed steps, vs MEASURED_PEAKS.json
   cpu_baseline the oracle (CPU restatement of the reference) on this box's host cores, bounded sample
   clocks       nvidia-smi samples taken during the timed region
+  vae_decode   extra, outside `value`: the rollout's latents decoded to pixels by the B200 VAE decoder (N = 1)
 N > 1 is data parallel over prompts (one rollout per rank per step, no data-path collective).
 """
 from __future__ import annotations
@@ -362,6 +363,7 @@ def run_product_arm(args) -> None:
     ms_total = max_over_ranks(e0.elapsed_time(e1))
     launches = ops.launches - launches0
     finite = bool(torch.isfinite(lat.float()).all().item())
+    lat_last = lat.clone()
 
     # ---- timed region 1b: the same K steps with every attention launch bracketed by CUDA events (roofline leg;
     # individual launches cannot be timed inside a graph replay, so this pass launches eagerly)
@@ -479,6 +481,13 @@ def run_product_arm(args) -> None:
         "breakdown": breakdown, "kernel_ms_per_step": kernel_ms, "finite": finite,
         "clocks": clk,
     }
+    if world == 1 and not args.no_vae:
+        # SURVEY.md section 8f rank 1, reported beside the headline (NOT part of `value`, whose metric excludes T5 and
+        # the VAE): decode of this rollout's latents to 81 frames 480x832 through B200VAEWrapper (random-init decoder)
+        try:
+            line["vae_decode"] = vae_decode_leg(ops, dev, lat_last, ms_total / args.steps)
+        except Exception as e:   # the headline line must survive a failure of the extra leg
+            line["vae_decode"] = {"error": f"{type(e).__name__}: {e}"[:300]}
     if world == 1 and not args.no_cpu_baseline:
         s = CpuOracleSample(cf)
         s.calibrate(args.cpu_seconds)
@@ -492,12 +501,35 @@ def run_product_arm(args) -> None:
     shutdown()
 
 
+def vae_decode_leg(ops, dev, latents, rollout_ms: float) -> dict:
+    from self_forcing_b200.vae import B200VAEWrapper, decode_flops, random_decoder_weights
+    wrap = B200VAEWrapper(device=dev, ops=ops)
+    sd, shapes = random_decoder_weights(wrap.model)
+    wrap.model.load_state_dict(sd)
+    wrap.decode_to_pixel(latents[:, :2])                       # warm-up: both frame kinds
+    torch.cuda.synchronize()
+    before = ops.launches
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    px = wrap.decode_to_pixel(latents)
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1)
+    fl = decode_flops(wrap.model, shapes, latents.shape[1], latents.shape[3], latents.shape[4])
+    return {"ms_per_video": ms, "frames_per_s": px.shape[1] / (ms / 1e3), "tflop": fl / 1e12, "tflops": fl / ms / 1e9,
+            "gpu_launches": ops.launches - before, "out_shape": list(px.shape), "finite": bool(torch.isfinite(px).all()),
+            "rollout_plus_decode_frames_per_s": px.shape[1] / ((ms + rollout_ms) / 1e3),
+            "note": "latents -> pixels right after the rollout (implicit-GEMM tcgen05 convolutions, channels-last); "
+                    "random-init decoder weights; not included in `value`"}
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--no-vae", action="store_true", help="skip the extra VAE-decode leg")
     ap.add_argument("--mode", default="dp", choices=["dp", "ulysses"],
                     help="multi-GPU mode: dp = one video per GPU (default), ulysses = one video per group of 2/4 GPUs")
     ap.add_argument("--chunk-frames", type=int, default=3, help="latent frames per block (3 = headline, 1 = frame-wise)")
