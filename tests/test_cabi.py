@@ -38,6 +38,15 @@ def test_binding_covers_header(lib_path):
     assert isinstance(lib.sfb_last_error(), bytes)
 
 
+def test_graft_entry_build_runs(lib_path):
+    """The driver's build check: __graft_entry__.build() compiles (or finds) the library and verifies the ABI version."""
+    import importlib
+    import sys
+    sys.path.insert(0, ROOT)
+    entry = importlib.import_module("__graft_entry__")
+    entry.build()
+
+
 def test_argument_errors_are_reported_without_a_gpu(lib_path):
     """Argument validation happens before any CUDA call, so it is observable on a CPU box."""
     from self_forcing_b200 import _lib
@@ -48,6 +57,10 @@ def test_argument_errors_are_reported_without_a_gpu(lib_path):
     assert rc != 0 and b"multiples of 8" in lib.sfb_last_error()
     with pytest.raises(_lib.SfbError):
         _lib.check(rc, "sfb_gemm_bf16")
+    rc = lib.sfb_causal_conv3d_cl(1, 1, 4, 4, 16, 0, 1, 1, None, 8, 1, 3, None, 0, 1, None, 8, 0, None, 0, None)
+    assert rc != 0 and b"without a workspace" in lib.sfb_last_error()       # implicit path: no upsampling
+    rc = lib.sfb_cfg_unipc_step(1, None, 1, None, None, None, 1, 1, 1, 8, (ctypes.c_float * 12)(), 2, 2, None)
+    assert rc != 0 and b"history tensors missing" in lib.sfb_last_error()
 
 
 def test_no_cpu_fallback():
