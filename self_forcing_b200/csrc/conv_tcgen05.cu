@@ -20,20 +20,23 @@ constexpr int CV_BM = 128;
 constexpr int CV_BK = 64;
 constexpr int CV_THREADS = 192;
 
-template <int BN>
+// MT = accumulator sub-tiles per CTA: with MT = 2 one CTA owns 256 voxels (two M = 128 MMAs per k-step against the
+// SAME weight tile in shared memory), which halves the weight bytes crossing L2 -> SM per output voxel.
+template <int BN, int MT>
 struct ConvCfg {
-  static constexpr int A_BYTES = CV_BM * CV_BK * 2;
+  static constexpr int A_BYTES = MT * CV_BM * CV_BK * 2;
   static constexpr int B_BYTES = BN * CV_BK * 2;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-  static constexpr int STAGES = BN == 256 ? 4 : 6;
-  static constexpr int TMEM_COLS = 2 * BN;
+  static constexpr int STAGES = (BN == 256 || MT == 2) ? 4 : 6;
+  static constexpr int TMEM_COLS = 2 * MT * BN;
   static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 + 256;
+  static_assert(TMEM_COLS <= 512, "accumulators do not fit in TMEM");
 };
 
 struct ConvParams {
   int t_out, Ho, Wo, Cin;
   int kt, t_zero_pad;
-  int box_w_log2, box_h;            // spatial tile: box_h rows of (1 << box_w_log2) pixels = 128 voxels
+  int box_w_log2, box_h;            // spatial tile: box_h rows of (1 << box_w_log2) pixels = MT * 128 voxels
   int tiles_w, tiles_h, num_n_blocks, c_chunks;
   GemmParams g;                     // bias, out[0], ldo[0], residual, ldr, N (= Cout), seg_cols (= N)
 };
@@ -51,11 +54,11 @@ struct ConvTile {
   }
 };
 
-template <int BN, int EPI>
+template <int BN, int EPI, int MT>
 __global__ void __launch_bounds__(CV_THREADS, 1)
 conv3_implicit_kernel(const __grid_constant__ CUtensorMap tma_x, const __grid_constant__ CUtensorMap tma_w,
                       const ConvParams p) {
-  using Cfg = ConvCfg<BN>;
+  using Cfg = ConvCfg<BN, MT>;
   constexpr int STAGES = Cfg::STAGES;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -124,7 +127,7 @@ conv3_implicit_kernel(const __grid_constant__ CUtensorMap tma_x, const __grid_co
       const uint32_t acc_phase = (it >> 1) & 1;
       mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
       tc_fence_after();
-      const uint32_t d_tmem = tmem_base + acc * BN;
+      const uint32_t d_tmem = tmem_base + acc * (MT * BN);
       const int iters = (p.kt - t.dt0) * 9 * p.c_chunks;
       for (int kb = 0; kb < iters; ++kb) {
         mbar_wait(&full_bar[stage], phase);
@@ -134,7 +137,11 @@ conv3_implicit_kernel(const __grid_constant__ CUtensorMap tma_x, const __grid_co
           const uint64_t a_desc = umma_desc_sw128(a_addr, 16, 1024);
           const uint64_t b_desc = umma_desc_sw128(a_addr + Cfg::A_BYTES, 16, 1024);
 #pragma unroll
-          for (int k = 0; k < CV_BK / 16; ++k) umma_ss(d_tmem, a_desc + 2 * k, b_desc + 2 * k, idesc, (kb | k) != 0);
+          for (int k = 0; k < CV_BK / 16; ++k) {
+#pragma unroll
+            for (int m = 0; m < MT; ++m)   // sub-tile m = rows [128 m, 128 m + 128) of the A box, 16 KB further on
+              umma_ss(d_tmem + m * BN, a_desc + m * ((CV_BM * CV_BK * 2) >> 4) + 2 * k, b_desc + 2 * k, idesc, (kb | k) != 0);
+          }
           umma_commit(&empty_bar[stage]);
           if (kb == iters - 1) umma_commit(&tmem_full[acc]);
         }
@@ -146,7 +153,6 @@ conv3_implicit_kernel(const __grid_constant__ CUtensorMap tma_x, const __grid_co
     // ------------------------------ epilogue warps ------------------------------
     const int quarter = warp & 3;
     const int r = quarter * 32 + lane;                         // accumulator row = voxel (hh, ww) of the box
-    const int hh = r >> p.box_w_log2, ww = r & (box_w - 1);
     int it = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
       const ConvTile t(p, tile);
@@ -154,10 +160,15 @@ conv3_implicit_kernel(const __grid_constant__ CUtensorMap tma_x, const __grid_co
       const uint32_t acc_phase = (it >> 1) & 1;
       mbar_wait(&tmem_full[acc], acc_phase);
       tc_fence_after();
-      const int h = t.th * p.box_h + hh, w = t.tw * box_w + ww;
-      const bool ok = h < p.Ho && w < p.Wo;
-      const long long voxel = ((long long)t.to * p.Ho + h) * p.Wo + w;
-      gemm_epilogue_row_at<BN, EPI>(p.g, voxel, ok, t.n_blk * BN, tmem_base + ((uint32_t)(quarter * 32) << 16) + acc * BN);
+#pragma unroll 1
+      for (int m = 0; m < MT; ++m) {
+        const int rr = m * CV_BM + r;                            // row of the (MT * 128)-voxel box
+        const int h = t.th * p.box_h + (rr >> p.box_w_log2), w = t.tw * box_w + (rr & (box_w - 1));
+        const bool ok = h < p.Ho && w < p.Wo;
+        const long long voxel = ((long long)t.to * p.Ho + h) * p.Wo + w;
+        gemm_epilogue_row_at<BN, EPI>(p.g, voxel, ok, t.n_blk * BN,
+                                      tmem_base + ((uint32_t)(quarter * 32) << 16) + acc * (MT * BN) + m * BN);
+      }
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&tmem_empty[acc]);
@@ -174,10 +185,10 @@ conv3_implicit_kernel(const __grid_constant__ CUtensorMap tma_x, const __grid_co
 
 int device_sm_count();
 
-template <int BN, int EPI>
+template <int BN, int EPI, int MT>
 static int launch_conv3(const CUtensorMap& tx, const CUtensorMap& tw, const ConvParams& p, cudaStream_t stream) {
-  using Cfg = ConvCfg<BN>;
-  auto kern = conv3_implicit_kernel<BN, EPI>;
+  using Cfg = ConvCfg<BN, MT>;
+  auto kern = conv3_implicit_kernel<BN, EPI, MT>;
   static bool attr_set = false;
   if (!attr_set) {
     if (int e = check_cuda(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES),
@@ -201,10 +212,15 @@ int launch_conv3_implicit(const void* x, int t_in, int H, int W, int Cin, int t_
   ConvParams p{};
   p.t_out = t_in + t_zero_pad - (kt - 1);
   p.Ho = H; p.Wo = W; p.Cin = Cin; p.kt = kt; p.t_zero_pad = t_zero_pad;
-  // spatial box of 128 voxels: the widest power-of-two row segment that wastes the least area
+  const int bn = Cout <= 32 ? 32 : (Cout <= 128 ? 128 : 256);   // 32: the 3-channel head (padded to 8)
+  // two accumulator sub-tiles per CTA (256 voxels against one weight tile) where TMEM has room and the frame is large
+  // enough to keep every SM busy with 256-voxel tiles
+  const int sms_hint = device_sm_count();
+  const int mt = (bn == 128 && (long long)p.t_out * H * W >= 256LL * 4 * (sms_hint > 0 ? sms_hint : 148)) ? 2 : 1;
+  // spatial box of mt * 128 voxels: the widest power-of-two row segment that wastes the least area
   long long best = -1;
   for (int lg = 3; lg <= 7; ++lg) {
-    const int bw = 1 << lg, bh = CV_BM / bw;
+    const int bw = 1 << lg, bh = mt * CV_BM / bw;
     const long long area = (long long)((W + bw - 1) / bw) * bw * ((H + bh - 1) / bh) * bh;
     if (best < 0 || area <= best) { best = area; p.box_w_log2 = lg; p.box_h = bh; }
   }
@@ -212,7 +228,6 @@ int launch_conv3_implicit(const void* x, int t_in, int H, int W, int Cin, int t_
   p.tiles_w = (W + bw - 1) / bw;
   p.tiles_h = (H + p.box_h - 1) / p.box_h;
   p.c_chunks = (Cin + CV_BK - 1) / CV_BK;
-  const int bn = Cout <= 32 ? 32 : (Cout <= 128 ? 128 : 256);   // 32: the 3-channel head (padded to 8)
   p.num_n_blocks = (Cout + bn - 1) / bn;
   GemmParams& g = p.g;
   g.M = 0; g.N = Cout; g.K = kt * 9 * Cin;
@@ -236,9 +251,11 @@ int launch_conv3_implicit(const void* x, int t_in, int H, int W, int Cin, int t_
     if (int e = make_tmap_bf16(&tw, w, 2, dims, strides, box, true)) return e;
   }
   const bool res = residual != nullptr;
-  if (bn == 32) return res ? launch_conv3<32, EPI_RESIDUAL>(tx, tw, p, stream) : launch_conv3<32, EPI_BIAS>(tx, tw, p, stream);
-  if (bn == 128) return res ? launch_conv3<128, EPI_RESIDUAL>(tx, tw, p, stream) : launch_conv3<128, EPI_BIAS>(tx, tw, p, stream);
-  return res ? launch_conv3<256, EPI_RESIDUAL>(tx, tw, p, stream) : launch_conv3<256, EPI_BIAS>(tx, tw, p, stream);
+  if (bn == 32) return res ? launch_conv3<32, EPI_RESIDUAL, 1>(tx, tw, p, stream) : launch_conv3<32, EPI_BIAS, 1>(tx, tw, p, stream);
+  if (bn == 128 && mt == 2)
+    return res ? launch_conv3<128, EPI_RESIDUAL, 2>(tx, tw, p, stream) : launch_conv3<128, EPI_BIAS, 2>(tx, tw, p, stream);
+  if (bn == 128) return res ? launch_conv3<128, EPI_RESIDUAL, 1>(tx, tw, p, stream) : launch_conv3<128, EPI_BIAS, 1>(tx, tw, p, stream);
+  return res ? launch_conv3<256, EPI_RESIDUAL, 1>(tx, tw, p, stream) : launch_conv3<256, EPI_BIAS, 1>(tx, tw, p, stream);
 }
 
 }  // namespace sfb

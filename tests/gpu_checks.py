@@ -691,6 +691,9 @@ ALL = {
     "conv3d_implicit_head_8_channels": lambda: check_causal_conv3d(t_in=3, H=16, W=24, Cin=96, Cout=8, pad=0, implicit=True, seed=24),
     "conv3d_implicit_wide_rows": lambda: check_causal_conv3d(t_in=3, H=9, W=136, Cin=96, Cout=192, pad=0, residual=True, implicit=True, seed=25),
     "conv3d_implicit_many_tiles": lambda: check_causal_conv3d(t_in=5, H=40, W=72, Cin=384, Cout=384, pad=0, implicit=True, seed=26),
+    # >= 256 * 4 * SMs voxels with Cout <= 128: the 256-voxel (two accumulator sub-tiles) variant, ragged H and W
+    "conv3d_implicit_dual_tile": lambda: check_causal_conv3d(t_in=5, H=205, W=250, Cin=96, Cout=96, pad=0, residual=True, implicit=True, seed=27),
+    "conv2d_implicit_dual_tile": lambda: check_causal_conv3d(t_in=2, H=300, W=264, Cin=192, Cout=96, kt=1, pad=0, implicit=True, seed=28),
     "upsample2x": check_upsample2x,
     "vae_decoder_implicit": lambda: check_vae_decoder(implicit=True),
     "gemm_f32_logits": check_gemm_f32,
