@@ -502,6 +502,7 @@ def run_product_arm(args) -> None:
 
 
 def vae_decode_leg(ops, dev, latents, rollout_ms: float) -> dict:
+    import torch
     from self_forcing_b200.vae import B200VAEWrapper, decode_flops, random_decoder_weights
     wrap = B200VAEWrapper(device=dev, ops=ops)
     sd, shapes = random_decoder_weights(wrap.model)
