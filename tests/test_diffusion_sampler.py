@@ -5,7 +5,7 @@ import pytest
 import torch
 
 from _torch_ops import TorchOps
-from helpers import DIFFUSION_CASES, golden, make_product_diffusion_pipeline, negative_embeds, rel_l2, synthetic_inputs
+from helpers import golden, make_product_diffusion_pipeline, negative_embeds, rel_l2, synthetic_inputs
 from oracle import causal_wan_oracle as O
 from oracle import unipc_oracle as U
 from oracle.make_golden import UNIPC_TRACE, unipc_trace_flow
