@@ -93,3 +93,29 @@ def test_state_dict_contract():
     assert dec.geom["decoder.upsamples.3.resample.1"] == (1, 3)
     with pytest.raises(NotImplementedError):
         B200VAEWrapper(state_dict=p, ops=TorchOps()).encode_to_latent(None)
+
+
+def test_rollout_to_pixels_through_the_pipeline():
+    """Drop-in composition: the few-step pipeline with B200VAEWrapper injected as `vae=` (the reference passes
+    `WanVAEWrapper()` there, inference.py:57-79) returns the video the reference's tail computes --
+    `(decode_to_pixel(latents) * 0.5 + 0.5).clamp(0, 1)` (causal_inference.py:248-250) -- checked in fp32 against the
+    oracle rollout followed by the oracle decoder."""
+    from helpers import ROLLOUT_CASES, make_product_pipeline, patched_randn_like
+    case = ROLLOUT_CASES["tiny_test_yaml"]
+    pipe, cfg, params, pe, noise = make_product_pipeline(case, "cpu", ops=TorchOps(), dtype=torch.float32, hw=(8, 12))
+    vp = {k: v.float() for k, v in _params().items()}
+    dec = B200VAEWrapper(ops=TorchOps())
+    dec.model.load_state_dict(_params())
+    # the product decoder keeps bf16 weights; run it on bf16 latents like the real pipeline tail does
+
+    class _Bf16Latents(torch.nn.Module):
+        def decode_to_pixel(self, latent, use_cache=False):
+            return dec.decode_to_pixel(latent.to(torch.bfloat16), use_cache=use_cache)
+    pipe.vae = _Bf16Latents()
+    with patched_randn_like(3):
+        video, lat = pipe.inference(noise, ["synthetic"], return_latents=True)
+    assert video.shape == (1, 1 + 4 * (case["frames"] - 1), 3, 64, 96)
+    assert float(video.min()) >= 0.0 and float(video.max()) <= 1.0
+    with torch.no_grad():
+        ref = (V.decode_to_pixel(vp, V.VaeConfig(), lat) * 0.5 + 0.5).clamp(0, 1)
+    assert rel_l2(video, ref) <= 2.5e-2
