@@ -49,7 +49,7 @@ def make_product_pipeline(case: dict, device, ops=None, num_layers=2, ffn_dim=51
 
 
 def make_product_diffusion_pipeline(case: dict, device, ops=None, num_layers=2, ffn_dim=512, dtype=torch.bfloat16, seed=0,
-                                    scalar_rounding="bf16"):
+                                    scalar_rounding="bf16", hw=(60, 104)):
     """B200DiffusionWrapper + product CausalDiffusionInferencePipeline (CFG + UniPC) for a tiny-depth model.
     scalar_rounding "bf16" = how the CPU run of the reference treats the solver's 0-dim tensor scalars, i.e. what
     the golden vectors contain (self_forcing_b200/unipc.py)."""
@@ -60,7 +60,7 @@ def make_product_diffusion_pipeline(case: dict, device, ops=None, num_layers=2, 
     w = B200DiffusionWrapper(model_config=dict(WAN_T2V_1_3B, ffn_dim=ffn_dim, num_layers=num_layers),
                              timestep_shift=case["shift"], device=device, ops=ops, dtype=dtype)
     w.model.load_state_dict(params, strict=True)
-    pe, noise = synthetic_inputs(1, case["frames"])
+    pe, noise = synthetic_inputs(1, case["frames"], *hw)
     pe, noise = pe.to(device=device, dtype=dtype), noise.to(device=device, dtype=dtype)
     neg = negative_embeds().to(device=device, dtype=dtype)
     args = diffusion_args(case, sampling_steps=case["sampling_steps"], unipc_scalar_rounding=scalar_rounding)

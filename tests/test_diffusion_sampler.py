@@ -125,3 +125,26 @@ def test_product_diffusion_pipeline_matches_reference_golden():
     assert torch.equal(lat, lat2)
     with pytest.raises(NotImplementedError):
         pipe.inference(noise, ["synthetic"], object(), None, None)
+
+
+@pytest.mark.parametrize("indep,frames,init_frames,nfpb", [(False, 2, 2, 2), (True, 2, 1, 1), (True, 3, 0, 1)])
+def test_product_diffusion_pipeline_wiring_fp32(indep, frames, init_frames, nfpb):
+    """fp32 on both sides removes rounding noise, so the conditioning-frame paths (video continuation, image-to-video
+    with a lone first frame, and a first chunk of one frame) must reproduce the oracle driver: positive / negative cache
+    halves, frame offsets, the solver restarted per chunk, the clean-context refresh."""
+    case = dict(frames=frames, num_frame_per_block=nfpb, independent_first_frame=indep, shift=5.0, sampling_steps=4,
+                guidance_scale=3.0)
+    pipe, cfg, params, pe, neg, noise = make_product_diffusion_pipeline(case, "cpu", ops=TorchOps(), dtype=torch.float32,
+                                                                        scalar_rounding="fp32", hw=(16, 24))
+    init = None
+    if init_frames:
+        init = torch.randn(1, init_frames, 16, 16, 24, generator=torch.Generator().manual_seed(4))
+    _, lat = pipe.inference(noise, ["synthetic"], None, None, None, initial_latent=init, return_latents=True)
+    ow = O.OracleWrapper(params, cfg, case["shift"])
+    with torch.no_grad():
+        tr = U.diffusion_rollout(ow, noise, pe, neg, case["guidance_scale"], nfpb, case["sampling_steps"], case["shift"],
+                                 independent_first_frame=indep, initial_latent=init)
+    assert lat.shape == tr.latents.shape == (1, frames + init_frames, 16, 16, 24)
+    assert rel_l2(lat, tr.latents) < 1e-4
+    idx = tuple(int(c[0][k]) for c in (pipe.kv_cache_pos, pipe.kv_cache_neg) for k in ("global_end_index", "local_end_index"))
+    assert idx == tr.index_trace[-1]
