@@ -75,6 +75,18 @@ ROLLOUT_CASES = {
 }
 
 
+# the rolling KV window driven through the PIPELINE (the model-level fixture below uses a small grid): 4 chunks of one frame,
+# a 2-frame local window and a 1-frame attention sink -> the cache rolls on chunks 3 and 4 (causal_model.py:207-221)
+ROLLING_ROLLOUT_CASES = {
+    "rolling_window": dict(frames=4, num_frame_per_block=1, independent_first_frame=False, shift=5.0, local_attn_size=2,
+                           sink_size=1),
+}
+
+
+def rollout_cfg(case: dict) -> O.OracleConfig:
+    return O.OracleConfig(**O.WAN_TINY, local_attn_size=case.get("local_attn_size", -1), sink_size=case.get("sink_size", 0))
+
+
 def initial_latent_for(case: dict, H: int = 60, W: int = 104):
     n = case.get("initial_frames", 0)
     if not n:
@@ -332,6 +344,12 @@ def main():
         roll[name] = dict(latents=lat, final_index=idx, case=case)
         print(name, lat.shape, idx, float(lat.float().std()))
     torch.save(roll, os.path.join(GOLDEN, "rollout_tiny.pt"))
+    rolling = {}
+    for name, case in ROLLING_ROLLOUT_CASES.items():
+        lat, idx = reference_rollout(ref, case, params, rollout_cfg(case))
+        rolling[name] = dict(latents=lat, final_index=idx, case=case)
+        print(name, lat.shape, idx)
+    torch.save(rolling, os.path.join(GOLDEN, "rollout_rolling.pt"))
 
     torch.save(reference_rolling(ref), os.path.join(GOLDEN, "model_rolling.pt"))
     torch.save(reference_masks(ref), os.path.join(GOLDEN, "block_masks.pt"))

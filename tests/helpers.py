@@ -7,7 +7,7 @@ import types
 import torch
 
 from oracle import causal_wan_oracle as O
-from oracle.make_golden import (DIFFUSION_CASES, NEGATIVE_PROMPT, ROLLOUT_CASES, SeededNoise, _IdentityVAE,
+from oracle.make_golden import (DIFFUSION_CASES, NEGATIVE_PROMPT, ROLLING_ROLLOUT_CASES, ROLLOUT_CASES, SeededNoise, _IdentityVAE,
                                 _TextEncoder, _TextEncoder2, diffusion_args, initial_latent_for, negative_embeds,
                                 patched_randn_like, synthetic_inputs)
 
@@ -24,7 +24,7 @@ def rel_l2(a, b) -> float:
 
 
 def pipeline_args(case: dict, **extra):
-    extra = {k: v for k, v in extra.items() if k != "initial_frames"}
+    extra = {k: v for k, v in extra.items() if k not in ("initial_frames", "local_attn_size", "sink_size")}
     return types.SimpleNamespace(denoising_step_list=[1000, 750, 500, 250], warp_denoising_step=True,
                                  num_frame_per_block=case["num_frame_per_block"],
                                  independent_first_frame=case["independent_first_frame"], context_noise=0,
@@ -36,10 +36,11 @@ def make_product_pipeline(case: dict, device, ops=None, num_layers=2, ffn_dim=51
     """B200DiffusionWrapper + product CausalInferencePipeline for a tiny-depth, full-width model."""
     from self_forcing_b200.pipeline import CausalInferencePipeline
     from self_forcing_b200.wrapper import WAN_T2V_1_3B, B200DiffusionWrapper
-    cfg = O.OracleConfig(dim=1536, ffn_dim=ffn_dim, num_heads=12, num_layers=num_layers)
+    window = dict(local_attn_size=case.get("local_attn_size", -1), sink_size=case.get("sink_size", 0))
+    cfg = O.OracleConfig(dim=1536, ffn_dim=ffn_dim, num_heads=12, num_layers=num_layers, **window)
     params = O.make_random_params(cfg, seed=seed, dtype=dtype)
     w = B200DiffusionWrapper(model_config=dict(WAN_T2V_1_3B, ffn_dim=ffn_dim, num_layers=num_layers),
-                             timestep_shift=case["shift"], device=device, ops=ops, dtype=dtype)
+                             timestep_shift=case["shift"], device=device, ops=ops, dtype=dtype, **window)
     w.model.load_state_dict(params, strict=True)
     pe, noise = synthetic_inputs(1, case["frames"], *hw)
     pe, noise = pe.to(device=device, dtype=dtype), noise.to(device=device, dtype=dtype)

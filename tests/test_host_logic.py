@@ -114,6 +114,20 @@ def test_pipeline_bf16_vs_reference_golden():
     assert (int(pipe.kv_cache1[0]["global_end_index"]), int(pipe.kv_cache1[0]["local_end_index"])) == tuple(g["final_index"])
 
 
+def test_rolling_window_pipeline_vs_reference_golden():
+    """Host cache plan + index mirror under a rolling local window (2 frames, sink 1) through the whole pipeline."""
+    from helpers import ROLLING_ROLLOUT_CASES
+    g = golden("rollout_rolling.pt")["rolling_window"]
+    case = ROLLING_ROLLOUT_CASES["rolling_window"]
+    pipe, *_, noise = make_product_pipeline(case, "cpu", ops=TorchOps())
+    assert pipe.local_attn_size == 2
+    with patched_randn_like(3):
+        _, lat = pipe.inference(noise, ["synthetic"], return_latents=True)
+    assert pipe.kv_cache1[0]["k"].shape[1] == 2 * 1560
+    assert (int(pipe.kv_cache1[0]["global_end_index"]), int(pipe.kv_cache1[-1]["local_end_index"])) == tuple(g["final_index"])
+    assert rel_l2(lat, g["latents"]) <= 1e-2
+
+
 def test_skip_refresh_tail_is_output_neutral():
     case = dict(ROLLOUT_CASES["tiny_test_yaml"], frames=2, independent_first_frame=False)
     outs = []

@@ -46,6 +46,24 @@ def test_rollout_matches_reference_golden(name):
     assert rel_l2(tr.latents, g["latents"]) <= TOL
 
 
+def test_rolling_window_rollout_matches_reference_golden():
+    """The rolling KV window driven through the pipeline: 2-frame local window + 1-frame sink, four one-frame chunks,
+    so the cache rolls on chunks 3 and 4 while the global index keeps growing."""
+    from oracle.make_golden import ROLLING_ROLLOUT_CASES, rollout_cfg
+    g = golden("rollout_rolling.pt")["rolling_window"]
+    case = ROLLING_ROLLOUT_CASES["rolling_window"]
+    assert g["case"] == case
+    cfg = rollout_cfg(case)
+    ow = O.OracleWrapper(O.make_random_params(O.OracleConfig(**O.WAN_TINY), seed=0), cfg, case["shift"])
+    pe, noise = synthetic_inputs(1, case["frames"])
+    steps = O.warp_denoising_steps(ow.scheduler, [1000, 750, 500, 250])
+    with torch.no_grad(), patched_randn_like(3):
+        tr = O.rollout(ow, noise, pe, steps, case["num_frame_per_block"])
+    assert tr.index_trace[4::5] == [(1560, 1560), (3120, 3120), (4680, 3120), (6240, 3120)]   # after each chunk's refresh
+    assert tr.index_trace[-1] == tuple(g["final_index"]) == (6240, 3120)
+    assert rel_l2(tr.latents, g["latents"]) <= TOL
+
+
 def test_rolling_sink_cache_model_level():
     g = golden("model_rolling.pt")
     r = ROLLING
