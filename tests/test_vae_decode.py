@@ -1,6 +1,8 @@
 """VAE decode, CPU side: the oracle against the vectors of the unmodified reference
 `WanVAE_`, then the product's host logic (weight packing, feature-cache bookkeeping, "Rep" first frame, frame
 interleave of the temporal upsampling) through the torch test double."""
+import itertools
+
 import pytest
 import torch
 
@@ -119,3 +121,29 @@ def test_rollout_to_pixels_through_the_pipeline():
     with torch.no_grad():
         ref = (V.decode_to_pixel(vp, V.VaeConfig(), lat) * 0.5 + 0.5).clamp(0, 1)
     assert rel_l2(video, ref) <= 2.5e-2
+
+
+@pytest.mark.parametrize("splits", [(1, 1, 2), (3, 1), (1, 3)])
+def test_streaming_decode_is_split_invariant(splits):
+    """`cached_decode` semantics: however a video's latent frames are cut into calls, the pixels are the same (the
+    feature cache carries the last two input frames of every causal convolution across calls; only the very first
+    frame skips the temporal upsampling).  Host logic through the test double, bit-exact."""
+    w = B200VAEWrapper(state_dict=_params(), ops=TorchOps())
+    lat = vae_latents(frames=sum(splits), seed_offset=sum(splits))
+    whole = w.decode_to_pixel(lat)
+    w.model.clear_cache()
+    parts, at = [], 0
+    for n in splits:
+        parts.append(w.decode_to_pixel(lat[:, at:at + n], use_cache=True))
+        at += n
+    assert [p.shape[1] for p in parts][0] == 1 + 4 * (splits[0] - 1)
+    assert torch.equal(torch.cat(parts, dim=1), whole)
+    # and the oracle agrees with the product about the continuation
+    cfg, p = V.VaeConfig(), _params()
+    cache = [None] * V.cache_slots(cfg)
+    ends = list(itertools.accumulate(splits))
+    z = lat.permute(0, 2, 1, 3, 4)
+    with torch.no_grad():
+        o = torch.cat([V.decode(p, cfg, z[:, :, a:b], cache) for a, b in zip([0] + ends[:-1], ends)], dim=2)
+        one_shot = V.decode(p, cfg, z)
+    assert torch.equal(o, one_shot)
