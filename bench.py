@@ -18,6 +18,8 @@ One JSON line on stdout (rank 0).  Keys follow the driver contract:
   cpu_baseline the oracle (CPU restatement of the reference) on this box's host cores, bounded sample
   clocks       nvidia-smi samples taken during the timed region
   vae_decode   extra, outside `value`: the rollout's latents decoded to pixels by the B200 VAE decoder (N = 1)
+  gpu_eager_baseline  extra: the oracle run in PyTorch eager mode on the same GPU (cuBLAS + SDPA), the "beat this"
+               number of SURVEY.md section 8d (N = 1)
 N > 1 is data parallel over prompts (one rollout per rank per step, no data-path collective).
 """
 from __future__ import annotations
@@ -488,6 +490,14 @@ def run_product_arm(args) -> None:
             line["vae_decode"] = vae_decode_leg(ops, dev, lat_last, ms_total / args.steps)
         except Exception as e:   # the headline line must survive a failure of the extra leg
             line["vae_decode"] = {"error": f"{type(e).__name__}: {e}"[:300]}
+    if world == 1 and not args.no_gpu_eager:
+        # "additionally report the reference GPU eager path (cuBLAS + FA2 / SDPA) on the same
+        # B200 as the beat-this number".  The reference checkout cannot travel to this box, so its restatement (the
+        # oracle, same op sequence in plain PyTorch) runs in eager mode on this GPU with the product's weights and inputs.
+        try:
+            line["gpu_eager_baseline"] = gpu_eager_leg(gen, cf, pe_dev, noise_dev, value)
+        except Exception as e:   # an extra leg must never take the headline line down
+            line["gpu_eager_baseline"] = {"error": f"{type(e).__name__}: {e}"[:300]}
     if world == 1 and not args.no_cpu_baseline:
         s = CpuOracleSample(cf)
         s.calibrate(args.cpu_seconds)
@@ -499,6 +509,38 @@ def run_product_arm(args) -> None:
         json.dump(line, f, indent=1)
     print(json.dumps(line), flush=True)
     shutdown()
+
+
+def gpu_eager_leg(gen, chunk_frames: int, pe_dev, noise_dev, product_fps: float) -> dict:
+    """One full rollout of the ORACLE (the CPU restatement of the reference's PyTorch path) in eager mode on the GPU:
+    cuBLAS for every Linear, torch SDPA for attention, op-by-op elementwise kernels with the reference's float64 RoPE /
+    sinusoid / flow->x0, `.item()` index reads per forward -- what the unmodified reference does on a GPU, minus its
+    flash_attn varlen packing.  Same random-init weights (the product model's state_dict) and the same inputs.  A
+    reported baseline, not part of `value`; the oracle is only ever the thing compared against."""
+    import torch
+    from oracle import causal_wan_oracle as O
+    cfg = O.OracleConfig(dim=C, ffn_dim=FFN, num_heads=NH, num_layers=NL)
+    params = {k: v for k, v in gen.model.state_dict().items() if not k.startswith("pose_proj")}
+    ow = O.OracleWrapper(params, cfg, SHIFT)
+    steps = O.warp_denoising_steps(ow.scheduler, DENOISE_STEPS)
+    sync = torch.cuda.synchronize if noise_dev.is_cuda else (lambda: None)
+    with torch.no_grad():
+        O.rollout(ow, noise_dev, pe_dev, steps, chunk_frames, max_chunks=1)      # warm-up: cuBLAS / SDPA heuristics
+        sync()
+        t0 = time.perf_counter()      # host clock around a synchronised region: eager mode is host-driven by nature
+        tr = O.rollout(ow, noise_dev, pe_dev, steps, chunk_frames)
+        sync()
+        ms = (time.perf_counter() - t0) * 1e3
+    frames = (noise_dev.shape[1] - 1) * 4 + 1
+    fps = frames / (ms / 1e3)
+    finite = bool(torch.isfinite(tr.latents.float()).all())
+    del tr
+    if noise_dev.is_cuda:
+        torch.cuda.empty_cache()
+    return {"value": fps, "unit": UNIT, "ms_per_step": ms, "kind": "port", "finite": finite,
+            "what": "oracle (restatement of the reference's PyTorch path) in eager mode on this GPU: cuBLAS GEMMs, torch "
+                    "SDPA, op-by-op elementwise kernels, per-forward .item() syncs; same weights and inputs as the product",
+            "product_speedup": product_fps / fps}
 
 
 def vae_decode_leg(ops, dev, latents, rollout_ms: float) -> dict:
@@ -531,6 +573,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-vae", action="store_true", help="skip the extra VAE-decode leg")
+    ap.add_argument("--no-gpu-eager", action="store_true", help="skip the oracle-in-eager-mode-on-the-GPU baseline leg")
     ap.add_argument("--mode", default="dp", choices=["dp", "ulysses"],
                     help="multi-GPU mode: dp = one video per GPU (default), ulysses = one video per group of 2/4 GPUs")
     ap.add_argument("--chunk-frames", type=int, default=3, help="latent frames per block (3 = headline, 1 = frame-wise)")

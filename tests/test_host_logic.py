@@ -253,6 +253,19 @@ def test_reference_arm_runs_on_rank0_only():
     assert r.returncode == 0 and r.stdout.strip() == ""
 
 
+def test_bench_gpu_eager_leg_logic(monkeypatch):
+    """bench.py's `gpu_eager_baseline` leg (the oracle in eager mode with the product's own weights) on a 2-layer
+    model: the product's state_dict must be directly usable as the oracle's parameter dict."""
+    import bench
+    monkeypatch.setattr(bench, "NL", 2)
+    monkeypatch.setattr(bench, "FFN", 512)
+    case = dict(frames=2, num_frame_per_block=1, independent_first_frame=False, shift=bench.SHIFT)
+    pipe, cfg, params, pe, noise = make_product_pipeline(case, "cpu", ops=TorchOps())
+    out = bench.gpu_eager_leg(pipe.generator, 1, pe, noise, product_fps=10.0)
+    assert out["finite"] and out["value"] > 0 and out["kind"] == "port"
+    assert out["product_speedup"] == pytest.approx(10.0 / out["value"])
+
+
 def test_bench_flop_model_matches_survey():
     """bench.py's algorithmic FLOP count is the SURVEY.md section 8d figure (990.3 TFLOP chunk-wise, 943.2 frame-wise)."""
     import importlib.util
