@@ -148,3 +148,36 @@ def test_product_diffusion_pipeline_wiring_fp32(indep, frames, init_frames, nfpb
     assert rel_l2(lat, tr.latents) < 1e-4
     idx = tuple(int(c[0][k]) for c in (pipe.kv_cache_pos, pipe.kv_cache_neg) for k in ("global_end_index", "local_end_index"))
     assert idx == tr.index_trace[-1]
+
+
+@pytest.mark.parametrize("steps,shift,order", [(50, 5.0, 2), (7, 3.0, 2), (5, 8.0, 1)])
+def test_unipc_is_exact_for_a_perfect_model(steps, shift, order):
+    """Size-independent property: if the model always predicts the true clean sample (flow = (x - x0) / sigma), every
+    first-difference term of UniP / UniC vanishes and the solver must walk the exact path x_i = (1 - sigma_i) x0 +
+    sigma_i eps, ending at x0 -- for any step count, shift and solver order.  fp32 through the host scheduler."""
+    g = torch.Generator().manual_seed(5)
+    x0, eps = torch.randn(1, 2, 16, 6, 10, generator=g), torch.randn(1, 2, 16, 6, 10, generator=g)
+    s = FlowUniPCMultistepScheduler(shift=1, solver_order=order, ops=TorchOps())
+    s.set_timesteps(steps, device="cpu", shift=shift)
+    sig = s.sigmas
+    x = (1 - sig[0]) * x0 + sig[0] * eps
+    for i, t in enumerate(s.timesteps):
+        flow = (x - x0) / sig[i]
+        x = s.step(flow, t, x, return_dict=False)[0]
+        expect = (1 - sig[i + 1]) * x0 + sig[i + 1] * eps
+        assert rel_l2(x, expect) < 2e-5, (i, rel_l2(x, expect))
+    assert rel_l2(x, x0) < 2e-5
+
+
+def test_guidance_scale_one_equals_conditional_flow():
+    """flow = uncond + 1.0 * (cond - uncond) is the conditional flow up to one rounding: the fused guided step with
+    g = 1 and the plain step on the conditional flow agree."""
+    g = torch.Generator().manual_seed(6)
+    x, fc, fu = (torch.randn(1, 1, 16, 6, 10, generator=g) for _ in range(3))
+    outs = []
+    for guided in (True, False):
+        s = FlowUniPCMultistepScheduler(shift=1, ops=TorchOps())
+        s.set_timesteps(4, device="cpu", shift=5.0)
+        kw = dict(model_output_uncond=fu, guidance_scale=1.0) if guided else {}
+        outs.append(s.step(fc, s.timesteps[0], x, return_dict=False, **kw)[0])
+    assert rel_l2(outs[0], outs[1]) < 1e-6
