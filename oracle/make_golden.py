@@ -288,7 +288,37 @@ def reference_vae_decode(case=VAE_CASE):
         model.clear_cache()
         # the same weights evaluated in fp32: the yardstick for "how far apart may two bf16 evaluations be"
         exact = model.float().decode(zs.float(), [torch.tensor(V.LATENT_MEAN), 1.0 / torch.tensor(V.LATENT_STD)])
-    return dict(case=case, pixels=full, streamed=torch.cat([first, second], dim=2), pixels_fp32=exact)
+    out = dict(case=case, pixels=full, streamed=torch.cat([first, second], dim=2), pixels_fp32=exact)
+    # the demo's streaming decoder (demo_utils/vae_block3.py): explicit feature-cache list, all-zero tensors to start
+    # with (demo_utils/constant.py ZERO_VAE_CACHE), so even the first frame goes through the temporal upsampling
+    blk = ref_shim.load_reference_vae_block3()
+    stream = blk.VAEDecoderWrapper()
+    missing, unexpected = stream.load_state_dict(params, strict=False)
+    assert not missing and not unexpected, (missing, unexpected)
+    stream = stream.to(torch.bfloat16).eval()
+    h, w = case["hw"]
+    zero_cache = [torch.zeros(1, c, 2, h * s_, w * s_, dtype=torch.bfloat16) for c, s_ in vae_stream_cache_layout(cfg)]
+    with torch.no_grad(), contextlib.redirect_stdout(io.StringIO()):
+        a, cache = stream(lat[:, :2], *zero_cache)
+        b, cache = stream(lat[:, 2:], *cache)
+    out["block3_pixels"] = torch.cat([a, b], dim=1)
+    out["block3_cache_sum"] = torch.stack([c.float().abs().sum() for c in cache])
+    return out
+
+
+def vae_stream_cache_layout(cfg):
+    """(channels, spatial scale) of the 32 feature-cache slots in walk order (demo_utils/constant.py:5-38)."""
+    plan, dims = cfg.stage_plan()
+    slots = [(cfg.z_dim, 1)] + [(dims[0], 1)] * 4
+    scale = 1
+    for kind, _, cin, cout in plan:
+        if kind == "res":
+            slots += [(cin, scale), (cout, scale)]
+        else:
+            if kind == "up3d":
+                slots.append((cin, scale))
+            scale *= 2
+    return slots + [(dims[-1], scale)]
 
 
 MASK_CASES = {

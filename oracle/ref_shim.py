@@ -200,6 +200,32 @@ def load_reference_vae(root: str = REF_ROOT):
     return mod
 
 
+def load_reference_vae_block3(root: str = REF_ROOT):
+    """`demo_utils/vae_block3.py` (the streaming decoder with an explicit feature-cache list); it imports its layers from
+    `wan.modules.vae`, so the real module stands in for the stub while it loads."""
+    import importlib.util
+    name = "_sfb_reference_vae_block3"
+    if name in sys.modules:
+        return sys.modules[name]
+    real = load_reference_vae(root)
+    if "wan" not in sys.modules:
+        _shell("wan", os.path.join(root, "wan"))
+        _shell("wan.modules", os.path.join(root, "wan", "modules"))
+    stub = sys.modules.get("wan.modules.vae")
+    sys.modules["wan.modules.vae"] = real
+    try:
+        spec = importlib.util.spec_from_file_location(name, os.path.join(root, "demo_utils", "vae_block3.py"))
+        mod = importlib.util.module_from_spec(spec)
+        sys.modules[name] = mod
+        spec.loader.exec_module(mod)
+    finally:
+        if stub is not None:
+            sys.modules["wan.modules.vae"] = stub
+        else:
+            sys.modules.pop("wan.modules.vae", None)
+    return mod
+
+
 def make_reference_wrapper(ref, model_cfg: dict, timestep_shift: float, seed: int = 0,
                            dtype=torch.bfloat16):
     """Random-init `WanDiffusionWrapper` without `from_pretrained` (wan_wrapper.py:139-147).

@@ -276,6 +276,31 @@ class B200VAEDecoder:
         return torch.cat(frames, dim=0)
 
 
+class B200VAEDecoderWrapper(torch.nn.Module):
+    """The demo's streaming decoder (demo_utils/vae_block3.py:130-185): `forward(z, *feat_cache) -> (pixels, feat_cache)`
+    with the 32 feature-cache tensors owned by the caller (channels-first `[1, C, 2, H, W]`, all zeros to start with --
+    demo_utils/constant.py:5-38 -- in which case even the first frame is temporally upsampled)."""
+
+    def __init__(self, state_dict: Optional[Dict[str, torch.Tensor]] = None, device=None, ops=None):
+        super().__init__()
+        self.model = B200VAEDecoder(ops=ops, device=device)
+        if state_dict is not None:
+            self.model.load_state_dict(state_dict, strict=False)
+
+    def forward(self, z: torch.Tensor, *feat_cache):
+        """z [1, F, 16, h, w] -> (fp32 pixels [1, T, 3, 8h, 8w] in [-1, 1], list of updated cache tensors)."""
+        assert z.shape[0] == 1, "the streaming decoder works on one video"
+        dec = self.model
+        if len(feat_cache) != dec.cache_slots():
+            raise ValueError(f"expected {dec.cache_slots()} feature-cache entries, got {len(feat_cache)}")
+        # caller layout [1, C, T, H, W] <-> channels-last frames [T, H, W, C]
+        dec.cache = [c if c is None or isinstance(c, str) else c[0].permute(1, 2, 3, 0).contiguous() for c in feat_cache]
+        pixels = dec.decode(z[0].permute(1, 0, 2, 3), use_cache=True)
+        out_cache = [c if c is None or isinstance(c, str) else c.permute(3, 0, 1, 2).unsqueeze(0) for c in dec.cache]
+        dec.cache = None
+        return pixels.unsqueeze(0), out_cache
+
+
 class B200VAEWrapper(torch.nn.Module):
     """`WanVAEWrapper` (utils/wan_wrapper.py:58-117), decode side."""
 

@@ -10,7 +10,7 @@ from _torch_ops import TorchOps
 from helpers import golden, rel_l2
 from oracle import vae_oracle as V
 from oracle.make_golden import VAE_CASE, vae_latents
-from self_forcing_b200.vae import B200VAEDecoder, B200VAEWrapper
+from self_forcing_b200.vae import B200VAEDecoder, B200VAEDecoderWrapper, B200VAEWrapper
 
 
 def _params():
@@ -147,3 +147,40 @@ def test_streaming_decode_is_split_invariant(splits):
         o = torch.cat([V.decode(p, cfg, z[:, :, a:b], cache) for a, b in zip([0] + ends[:-1], ends)], dim=2)
         one_shot = V.decode(p, cfg, z)
     assert torch.equal(o, one_shot)
+
+
+def test_streaming_decoder_with_caller_owned_cache():
+    """demo_utils/vae_block3.py: the 32 feature-cache tensors travel through the call (`forward(z, *cache) -> (pixels,
+    cache)`), starting from all-zero tensors -- then the first frame is temporally upsampled too (3 latent frames ->
+    12 pixel frames).  Oracle: identical to the unmodified reference module; product host logic: within the bf16 bar."""
+    from oracle.make_golden import vae_stream_cache_layout
+    g = golden("vae_decode_tiny.pt")
+    cfg, p = V.VaeConfig(), _params()
+    lat = vae_latents()
+    h, w = VAE_CASE["hw"]
+    layout = vae_stream_cache_layout(cfg)
+    assert len(layout) == 32 and layout[0] == (16, 1) and layout[12] == (192, 2) and layout[-1] == (96, 8)
+
+    def zeros():
+        return [torch.zeros(1, c, 2, h * s, w * s, dtype=torch.bfloat16) for c, s in layout]
+
+    # oracle: the explicit cache list is the oracle's own cache argument (channels-first like the reference)
+    cache = zeros()
+    z = lat.permute(0, 2, 1, 3, 4)
+    with torch.no_grad():
+        a = V.decode(p, cfg, z[:, :, :2], cache)
+        b = V.decode(p, cfg, z[:, :, 2:], cache)
+    ref = g["block3_pixels"]
+    assert torch.equal(torch.cat([a, b], dim=2).float().clamp(-1, 1).permute(0, 2, 1, 3, 4), ref)
+    assert torch.allclose(torch.stack([c.float().abs().sum() for c in cache]), g["block3_cache_sum"])
+
+    # product host logic through the test double
+    dec = B200VAEDecoderWrapper(state_dict=p, ops=TorchOps())
+    pa, cache = dec(lat[:, :2], *zeros())
+    pb, cache = dec(lat[:, 2:], *cache)
+    out = torch.cat([pa, pb], dim=1)
+    assert out.shape == ref.shape == (1, 12, 3, 8 * h, 8 * w)
+    assert rel_l2(out, ref) <= 2.5e-2
+    assert len(cache) == 32 and all(c.shape == z0.shape for c, z0 in zip(cache, zeros()))
+    with pytest.raises(ValueError):
+        dec(lat[:, :1], *zeros()[:5])
