@@ -29,8 +29,9 @@ struct GemmCfg {
   static constexpr int A_BYTES = BLOCK_M * BLOCK_K * 2;
   static constexpr int B_BYTES = BLOCK_N * BLOCK_K * 2;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-  static constexpr int STAGES = (BLOCK_N == 256) ? 4 : (BLOCK_N == 128 ? 6 : 8);
-  static constexpr int TMEM_COLS = (2 * BLOCK_N < 32) ? 32 : 2 * BLOCK_N;
+  static constexpr int STAGES = (BLOCK_N == 256) ? 4 : (BLOCK_N == 192 ? 5 : (BLOCK_N == 128 ? 6 : 8));
+  // two accumulator buffers; TMEM is allocated in powers of two (192-column tiles take 512 and use 2 x 192 of them)
+  static constexpr int TMEM_COLS = 2 * BLOCK_N <= 32 ? 32 : (2 * BLOCK_N <= 128 ? 128 : (2 * BLOCK_N <= 256 ? 256 : 512));
   static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
 };
 
@@ -217,7 +218,7 @@ extern "C" int sfb_gemm_bf16(const void* x, long long ldx, const void* w, long l
   const bool pair = block_n == 512 || block_n == 513;   // 513: pair tiles with the stream-K schedule forced on
   const bool force_streamk = block_n == 513;
   if (pair) block_n = 256;
-  if (block_n != 64 && block_n != 128 && block_n != 256) { set_error("sfb_gemm_bf16: block_n must be 64/128/256/512"); return SFB_ERR_INVALID; }
+  if (block_n != 64 && block_n != 128 && block_n != 192 && block_n != 256) { set_error("sfb_gemm_bf16: block_n must be 64/128/192/256/512"); return SFB_ERR_INVALID; }
   if (epilogue == EPI_F32 && (pair || seg_cols != N)) { set_error("sfb_gemm_bf16: the fp32-output epilogue takes one-CTA tiles and one output segment"); return SFB_ERR_INVALID; }
   if (seg_cols % block_n && seg_cols != N) { set_error("sfb_gemm_bf16: seg_cols=%d not a multiple of the N tile %d", seg_cols, block_n); return SFB_ERR_INVALID; }
   if ((epilogue == EPI_RESIDUAL || epilogue == EPI_GATE_RES) && residual == nullptr) { set_error("sfb_gemm_bf16: residual epilogue without residual"); return SFB_ERR_INVALID; }
@@ -264,6 +265,9 @@ extern "C" int sfb_gemm_bf16(const void* x, long long ldx, const void* w, long l
   switch (block_n) {
     case 64: return dispatch_epi<64>(epilogue, ta, tb, p, sms, stream);
     case 128: return dispatch_epi<128>(epilogue, ta, tb, p, sms, stream);
+    // 128 x 192 tiles: 4680 x 1536 outputs = 37 x 8 = 296 tiles = exactly two waves of 148 SMs.  Explicit request only
+    // (block_n = 192) until it has been measured against the CTA-pair tiles on the K = 8960 FFN2 shape.
+    case 192: return dispatch_epi<192>(epilogue, ta, tb, p, sms, stream);
     default: return dispatch_epi<256>(epilogue, ta, tb, p, sms, stream);
   }
 }

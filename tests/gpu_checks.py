@@ -605,6 +605,13 @@ def check_model_forward(F_=1, H=60, W=104, seed=0):
     return _finish("model_forward", m, 1e-2)
 
 
+# Checks of code paths that exist but have not yet been measured / validated on hardware: NOT part of the pytest suite;
+# run them with `python tools/gpu_report.py --pending` and move them into ALL once green.
+PENDING = {
+    "gemm_bn192_ffn2": lambda: check_gemm(M=4680, N=1536, K=8960, epilogue=3, rows_per_gate=1560, block_n=192, seed=31),
+    "gemm_bn192_tail": lambda: check_gemm(M=300, N=384, K=200, epilogue=2, block_n=192, seed=32),
+}
+
 ALL = {
     "gemm_small": lambda: check_gemm(),
     "gemm_bn64": lambda: check_gemm(M=200, N=64, K=1536, block_n=64),
@@ -708,7 +715,7 @@ if __name__ == "__main__":
     import json
     name = sys.argv[1]
     try:
-        res = ALL[name]()
+        res = (ALL.get(name) or PENDING[name])()
         print("RESULT " + json.dumps(dict(name=name, ok=True, metrics=res)))
     except AssertionError as e:
         print("RESULT " + json.dumps(dict(name=name, ok=False, error=str(e)[:2000])))
