@@ -559,7 +559,13 @@ def vae_decode_leg(ops, dev, latents, rollout_ms: float) -> dict:
     torch.cuda.synchronize()
     ms = e0.elapsed_time(e1)
     fl = decode_flops(wrap.model, shapes, latents.shape[1], latents.shape[3], latents.shape[4])
-    return {"ms_per_video": ms, "frames_per_s": px.shape[1] / (ms / 1e3), "tflop": fl / 1e12, "tflops": fl / ms / 1e9,
+    pk = peaks()
+    return {"roofline": {"kernel": "conv3_implicit_kernel (implicit-GEMM 3x3 convolutions, 84 % of the decode's FLOPs x time)",
+                         "bound": "tensor", "achieved": fl / ms / 1e9, "peak": pk["sustained"], "unit": "TFLOP/s",
+                         "frac": fl / ms / 1e9 / pk["sustained"], "peak_kind": "sustained bf16 cuBLAS, " + pk["source"],
+                         "note": "algorithmic FLOPs of all convolutions + the middle attention / wall time of the whole "
+                                 "decode (norm kernels and launch gaps included); ncu per kernel: profiles/r01o_ncu_conv_kernels.json"},
+            "ms_per_video": ms, "frames_per_s": px.shape[1] / (ms / 1e3), "tflop": fl / 1e12, "tflops": fl / ms / 1e9,
             "gpu_launches": ops.launches - before, "out_shape": list(px.shape), "finite": bool(torch.isfinite(px).all()),
             "rollout_plus_decode_frames_per_s": px.shape[1] / ((ms + rollout_ms) / 1e3),
             "note": "latents -> pixels right after the rollout (implicit-GEMM tcgen05 convolutions, channels-last); "

@@ -61,6 +61,7 @@ def main():
         workload=f"wan2.1 vae decode, {a.frames} latent frames {h}x{w} -> {out.shape[1]} frames {8 * h}x{8 * w}, "
                  "random-init decoder, channels-last, " + ("gather + tcgen05 GEMM" if a.gather else "implicit-GEMM tcgen05 convolutions"),
         seconds_per_video=sec, frames_per_s=out.shape[1] / sec, tflop=fl / 1e12, tflops=fl / sec / 1e12,
+        frac_of_sustained_peak=fl / sec / 1e12 / 1397.2,
         launches=(ops.launches - before) // a.runs, peak_mem_gb=torch.cuda.max_memory_allocated() / 2 ** 30,
         implicit_conv=not a.gather, finite=bool(torch.isfinite(out).all()), out_shape=list(out.shape),
         breakdown=breakdown)), flush=True)
