@@ -560,7 +560,7 @@ def vae_decode_leg(ops, dev, latents, rollout_ms: float) -> dict:
     ms = e0.elapsed_time(e1)
     fl = decode_flops(wrap.model, shapes, latents.shape[1], latents.shape[3], latents.shape[4])
     pk = peaks()
-    return {"roofline": {"kernel": "conv3_implicit_kernel (implicit-GEMM 3x3 convolutions, 84 % of the decode's FLOPs x time)",
+    return {"roofline": {"kernel": "conv3_implicit_kernel (implicit-GEMM 3x3 convolutions, ~78 % of the decode time)",
                          "bound": "tensor", "achieved": fl / ms / 1e9, "peak": pk["sustained"], "unit": "TFLOP/s",
                          "frac": fl / ms / 1e9 / pk["sustained"], "peak_kind": "sustained bf16 cuBLAS, " + pk["source"],
                          "note": "algorithmic FLOPs of all convolutions + the middle attention / wall time of the whole "
