@@ -58,3 +58,43 @@ def test_bidirectional_reference_equals_golden_and_oracle():
     cfg = G.bidirectional_cfg()
     with torch.no_grad():
         assert torch.equal(O.bidirectional_forward(O.make_random_params(cfg, seed=9), cfg, x, t, ctx), g["flow"])
+
+
+@pytest.mark.parametrize("steps,shift,order,dtype", [(50, 8.0, 2, torch.bfloat16), (9, 3.0, 2, torch.float32),
+                                                      (12, 5.0, 1, torch.bfloat16), (3, 1.0, 2, torch.float32)])
+def test_unipc_oracle_equals_live_reference(steps, shift, order, dtype):
+    """Beyond the committed trace: other step counts, shifts, solver order 1, both dtypes -- bit for bit."""
+    from oracle import unipc_oracle as U
+    from oracle.make_golden import unipc_trace_flow
+    ref = ref_shim.load_reference()
+    r = ref.FlowUniPCMultistepScheduler(num_train_timesteps=1000, shift=1, use_dynamic_shifting=False, solver_order=order)
+    r.set_timesteps(steps, device="cpu", shift=shift)
+    o = U.OracleUniPC(solver_order=order)
+    o.set_timesteps(steps, shift)
+    assert torch.equal(r.timesteps, o.timesteps) and torch.equal(r.sigmas, o.sigmas)
+    xr = xo = torch.randn(1, 2, 16, 6, 8, generator=torch.Generator().manual_seed(steps)).to(dtype)
+    for i, t in enumerate(r.timesteps):
+        xr = r.step(unipc_trace_flow(xr, i), t, xr, return_dict=False)[0]
+        xo = o.step(unipc_trace_flow(xo, i), t, xo)
+        assert torch.equal(xr, xo), i
+
+
+@pytest.mark.parametrize("frames,hw,seed", [(1, (2, 4), 1), (4, (6, 4), 2)])
+def test_vae_oracle_equals_live_reference(frames, hw, seed):
+    """Other grids / frame counts than the committed fixture, including a single-frame video (no temporal upsampling at
+    all) and a different weight draw."""
+    from oracle import vae_oracle as V
+    rv = ref_shim.load_reference_vae()
+    cfg = V.VaeConfig()
+    params = V.make_random_vae_params(cfg, seed=seed)
+    model = rv.WanVAE_(dim=96, z_dim=16, dim_mult=[1, 2, 4, 4], num_res_blocks=2, attn_scales=[],
+                       temperal_downsample=[False, True, True], dropout=0.0)
+    model.load_state_dict(params, strict=False)
+    model = model.to(torch.bfloat16).eval()
+    z = torch.randn(1, 16, frames, *hw, generator=torch.Generator().manual_seed(seed)).to(torch.bfloat16)
+    scale = [torch.tensor(V.LATENT_MEAN).to(torch.bfloat16), 1.0 / torch.tensor(V.LATENT_STD).to(torch.bfloat16)]
+    with torch.no_grad():
+        want = model.decode(z, scale)
+        got = V.decode(params, cfg, z)
+    assert want.shape == (1, 3, 1 + 4 * (frames - 1), 8 * hw[0], 8 * hw[1])
+    assert torch.equal(got, want)
