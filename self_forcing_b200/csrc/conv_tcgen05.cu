@@ -12,6 +12,8 @@
 //
 // Same roles as gemm_tcgen05.cu: warp 0 TMA producer, warp 1 MMA issuer (tcgen05.mma cta_group::1, M=128, N=BN),
 // warps 2-5 epilogue (double-buffered TMEM accumulator; bias / residual fused, reference rounding points).
+#include <stdlib.h>
+
 #include "gemm_common.cuh"
 
 namespace sfb {
@@ -27,10 +29,11 @@ struct ConvCfg {
   static constexpr int A_BYTES = MT * CV_BM * CV_BK * 2;
   static constexpr int B_BYTES = BN * CV_BK * 2;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-  static constexpr int STAGES = (BN == 256 || MT == 2) ? 4 : 6;
-  static constexpr int TMEM_COLS = 2 * MT * BN;
+  static constexpr int STAGES = (BN == 256 || MT == 2) ? 4 : (BN == 192 ? 5 : 6);
+  // TMEM is allocated in powers of two: 2 x 192 accumulator columns take a 512-column allocation
+  static constexpr int TMEM_COLS = 2 * MT * BN <= 64 ? 64 : (2 * MT * BN <= 256 ? 256 : 512);
   static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 + 256;
-  static_assert(TMEM_COLS <= 512, "accumulators do not fit in TMEM");
+  static_assert(2 * MT * BN <= 512, "accumulators do not fit in TMEM");
 };
 
 struct ConvParams {
@@ -212,7 +215,11 @@ int launch_conv3_implicit(const void* x, int t_in, int H, int W, int Cin, int t_
   ConvParams p{};
   p.t_out = t_in + t_zero_pad - (kt - 1);
   p.Ho = H; p.Wo = W; p.Cin = Cin; p.kt = kt; p.t_zero_pad = t_zero_pad;
-  const int bn = Cout <= 32 ? 32 : (Cout <= 128 ? 128 : 256);   // 32: the 3-channel head (padded to 8)
+  // 32: the 3-channel head (padded to 8).  192-column tiles for the 192-channel layers (no padded MMA columns: that kernel
+  // runs at 92 % tensor-pipe active with a quarter of its columns padding) are wired but not yet measured:
+  // SFB_CONV_EXACT_N=1 selects them.
+  static const bool exact_n = getenv("SFB_CONV_EXACT_N") != nullptr;
+  const int bn = Cout <= 32 ? 32 : (Cout <= 128 ? 128 : ((exact_n && Cout == 192) ? 192 : 256));
   // two accumulator sub-tiles per CTA (256 voxels against one weight tile) where TMEM has room and the frame is large
   // enough to keep every SM busy with 256-voxel tiles
   const int sms_hint = device_sm_count();
@@ -255,6 +262,7 @@ int launch_conv3_implicit(const void* x, int t_in, int H, int W, int Cin, int t_
   if (bn == 128 && mt == 2)
     return res ? launch_conv3<128, EPI_RESIDUAL, 2>(tx, tw, p, stream) : launch_conv3<128, EPI_BIAS, 2>(tx, tw, p, stream);
   if (bn == 128) return res ? launch_conv3<128, EPI_RESIDUAL, 1>(tx, tw, p, stream) : launch_conv3<128, EPI_BIAS, 1>(tx, tw, p, stream);
+  if (bn == 192) return res ? launch_conv3<192, EPI_RESIDUAL, 1>(tx, tw, p, stream) : launch_conv3<192, EPI_BIAS, 1>(tx, tw, p, stream);
   return res ? launch_conv3<256, EPI_RESIDUAL, 1>(tx, tw, p, stream) : launch_conv3<256, EPI_BIAS, 1>(tx, tw, p, stream);
 }
 

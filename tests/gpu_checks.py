@@ -610,6 +610,10 @@ def check_model_forward(F_=1, H=60, W=104, seed=0):
 PENDING = {
     "gemm_bn192_ffn2": lambda: check_gemm(M=4680, N=1536, K=8960, epilogue=3, rows_per_gate=1560, block_n=192, seed=31),
     "gemm_bn192_tail": lambda: check_gemm(M=300, N=384, K=200, epilogue=2, block_n=192, seed=32),
+    # SFB_CONV_EXACT_N is read once per process, and tools/gpu_report.py runs every check in its own process
+    "conv3d_implicit_exact_n192": lambda: (os.environ.__setitem__("SFB_CONV_EXACT_N", "1"),
+                                           check_causal_conv3d(t_in=4, H=24, W=40, Cin=192, Cout=192, pad=0, residual=True,
+                                                               implicit=True, seed=33))[1],
 }
 
 ALL = {
