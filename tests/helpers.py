@@ -7,9 +7,10 @@ import types
 import torch
 
 from oracle import causal_wan_oracle as O
-from oracle.make_golden import (DIFFUSION_CASES, NEGATIVE_PROMPT, ROLLING_ROLLOUT_CASES, ROLLOUT_CASES, SeededNoise, _IdentityVAE,
-                                _TextEncoder, _TextEncoder2, diffusion_args, initial_latent_for, negative_embeds,
-                                patched_randn_like, synthetic_inputs)
+# the fixture definitions live next to the script that generated them; re-exported here for the test modules
+from oracle.make_golden import (DIFFUSION_CASES, NEGATIVE_PROMPT, ROLLING_ROLLOUT_CASES, ROLLOUT_CASES,  # noqa: F401
+                                SeededNoise, _IdentityVAE, _TextEncoder, _TextEncoder2, diffusion_args,  # noqa: F401
+                                initial_latent_for, negative_embeds, patched_randn_like, synthetic_inputs)  # noqa: F401
 
 GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 

@@ -1,6 +1,5 @@
 """The CPU oracle against the golden vectors produced by the unmodified reference
 (oracle/make_golden.py).  This is what pins the oracle."""
-import numpy as np
 import pytest
 import torch
 

@@ -1,12 +1,9 @@
 """Live pinning of the oracle against the unmodified reference (build container only: the reference
 checkout does not travel to the GPU box, where these tests skip)."""
-import contextlib
-import io
-
 import pytest
 import torch
 
-from helpers import ROLLOUT_CASES, patched_randn_like, synthetic_inputs
+from helpers import synthetic_inputs
 from oracle import causal_wan_oracle as O
 from oracle import ref_shim
 

@@ -5,7 +5,7 @@ rollout; cache indices bit-exact."""
 import pytest
 import torch
 
-from helpers import ROLLOUT_CASES, golden, initial_latent_for, make_product_pipeline, patched_randn_like, rel_l2, synthetic_inputs
+from helpers import ROLLOUT_CASES, golden, initial_latent_for, make_product_pipeline, patched_randn_like, rel_l2
 from oracle import causal_wan_oracle as O
 
 pytestmark = pytest.mark.gpu
