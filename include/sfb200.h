@@ -21,7 +21,7 @@
 extern "C" {
 #endif
 
-#define SFB_ABI_VERSION 7
+#define SFB_ABI_VERSION 8
 
 const char* sfb_last_error(void);
 int sfb_abi_version(void);
@@ -208,6 +208,22 @@ int sfb_transpose_bf16(const void* in, long long ldi, void* out, long long ldo, 
 
 /* Decoder output [T*HW, ldy >= 3] bf16 (channels-last RGB) -> fp32 [T, 3, HW] clamped to [-1, 1] (wan_wrapper.py:110). */
 int sfb_vae_pixel_out(const void* y, int ldy, void* out, int T, long long HW, void* stream);
+
+/* ---- UMT5 text encoder (the step right before the rollout: utils/wan_wrapper.py:38-52 -> wan/modules/t5.py:303-312);
+ * its projections are sfb_gemm_bf16 calls.  Written after round 1's GPU budget was spent: not yet validated on hardware. */
+
+/* T5LayerNorm (t5.py:61-66): y = w * bf16(x * rsqrt(mean(x^2) + eps)), statistics in fp32.  C multiple of 8. */
+int sfb_t5_rmsnorm(const void* x, long long ldx, void* y, long long ldy, int rows, int C, float eps, const void* weight,
+                   void* stream);
+
+/* p[r][:] = bf16(softmax_fp32(bf16(s[r][:] + bias[r][:]))) with keys whose key_mask[c] == 0 held at finfo(bf16).min
+ * (t5.py:103-115: un-scaled logits + relative position bias; key_mask may be NULL).  s, bias, p bf16. */
+int sfb_softmax_bias_rows(const void* s, long long lds, const void* bias, long long ldb, const int* key_mask, void* p,
+                          long long ldp, int rows, int cols, void* stream);
+
+/* out = bf16(fc1 * gelu(gate)) with the tanh GELU evaluated op by op in bf16 like t5.py:46-50, :136-137. */
+int sfb_t5_gated_gelu(const void* fc1, long long ld1, const void* gate, long long ldg, void* out, long long ldo, int rows,
+                      int cols, void* stream);
 
 #ifdef __cplusplus
 }

@@ -321,6 +321,47 @@ def vae_stream_cache_layout(cfg):
     return slots + [(dims[-1], scale)]
 
 
+# UMT5 text encoder: narrow / shallow instance of the same architecture, two prompts of
+# different lengths padded to 24 tokens
+T5_CASE = dict(vocab=200, dim=256, dim_attn=256, dim_ffn=640, num_heads=4, num_layers=3, num_buckets=32, seq=24,
+               lengths=(24, 9), seed=41)
+
+
+def t5_case_inputs(case=T5_CASE):
+    g = torch.Generator().manual_seed(case["seed"] + 1)
+    ids = torch.randint(1, case["vocab"], (len(case["lengths"]), case["seq"]), generator=g)
+    mask = torch.zeros_like(ids)
+    for i, n in enumerate(case["lengths"]):
+        mask[i, :n] = 1
+        ids[i, n:] = 0
+    return ids, mask
+
+
+def t5_case_cfg(case=T5_CASE):
+    from . import t5_oracle as T
+    return T.T5Config(**{k: case[k] for k in ("vocab", "dim", "dim_attn", "dim_ffn", "num_heads", "num_layers", "num_buckets")})
+
+
+def reference_t5(case=T5_CASE):
+    from . import t5_oracle as T
+    t5 = ref_shim.load_reference_t5()
+    cfg = t5_case_cfg(case)
+    params = T.make_random_t5_params(cfg, seed=case["seed"])
+    out = {"case": case}
+    for name, dtype in (("bf16", torch.bfloat16), ("fp32", torch.float32)):
+        m = t5.T5Encoder(vocab=cfg.vocab, dim=cfg.dim, dim_attn=cfg.dim_attn, dim_ffn=cfg.dim_ffn, num_heads=cfg.num_heads,
+                         num_layers=cfg.num_layers, num_buckets=cfg.num_buckets, shared_pos=False, dropout=0.1)
+        m.load_state_dict(params, strict=True)
+        m = m.to(dtype).eval()
+        ids, mask = t5_case_inputs(case)
+        with torch.no_grad():
+            ctx = m(ids, mask)
+            for u, n in zip(ctx, mask.gt(0).sum(dim=1).long()):     # wan_wrapper.py:47-48
+                u[n:] = 0.0
+        out["context_" + name] = ctx
+    return out
+
+
 MASK_CASES = {
     "causal_6f_2blk": ("causal", dict(num_frames=6, frame_seqlen=200, num_frame_per_block=2, local_attn_size=-1)),
     "causal_6f_local2": ("causal", dict(num_frames=6, frame_seqlen=200, num_frame_per_block=1, local_attn_size=2)),
@@ -393,6 +434,7 @@ def main():
         print(name, lat.shape, idx, float(lat.float().std()))
     torch.save(diff, os.path.join(GOLDEN, "diffusion_tiny.pt"))
     torch.save(reference_vae_decode(), os.path.join(GOLDEN, "vae_decode_tiny.pt"))
+    torch.save(reference_t5(), os.path.join(GOLDEN, "t5_tiny.pt"))
     for f in sorted(os.listdir(GOLDEN)):
         print(f, os.path.getsize(os.path.join(GOLDEN, f)))
 

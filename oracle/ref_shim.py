@@ -226,6 +226,29 @@ def load_reference_vae_block3(root: str = REF_ROOT):
     return mod
 
 
+def load_reference_t5(root: str = REF_ROOT):
+    """The reference's real `wan/modules/t5.py`, loaded under a private name inside the `wan.modules` package shell (it
+    imports `.tokenizers`, stubbed above).  Its `T5EncoderModel` class evaluates `torch.cuda.current_device()` as a
+    default argument at import time, so that call is answered with 0 while the module loads."""
+    import importlib.util
+    name = "wan.modules._sfb_reference_t5"
+    if name in sys.modules:
+        return sys.modules[name]
+    if "wan.modules.tokenizers" not in sys.modules:
+        load_reference(root)
+    spec = importlib.util.spec_from_file_location(name, os.path.join(root, "wan", "modules", "t5.py"))
+    mod = importlib.util.module_from_spec(spec)
+    mod.__package__ = "wan.modules"
+    sys.modules[name] = mod
+    real = torch.cuda.current_device
+    torch.cuda.current_device = lambda: 0
+    try:
+        spec.loader.exec_module(mod)
+    finally:
+        torch.cuda.current_device = real
+    return mod
+
+
 def make_reference_wrapper(ref, model_cfg: dict, timestep_shift: float, seed: int = 0,
                            dtype=torch.bfloat16):
     """Random-init `WanDiffusionWrapper` without `from_pretrained` (wan_wrapper.py:139-147).

@@ -14,7 +14,7 @@ LIB_PATH = os.path.join(HERE, "libsfb200.so")
 P, LL, I, F = c_void_p, c_longlong, c_int, c_float
 PP = ctypes.POINTER(c_void_p)
 FP = ctypes.POINTER(c_float)   # host array of floats
-ABI_VERSION = 7
+ABI_VERSION = 8
 
 # name -> argtypes, mirroring include/sfb200.h one to one
 SIGNATURES = {
@@ -39,6 +39,10 @@ SIGNATURES = {
     "sfb_softmax_rows": [P, LL, P, LL, I, I, F, P],
     "sfb_transpose_bf16": [P, LL, P, LL, I, I, P],
     "sfb_vae_pixel_out": [P, I, P, I, LL, P],
+    # UMT5 text encoder
+    "sfb_t5_rmsnorm": [P, LL, P, LL, I, I, F, P, P],
+    "sfb_softmax_bias_rows": [P, LL, P, LL, P, P, LL, I, I, P],
+    "sfb_t5_gated_gelu": [P, LL, P, LL, P, LL, I, I, P],
     # Ulysses head-parallel path: PP = host array of device pointers (ctypes c_void_p * n)
     "sfb_qk_norm_rope_sp": [P, LL, P, LL, P, LL, P, P, F, P, P, I, I, I, I, I, I, I, I, I, I, PP, LL, PP, PP, LL, P],
     "sfb_attention_fwd_sp": [P, LL, P, P, LL, PP, I, I, LL, I, I, I, I, F, P, LL, P],

@@ -363,6 +363,28 @@ class CudaOps:
         _lib.check(self.lib.sfb_transpose_bf16(x.data_ptr(), x.stride(0), out.data_ptr(), out.stride(0), x.shape[0],
                                                x.shape[1], self._stream()), "sfb_transpose_bf16")
 
+    # -- UMT5 text encoder ------------------------------------------------------------------
+    @_op
+    def t5_rmsnorm(self, x, w, y, eps: float):
+        _check_2d(x, "x"); _check_2d(y, "y")
+        _lib.check(self.lib.sfb_t5_rmsnorm(x.data_ptr(), x.stride(0), y.data_ptr(), y.stride(0), x.shape[0], x.shape[1], eps,
+                                           w.data_ptr(), self._stream()), "sfb_t5_rmsnorm")
+
+    @_op
+    def softmax_bias_rows(self, s, bias, key_mask, p):
+        """s, bias, p bf16 [rows, cols]; key_mask int32 [cols] or None."""
+        _check_2d(s, "s"); _check_2d(bias, "bias"); _check_2d(p, "p")
+        assert key_mask is None or (key_mask.dtype == torch.int32 and key_mask.is_contiguous())
+        _lib.check(self.lib.sfb_softmax_bias_rows(s.data_ptr(), s.stride(0), bias.data_ptr(), bias.stride(0), _ptr(key_mask),
+                                                  p.data_ptr(), p.stride(0), s.shape[0], s.shape[1], self._stream()),
+                   "sfb_softmax_bias_rows")
+
+    @_op
+    def t5_gated_gelu(self, fc1, gate, out):
+        _check_2d(fc1, "fc1"); _check_2d(gate, "gate"); _check_2d(out, "out")
+        _lib.check(self.lib.sfb_t5_gated_gelu(fc1.data_ptr(), fc1.stride(0), gate.data_ptr(), gate.stride(0), out.data_ptr(),
+                                              out.stride(0), fc1.shape[0], fc1.shape[1], self._stream()), "sfb_t5_gated_gelu")
+
     @_op
     def vae_pixel_out(self, y, out):
         """y [T*H*W, ld >= 3] bf16, out fp32 [T, 3, H, W] contiguous."""

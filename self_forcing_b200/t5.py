@@ -1,0 +1,162 @@
+"""UMT5 text encoder on the B200 kernels -- the step right before the rollout.
+
+Mirrors `WanTextEncoder.forward(text_prompts) -> {"prompt_embeds": [B, 512, 4096]}` (utils/wan_wrapper.py:18-52) and
+underneath it `T5Encoder.forward(ids, mask)` (wan/modules/t5.py:303-312).  `load_state_dict` takes the reference's keys
+(`token_embedding.weight`, `blocks.N.{norm1,norm2}.weight`, `blocks.N.attn.{q,k,v,o}.weight`,
+`blocks.N.pos_embedding.embedding.weight`, `blocks.N.ffn.{gate.0,fc1,fc2}.weight`, `norm.weight`).  The tokenizer is not
+part of the device path: pass any callable `tokenizer(text_prompts) -> (ids [B, L] int64, mask [B, L])`.
+
+Schedule per layer (L = 512 tokens, C = 4096): T5 norm -> ONE GEMM for q | k | v (weights stacked once at load) ->
+per head: un-scaled q.k^T GEMM, `sfb_softmax_bias_rows` (relative position bias + key mask, fp32 softmax), P.V GEMM
+written straight into the head's columns -> o GEMM with the residual fused -> T5 norm -> ONE GEMM for fc1 | gate ->
+`sfb_t5_gated_gelu` (the reference's op-by-op tanh GELU) -> fc2 GEMM with the residual fused.  The per-layer position
+bias `[H, L, L]` is a table lookup done once per sequence length.
+
+STATUS: the host logic is pinned against the unmodified reference on the CPU (tests/test_t5_encoder.py through the
+test double); the three new kernels were written after round 1's GPU budget was spent and are registered as pending
+hardware validation (tests/gpu_checks.py: PENDING).  The encoder runs once per prompt (4.7 TFLOP); the per-head
+attention is launch-bound (64 heads x 4 launches) and is the first thing to batch once measured.
+"""
+from __future__ import annotations
+
+import math
+from typing import Callable, Dict, List, Optional
+
+import torch
+
+EPI_BIAS, EPI_RESIDUAL = 0, 2
+
+
+def relative_buckets(lq: int, lk: int, num_buckets: int = 32, max_dist: int = 128) -> torch.Tensor:
+    """Bidirectional T5 bucket of every (query, key) offset (t5.py:245-264) -- integers, computed on the host."""
+    rel = torch.arange(lk).unsqueeze(0) - torch.arange(lq).unsqueeze(1)
+    nb = num_buckets // 2
+    out = (rel > 0).long() * nb
+    rel = rel.abs()
+    exact = nb // 2
+    large = exact + (torch.log(rel.float() / exact) / math.log(max_dist / exact) * (nb - exact)).long()
+    large = torch.min(large, torch.full_like(large, nb - 1))
+    return out + torch.where(rel < exact, rel, large)
+
+
+class B200T5Encoder:
+    def __init__(self, vocab: int = 256384, dim: int = 4096, dim_attn: int = 4096, dim_ffn: int = 10240,
+                 num_heads: int = 64, num_layers: int = 24, num_buckets: int = 32, shared_pos: bool = False,
+                 eps: float = 1e-6, ops=None, device=None):
+        if shared_pos:
+            raise NotImplementedError("B200 T5 encoder: per-layer position bias only (umt5: shared_pos=False)")
+        if dim_attn % num_heads or (dim_attn // num_heads) % 8:
+            raise ValueError("head width must be a multiple of 8")
+        self.vocab, self.dim, self.dim_attn, self.dim_ffn = vocab, dim, dim_attn, dim_ffn
+        self.num_heads, self.num_layers, self.num_buckets, self.eps = num_heads, num_layers, num_buckets, eps
+        self._ops = ops
+        self.device = torch.device(device) if device is not None else torch.device("cpu")
+        self.w: Dict[str, torch.Tensor] = {}
+        self._bias: Dict[int, List[torch.Tensor]] = {}
+
+    @property
+    def ops(self):
+        if self._ops is None:
+            from .ops import CudaOps
+            self._ops = CudaOps()
+        return self._ops
+
+    def expected_keys(self) -> List[str]:
+        keys = ["token_embedding.weight", "norm.weight"]
+        for i in range(self.num_layers):
+            b = f"blocks.{i}."
+            keys += [b + "norm1.weight", b + "norm2.weight", b + "attn.q.weight", b + "attn.k.weight", b + "attn.v.weight",
+                     b + "attn.o.weight", b + "pos_embedding.embedding.weight", b + "ffn.gate.0.weight", b + "ffn.fc1.weight",
+                     b + "ffn.fc2.weight"]
+        return keys
+
+    def load_state_dict(self, sd: Dict[str, torch.Tensor], strict: bool = True):
+        want = self.expected_keys()
+        missing = [k for k in want if k not in sd]
+        unexpected = [k for k in sd if k not in want]
+        if missing or (strict and unexpected):
+            raise KeyError(f"T5 encoder state_dict: missing {missing[:5]}, unexpected {unexpected[:5]}")
+        dev, bf = self.device, torch.bfloat16
+        get = lambda k: sd[k].detach().to(device=dev, dtype=bf).contiguous()   # noqa: E731
+        self.w = {"token_embedding.weight": get("token_embedding.weight"), "norm.weight": get("norm.weight")}
+        for i in range(self.num_layers):
+            b = f"blocks.{i}."
+            for k in ("norm1.weight", "norm2.weight", "attn.o.weight", "pos_embedding.embedding.weight", "ffn.fc2.weight"):
+                self.w[b + k] = get(b + k)
+            # stacked projections: one GEMM each for q | k | v and fc1 | gate
+            self.w[b + "qkv"] = torch.cat([get(b + "attn.q.weight"), get(b + "attn.k.weight"), get(b + "attn.v.weight")]).contiguous()
+            self.w[b + "fc1_gate"] = torch.cat([get(b + "ffn.fc1.weight"), get(b + "ffn.gate.0.weight")]).contiguous()
+        self._bias.clear()
+        return missing, unexpected
+
+    def _position_bias(self, L: int) -> List[torch.Tensor]:
+        """[H, L, L] bf16 per layer: embedding rows looked up by bucket (t5.py:233-243)."""
+        if L not in self._bias:
+            buckets = relative_buckets(L, L, self.num_buckets).to(self.device)
+            self._bias[L] = [self.w[f"blocks.{i}.pos_embedding.embedding.weight"][buckets].permute(2, 0, 1).contiguous()
+                             for i in range(self.num_layers)]
+        return self._bias[L]
+
+    @torch.no_grad()
+    def __call__(self, ids: torch.Tensor, mask: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """ids [B, L] int64, mask [B, L] (non-zero = real token) -> bf16 [B, L, dim]."""
+        if not self.w:
+            raise RuntimeError("B200T5Encoder: load_state_dict first")
+        ops, dev = self.ops, self.device
+        B, L = ids.shape
+        C, A, Fd, H = self.dim, self.dim_attn, self.dim_ffn, self.num_heads
+        hd = A // H
+        bias = self._position_bias(L)
+        bf = torch.bfloat16
+        out = torch.empty(B, L, C, dtype=bf, device=dev)
+        h = torch.empty(L, C, dtype=bf, device=dev)
+        qkv = torch.empty(L, 3 * A, dtype=bf, device=dev)
+        scores = torch.empty(L, L, dtype=bf, device=dev)
+        probs = torch.empty(L, L, dtype=bf, device=dev)
+        vt = torch.empty(hd, L, dtype=bf, device=dev)
+        attn = torch.empty(L, A, dtype=bf, device=dev)
+        ff = torch.empty(L, 2 * Fd, dtype=bf, device=dev)
+        gated = torch.empty(L, Fd, dtype=bf, device=dev)
+        for b in range(B):
+            x = self.w["token_embedding.weight"][ids[b].to(dev)].contiguous()            # [L, C]
+            key_mask = None if mask is None else mask[b].to(device=dev, dtype=torch.int32).contiguous()
+            for i in range(self.num_layers):
+                p = f"blocks.{i}."
+                ops.t5_rmsnorm(x, self.w[p + "norm1.weight"], h, self.eps)
+                ops.gemm(h, self.w[p + "qkv"], None, qkv)
+                for hh in range(H):
+                    q = qkv[:, hh * hd:(hh + 1) * hd]
+                    k = qkv[:, A + hh * hd:A + (hh + 1) * hd]
+                    v = qkv[:, 2 * A + hh * hd:2 * A + (hh + 1) * hd]
+                    ops.gemm(q, k, None, scores)                                          # T5 does not scale the logits
+                    ops.softmax_bias_rows(scores, bias[i][hh], key_mask, probs)
+                    ops.transpose(v, vt)
+                    ops.gemm(probs, vt, None, attn[:, hh * hd:(hh + 1) * hd])
+                x2 = torch.empty_like(x)
+                ops.gemm(attn, self.w[p + "attn.o.weight"], None, x2, epilogue=EPI_RESIDUAL, residual=x)
+                ops.t5_rmsnorm(x2, self.w[p + "norm2.weight"], h, self.eps)
+                ops.gemm(h, self.w[p + "fc1_gate"], None, ff)
+                ops.t5_gated_gelu(ff[:, :Fd], ff[:, Fd:], gated)
+                x = torch.empty_like(x2)
+                ops.gemm(gated, self.w[p + "ffn.fc2.weight"], None, x, epilogue=EPI_RESIDUAL, residual=x2)
+            ops.t5_rmsnorm(x, self.w["norm.weight"], out[b], self.eps)
+        return out
+
+
+class B200TextEncoder(torch.nn.Module):
+    """`WanTextEncoder` (utils/wan_wrapper.py:18-52) with the tokenizer injected."""
+
+    def __init__(self, tokenizer: Callable, state_dict: Optional[Dict[str, torch.Tensor]] = None, device=None, ops=None,
+                 **t5_config):
+        super().__init__()
+        self.tokenizer = tokenizer
+        self.text_encoder = B200T5Encoder(ops=ops, device=device, **t5_config)
+        if state_dict is not None:
+            self.text_encoder.load_state_dict(state_dict)
+
+    def forward(self, text_prompts: List[str]) -> dict:
+        ids, mask = self.tokenizer(text_prompts)
+        context = self.text_encoder(ids, mask)
+        for u, n in zip(context, mask.gt(0).sum(dim=1).long()):
+            u[int(n):] = 0.0                                    # padding rows are zero (wan_wrapper.py:47-48)
+        return {"prompt_embeds": context}

@@ -225,3 +225,22 @@ class TorchOps:
         self.launches += 1
         T, _, H, W = out.shape
         out.copy_(y[:, :3].float().clamp(-1, 1).reshape(T, H, W, 3).permute(0, 3, 1, 2))
+
+    # ---- UMT5 text encoder ops ----------------------------------------------------------------------------------
+    def t5_rmsnorm(self, x, w, y, eps):
+        self.launches += 1
+        n = x * torch.rsqrt(x.float().pow(2).mean(dim=-1, keepdim=True) + eps)
+        y.copy_(w * (n.type_as(w) if w.dtype in (torch.float16, torch.bfloat16) else n))
+
+    def softmax_bias_rows(self, s, bias, key_mask, p):
+        self.launches += 1
+        ab = bias.clone()
+        if key_mask is not None:
+            ab.masked_fill_(key_mask.view(1, -1) == 0, torch.finfo(s.dtype).min)
+        p.copy_(F.softmax((s + ab).float(), dim=-1).to(p.dtype))
+
+    def t5_gated_gelu(self, fc1, gate, out):
+        self.launches += 1
+        import math
+        g = 0.5 * gate * (1.0 + torch.tanh(math.sqrt(2.0 / math.pi) * (gate + 0.044715 * torch.pow(gate, 3.0))))
+        out.copy_(fc1 * g)

@@ -605,11 +605,68 @@ def check_model_forward(F_=1, H=60, W=104, seed=0):
     return _finish("model_forward", m, 1e-2)
 
 
+# ---- UMT5 text encoder kernels (pending hardware validation) ----------------------
+def check_t5_rmsnorm(rows=300, C=4096, seed=0):
+    x, w = _randn(rows, C, seed=seed, scale=3.0), _randn(C, seed=seed + 1) * 0.1 + 1
+
+    def run(ops, o):
+        ops.t5_rmsnorm(x, w, o["y"], 1e-6)
+    return _against_double("t5_rmsnorm", run, dict(y=torch.zeros(rows, C, device="cuda", dtype=BF)))
+
+
+def check_softmax_bias_rows(rows=200, cols=512, seed=0):
+    s, b = _randn(rows, cols, seed=seed, scale=4.0), _randn(rows, cols, seed=seed + 1)
+    mask = torch.ones(cols, device="cuda", dtype=torch.int32)
+    mask[300:] = 0
+
+    def run(ops, o):
+        ops.softmax_bias_rows(s, b, mask, o["p"])
+        ops.softmax_bias_rows(s, b, None, o["q"])
+    m = _against_double("softmax_bias_rows", run, dict(p=torch.zeros(rows, cols, device="cuda", dtype=BF),
+                                                       q=torch.zeros(rows, cols, device="cuda", dtype=BF)), tol=5e-3)
+    return m
+
+
+def check_t5_gated_gelu(rows=300, cols=640, seed=0):
+    a, g = _randn(rows, cols, seed=seed), _randn(rows, cols, seed=seed + 1, scale=2.0)
+
+    def run(ops, o):
+        ops.t5_gated_gelu(a, g, o["y"])
+    return _against_double("t5_gated_gelu", run, dict(y=torch.zeros(rows, cols, device="cuda", dtype=BF)), tol=5e-3)
+
+
+def check_t5_encoder():
+    """Whole (tiny) encoder on the B200 against the unmodified reference's output (CPU, bf16) and its fp32 run."""
+    from helpers import golden
+    from oracle import t5_oracle as T
+    from oracle.make_golden import T5_CASE, t5_case_cfg, t5_case_inputs
+    from self_forcing_b200.t5 import B200T5Encoder
+    g = golden("t5_tiny.pt")
+    cfg = t5_case_cfg()
+    enc = B200T5Encoder(vocab=cfg.vocab, dim=cfg.dim, dim_attn=cfg.dim_attn, dim_ffn=cfg.dim_ffn, num_heads=cfg.num_heads,
+                        num_layers=cfg.num_layers, ops=_ops(), device="cuda")
+    enc.load_state_dict(T.make_random_t5_params(cfg, seed=T5_CASE["seed"]))
+    ids, mask = t5_case_inputs()
+    out = enc(ids.cuda(), mask.cuda()).cpu()
+    for u, n in zip(out, T5_CASE["lengths"]):
+        u[n:] = 0
+    torch.cuda.synchronize()
+    m = dict(err_vs_ref_bf16=rel_l2(out, g["context_bf16"]), vs_fp32=rel_l2(out, g["context_fp32"]),
+             ref_noise_floor=rel_l2(g["context_bf16"], g["context_fp32"]))
+    assert m["vs_fp32"] <= 1.25 * m["ref_noise_floor"], m
+    return _finish("t5_encoder", m, 3e-2)
+
+
 # Checks of code paths that exist but have not yet been measured / validated on hardware: NOT part of the pytest suite;
 # run them with `python tools/gpu_report.py --pending` and move them into ALL once green.
 PENDING = {
     "gemm_bn192_ffn2": lambda: check_gemm(M=4680, N=1536, K=8960, epilogue=3, rows_per_gate=1560, block_n=192, seed=31),
     "gemm_bn192_tail": lambda: check_gemm(M=300, N=384, K=200, epilogue=2, block_n=192, seed=32),
+    "t5_rmsnorm_c4096": check_t5_rmsnorm,
+    "t5_rmsnorm_c256": lambda: check_t5_rmsnorm(rows=77, C=256, seed=3),
+    "softmax_bias_rows": check_softmax_bias_rows,
+    "t5_gated_gelu": check_t5_gated_gelu,
+    "t5_encoder": check_t5_encoder,
     # SFB_CONV_EXACT_N is read once per process, and tools/gpu_report.py runs every check in its own process
     "conv3d_implicit_exact_n192": lambda: (os.environ.__setitem__("SFB_CONV_EXACT_N", "1"),
                                            check_causal_conv3d(t_in=4, H=24, W=40, Cin=192, Cout=192, pad=0, residual=True,
