@@ -104,6 +104,27 @@ def test_pipeline_orchestration_fp32_exact(name):
     assert ops.launches > 0
 
 
+def test_pipeline_orchestration_batch2_fp32():
+    """Two different prompts / noise samples in one batch (BASELINE config 4 runs B > 1 per GPU when memory allows):
+    per-sample cache rows, per-sample text K/V and [B, F] timesteps must stay separate -- fp32 against the oracle."""
+    case = ROLLOUT_CASES["chunkwise"]
+    pipe, cfg, params, _, _ = make_product_pipeline(case, "cpu", ops=TorchOps(), dtype=torch.float32, hw=(16, 24))
+    g = torch.Generator().manual_seed(12)
+    pe = torch.randn(2, 512, 4096, generator=g)
+    noise = torch.randn(2, case["frames"], 16, 16, 24, generator=g)
+    from helpers import _TextEncoder
+    pipe.text_encoder = _TextEncoder(pe)
+    with patched_randn_like(3):
+        _, lat = pipe.inference(noise, ["a", "b"], return_latents=True)
+    ow = O.OracleWrapper(params, cfg, case["shift"])
+    steps = O.warp_denoising_steps(ow.scheduler, [1000, 750, 500, 250])
+    with torch.no_grad(), patched_randn_like(3):
+        tr = O.rollout(ow, noise, pe, steps, case["num_frame_per_block"])
+    assert rel_l2(lat, tr.latents) < 1e-5
+    assert rel_l2(lat[0], lat[1]) > 0.5                          # the two samples really differ
+    assert pipe.kv_cache1[0]["k"].shape[0] == 2
+
+
 def test_pipeline_bf16_vs_reference_golden():
     case = ROLLOUT_CASES["tiny_test_yaml"]
     g = golden("rollout_tiny.pt")["tiny_test_yaml"]
