@@ -185,6 +185,8 @@ static int dispatch_epi(int epi, const CUtensorMap& ta, const CUtensorMap& tb, c
 }
 
 int device_sm_count();
+int launch_gemm_single_staged(int epi, int bn, const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& p, int num_sms,
+                              cudaStream_t stream);   // gemm1s_tcgen05.cu
 int launch_gemm_pair(int epi, const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& p, int num_sms,
                      cudaStream_t stream);
 long long gemm_pair_workspace_bytes();
@@ -214,6 +216,16 @@ extern "C" int sfb_gemm_bf16(const void* x, long long ldx, const void* w, long l
     // Tile choice: wide tiles amortise smem traffic; narrow problems take 128 so the tile count
     // fills the 148 SMs (M=4680: N=1536 -> 37x12 = 444 = 3 waves of 148).
     block_n = (N % 256 == 0 && N >= 4096) ? 256 : (N % 128 == 0 ? 128 : 64);
+  }
+  // 1192 / 1256: one-CTA 128 x 192 / 128 x 256 tiles with the staged TMA-store epilogue (gemm1s_tcgen05.cu; explicit
+  // request only, pending hardware validation)
+  const bool staged = block_n == 1192 || block_n == 1256;
+  if (staged) {
+    block_n -= 1000;
+    if (epilogue == EPI_F32 || N % block_n || seg_cols % block_n) {
+      set_error("sfb_gemm_bf16: staged one-CTA tiles need N and seg_cols to be multiples of %d and a bf16 epilogue", block_n);
+      return SFB_ERR_INVALID;
+    }
   }
   const bool pair = block_n == 512 || block_n == 513;   // 513: pair tiles with the stream-K schedule forced on
   const bool force_streamk = block_n == 513;
@@ -257,6 +269,7 @@ extern "C" int sfb_gemm_bf16(const void* x, long long ldx, const void* w, long l
   }
   const int sms = device_sm_count();
   if (sms <= 0) return SFB_ERR_CUDA;
+  if (staged) return launch_gemm_single_staged(epilogue, block_n, ta, tb, p, sms, stream);
   if (pair) {
     gemm_pair_workspace(workspace, workspace_bytes, p);
     p.streamk = force_streamk ? 1 : 0;   // request; launch_gemm_pair decides

@@ -662,6 +662,11 @@ def check_t5_encoder():
 PENDING = {
     "gemm_bn192_ffn2": lambda: check_gemm(M=4680, N=1536, K=8960, epilogue=3, rows_per_gate=1560, block_n=192, seed=31),
     "gemm_bn192_tail": lambda: check_gemm(M=300, N=384, K=200, epilogue=2, block_n=192, seed=32),
+    "gemm_1s192_ffn2": lambda: check_gemm(M=4680, N=1536, K=8960, epilogue=3, rows_per_gate=1560, block_n=1192, seed=34),
+    "gemm_1s192_o_proj": lambda: check_gemm(M=4680, N=1536, K=1536, epilogue=3, rows_per_gate=1560, block_n=1192, seed=35),
+    "gemm_1s192_tail_residual": lambda: check_gemm(M=300, N=384, K=200, epilogue=2, block_n=1192, seed=36),
+    "gemm_1s256_gelu": lambda: check_gemm(M=700, N=512, K=320, epilogue=1, block_n=1256, seed=37),
+    "gemm_1s256_qkv": lambda: check_gemm(M=4680, N=4608, K=1536, block_n=1256, seed=38),
     "t5_rmsnorm_c4096": check_t5_rmsnorm,
     "t5_rmsnorm_c256": lambda: check_t5_rmsnorm(rows=77, C=256, seed=3),
     "softmax_bias_rows": check_softmax_bias_rows,
