@@ -62,11 +62,13 @@ class IndexMirror:
 
     The pipeline resets a cache by *rebinding* fresh index tensors (pipeline/causal_inference.py:125-132),
     so the mirror is keyed on tensor identity: a tensor we have not written ourselves is read back once
-    (one batched device->host copy for all layers), everything after that is host arithmetic.
+    (one batched device->host copy for all layers), everything after that is host arithmetic.  An in-place edit by
+    the caller (`.zero_()`, `.fill_(0)` -- the reference would see it through `.item()`) bumps the tensors'
+    `_version` counters, which the entry records: a changed version is re-read from the device like a rebind.
     """
 
     def __init__(self):
-        self._known: Dict[int, Tuple[torch.Tensor, torch.Tensor, int, int]] = {}   # id(global tensor) -> entry
+        self._known: Dict[int, tuple] = {}   # id(global tensor) -> (global, local, g, l, global._version, local._version)
 
     def read(self, kv_cache: List[dict]) -> List[Tuple[int, int]]:
         out: List[Tuple[int, int]] = [None] * len(kv_cache)  # type: ignore
@@ -74,7 +76,7 @@ class IndexMirror:
         for i, c in enumerate(kv_cache):
             g, l = c["global_end_index"], c["local_end_index"]
             hit = self._known.get(id(g))
-            if hit is not None and hit[0] is g and hit[1] is l:
+            if hit is not None and hit[0] is g and hit[1] is l and hit[4] == g._version and hit[5] == l._version:
                 out[i] = (hit[2], hit[3])
             else:
                 unknown.append(i)
@@ -85,8 +87,7 @@ class IndexMirror:
                                            kv_cache[i]["local_end_index"].reshape(1)]) for i in unknown]).cpu()
             for row, i in zip(vals.tolist(), unknown):
                 c = kv_cache[i]
-                self._known[id(c["global_end_index"])] = (c["global_end_index"], c["local_end_index"],
-                                                          int(row[0]), int(row[1]))
+                self._remember(c, int(row[0]), int(row[1]))
                 out[i] = (int(row[0]), int(row[1]))
         return out
 
@@ -94,9 +95,14 @@ class IndexMirror:
         """Store the new indices into the dict's device tensors (causal_model.py:235-236) and the mirror."""
         groups: Dict[int, List[torch.Tensor]] = {}
         for i, (c, (g, l)) in enumerate(zip(kv_cache, values)):
-            self._known[id(c["global_end_index"])] = (c["global_end_index"], c["local_end_index"], g, l)
             groups.setdefault(g, []).append(c["global_end_index"])
             groups.setdefault(l, []).append(c["local_end_index"])
         for value, tensors in groups.items():
             src = torch.full((1,), value, dtype=tensors[0].dtype, device=tensors[0].device)
             torch._foreach_copy_(tensors, [src] * len(tensors))
+        for c, (g, l) in zip(kv_cache, values):   # after the copies: they bump the version counters
+            self._remember(c, g, l)
+
+    def _remember(self, c: dict, g: int, l: int) -> None:
+        gt, lt = c["global_end_index"], c["local_end_index"]
+        self._known[id(gt)] = (gt, lt, g, l, gt._version, lt._version)

@@ -142,6 +142,7 @@ class B200CausalWanModel(nn.Module):
         # removes the launch gaps (measured 29.6 -> 28.0 ms at S = 18720).  One graph per distinct static signature
         # (shapes, cache pointers, cache plan), captured on its second occurrence.
         self.use_cuda_graphs = True
+        self.max_cuda_graphs = 64
         self._graphs: Dict[tuple, object] = {}
         self.register_load_state_dict_post_hook(lambda module, incompatible: module.invalidate_packed())
         self._register_load_state_dict_pre_hook(self._drop_foreign_keys)
@@ -370,13 +371,18 @@ class B200CausalWanModel(nn.Module):
         if not eligible:
             return self._device_forward(x, t, context, env)
         kv, ca, NL = env["kv_cache"], env["crossattn_cache"], env["NL"]
-        key = (tuple(x.shape), t.dtype, env["current_start"], env["return_x0"], env["skip_output"], tuple(env["plans"]),
+        key = (tuple(x.shape), tuple(t.shape), t.dtype, env["current_start"], env["return_x0"], env["skip_output"], tuple(env["plans"]),
                tuple(c["k"].data_ptr() for c in kv[:NL]), tuple(c["v"].data_ptr() for c in kv[:NL]),
                tuple(c["k"].data_ptr() for c in ca[:NL]), tuple(c["v"].data_ptr() for c in ca[:NL]))
         ent = self._graphs.get(key)
         if ent is None:                       # first occurrence: run eagerly (also warms every lazy initialisation)
+            # bounded: a long / rolling rollout meets a new (current_start, plan) every chunk and each captured graph
+            # owns ~430 nodes plus a private pool -- evict the least recently used entries beyond the cap
+            while len(self._graphs) >= self.max_cuda_graphs:
+                self._graphs.pop(next(iter(self._graphs)))
             self._graphs[key] = "seen"
             return self._device_forward(x, t, context, env)
+        self._graphs[key] = self._graphs.pop(key)   # mark as most recently used (dicts keep insertion order)
         if sp is not None:
             env = dict(env, defer_gather=True)   # keep the NCCL collective out of the captured graph
         if ent == "seen":                     # second occurrence: capture
@@ -480,7 +486,7 @@ class B200CausalWanModel(nn.Module):
                          gate=m[:, 2], gate_stride=mstride, rows_per_gate=mod_rows, gate_row_offset=off)
             elif B == 1:   # V projection lands directly in its cache slot
                 ops.gemm(ws["h"], pb["wqkv"], pb["bqkv"], None, seg_cols=C,
-                         outs=[ws["q_lin"], ws["k_lin"], v_slot.reshape(L, C)])
+                         outs=[ws["q_lin"], ws["k_lin"], v_slot.view(L, C)])   # .view: a non-viewable cache layout must raise
                 v_src = None
             else:
                 ops.gemm(ws["h"], pb["wqkv"], pb["bqkv"], None, seg_cols=C,

@@ -51,7 +51,7 @@ class B200DiffusionWrapper(nn.Module):
             self.model.to(device)
         self.model.to(dtype)
         if state is not None:
-            self.model.load_state_dict(state, strict=False)
+            load_checkpoint_strict(self.model, state)
         elif init_seed is not None:
             self.model.init_weights(init_seed)
         self.model.eval()
@@ -115,8 +115,38 @@ def _read_checkpoint_dir(path: str):
         for f in files:
             state.update(load_file(os.path.join(path, f)))
     else:
-        pth = [f for f in os.listdir(path) if f.endswith((".pth", ".pt", ".bin"))]
-        if not pth:
-            raise FileNotFoundError(f"no weights found under {path}")
-        state = torch.load(os.path.join(path, pth[0]), map_location="cpu")
+        # a Wan model directory also holds the T5 / VAE / CLIP checkpoints: pick the DiT weights by name, never by
+        # listdir order
+        pth = sorted(f for f in os.listdir(path) if f.endswith((".pth", ".pt", ".bin")))
+        dit = [f for f in pth if f.startswith("diffusion_pytorch_model")]
+        if not dit:
+            raise FileNotFoundError(f"no diffusion_pytorch_model*.safetensors/.pth/.pt/.bin under {path} "
+                                    f"(found {pth or 'nothing'})")
+        for f in dit:
+            state.update(torch.load(os.path.join(path, f), map_location="cpu"))
     return cfg, state
+
+
+def unwrap_checkpoint(state: dict) -> dict:
+    """Self-Forcing training checkpoints are `{generator | generator_ema: {"model.<key>": tensor}}`
+    (trainer/distillation.py:203-228, loaded at inference.py:69-71); HF checkpoints are flat.  Returns the flat
+    `<key>: tensor` dict of the DiT, with the fork's `pose_proj.*` dropped."""
+    for outer in ("generator_ema", "generator"):
+        if outer in state and isinstance(state[outer], dict):
+            state = state[outer]
+            break
+    if state and all(k.startswith("model.") for k in state):
+        state = {k[len("model."):]: v for k, v in state.items()}
+    return {k: v for k, v in state.items() if not k.startswith("pose_proj.")}
+
+
+def load_checkpoint_strict(model: nn.Module, state: dict) -> None:
+    """The model's parameters are created with torch.empty, so a checkpoint whose keys do not match would leave it
+    running on uninitialised memory: every parameter must be found, unknown keys are an error too."""
+    flat = unwrap_checkpoint(state)
+    want = set(model.state_dict().keys())
+    missing, unexpected = sorted(want - set(flat)), sorted(set(flat) - want)
+    if missing or unexpected:
+        raise KeyError(f"checkpoint does not match the model: {len(missing)} missing (e.g. {missing[:3]}), "
+                       f"{len(unexpected)} unexpected (e.g. {unexpected[:3]})")
+    model.load_state_dict(flat, strict=True)

@@ -605,7 +605,7 @@ def check_model_forward(F_=1, H=60, W=104, seed=0):
     return _finish("model_forward", m, 1e-2)
 
 
-# ---- UMT5 text encoder kernels (pending hardware validation) ----------------------
+# ---- UMT5 text encoder kernels ----------------------
 def check_t5_rmsnorm(rows=300, C=4096, seed=0):
     x, w = _randn(rows, C, seed=seed, scale=3.0), _randn(C, seed=seed + 1) * 0.1 + 1
 
@@ -667,11 +667,6 @@ PENDING = {
     "gemm_1s192_tail_residual": lambda: check_gemm(M=300, N=384, K=200, epilogue=2, block_n=1192, seed=36),
     "gemm_1s256_gelu": lambda: check_gemm(M=700, N=512, K=320, epilogue=1, block_n=1256, seed=37),
     "gemm_1s256_qkv": lambda: check_gemm(M=4680, N=4608, K=1536, block_n=1256, seed=38),
-    "t5_rmsnorm_c4096": check_t5_rmsnorm,
-    "t5_rmsnorm_c256": lambda: check_t5_rmsnorm(rows=77, C=256, seed=3),
-    "softmax_bias_rows": check_softmax_bias_rows,
-    "t5_gated_gelu": check_t5_gated_gelu,
-    "t5_encoder": check_t5_encoder,
     # SFB_CONV_EXACT_N is read once per process, and tools/gpu_report.py runs every check in its own process
     "conv3d_implicit_exact_n192": lambda: (os.environ.__setitem__("SFB_CONV_EXACT_N", "1"),
                                            check_causal_conv3d(t_in=4, H=24, W=40, Cin=192, Cout=192, pad=0, residual=True,
@@ -774,6 +769,12 @@ ALL = {
     "vae_pixel_out": check_vae_pixel_out,
     "vae_decoder_gather": check_vae_decoder,
     "model_forward": check_model_forward,
+    # UMT5 text encoder (validated on B200 in round 2: profiles/r02a_pending_report.json)
+    "t5_rmsnorm_c4096": check_t5_rmsnorm,
+    "t5_rmsnorm_c256": lambda: check_t5_rmsnorm(rows=77, C=256, seed=3),
+    "softmax_bias_rows": check_softmax_bias_rows,
+    "t5_gated_gelu": check_t5_gated_gelu,
+    "t5_encoder": check_t5_encoder,
 }
 
 
