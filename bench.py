@@ -68,37 +68,63 @@ def peaks() -> dict:
     return dict(burst=1590.0, sustained=1400.0, hbm=6650.0, source="fallback (B200_PROFILING.md)")
 
 
-def ncu_traffic():
-    """dram__bytes_read.sum + dram__bytes_write.sum of one attention launch from the committed ncu --set full capture
-    (profiles/, Lq 4680 x S 18720 x 12 heads: 144 MB algorithmic Q + K + V + O) -- or None if no capture is committed."""
-    path = os.path.join(ROOT, "profiles", "r01e_ncu_tensor_kernels.json")
+NCU_SUMMARY = os.path.join(ROOT, "profiles", "r02_ncu_kernels.json")   # written by tools/ncu_summary.py from --set full captures
+
+
+def _ncu_summary():
     try:
-        k = next(iter(json.load(open(path))["r01e_attn"].values()))
-        unit = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
-        tot = 0.0
-        for key in ("dram__bytes_read.sum", "dram__bytes_write.sum"):
-            val, u = k[key].split()
-            tot += float(val) * unit[u]
-        return tot
+        return json.load(open(NCU_SUMMARY))
     except Exception:
         return None
+
+
+def _bytes(text: str) -> float:
+    val, unit = text.split()
+    return float(val.replace(",", "")) * {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}[unit]
+
+
+def ncu_traffic(kernel_substr: str = "attention_fwd_kernel"):
+    """dram__bytes_read.sum + dram__bytes_write.sum of ONE launch of the shipping kernel from the committed ncu
+    --set full capture -- only if that capture's kernel name matches the kernel launched today, else None."""
+    d = _ncu_summary()
+    if not d:
+        return None, None
+    for name, k in d.get("kernels", {}).items():
+        if kernel_substr in name and "dram__bytes_read.sum" in k:
+            try:
+                return _bytes(k["dram__bytes_read.sum"]) + _bytes(k["dram__bytes_write.sum"]), f"{name} ({k.get('shape', '?')})"
+            except Exception:
+                return None, None
+    return None, None
 
 
 def ncu_tensor_pipe():
-    """sm__pipe_tensor_cycles_active (% of active cycles) of the tensor-core kernels from the committed ncu --set full
-    captures (profiles/r01e_ncu_tensor_kernels.json) -- evidence quoted next to the live numbers, not measured here."""
-    path = os.path.join(ROOT, "profiles", "r01e_ncu_tensor_kernels.json")
-    key = "sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active"
-    try:
-        d = json.load(open(path))
-        out = {}
-        for group in ("r01e_attn", "r01e_gemm"):
-            for name, k in d[group].items():
-                out[name.replace("void ", "")] = float(k[key].split()[0])
-        out["source"] = "profiles/r01e_ncu_tensor_kernels.json (ncu --set full --clock-control none; gemm2<0> = QKV bias epilogue, gemm2<3> = N=1536 gate+residual)"
-        return out
-    except Exception:
+    """sm__pipe_tensor_cycles_active (% of active cycles) per captured kernel -- evidence quoted beside the live numbers."""
+    d = _ncu_summary()
+    if not d:
         return None
+    key = "sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active"
+    out = {}
+    for name, k in d.get("kernels", {}).items():
+        if key in k:
+            try:
+                out[name] = float(k[key].split()[0])
+            except Exception:
+                pass
+    out["source"] = "profiles/r02_ncu_kernels.json (ncu --set full --clock-control none)"
+    return out
+
+
+def config_dict(chunk_frames: int, world: int = 1, sp_size: int = 1, skip_refresh_tail: bool = False,
+                cuda_graphs: bool = True) -> dict:
+    """The `config` object of the JSON line -- identical for the product arm and the reference arm."""
+    n_videos = world // sp_size
+    return {"workload": workload_name(chunk_frames),
+            "parallelism": f"dp{world}" if sp_size == 1 else f"dp{n_videos} x ulysses{sp_size} (head-parallel, peer-memory all-to-all)",
+            "weights": "random-init 1.3B architecture",
+            "frames_per_step_per_gpu": PIX_FRAMES, "forwards_per_step": (LAT_FRAMES // chunk_frames) * 5,
+            "l2": "inputs larger than L2 (2.8 GB weights + 6 GB KV cache stream through the 126 MB L2 every forward)",
+            "skip_refresh_tail": bool(skip_refresh_tail), "cuda_graphs": bool(cuda_graphs)}
 
 
 def workload_name(chunk_frames: int) -> str:
@@ -164,10 +190,15 @@ class ClockSampler:
 # CPU oracle sample (cpu_baseline leg and the --impl reference arm)
 # ------------------------------------------------------------------------------------------------
 class CpuOracleSample:
-    """One oracle forward of chunk 0 of the rollout (L = S = chunk tokens, 1.3B layer shapes, bf16, all
-    host threads) with `layers` of the 30 identical transformer layers; the rollout time is extrapolated
-    by algorithmic FLOPs.  The oracle is the CPU restatement of the reference's own PyTorch path
-    (oracle/causal_wan_oracle.py) -- the reference checkout itself cannot travel to the GPU box."""
+    """the reference's CPU path (oracle port) timed on chunk 0 (S = L) AND on one late-chunk
+    forward at S = 32760 (the last chunk of the video, attending to the full cache), bf16, all host threads, with
+    `layers` of the 30 identical transformer layers (as many as the time budget allows).  The rollout time follows
+    from the two measured points: per-layer time is linear in the KV window S (F(L,S) = linear part + attention
+    proportional to S), so t(S) is interpolated between them for the 35 (or 105) forwards -- no
+    FLOP-based guess of the attention cost.  The oracle is the CPU restatement of the reference's own PyTorch path
+    (oracle/causal_wan_oracle.py); the reference checkout itself cannot travel to the GPU box."""
+
+    S_LATE = LAT_FRAMES * FRAME_TOKENS   # 32760
 
     def __init__(self, chunk_frames: int):
         import torch
@@ -188,34 +219,57 @@ class CpuOracleSample:
         self.w = O.OracleWrapper(O.make_random_params(cfg, seed=0), cfg, SHIFT)
         steps = O.warp_denoising_steps(self.w.scheduler, DENOISE_STEPS)
         self.ts = torch.ones([1, self.chunk_frames], dtype=torch.int64) * steps[0]
-        self.kv = O.new_kv_cache(cfg, 1, FRAME_TOKENS, torch.bfloat16, "cpu", cache_tokens=self.L)
+        self.kv_first = O.new_kv_cache(cfg, 1, FRAME_TOKENS, torch.bfloat16, "cpu", cache_tokens=self.L)
+        # the last chunk's view of the cache: S_LATE - L tokens of earlier (random) context already in place
+        self.kv_late = O.new_kv_cache(cfg, 1, FRAME_TOKENS, torch.bfloat16, "cpu", cache_tokens=self.S_LATE)
+        g = torch.Generator().manual_seed(5)
+        for c in self.kv_late:
+            c["k"].copy_(torch.randn(c["k"].shape, generator=g).to(torch.bfloat16))
+            c["v"].copy_(torch.randn(c["v"].shape, generator=g).to(torch.bfloat16))
+            c["global_end_index"].fill_(self.S_LATE - self.L)
+            c["local_end_index"].fill_(self.S_LATE - self.L)
         self.ca = O.new_crossattn_cache(cfg, 1, torch.bfloat16, "cpu")
         self.layers = layers
 
-    def step(self) -> float:
+    def step(self):
+        """-> (seconds of the chunk-0 forward, seconds of the S = 32760 forward).  Re-denoising a chunk overwrites its
+        cache slot in place (causal_model.py:226-229), so the calls are repeatable."""
         with self.torch.no_grad():
             t0 = time.perf_counter()
-            self.w(self.x, self.pe, self.ts, self.kv, self.ca, 0)   # re-denoising chunk 0 overwrites in place
-            return time.perf_counter() - t0
+            self.w(self.x, self.pe, self.ts, self.kv_first, self.ca, 0)
+            t1 = time.perf_counter()
+            self.w(self.x, self.pe, self.ts, self.kv_late, self.ca, self.S_LATE - self.L)
+            t2 = time.perf_counter()
+        return t1 - t0, t2 - t1
 
     def calibrate(self, seconds_per_step: float) -> None:
         self.prepare(1)
         self.step()                      # first call also fills the cross-attention cache
-        t1 = self.step()
+        t1 = sum(self.step())
         layers = max(1, min(NL, int(seconds_per_step / max(t1, 1e-3))))
         if layers != 1:
             self.prepare(layers)
             self.step()
 
-    def fps(self, seconds: float) -> float:
-        scale = rollout_flops(self.chunk_frames) / forward_flops(self.L, self.L, self.layers)
-        return PIX_FRAMES / (seconds * scale)
+    def rollout_seconds(self, t_first: float, t_late: float) -> float:
+        """Per-forward time interpolated linearly in S between the two measured points, summed over the rollout."""
+        scale = NL / self.layers
+        if self.S_LATE == self.L:
+            return t_first * scale * 5
+        slope = (t_late - t_first) / (self.S_LATE - self.L)
+        n_chunks = LAT_FRAMES // self.chunk_frames
+        return scale * sum((len(DENOISE_STEPS) + 1) * (t_first + slope * (i * self.L)) for i in range(n_chunks))
 
-    def describe(self, seconds: float) -> str:
-        fl = forward_flops(self.L, self.L, self.layers)
-        return (f"oracle forward of chunk 0 (L=S={self.L}) with {self.layers} of {NL} layers = {fl / 1e12:.2f} TFLOP in "
-                f"{seconds:.2f} s on {self.threads} threads (bf16, SDPA); rollout extrapolated by algorithmic FLOPs "
-                f"({rollout_flops(self.chunk_frames) / 1e12:.1f} TFLOP)")
+    def fps(self, sec) -> float:
+        return PIX_FRAMES / self.rollout_seconds(*sec)
+
+    def describe(self, sec) -> str:
+        t_first, t_late = sec
+        fl = forward_flops(self.L, self.L, self.layers) + forward_flops(self.L, self.S_LATE, self.layers)
+        return (f"oracle forward of chunk 0 (L=S={self.L}) in {t_first:.2f} s + forward of the last chunk (S={self.S_LATE}) "
+                f"in {t_late:.2f} s, {self.layers} of {NL} layers = {fl / 1e12:.2f} TFLOP on {self.threads} threads (bf16, SDPA); "
+                f"rollout of {(LAT_FRAMES // self.chunk_frames) * 5} forwards = {self.rollout_seconds(*sec):.1f} s by linear "
+                f"interpolation in S between the two measured points")
 
 
 def run_reference_arm(args) -> None:
@@ -230,13 +284,13 @@ def run_reference_arm(args) -> None:
     for _ in range(args.warmup):
         s.step()
     times = [s.step() for _ in range(args.steps)]
-    sec = sum(times) / len(times)
+    sec = (sum(t[0] for t in times) / len(times), sum(t[1] for t in times) / len(times))
     fps = s.fps(sec)
     line = {
         "impl": "reference", "metric": METRIC, "value": fps, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
-        "warmup": args.warmup, "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "weak",
+        "warmup": args.warmup, "ms_per_step": sum(sec) * 1e3, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
-        "config": {"workload": workload_name(args.chunk_frames), "device": "cpu", "weights": "random-init"},
+        "config": config_dict(args.chunk_frames, max(1, args.gpus)), "device": "cpu (host cores of the GPU box)",
         "cpu_baseline": {"value": fps, "unit": UNIT, "cores": s.threads, "kind": "port", "sample": s.describe(sec)},
         "e2e": {"value": fps, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -441,7 +495,9 @@ def run_product_arm(args) -> None:
     # HBM-bound kernels: algorithmic bytes (rows read + written, SURVEY.md 8d / DESIGN.md 4) over the event-timed launches
     Lrows = cf * FRAME_TOKENS // sp_size
     hbm_lines = []
-    for kname, passes in (("qk_norm_rope", 6), ("qk_norm_rope_sp", 6), ("ln_modulate", 2), ("ln_affine", 2), ("rmsnorm", 2)):
+    # qk_norm_rope at batch 1: V goes straight from the QKV GEMM into its cache slot, the kernel reads q, k and writes
+    # q, k (4 passes); the sequence-parallel form also moves V (6 passes)
+    for kname, passes in (("qk_norm_rope", 4), ("qk_norm_rope_sp", 6), ("ln_modulate", 2), ("ln_affine", 2), ("rmsnorm", 2)):
         gk = groups.get(kname)
         if gk and gk[1] > 0:
             nbytes = passes * Lrows * C * 2.0 * gk[0]
@@ -450,17 +506,23 @@ def run_product_arm(args) -> None:
                               "frac": gbs / pk["hbm"], "bytes_per_launch": passes * Lrows * C * 2.0,
                               "note": "per-launch CUDA events of the eager breakdown pass (includes launch gaps of ~10 us kernels)"})
     total_fl = rollout_flops(cf)
+    traffic, traffic_src = ncu_traffic()
+    # per-shape view of the projections (event-timed eager launches of the breakdown pass)
+    gemm_shapes = {}
+    for name, tag, ms in prof:
+        if name == "gemm":
+            g = gemm_shapes.setdefault(f"M{tag[1]}_N{tag[2]}_K{tag[3]}_epi{tag[4] if len(tag) > 4 else '?'}", [0, 0.0, 0.0])
+            g[0] += 1
+            g[1] += ms
+            g[2] += 2.0 * tag[1] * tag[2] * tag[3]
+    gemm_shapes = {k: {"launches": g[0], "us_per_launch": round(g[1] / g[0] * 1e3, 2), "tflops": round(g[2] / g[1] / 1e9, 1)}
+                   for k, g in sorted(gemm_shapes.items(), key=lambda kv: -kv[1][1]) if g[1] > 0}
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms_total / args.steps, "higher_is_better": True,
         "scaling": "weak" if sp_size == 1 else "strong", "vs_baseline": None,
         "dtype": "bf16", "data": "synthetic",
-        "config": {"workload": workload_name(cf),
-                   "parallelism": f"dp{world}" if sp_size == 1 else f"dp{n_videos} x ulysses{sp_size} (head-parallel, peer-memory all-to-all)",
-                   "weights": "random-init 1.3B architecture",
-                   "frames_per_step_per_gpu": PIX_FRAMES, "forwards_per_step": (LAT_FRAMES // cf) * 5,
-                   "l2": "inputs larger than L2 (2.8 GB weights + 6 GB KV cache stream through the 126 MB L2 every forward)",
-                   "skip_refresh_tail": bool(args.skip_refresh_tail), "cuda_graphs": bool(gen.model.use_cuda_graphs)},
+        "config": config_dict(cf, world, sp_size, args.skip_refresh_tail, gen.model.use_cuda_graphs),
         "per_gpu": value / world,
         "model_tflops": total_fl * n_videos * args.steps / (ms_total / 1e3) / 1e12,
         "model_frac_of_peak": total_fl * n_videos * args.steps / (ms_total / 1e3) / 1e12 / pk["sustained"] / world,
@@ -469,10 +531,10 @@ def run_product_arm(args) -> None:
         "gpu_launches": launches,
         "roofline": {"kernel": "attention_fwd_kernel (self-attention over the KV window)", "bound": "tensor",
                      "achieved": achieved, "peak": pk["sustained"], "unit": "TFLOP/s",
-                     "frac": achieved / pk["sustained"], "traffic": ncu_traffic(),
-                     "traffic_note": "bytes of ONE launch (Lq 4680, S 18720, H 12; algorithmic Q+K+V+O = 144 MB) from the "
-                                     "committed ncu capture profiles/r01e_ncu_tensor_kernels.json; `achieved` sums all "
-                                     "self-attention launches of the timed steps (S = 4680 .. 32760)",
+                     "frac": achieved / pk["sustained"], "traffic": traffic,
+                     "traffic_note": (f"dram bytes of ONE launch of {traffic_src} from {os.path.basename(NCU_SUMMARY)}; "
+                                      if traffic is not None else "no committed capture of the shipping kernel; ") +
+                                     "`achieved` sums all self-attention launches of the timed steps (S = 4680 .. 32760)",
                      "peak_kind": "sustained bf16 cuBLAS, " + pk["source"], "frac_of_burst": achieved / pk["burst"],
                      "launches_timed": len(self_attn), "ms_in_timed_region": ms_attn,
                      "timed_region": "second pass of the same K steps, launched eagerly with CUDA events around each attention launch"},
@@ -480,7 +542,7 @@ def run_product_arm(args) -> None:
                           "achieved": gemm[2] / gemm[1] / 1e9 if gemm[1] else 0.0, "peak": pk["sustained"],
                           "unit": "TFLOP/s", "frac": (gemm[2] / gemm[1] / 1e9 if gemm[1] else 0.0) / pk["sustained"]},
         "roofline_hbm": hbm_lines, "ncu_tensor_pipe_pct": ncu_tensor_pipe(),
-        "breakdown": breakdown, "kernel_ms_per_step": kernel_ms, "finite": finite,
+        "breakdown": breakdown, "gemm_shapes": gemm_shapes, "kernel_ms_per_step": kernel_ms, "finite": finite,
         "clocks": clk,
     }
     if world == 1 and not args.no_vae:
@@ -495,7 +557,9 @@ def run_product_arm(args) -> None:
         # B200 as the beat-this number".  The reference checkout cannot travel to this box, so its restatement (the
         # oracle, same op sequence in plain PyTorch) runs in eager mode on this GPU with the product's weights and inputs.
         try:
-            line["gpu_eager_baseline"] = gpu_eager_leg(gen, cf, pe_dev, noise_dev, value)
+            line["gpu_eager_baseline"] = gpu_eager_leg(gen, cf, pe_dev, noise_dev, value, resident_step)
+            pr = line["gpu_eager_baseline"].get("parity_vs_product")
+            line["parity_rel_l2"] = pr["latents_rel_l2"] if pr else None
         except Exception as e:   # an extra leg must never take the headline line down
             line["gpu_eager_baseline"] = {"error": f"{type(e).__name__}: {e}"[:300]}
     if world == 1 and not args.no_cpu_baseline:
@@ -511,7 +575,7 @@ def run_product_arm(args) -> None:
     shutdown()
 
 
-def gpu_eager_leg(gen, chunk_frames: int, pe_dev, noise_dev, product_fps: float) -> dict:
+def gpu_eager_leg(gen, chunk_frames: int, pe_dev, noise_dev, product_fps: float, product_rollout=None) -> dict:
     """One full rollout of the ORACLE (the CPU restatement of the reference's PyTorch path) in eager mode on the GPU:
     cuBLAS for every Linear, torch SDPA for attention, op-by-op elementwise kernels with the reference's float64 RoPE /
     sinusoid / flow->x0, `.item()` index reads per forward -- what the unmodified reference does on a GPU, minus its
@@ -527,10 +591,22 @@ def gpu_eager_leg(gen, chunk_frames: int, pe_dev, noise_dev, product_fps: float)
     with torch.no_grad():
         O.rollout(ow, noise_dev, pe_dev, steps, chunk_frames, max_chunks=1)      # warm-up: cuBLAS / SDPA heuristics
         sync()
+        torch.manual_seed(4321)       # same re-noise stream (torch.randn_like on the CUDA generator) for both sides
         t0 = time.perf_counter()      # host clock around a synchronised region: eager mode is host-driven by nature
         tr = O.rollout(ow, noise_dev, pe_dev, steps, chunk_frames)
         sync()
         ms = (time.perf_counter() - t0) * 1e3
+        parity = None
+        if product_rollout is not None:
+            # the product's rollout on the same inputs and noise stream: the parity figure the north-star asks for
+            torch.manual_seed(4321)
+            lat = product_rollout()
+            sync()
+            d = (lat.double() - tr.latents.double())
+            per_chunk = [float(d[:, i:i + chunk_frames].norm() / tr.latents[:, i:i + chunk_frames].double().norm())
+                         for i in range(0, lat.shape[1], chunk_frames)]
+            parity = {"latents_rel_l2": float(d.norm() / tr.latents.double().norm()), "per_chunk_max": max(per_chunk),
+                      "tolerance": 1e-2, "index_exact": tr.index_trace[-1] == (lat.shape[1] * FRAME_TOKENS,) * 2}
     frames = (noise_dev.shape[1] - 1) * 4 + 1
     fps = frames / (ms / 1e3)
     finite = bool(torch.isfinite(tr.latents.float()).all())
@@ -540,7 +616,7 @@ def gpu_eager_leg(gen, chunk_frames: int, pe_dev, noise_dev, product_fps: float)
     return {"value": fps, "unit": UNIT, "ms_per_step": ms, "kind": "port", "finite": finite,
             "what": "oracle (restatement of the reference's PyTorch path) in eager mode on this GPU: cuBLAS GEMMs, torch "
                     "SDPA, op-by-op elementwise kernels, per-forward .item() syncs; same weights and inputs as the product",
-            "product_speedup": product_fps / fps}
+            "product_speedup": product_fps / fps, "parity_vs_product": parity}
 
 
 def vae_decode_leg(ops, dev, latents, rollout_ms: float) -> dict:

@@ -40,10 +40,10 @@ int sfb_abi_version(void);
  * :277-279 (ffn), :351/:366 (head), :458-462 (patch/text embed); wan/modules/model.py:172,177-178,193.
  * `gate` row for output row r is gate + ((r + gate_row_offset) / rows_per_gate) * gate_stride (per-frame adaLN
  * gate; gate_row_offset = chunk-global index of row 0 for sequence-parallel callers that hold a slice of the rows).
- * out may alias residual.  block_n: 0 = choose; 64/128/192/256 = one-CTA tiles of 128 x block_n (192 only on
- * request: 4680 x 1536 outputs are exactly two waves of 128 x 192 tiles); 1192 / 1256 = the same one-CTA 128 x 192 /
- * 128 x 256 tiles with the pair kernel's staged TMA-store epilogue (on request, N % tile == 0); 512 = CTA-pair
- * (tcgen05 cta_group::2) tiles of 256 x 256; 513 = the same with the stream-K schedule (needs the workspace). */
+ * out may alias residual.  block_n: 0 = choose; 64/128/256 = one-CTA tiles of 128 x block_n; 512 = CTA-pair
+ * (tcgen05 cta_group::2) tiles of 256 x 256; 515 = pair tiles in clusters of two pairs that share the A operand by
+ * TMA multicast (N and seg_cols must be multiples of 256 for both).  workspace / workspace_bytes are ignored (kept
+ * for ABI stability). */
 int sfb_gemm_bf16(const void* x, long long ldx, const void* w, long long ldw, const void* bias,
                   int M, int N, int K, int epilogue,
                   void* out0, long long ldo0, void* out1, long long ldo1, void* out2, long long ldo2, int seg_cols,

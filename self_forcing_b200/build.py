@@ -16,7 +16,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libsfb200.so")
 OBJ_DIR = os.path.join(HERE, "build")
-SOURCES = ["runtime.cu", "gemm_tcgen05.cu", "gemm1s_tcgen05.cu", "gemm2_tcgen05.cu", "attention_tcgen05.cu", "fused_elementwise.cu", "sampler.cu", "vae.cu", "conv_tcgen05.cu", "t5.cu", "comm.cu"]
+SOURCES = ["runtime.cu", "gemm_tcgen05.cu", "gemm2_tcgen05.cu", "attention_tcgen05.cu", "fused_elementwise.cu", "sampler.cu", "vae.cu", "conv_tcgen05.cu", "t5.cu", "comm.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "--extended-lambda", "-Xcompiler", "-fPIC", "-Xcompiler", "-fvisibility=default"]
 

@@ -27,8 +27,7 @@
 //
 // Softmax arithmetic: x = s * scale_log2 - m with packed fp32x2 FMAs, 2^x on MUFU.EX2 (16 lanes/clk/SM --
 // for head_dim 128 that is exactly the rate at which the tensor pipe consumes P, so the exponentials,
-// not the MMAs, are the critical resource) with an optional share computed by a degree-3 polynomial on
-// the FMA pipe (template EMU), row sums with packed adds.
+// not the MMAs, are the critical resource), row sums with packed adds.
 #include <math.h>
 #include <stdio.h>
 #include <stdlib.h>
@@ -60,8 +59,6 @@ constexpr int ATT_TILE_BYTES = 128 * 128 * 2;    // 32 KB: two 16 KB halves (d 0
 constexpr int ATT_HALF_BYTES = 128 * 64 * 2;
 constexpr int ATT_KV_STAGES = 2;
 constexpr int ATT_SMEM_BYTES = 2 * ATT_TILE_BYTES + 2 * ATT_KV_STAGES * ATT_TILE_BYTES + 1024 + 256;
-constexpr int ATT_DEFAULT_EMU = 0;   // measured: 0 -> 1166, 1 -> 1115, 2 -> 1063 TFLOP/s at Lq 4680 x S 32760 (the softmax is issue-bound)
-constexpr bool ATT_DEFAULT_ALU_PACK = false;
 constexpr int ATT_SLOT_FLOATS = ATT_BM * ATT_D + 2 * ATT_BM;   // one (tile, segment) partial
 constexpr int ATT_MIN_SPLIT_KV_TILES = 48;                     // shorter KV (measured: S = 4680 is better whole, S >= 9360 split): whole items per CTA
 constexpr int ATT_MAX_GROUPS = 4;
@@ -89,46 +86,11 @@ __device__ __forceinline__ float fast_exp2(float x) {
   return y;
 }
 
-__device__ __forceinline__ unsigned long long f2_bits(float2 v) {
-  return (unsigned long long)__float_as_uint(v.x) | ((unsigned long long)__float_as_uint(v.y) << 32);
-}
-
-// 2^x for two values on the FMA pipe: Cody-Waite range reduction + degree-3 minimax polynomial
-// (rel. error 8.8e-5, far below the bf16 rounding of P).  x <= ~8 (lazy-rescale bound).
-__device__ __forceinline__ float2 poly_exp2x2(float2 x) {
-  x.x = fmaxf(x.x, -125.0f);
-  x.y = fmaxf(x.y, -125.0f);
-  unsigned long long rb;
-  asm("add.rm.ftz.f32x2 %0, %1, %2;" : "=l"(rb) : "l"(f2_bits(x)), "l"(f2_bits(make_float2(12582912.0f, 12582912.0f))));
-  const float2 r = make_float2(__uint_as_float((uint32_t)rb), __uint_as_float((uint32_t)(rb >> 32)));   // 1.5*2^23 + floor(x)
-  const float2 fl = __fadd2_rn(r, make_float2(-12582912.0f, -12582912.0f));          // floor(x)
-  const float2 f = __ffma2_rn(fl, make_float2(-1.0f, -1.0f), x);                       // frac(x) in [0, 1)
-  float2 q = __ffma2_rn(make_float2(0.077119089663028717f, 0.077119089663028717f), f,
-                        make_float2(0.227564394474029541f, 0.227564394474029541f));
-  q = __ffma2_rn(q, f, make_float2(0.695146143436431885f, 0.695146143436431885f));
-  q = __ffma2_rn(q, f, make_float2(1.0f, 1.0f));
-  q.x = __int_as_float(__float_as_int(q.x) + (__float_as_int(r.x) << 23));
-  q.y = __int_as_float(__float_as_int(q.y) + (__float_as_int(r.y) << 23));
-  return q;
-}
-
-// fp32 pair -> packed bf16 (round to nearest even) with integer ALU ops instead of F2FP: conversions execute on the
-// same XU pipe as MUFU.EX2 (16 lanes/clk/SM), which is the scarcest resource of the softmax.  Inputs are finite, >= 0.
-__device__ __forceinline__ uint32_t pack_bf16_alu(float a, float b) {
-  uint32_t ua = __float_as_uint(a), ub = __float_as_uint(b);
-  ua += 0x7FFFu + ((ua >> 16) & 1u);
-  ub += 0x7FFFu + ((ub >> 16) & 1u);
-  return __byte_perm(ua, ub, 0x7632);
-}
-
 template <int REGS>
 __device__ __forceinline__ void setmaxnreg_inc() { asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(REGS)); }
 template <int REGS>
 __device__ __forceinline__ void setmaxnreg_dec() { asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(REGS)); }
 
-// EMU: how many of every 4 exponential PAIRS run on the FMA pipe instead of MUFU (0, 1 or 2).
-// ALU_PACK: round P to bf16 with integer ops instead of F2FP (XU pipe).
-template <int EMU, bool ALU_PACK>
 __global__ void __launch_bounds__(ATT_THREADS, 1)
 attention_fwd_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_constant__ CUtensorMap tma_k,
                      const __grid_constant__ CUtensorMap tma_v, const AttnParams p) {
@@ -431,14 +393,10 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_con
             const float2 x = __ffma2_rn(make_float2(__uint_as_float(s[c * 32 + 2 * i]), __uint_as_float(s[c * 32 + 2 * i + 1])),
                                         sl2v, negv);
             float2 e;
-            if ((i & 3) < EMU) {
-              e = poly_exp2x2(x);
-            } else {
-              e.x = fast_exp2(x.x);
-              e.y = fast_exp2(x.y);
-            }
+            e.x = fast_exp2(x.x);
+            e.y = fast_exp2(x.y);
             if (i & 1) sum_b = __fadd2_rn(sum_b, e); else sum_a = __fadd2_rn(sum_a, e);
-            pk[i] = ALU_PACK ? pack_bf16_alu(e.x, e.y) : pack_bf16(e.x, e.y);
+            pk[i] = pack_bf16(e.x, e.y);
           }
           tmem_st16(s_addr + c * 16, pk);   // P_t aliases the first 64 columns of S_t
           if (c & 1) {                      // publish this half of P (64 KV columns)
@@ -678,23 +636,11 @@ static int attention_launch(const void* q, long long q_row_stride, long long q_b
   }
   p.dbg = timing ? dbg_buf : nullptr;
 
-  static int emu = -1;
-  static bool alu_pack = false;
-  if (emu < 0) {
-    const char* env = getenv("SFB_ATTN_EMU");   // tuning knob; the default is the measured best
-    int want = env ? atoi(env) : ATT_DEFAULT_EMU;
-    if (want < 0 || want > 2) want = ATT_DEFAULT_EMU;
-    for (auto kern : {attention_fwd_kernel<0, false>, attention_fwd_kernel<1, false>, attention_fwd_kernel<2, false>,
-                      attention_fwd_kernel<0, true>, attention_fwd_kernel<1, true>, attention_fwd_kernel<2, true>})
-      if (int e = check_cuda(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT_SMEM_BYTES),
-                             "cudaFuncSetAttribute(attention)"))
-        return e;
-    const char* ap = getenv("SFB_ATTN_ALU_PACK");
-    alu_pack = ap ? (ap[0] == '1') : ATT_DEFAULT_ALU_PACK;
-    emu = want;
-  }
-  auto kern = alu_pack ? (emu == 0 ? attention_fwd_kernel<0, true> : (emu == 1 ? attention_fwd_kernel<1, true> : attention_fwd_kernel<2, true>))
-                       : (emu == 0 ? attention_fwd_kernel<0, false> : (emu == 1 ? attention_fwd_kernel<1, false> : attention_fwd_kernel<2, false>));
+  // (measured in round 1 and removed: a degree-3 polynomial exp2 on the FMA pipe for 25 / 50 % of the exponentials --
+  // 1115 / 1063 vs 1166 TFLOP/s at Lq 4680 x S 32760 -- and integer-ALU bf16 packing of P: the softmax is issue-bound)
+  auto kern = attention_fwd_kernel;
+  static SmemOptIn optin;
+  if (int e = optin.ensure(kern, ATT_SMEM_BYTES, "cudaFuncSetAttribute(attention)")) return e;
   kern<<<grid, ATT_THREADS, ATT_SMEM_BYTES, stream>>>(tq, tk, tv, p);
   if (int e = check_cuda(cudaGetLastError(), "attention launch")) return e;
   if (timing) {   // diagnostic: per-phase cycles of one softmax warp, averaged over CTAs, per KV step

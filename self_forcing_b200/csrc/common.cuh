@@ -6,6 +6,8 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include <atomic>
+
 #define SFB_OK 0
 #define SFB_ERR_INVALID 1
 #define SFB_ERR_CUDA 2
@@ -19,6 +21,26 @@ int check_cuda(cudaError_t e, const char* what);
 // for dims 1..rank-1.  Returns SFB_OK or an error (message in sfb_last_error()).
 int make_tmap_bf16(CUtensorMap* out, const void* base, int rank, const uint64_t* dims,
                    const uint64_t* strides_bytes, const uint32_t* box, bool swizzle128);
+
+// cudaFuncSetAttribute(MaxDynamicSharedMemorySize) is a PER-DEVICE property of a kernel: a process that drives several
+// GPUs (teacher + generator, two pipelines) needs the opt-in on each of them.  One of these per kernel instantiation
+// (a function-local static): bytes already granted per device, updated atomically so host threads may race.
+struct SmemOptIn {
+  std::atomic<int> granted[64];
+  template <class Kernel>
+  int ensure(Kernel kern, int bytes, const char* what) {
+    int dev = 0;
+    if (int e = check_cuda(cudaGetDevice(&dev), "cudaGetDevice")) return e;
+    if (dev < 0 || dev >= 64) {   // beyond the table: set it on every launch (cheap)
+      return check_cuda(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes), what);
+    }
+    if (granted[dev].load(std::memory_order_acquire) >= bytes) return SFB_OK;
+    if (int e = check_cuda(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes), what)) return e;
+    int seen = granted[dev].load(std::memory_order_relaxed);
+    while (seen < bytes && !granted[dev].compare_exchange_weak(seen, bytes, std::memory_order_release)) {}
+    return SFB_OK;
+  }
+};
 
 // ------------------------------------------------------------------------------------
 // bf16 helpers -- the reference computes every elementwise op in fp32 and rounds to bf16

@@ -192,13 +192,8 @@ template <int BN, int EPI, int MT>
 static int launch_conv3(const CUtensorMap& tx, const CUtensorMap& tw, const ConvParams& p, cudaStream_t stream) {
   using Cfg = ConvCfg<BN, MT>;
   auto kern = conv3_implicit_kernel<BN, EPI, MT>;
-  static bool attr_set = false;
-  if (!attr_set) {
-    if (int e = check_cuda(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES),
-                           "cudaFuncSetAttribute(conv3)"))
-      return e;
-    attr_set = true;
-  }
+  static SmemOptIn optin;
+  if (int e = optin.ensure(kern, Cfg::SMEM_BYTES, "cudaFuncSetAttribute(conv3)")) return e;
   const int sms = device_sm_count();
   if (sms <= 0) return SFB_ERR_CUDA;
   const long long tiles = (long long)p.t_out * p.tiles_h * p.tiles_w * p.num_n_blocks;
@@ -215,11 +210,9 @@ int launch_conv3_implicit(const void* x, int t_in, int H, int W, int Cin, int t_
   ConvParams p{};
   p.t_out = t_in + t_zero_pad - (kt - 1);
   p.Ho = H; p.Wo = W; p.Cin = Cin; p.kt = kt; p.t_zero_pad = t_zero_pad;
-  // 32: the 3-channel head (padded to 8).  192-column tiles for the 192-channel layers (no padded MMA columns: that kernel
-  // runs at 92 % tensor-pipe active with a quarter of its columns padding) are wired but not yet measured:
-  // SFB_CONV_EXACT_N=1 selects them.
-  static const bool exact_n = getenv("SFB_CONV_EXACT_N") != nullptr;
-  const int bn = Cout <= 32 ? 32 : (Cout <= 128 ? 128 : ((exact_n && Cout == 192) ? 192 : 256));
+  // 32: the 3-channel head (padded to 8); 192-column tiles for the 192-channel layers (no padded MMA columns; measured
+  // 0.467 -> 0.461 s per decoded video on B200, profiles/r02b_vae_exact_n.json)
+  const int bn = Cout <= 32 ? 32 : (Cout <= 128 ? 128 : (Cout == 192 ? 192 : 256));
   // two accumulator sub-tiles per CTA (256 voxels against one weight tile) where TMEM has room and the frame is large
   // enough to keep every SM busy with 256-voxel tiles
   const int sms_hint = device_sm_count();

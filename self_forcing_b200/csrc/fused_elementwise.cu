@@ -584,11 +584,9 @@ extern "C" int sfb_skinny_linear(const void* x, long long ldx, const void* w, lo
   if (M <= 0 || N <= 0 || K <= 0 || (K % 256) || (ldw % 8)) { set_error("sfb_skinny_linear: need K %% 256 == 0 (got %d) and ldw %% 8 == 0", K); return SFB_ERR_INVALID; }
   const size_t smem = (size_t)SKINNY_M * K * sizeof(float);
   if (smem > 200 * 1024) { set_error("sfb_skinny_linear: K=%d too large", K); return SFB_ERR_INVALID; }
-  static size_t configured = 0;
-  if (smem > 48 * 1024 && smem > configured) {
-    if (int e = check_cuda(cudaFuncSetAttribute(skinny_linear_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), "cudaFuncSetAttribute(skinny)")) return e;
-    configured = smem;
-  }
+  static SmemOptIn optin;
+  if (smem > 48 * 1024)
+    if (int e = optin.ensure(skinny_linear_kernel, (int)smem, "cudaFuncSetAttribute(skinny)")) return e;
   dim3 grid((N + 7) / 8, (M + SKINNY_M - 1) / SKINNY_M);
   skinny_linear_kernel<<<grid, 256, smem, (cudaStream_t)stream>>>((const bf16*)x, ldx, (const bf16*)w, ldw,
                                                                 (const bf16*)bias, (bf16*)y, ldy, M, N, K, silu_in);

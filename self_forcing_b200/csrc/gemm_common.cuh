@@ -21,12 +21,7 @@ struct GemmParams {
   long long gate_stride;
   int rows_per_gate;
   int gate_row_offset;         // chunk-global index of row 0 (sequence-parallel callers hold a slice of the rows)
-  // stream-K (CTA-pair kernel only): the tile x k-block space is cut into one contiguous range per CTA pair; a tile
-  // cut in two leaves its tail (fp32, transposed) in sk_ws and the owner of its head adds it before the epilogue
-  int streamk;
-  float* sk_ws;                // [pairs][2 CTAs][256 cols][128 rows] fp32
-  int* sk_flags;               // [pairs][2 CTAs], holds sk_epoch once the partial is complete
-  int sk_epoch;
+  long long* dbg;              // SFB_GEMM_TIMING=1: per-CTA clock64 timeline [grid][16], else nullptr
 };
 
 __device__ __forceinline__ float gelu_tanh_f(float x) {
@@ -38,16 +33,26 @@ __device__ __forceinline__ float gelu_tanh_f(float x) {
 }
 
 
-// Fused epilogue math on 8 consecutive accumulator columns (one 16-byte bf16 chunk), shared by both
-// store paths.  bias/gate point at the chunk's first column; res holds the residual chunk.
-template <int EPI>
-__device__ __forceinline__ uint4 gemm_epilogue_chunk(const uint32_t* acc8, const __nv_bfloat16* bias,
-                                                     const __nv_bfloat16* gate, uint4 res) {
+// GELU(tanh) with the hardware tanh (one MUFU op instead of ex2 + rcp): used by the clustered GEMM whose FFN1 epilogue
+// was XU-pipe / issue bound (14.8 k cycles per 128 x 256 tile against a 12.3 k-cycle main loop, profiles/r02b).
+// tanh.approx.f32 has ~2^-11 relative error, an order below the bf16 rounding that follows.
+__device__ __forceinline__ float gelu_tanh_fast(float x) {
+  const float kBeta = 0.7978845608028654f, kKappa = 0.044715f;
+  const float u = kBeta * (x + kKappa * x * x * x);
+  float t;
+  asm("tanh.approx.f32 %0, %1;" : "=f"(t) : "f"(u));
+  const float hx = 0.5f * x;
+  return fmaf(hx, t, hx);
+}
+
+// Fused epilogue math on 8 consecutive accumulator columns (one 16-byte bf16 chunk), shared by all store paths.
+// b / gq / res hold the chunk's bias, gate and residual values (ignored where the epilogue has none).
+template <int EPI, bool FAST_GELU = false>
+__device__ __forceinline__ uint4 gemm_epilogue_vals(const uint32_t* acc8, bool has_bias, uint4 b, uint4 gq, uint4 res) {
   float f[8];
 #pragma unroll
   for (int i = 0; i < 8; ++i) f[i] = __uint_as_float(acc8[i]);
-  if (bias != nullptr) {
-    const uint4 b = __ldg(reinterpret_cast<const uint4*>(bias));
+  if (has_bias) {
     const uint32_t bw[4] = {b.x, b.y, b.z, b.w};
 #pragma unroll
     for (int i = 0; i < 4; ++i) { f[2 * i] += bf_lo(bw[i]); f[2 * i + 1] += bf_hi(bw[i]); }
@@ -57,12 +62,11 @@ __device__ __forceinline__ uint4 gemm_epilogue_chunk(const uint32_t* acc8, const
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
       const uint32_t y2 = round_pair(f[2 * i], f[2 * i + 1]);
-      f[2 * i] = gelu_tanh_f(bf_lo(y2));
-      f[2 * i + 1] = gelu_tanh_f(bf_hi(y2));
+      f[2 * i] = FAST_GELU ? gelu_tanh_fast(bf_lo(y2)) : gelu_tanh_f(bf_lo(y2));
+      f[2 * i + 1] = FAST_GELU ? gelu_tanh_fast(bf_hi(y2)) : gelu_tanh_f(bf_hi(y2));
     }
   }
   if (EPI == EPI_GATE_RES) {
-    const uint4 gq = __ldg(reinterpret_cast<const uint4*>(gate));
     const uint32_t gw[4] = {gq.x, gq.y, gq.z, gq.w};
     const uint32_t rw[4] = {res.x, res.y, res.z, res.w};
 #pragma unroll
@@ -87,6 +91,16 @@ __device__ __forceinline__ uint4 gemm_epilogue_chunk(const uint32_t* acc8, const
   o.z = pack_bf16(f[4], f[5]);
   o.w = pack_bf16(f[6], f[7]);
   return o;
+}
+
+// bias / gate point at the chunk's first column in global memory (nullptr = none)
+template <int EPI>
+__device__ __forceinline__ uint4 gemm_epilogue_chunk(const uint32_t* acc8, const __nv_bfloat16* bias,
+                                                     const __nv_bfloat16* gate, uint4 res) {
+  uint4 b = make_uint4(0, 0, 0, 0), gq = make_uint4(0, 0, 0, 0);
+  if (bias != nullptr) b = __ldg(reinterpret_cast<const uint4*>(bias));
+  if (EPI == EPI_GATE_RES) gq = __ldg(reinterpret_cast<const uint4*>(gate));
+  return gemm_epilogue_vals<EPI>(acc8, bias != nullptr, b, gq, res);
 }
 
 // One thread owns accumulator row `row` (TMEM lane) of a tile that starts at column n0 and is

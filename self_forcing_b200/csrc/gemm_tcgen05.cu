@@ -29,8 +29,8 @@ struct GemmCfg {
   static constexpr int A_BYTES = BLOCK_M * BLOCK_K * 2;
   static constexpr int B_BYTES = BLOCK_N * BLOCK_K * 2;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-  static constexpr int STAGES = (BLOCK_N == 256) ? 4 : (BLOCK_N == 192 ? 5 : (BLOCK_N == 128 ? 6 : 8));
-  // two accumulator buffers; TMEM is allocated in powers of two (192-column tiles take 512 and use 2 x 192 of them)
+  static constexpr int STAGES = (BLOCK_N == 256) ? 4 : (BLOCK_N == 128 ? 6 : 8);
+  // two accumulator buffers; TMEM is allocated in powers of two
   static constexpr int TMEM_COLS = 2 * BLOCK_N <= 32 ? 32 : (2 * BLOCK_N <= 128 ? 128 : (2 * BLOCK_N <= 256 ? 256 : 512));
   static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
 };
@@ -157,13 +157,8 @@ static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const GemmP
                        cudaStream_t stream) {
   using Cfg = GemmCfg<BLOCK_N>;
   auto kern = gemm_bf16_kernel<BLOCK_N, EPI>;
-  static bool attr_set = false;
-  if (!attr_set) {
-    if (int e = check_cuda(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES),
-                           "cudaFuncSetAttribute(gemm)"))
-      return e;
-    attr_set = true;
-  }
+  static SmemOptIn optin;
+  if (int e = optin.ensure(kern, Cfg::SMEM_BYTES, "cudaFuncSetAttribute(gemm)")) return e;
   const int tiles = p.num_m_blocks * p.num_n_blocks;
   const int grid = tiles < num_sms ? tiles : num_sms;
   kern<<<grid, GEMM_THREADS, Cfg::SMEM_BYTES, stream>>>(ta, tb, p);
@@ -185,12 +180,8 @@ static int dispatch_epi(int epi, const CUtensorMap& ta, const CUtensorMap& tb, c
 }
 
 int device_sm_count();
-int launch_gemm_single_staged(int epi, int bn, const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& p, int num_sms,
-                              cudaStream_t stream);   // gemm1s_tcgen05.cu
-int launch_gemm_pair(int epi, const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& p, int num_sms,
-                     cudaStream_t stream);
-long long gemm_pair_workspace_bytes();
-void gemm_pair_workspace(void* ws, long long bytes, GemmParams& p);
+int launch_gemm_cluster(int epi, int pairs_per_cluster, const void* x, long long ldx, const CUtensorMap& tb,
+                        const GemmParams& p, int num_sms, cudaStream_t stream);   // gemm2_tcgen05.cu
 
 }  // namespace sfb
 
@@ -209,29 +200,21 @@ extern "C" int sfb_gemm_bf16(const void* x, long long ldx, const void* w, long l
     return SFB_ERR_INVALID;
   }
   if (seg_cols <= 0) seg_cols = N;
-  // block_n: 0 = choose; 64 / 128 / 256 = one-CTA tiles of 128 x block_n; 512 = CTA-pair tiles of 256 x 256
-  // (tcgen05 cta_group::2, gemm2_tcgen05.cu) -- the default whenever N and the segments are multiples of 256.
-  if (block_n == 0 && N % 256 == 0 && seg_cols % 256 == 0 && M > 128 && epilogue != EPI_F32) block_n = 512;
+  // block_n: 0 = choose; 64 / 128 / 256 = one-CTA tiles of 128 x block_n; 512 = CTA-pair tiles of 256 x 256 (tcgen05
+  // cta_group::2, gemm2_tcgen05.cu) -- the default whenever N and the segments are multiples of 256; 515 = pair tiles in
+  // clusters of two pairs sharing A by TMA multicast (default for long-K, narrow-N problems: FFN2).
+  if (block_n == 0 && N % 256 == 0 && seg_cols % 256 == 0 && M > 128 && epilogue != EPI_F32)
+    block_n = (K >= 4096 && N <= 2048 && M >= 2048) ? 515 : 512;
   if (block_n == 0) {
-    // Tile choice: wide tiles amortise smem traffic; narrow problems take 128 so the tile count
-    // fills the 148 SMs (M=4680: N=1536 -> 37x12 = 444 = 3 waves of 148).
+    // narrow problems take 128-wide tiles so the tile count fills the SMs
     block_n = (N % 256 == 0 && N >= 4096) ? 256 : (N % 128 == 0 ? 128 : 64);
   }
-  // 1192 / 1256: one-CTA 128 x 192 / 128 x 256 tiles with the staged TMA-store epilogue (gemm1s_tcgen05.cu; explicit
-  // request only, pending hardware validation)
-  const bool staged = block_n == 1192 || block_n == 1256;
-  if (staged) {
-    block_n -= 1000;
-    if (epilogue == EPI_F32 || N % block_n || seg_cols % block_n) {
-      set_error("sfb_gemm_bf16: staged one-CTA tiles need N and seg_cols to be multiples of %d and a bf16 epilogue", block_n);
-      return SFB_ERR_INVALID;
-    }
-  }
-  const bool pair = block_n == 512 || block_n == 513;   // 513: pair tiles with the stream-K schedule forced on
-  const bool force_streamk = block_n == 513;
+  const int cluster_pairs = block_n == 512 ? 1 : (block_n == 515 ? 2 : 0);
+  const bool pair = cluster_pairs != 0;
   if (pair) block_n = 256;
-  if (block_n != 64 && block_n != 128 && block_n != 192 && block_n != 256) { set_error("sfb_gemm_bf16: block_n must be 64/128/192/256/512"); return SFB_ERR_INVALID; }
+  if (block_n != 64 && block_n != 128 && block_n != 256) { set_error("sfb_gemm_bf16: block_n must be 0/64/128/256/512/515"); return SFB_ERR_INVALID; }
   if (epilogue == EPI_F32 && (pair || seg_cols != N)) { set_error("sfb_gemm_bf16: the fp32-output epilogue takes one-CTA tiles and one output segment"); return SFB_ERR_INVALID; }
+  if (pair && (N % 256 || seg_cols % 256)) { set_error("sfb_gemm_bf16: pair tiles need N and seg_cols to be multiples of 256"); return SFB_ERR_INVALID; }
   if (seg_cols % block_n && seg_cols != N) { set_error("sfb_gemm_bf16: seg_cols=%d not a multiple of the N tile %d", seg_cols, block_n); return SFB_ERR_INVALID; }
   if ((epilogue == EPI_RESIDUAL || epilogue == EPI_GATE_RES) && residual == nullptr) { set_error("sfb_gemm_bf16: residual epilogue without residual"); return SFB_ERR_INVALID; }
   if (epilogue == EPI_GATE_RES && (gate == nullptr || rows_per_gate <= 0)) { set_error("sfb_gemm_bf16: gate epilogue without gate"); return SFB_ERR_INVALID; }
@@ -269,22 +252,14 @@ extern "C" int sfb_gemm_bf16(const void* x, long long ldx, const void* w, long l
   }
   const int sms = device_sm_count();
   if (sms <= 0) return SFB_ERR_CUDA;
-  if (staged) return launch_gemm_single_staged(epilogue, block_n, ta, tb, p, sms, stream);
-  if (pair) {
-    gemm_pair_workspace(workspace, workspace_bytes, p);
-    p.streamk = force_streamk ? 1 : 0;   // request; launch_gemm_pair decides
-    return launch_gemm_pair(epilogue, ta, tb, p, sms, stream);
-  }
+  if (pair) return launch_gemm_cluster(epilogue, cluster_pairs, x, ldx, tb, p, sms, stream);
   switch (block_n) {
     case 64: return dispatch_epi<64>(epilogue, ta, tb, p, sms, stream);
     case 128: return dispatch_epi<128>(epilogue, ta, tb, p, sms, stream);
-    // 128 x 192 tiles: 4680 x 1536 outputs = 37 x 8 = 296 tiles = exactly two waves of 148 SMs.  Explicit request only
-    // (block_n = 192) until it has been measured against the CTA-pair tiles on the K = 8960 FFN2 shape.
-    case 192: return dispatch_epi<192>(epilogue, ta, tb, p, sms, stream);
     default: return dispatch_epi<256>(epilogue, ta, tb, p, sms, stream);
   }
 }
 
-// Scratch (bytes) the CTA-pair GEMM uses for stream-K partial tiles; zero-initialise it once.  One launch at a time
-// may use a given workspace (launches on one stream are fine).
-extern "C" long long sfb_gemm_workspace_bytes(void) { return sfb::gemm_pair_workspace_bytes(); }
+// Kept for ABI stability: the GEMM needs no scratch any more (the stream-K schedule that used it was measured and
+// removed, see gemm2_tcgen05.cu); `workspace` / `workspace_bytes` of sfb_gemm_bf16 are ignored.
+extern "C" long long sfb_gemm_workspace_bytes(void) { return 0; }

@@ -58,7 +58,6 @@ class CudaOps:
         self._prof = None
         self._prof_only = None
         self._attn_ws = {}    # device index -> uint8 scratch for the split-KV attention schedule
-        self._gemm_ws = {}    # device index -> zero-initialised scratch for the stream-K GEMM schedule
         self._conv_ws = {}    # device index -> staging buffer of the VAE convolutions' gathered operand
         self.conv_workspace_bytes = 1 << 30
 
@@ -115,17 +114,12 @@ class CudaOps:
             segs.append(None)
         if residual is not None:
             _check_2d(residual, "residual")
-        ws = self._gemm_ws.get(x.device.index)
-        if ws is None:
-            with torch.cuda.device(x.device):
-                ws = torch.zeros(int(self.lib.sfb_gemm_workspace_bytes()), dtype=torch.uint8, device=x.device)
-            self._gemm_ws[x.device.index] = ws
         _lib.check(self.lib.sfb_gemm_bf16(
             x.data_ptr(), x.stride(0), w.data_ptr(), w.stride(0), _ptr(bias), M, N, K, epilogue,
             _ptr(segs[0]), segs[0].stride(0), _ptr(segs[1]), segs[1].stride(0) if segs[1] is not None else 0,
             _ptr(segs[2]), segs[2].stride(0) if segs[2] is not None else 0, seg_cols,
             _ptr(residual), residual.stride(0) if residual is not None else 0,
-            _ptr(gate), gate_stride, rows_per_gate, gate_row_offset, block_n, ws.data_ptr(), ws.numel(),
+            _ptr(gate), gate_stride, rows_per_gate, gate_row_offset, block_n, 0, 0,
             self._stream()), "sfb_gemm_bf16")
 
     # -- attention ------------------------------------------------------------------------

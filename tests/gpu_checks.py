@@ -85,7 +85,7 @@ def check_gemm(M=300, N=256, K=192, epilogue=0, block_n=0, rows_per_gate=100, se
     return _finish(f"gemm M{M} N{N} K{K} epi{epilogue} bn{block_n}", m, 3e-3)
 
 
-def check_gemm_segments(M=300, C=256, K=128, seed=0):
+def check_gemm_segments(M=300, C=256, K=128, seed=0, block_n=0):
     """QKV-style call: one GEMM, three destinations with different row strides (V into a cache slot)."""
     ops = _ops()
     x = _randn(M, K, seed=seed)
@@ -94,7 +94,7 @@ def check_gemm_segments(M=300, C=256, K=128, seed=0):
     q = torch.zeros(M, C, device="cuda", dtype=BF)
     k = torch.zeros(M, C + 64, device="cuda", dtype=BF)[:, :C]
     cache = torch.zeros(M + 50, C, device="cuda", dtype=BF)
-    ops.gemm(x, w, b, None, outs=[q, k, cache[20:20 + M]], seg_cols=C)
+    ops.gemm(x, w, b, None, outs=[q, k, cache[20:20 + M]], seg_cols=C, block_n=block_n)
     ref = (x.float() @ w.float().t() + b.float()).to(BF)
     m = dict(err_q=rel_l2(q, ref[:, :C]), err_k=rel_l2(k, ref[:, C:2 * C]), err_v=rel_l2(cache[20:20 + M], ref[:, 2 * C:]),
              err_untouched=float(cache[:20].float().abs().max() + cache[20 + M:].float().abs().max()))
@@ -660,20 +660,25 @@ def check_t5_encoder():
 # Checks of code paths that exist but have not yet been measured / validated on hardware: NOT part of the pytest suite;
 # run them with `python tools/gpu_report.py --pending` and move them into ALL once green.
 PENDING = {
-    "gemm_bn192_ffn2": lambda: check_gemm(M=4680, N=1536, K=8960, epilogue=3, rows_per_gate=1560, block_n=192, seed=31),
-    "gemm_bn192_tail": lambda: check_gemm(M=300, N=384, K=200, epilogue=2, block_n=192, seed=32),
-    "gemm_1s192_ffn2": lambda: check_gemm(M=4680, N=1536, K=8960, epilogue=3, rows_per_gate=1560, block_n=1192, seed=34),
-    "gemm_1s192_o_proj": lambda: check_gemm(M=4680, N=1536, K=1536, epilogue=3, rows_per_gate=1560, block_n=1192, seed=35),
-    "gemm_1s192_tail_residual": lambda: check_gemm(M=300, N=384, K=200, epilogue=2, block_n=1192, seed=36),
-    "gemm_1s256_gelu": lambda: check_gemm(M=700, N=512, K=320, epilogue=1, block_n=1256, seed=37),
-    "gemm_1s256_qkv": lambda: check_gemm(M=4680, N=4608, K=1536, block_n=1256, seed=38),
-    # SFB_CONV_EXACT_N is read once per process, and tools/gpu_report.py runs every check in its own process
-    "conv3d_implicit_exact_n192": lambda: (os.environ.__setitem__("SFB_CONV_EXACT_N", "1"),
-                                           check_causal_conv3d(t_in=4, H=24, W=40, Cin=192, Cout=192, pad=0, residual=True,
-                                                               implicit=True, seed=33))[1],
 }
 
 ALL = {
+    # CTA-pair kernel (gemm2_tcgen05.cu): 512 = one pair per cluster, 515 = two pairs sharing A by TMA multicast
+    **{f"gemm_c{np_}_{name}": (lambda kw=kw, np_=np_: check_gemm(block_n=(512, 515)[np_ - 1], **kw)) for np_ in (1, 2) for name, kw in {
+        "small": dict(M=300, N=512, K=192, seed=40),
+        "tail": dict(M=130, N=256, K=64, seed=41),
+        "one_cta_empty_residual": dict(M=700, N=256, K=1536, epilogue=2, seed=42),
+        "odd_n_blocks_gelu": dict(M=515, N=768, K=320, epilogue=1, seed=43),
+        "gate_two_vectors": dict(M=1000, N=768, K=320, epilogue=3, rows_per_gate=100, seed=44),
+        "gate_many_vectors": dict(M=1000, N=512, K=320, epilogue=3, rows_per_gate=30, gate_row_offset=77, seed=45),
+        "qkv_full": dict(M=4680, N=4608, K=1536, seed=46),
+        "o_proj_full": dict(M=4680, N=1536, K=1536, epilogue=3, rows_per_gate=1560, seed=47),
+        "ffn1_full": dict(M=4680, N=8960, K=1536, epilogue=1, seed=48),
+        "ffn2_full": dict(M=4680, N=1536, K=8960, epilogue=3, rows_per_gate=1560, seed=49),
+        "persistent_many_tiles": dict(M=4680, N=8960, K=256, epilogue=2, seed=50),
+    }.items()},
+    "gemm_c1_segments": lambda: check_gemm_segments(block_n=512, seed=51),
+    "gemm_c2_segments": lambda: check_gemm_segments(M=700, C=512, K=256, block_n=515, seed=52),
     "gemm_small": lambda: check_gemm(),
     "gemm_bn64": lambda: check_gemm(M=200, N=64, K=1536, block_n=64),
     "gemm_bn128": lambda: check_gemm(M=300, N=384, K=256, block_n=128),
@@ -720,10 +725,6 @@ ALL = {
     "ln_row_offset": check_ln_row_offset,
     "ln_row_offset_c5120": lambda: check_ln_row_offset(rows=200, C=5120, seed=3),
     "qk_norm_rope_c5120": lambda: check_qk_norm_rope(B=1, F_=2, Hh=4, Ww=6, C=5120, start_frame=0, seed=4),
-    "gemm_streamk_o_proj": lambda: check_gemm(M=4680, N=1536, K=1536, epilogue=3, rows_per_gate=1560, seed=11, block_n=513),
-    "gemm_streamk_qkv": lambda: check_gemm(M=4680, N=4608, K=1536, seed=12, block_n=513),
-    "gemm_streamk_cross_o": lambda: check_gemm(M=4680, N=1536, K=1536, epilogue=2, seed=13, block_n=513),
-    "gemm_streamk_repeat": lambda: [check_gemm(M=4680, N=1536, K=8960, epilogue=3, rows_per_gate=1560, seed=14 + i, block_n=513) for i in range(3)][-1],
     "gemm_gate_row_offset": lambda: check_gemm(M=700, N=512, K=256, epilogue=3, rows_per_gate=130, block_n=512, gate_row_offset=77),
     "gemm_gate_row_offset_1cta": lambda: check_gemm(M=300, N=384, K=256, epilogue=3, rows_per_gate=70, block_n=128, gate_row_offset=33),
     "patchify": check_patchify,
@@ -769,6 +770,8 @@ ALL = {
     "vae_pixel_out": check_vae_pixel_out,
     "vae_decoder_gather": check_vae_decoder,
     "model_forward": check_model_forward,
+    "conv3d_implicit_n192": lambda: check_causal_conv3d(t_in=4, H=24, W=40, Cin=192, Cout=192, pad=0, residual=True,
+                                                        implicit=True, seed=33),
     # UMT5 text encoder (validated on B200 in round 2: profiles/r02a_pending_report.json)
     "t5_rmsnorm_c4096": check_t5_rmsnorm,
     "t5_rmsnorm_c256": lambda: check_t5_rmsnorm(rows=77, C=256, seed=3),

@@ -40,13 +40,11 @@ def main():
     out = []
     only = sys.argv[1:]
     M = 4680
+    # (name, N, K, epilogue, block_n): 0 = the dispatcher's choice, 512 / 515 = pair tiles with 1 / 2 pairs per cluster
     gemms = [("qkv", 4608, 1536, 0, 0), ("qkv_1cta256", 4608, 1536, 0, 256), ("o_proj", 1536, 1536, 3, 0),
-             ("o_proj_1cta128", 1536, 1536, 3, 128), ("ffn1", 8960, 1536, 1, 0), ("ffn1_1cta256", 8960, 1536, 1, 256),
-             ("ffn2", 1536, 8960, 3, 0), ("ffn2_1cta128", 1536, 8960, 3, 128), ("head", 64, 1536, 0, 0),
-             ("o_proj_1cta192", 1536, 1536, 3, 192), ("ffn2_1cta192", 1536, 8960, 3, 192),
-             ("o_proj_1s192", 1536, 1536, 3, 1192), ("ffn2_1s192", 1536, 8960, 3, 1192), ("cross_o_1s192", 1536, 1536, 2, 1192),
-             ("qkv_1s256", 4608, 1536, 0, 1256), ("ffn1_1s256", 8960, 1536, 1, 1256),
-             ("qkv_streamk", 4608, 1536, 0, 513), ("o_proj_streamk", 1536, 1536, 3, 513), ("ffn2_streamk", 1536, 8960, 3, 513)]
+             ("o_proj_1cta128", 1536, 1536, 3, 128), ("cross_q", 1536, 1536, 0, 0), ("cross_o", 1536, 1536, 2, 0),
+             ("ffn1", 8960, 1536, 1, 0), ("ffn2", 1536, 8960, 3, 0), ("ffn2_np1", 1536, 8960, 3, 512),
+             ("ffn2_np2", 1536, 8960, 3, 515), ("head", 64, 1536, 0, 0)]
     for name, N, K, epi, bn in gemms:
         if only and not any(o in "gemm_" + name for o in only):
             continue
