@@ -19,7 +19,9 @@ One JSON line on stdout (rank 0).  Keys follow the driver contract:
   clocks       nvidia-smi samples taken during the timed region
   vae_decode   extra, outside `value`: the rollout's latents decoded to pixels by the B200 VAE decoder (N = 1)
   gpu_eager_baseline  extra: the oracle run in PyTorch eager mode on the same GPU (cuBLAS + SDPA), the "beat this"
-               number of SURVEY.md section 8d (N = 1)
+               number of SURVEY.md section 8d (N = 1); carries parity_vs_product (latents rel-L2 of the product's rollout)
+  ulysses      extra (N > 1): the same video made by head-parallel groups of 4 / 2 GPUs (strong scaling), with the
+               algorithmic all-to-all volume and the NVLink Tx counter of rank 0
 N > 1 is data parallel over prompts (one rollout per rank per step, no data-path collective).
 """
 from __future__ import annotations
@@ -460,6 +462,12 @@ def run_product_arm(args) -> None:
         dist.destroy_process_group()
         watchdog.cancel()
 
+    ulysses = None
+    if world > 1 and args.mode == "dp" and not args.no_ulysses_leg and world % 2 == 0:
+        try:
+            ulysses = ulysses_leg(args, world, rank, local, dev, ops, cf, ms_total / args.steps)
+        except Exception as e:      # the headline line must survive a failure of the extra leg
+            ulysses = {"error": f"{type(e).__name__}: {e}"[:300]}
     if world > 1:
         dist.barrier()
     if rank != 0:
@@ -545,6 +553,8 @@ def run_product_arm(args) -> None:
         "breakdown": breakdown, "gemm_shapes": gemm_shapes, "kernel_ms_per_step": kernel_ms, "finite": finite,
         "clocks": clk,
     }
+    if ulysses is not None:
+        line["ulysses"] = ulysses
     if world == 1 and not args.no_vae:
         # SURVEY.md section 8f rank 1, reported beside the headline (NOT part of `value`, whose metric excludes T5 and
         # the VAE): decode of this rollout's latents to 81 frames 480x832 through B200VAEWrapper (random-init decoder)
@@ -573,6 +583,80 @@ def run_product_arm(args) -> None:
         json.dump(line, f, indent=1)
     print(json.dumps(line), flush=True)
     shutdown()
+
+
+def nvlink_tx_kib(gpu_index: int):
+    """Sum of the NVLink data Tx counters (KiB) of one GPU from `nvidia-smi nvlink -gt d`, or None."""
+    try:
+        r = subprocess.run(["nvidia-smi", "nvlink", "-gt", "d", "-i", str(gpu_index)], capture_output=True, text=True, timeout=20)
+        tot, seen = 0, False
+        for ln in r.stdout.splitlines():
+            if "Data Tx" in ln:
+                seen = True
+                tot += int(ln.split(":")[-1].strip().split()[0])
+        return tot if seen else None
+    except Exception:
+        return None
+
+
+def ulysses_leg(args, world: int, rank: int, local: int, dev, ops, cf: int, dp_ms_per_video: float):
+    """Strong-scaling mode of SURVEY.md 8e, measured in the same run as the data-parallel line so the driver's SCALE record
+    carries it: ranks form head-parallel groups of P = 4 (or 2) GPUs that make ONE video together (peer-memory
+    all-to-all inside qk_norm_rope_sp / attention_fwd_sp); groups are data parallel.  Every rank takes part; rank 0
+    returns the record."""
+    import torch
+    import torch.distributed as dist
+    from self_forcing_b200.pipeline import CausalInferencePipeline
+    from self_forcing_b200.ulysses import UlyssesGroup
+    from self_forcing_b200.wrapper import WAN_T2V_1_3B, B200DiffusionWrapper
+    P = next(p for p in (4, 2) if world % p == 0)
+    groups = [dist.new_group(list(range(g0, g0 + P))) for g0 in range(0, world, P)]
+    video = rank // P
+    gen = B200DiffusionWrapper(model_config=dict(WAN_T2V_1_3B), timestep_shift=SHIFT, device=dev, init_seed=0, ops=ops)
+    gen.model.enable_ulysses(UlyssesGroup(groups[video], device=dev))
+    pe = torch.randn(1, T_CTX, 4096, generator=torch.Generator().manual_seed(1 + video)).to(torch.bfloat16).to(dev)
+    noise = torch.randn(1, LAT_FRAMES, 16, LAT_H, LAT_W, generator=torch.Generator().manual_seed(2 + video)).to(torch.bfloat16).to(dev)
+    pargs = types.SimpleNamespace(denoising_step_list=DENOISE_STEPS, warp_denoising_step=True, num_frame_per_block=cf,
+                                  independent_first_frame=False, context_noise=0, model_kwargs={}, skip_refresh_tail=False)
+    pipe = CausalInferencePipeline(pargs, dev, generator=gen, text_encoder=lambda text_prompts: {"prompt_embeds": pe}, vae=_NoVAE())
+    torch.manual_seed(99 + video)       # identical re-noise stream on the ranks of one video
+    for _ in range(3):                  # eager, capture, first replay
+        pipe.inference(noise, ["synthetic"], return_latents=True)
+    torch.cuda.synchronize()
+    dist.barrier()
+    tx0 = nvlink_tx_kib(local) if rank == 0 else None
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        _, lat = pipe.inference(noise, ["synthetic"], return_latents=True)
+    e1.record()
+    torch.cuda.synchronize()
+    dist.barrier()
+    tx1 = nvlink_tx_kib(local) if rank == 0 else None
+    t = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_video = float(t.item()) / args.steps
+    finite = bool(torch.isfinite(lat.float()).all().item())
+    gen.model._graphs.clear()
+    del pipe, gen
+    torch.cuda.empty_cache()
+    if rank != 0:
+        return None
+    L = cf * FRAME_TOKENS
+    forwards = (LAT_FRAMES // cf) * 5
+    a2a = 4.0 * (P - 1) / P * (L / P) * C * 2          # q, k, v out + attention output back, bytes per rank per layer
+    rec = {"parallelism": f"dp{world // P} x ulysses{P}", "group_size": P, "videos_in_flight": world // P,
+           "ms_per_video": ms_video, "frames_per_s_per_video": PIX_FRAMES / (ms_video / 1e3),
+           "frames_per_s_total": PIX_FRAMES * (world // P) / (ms_video / 1e3),
+           "speedup_vs_one_gpu_in_this_run": dp_ms_per_video / ms_video, "strong_scaling_efficiency": dp_ms_per_video / ms_video / P,
+           "a2a_bytes_per_rank_per_layer_algorithmic": a2a, "a2a_bytes_per_rank_per_video_algorithmic": a2a * NL * forwards,
+           "finite": finite, "steps": args.steps,
+           "note": "the two all-to-alls per block are st.global on peer-mapped pointers inside the producing kernels, separated by "
+                   "flag barriers in peer memory; NCCL only all-gathers the [L/P, 64] head output once per forward"}
+    if tx0 is not None and tx1 is not None:
+        rec["nvlink_tx_bytes_per_video_rank0"] = (tx1 - tx0) * 1024.0 / args.steps
+        rec["nvlink_tx_vs_algorithmic"] = rec["nvlink_tx_bytes_per_video_rank0"] / (a2a * NL * forwards)
+    return rec
 
 
 def gpu_eager_leg(gen, chunk_frames: int, pe_dev, noise_dev, product_fps: float, product_rollout=None) -> dict:
@@ -663,6 +747,7 @@ def main():
                     help="skip the unused tail of the clean-context refresh pass (NOT the default: changes the work)")
     ap.add_argument("--no-cuda-graphs", action="store_true", help="launch every kernel eagerly instead of replaying graphs")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-ulysses-leg", action="store_true", help="N > 1: skip the head-parallel (one video per 4 / 2 GPUs) sub-record")
     ap.add_argument("--ncu-rollout", action="store_true", help="run exactly one rollout (the command captured by ncu)")
     ap.add_argument("--cpu-seconds", type=float, default=15.0, help="CPU-oracle sample budget (seconds)")
     args = ap.parse_args()

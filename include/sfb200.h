@@ -92,11 +92,14 @@ int sfb_rmsnorm(const void* x, long long ldx, void* y, long long ldy, int rows, 
 /* Fused QK-RMSNorm + 3-D RoPE + KV-cache append (model.py:70-86, causal_model.py:28-56,196-200,
  * 222-229).  q_in/k_in/v_in: [B*L, C] projections.  RoPE tables cos/sin: fp32 [tab_rows, head_dim/2]
  * (columns = frame | height | width ladders).  q -> q_out[b][n], k/v -> k_out/v_out[b][n] where the
- * caller has already offset k_out/v_out to the cache write slot.  v_in == NULL skips the V copy. */
+ * caller has already offset k_out/v_out to the cache write slot.  v_in == NULL skips the V copy.
+ * start_frame_dev != NULL: the chunk's frame offset is read from that device int at run time instead of start_frame
+ * (one captured CUDA graph then serves every chunk of a rolling-window video; the caller keeps start_frame + F within
+ * the table). */
 int sfb_qk_norm_rope(const void* q_in, long long ldq, const void* k_in, long long ldk, const void* v_in, long long ldv,
                      const void* wq, const void* wk, float eps, const float* cos_tab, const float* sin_tab,
                      int tab_rows, int B, int L, int C, int head_dim, int F, int Hh, int Ww, int start_frame,
-                     void* q_out, long long q_out_row, long long q_out_batch,
+                     const int* start_frame_dev, void* q_out, long long q_out_row, long long q_out_batch,
                      void* k_out, void* v_out, long long kv_out_row, long long kv_out_batch, void* stream);
 
 /* ---- Ulysses head-parallel attention for one long video (wan/distributed/xdit_context_parallel.py:66-192) ----
@@ -125,6 +128,13 @@ int sfb_attention_fwd_sp(const void* q, long long q_row_stride, const void* k, c
  * mapped here (slot [n] = the rank's own call counter, advanced by the kernel, so the launch is CUDA-graph
  * replayable); every rank must call it the same number of times. */
 int sfb_peer_barrier(void* const* flag_ptrs, int rank, int n, void* stream);
+
+/* Rolling-window eviction of the KV cache (reference wan/modules/causal_model.py:212-221: the kept rows after the sink
+ * are shifted left by the number of evicted tokens -- `cache[:, sink:sink+keep] = cache[:, sink+ev:...].clone()`), for
+ * all layers' K and V tensors at once.  tensors_dev: DEVICE array of n_tensors pointers to [batch, rows, row_bytes]
+ * caches of identical geometry.  Rows [src_row, src_row + n_rows) move to [dst_row, ...), dst_row < src_row. */
+int sfb_kv_roll(const void* const* tensors_dev, int n_tensors, int batch, long long batch_stride_bytes,
+                long long row_bytes, long long dst_row, long long src_row, long long n_rows, void* stream);
 
 /* im2col of Conv3d(k = s = (1,2,2)) (causal_model.py:775-778): x[b][c][f][y][x] with element strides
  * -> out[(b,f,y/2,x/2)][c*4 + (y%2)*2 + x%2]. */

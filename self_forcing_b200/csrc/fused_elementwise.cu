@@ -7,6 +7,7 @@
 //   sfb_qk_norm_rope       RMSNorm(q|k) -> 3-D RoPE -> q buffer / KV-cache slot (+ V copy)
 //                                                               model.py:70-86, causal_model.py:28-56,222-229
 //   sfb_rmsnorm            RMSNorm (cross-attention q / context k)   model.py:172,177
+//   sfb_kv_roll            rolling-window eviction: shift the kept K/V rows left past the sink   causal_model.py:212-221
 //   sfb_patchify           Conv3d(k=s=(1,2,2)) im2col gather    causal_model.py:775-778
 //   sfb_sinusoid           timestep sinusoid table (f64)        model.py:15-25
 //   sfb_skinny_linear      few-row Linear (+SiLU) for the time MLPs   causal_model.py:464-467
@@ -19,6 +20,8 @@
 #include "common.cuh"
 
 namespace sfb {
+
+int device_sm_count();
 
 __device__ __forceinline__ uint4 ldg16(const void* p) { return __ldg(reinterpret_cast<const uint4*>(p)); }
 __device__ __forceinline__ void unpack8(const uint4& q, float (&f)[8]) {
@@ -151,6 +154,7 @@ struct RopeGeom {
   int L;            // tokens per sample in this call
   int Hh, Ww;       // token grid (height, width) of one frame
   int start_frame;  // frame offset of the chunk (current_start // (Hh*Ww))
+  const int* start_frame_dev;   // if set, the frame offset is read from device memory instead (CUDA-graph replay across chunks)
   int n_f, n_h;     // complex pairs on the frame / height axes (22, 21 for d=128); rest is width
 };
 
@@ -205,7 +209,9 @@ rmsnorm_kernel(const __nv_bfloat16* __restrict__ x, long long ldx, __nv_bfloat16
 
 // One warp per token: q and k rows normalised + rotated; q -> q_out, k -> cache slot, v -> cache slot.
 // Rows are (sample b, token n): source row = b * L + n; destinations use their own batch strides.
-template <int NV>
+// SCATTER = false: one destination (single GPU) -- no dynamic indexing of the destination table (which costs a local
+// copy of the parameter arrays and, under the 64-register cap, spills).
+template <int NV, bool SCATTER>
 __global__ void __launch_bounds__(ROW_WARPS * 32, row_kernel_blocks(NV))
 qk_norm_rope_kernel(const __nv_bfloat16* __restrict__ q_in, long long ldq, const __nv_bfloat16* __restrict__ k_in,
                     long long ldk, const __nv_bfloat16* __restrict__ v_in, long long ldv,
@@ -221,7 +227,20 @@ qk_norm_rope_kernel(const __nv_bfloat16* __restrict__ q_in, long long ldq, const
   const int f = n / fhw, rem = n - f * fhw;
   const int hh = rem / g.Ww, ww = rem - hh * g.Ww;
   const int half = head_dim / 2;
-  const int pos_f = g.start_frame + f;
+  const int pos_f = (g.start_frame_dev != nullptr ? __ldg(g.start_frame_dev) : g.start_frame) + f;
+
+  // A lane's 16-byte vectors all start at column (k * 32 + lane) * 8, i.e. at complex pair (lane % 16) * 4 of their head
+  // whenever head_dim is 128: the 4 (cos, sin) pairs of this token are the same for every vector of q and of k, so
+  // they are fetched once (8 scalar loads instead of 96 per lane -- the table lookups were most of the LSU work).
+  const bool fixed_pairs = head_dim == 128;
+  float cs4[4], sn4[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int pi = (lane & 15) * 4 + i;
+    const int pos = pi < g.n_f ? pos_f : (pi < g.n_f + g.n_h ? hh : ww);
+    cs4[i] = fixed_pairs ? __ldg(cos_tab + pos * half + pi) : 0.f;
+    sn4[i] = fixed_pairs ? __ldg(sin_tab + pos * half + pi) : 0.f;
+  }
 
   // q then k: load the row (packed), full-width RMS statistics, then per 16-byte vector: normalise, rotate the 4
   // complex pairs by the (frame | height | width) angles of this token, store to the vector's head-group destination
@@ -240,14 +259,19 @@ qk_norm_rope_kernel(const __nv_bfloat16* __restrict__ q_in, long long ldq, const
       rms_apply<NV>(raw[k], wgt, rstd, k, lane, v);
 #pragma unroll
       for (int i = 0; i < 4; ++i) {
-        const int pi = pair0 + i;
-        const int pos = pi < g.n_f ? pos_f : (pi < g.n_f + g.n_h ? hh : ww);
-        const float cs = __ldg(cos_tab + pos * half + pi), sn = __ldg(sin_tab + pos * half + pi);
+        float cs = cs4[i], sn = sn4[i];
+        if (!fixed_pairs) {
+          const int pi = pair0 + i;
+          const int pos = pi < g.n_f ? pos_f : (pi < g.n_f + g.n_h ? hh : ww);
+          cs = __ldg(cos_tab + pos * half + pi);
+          sn = __ldg(sin_tab + pos * half + pi);
+        }
         o[2 * i] = v[2 * i] * cs - v[2 * i + 1] * sn;
         o[2 * i + 1] = v[2 * i] * sn + v[2 * i + 1] * cs;
       }
-      const int grp = hs.groups == 1 ? 0 : c0 / hs.group_cols;
-      __nv_bfloat16* dst = (which == 0 ? hs.q[grp] : hs.k[grp]) + off + (c0 - grp * hs.group_cols);
+      const int grp = SCATTER ? c0 / hs.group_cols : 0;
+      __nv_bfloat16* dst = (SCATTER ? (which == 0 ? hs.q[grp] : hs.k[grp]) : (which == 0 ? hs.q[0] : hs.k[0])) + off +
+                           (c0 - grp * hs.group_cols);
       *reinterpret_cast<uint4*>(dst) = pack8(o);
     }
   }
@@ -256,10 +280,30 @@ qk_norm_rope_kernel(const __nv_bfloat16* __restrict__ q_in, long long ldq, const
 #pragma unroll
     for (int k = 0; k < NV; ++k) {
       const int c0 = (k * 32 + lane) * 8;
-      const int grp = hs.groups == 1 ? 0 : c0 / hs.group_cols;
-      *reinterpret_cast<uint4*>(hs.v[grp] + kv_off + (c0 - grp * hs.group_cols)) = ldg16(v_in + row * ldv + c0);
+      const int grp = SCATTER ? c0 / hs.group_cols : 0;
+      *reinterpret_cast<uint4*>((SCATTER ? hs.v[grp] : hs.v[0]) + kv_off + (c0 - grp * hs.group_cols)) = ldg16(v_in + row * ldv + c0);
     }
   }
+}
+
+// ------------------------------------------------------------------------------------
+// KV-cache roll (reference causal_model.py:212-221: `cache[:, sink:sink+keep] = cache[:, sink+ev:sink+ev+keep].clone()`)
+// for ALL layers' K and V tensors in one launch per phase: rows [dst, dst + n) <- rows [dst + shift, dst + shift + n),
+// n <= shift, so source and destination never overlap inside a launch; the host walks the kept range front to back.
+// A token row of every (tensor, batch) is contiguous, so each (tensor, batch) moves one contiguous span of bytes.
+// ------------------------------------------------------------------------------------
+__global__ void kv_roll_kernel(const uint4* const* __restrict__ tensors, long long batch_stride_v, long long dst_v,
+                               long long shift_v, long long n_v) {
+  uint4* base = const_cast<uint4*>(tensors[blockIdx.y]) + blockIdx.z * batch_stride_v + dst_v;
+  const uint4* src = base + shift_v;
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  // four independent 16-byte loads in flight per thread
+  for (; i + 3 * stride < n_v; i += 4 * stride) {
+    const uint4 a = __ldcs(src + i), b = __ldcs(src + i + stride), c = __ldcs(src + i + 2 * stride), d = __ldcs(src + i + 3 * stride);
+    base[i] = a; base[i + stride] = b; base[i + 2 * stride] = c; base[i + 3 * stride] = d;
+  }
+  for (; i < n_v; i += stride) base[i] = __ldcs(src + i);
 }
 
 // ------------------------------------------------------------------------------------
@@ -510,14 +554,15 @@ extern "C" int sfb_rmsnorm(const void* x, long long ldx, void* y, long long ldy,
 extern "C" int sfb_qk_norm_rope(const void* q_in, long long ldq, const void* k_in, long long ldk, const void* v_in,
                                 long long ldv, const void* wq, const void* wk, float eps, const float* cos_tab,
                                 const float* sin_tab, int tab_rows, int B, int L, int C, int head_dim, int F, int Hh,
-                                int Ww, int start_frame, void* q_out, long long q_out_row, long long q_out_batch,
-                                void* k_out, void* v_out, long long kv_out_row, long long kv_out_batch, void* stream) {
+                                int Ww, int start_frame, const int* start_frame_dev, void* q_out, long long q_out_row,
+                                long long q_out_batch, void* k_out, void* v_out, long long kv_out_row,
+                                long long kv_out_batch, void* stream) {
   if (B <= 0 || L <= 0 || L != F * Hh * Ww) { set_error("sfb_qk_norm_rope: L=%d != F*H*W=%d*%d*%d", L, F, Hh, Ww); return SFB_ERR_INVALID; }
   if (head_dim % 16 || C % head_dim) { set_error("sfb_qk_norm_rope: bad head_dim %d for C=%d", head_dim, C); return SFB_ERR_INVALID; }
   if (start_frame < 0 || start_frame + F > tab_rows || Hh > tab_rows || Ww > tab_rows) { set_error("sfb_qk_norm_rope: position beyond the %d-row RoPE table (start_frame=%d F=%d)", tab_rows, start_frame, F); return SFB_ERR_INVALID; }
   if ((ldq % 8) || (ldk % 8) || (ldv % 8) || (q_out_row % 8) || (kv_out_row % 8) || (q_out_batch % 8) || (kv_out_batch % 8)) { set_error("sfb_qk_norm_rope: strides must be multiples of 8"); return SFB_ERR_INVALID; }
   RopeGeom g;
-  g.L = L; g.Hh = Hh; g.Ww = Ww; g.start_frame = start_frame;
+  g.L = L; g.Hh = Hh; g.Ww = Ww; g.start_frame = start_frame; g.start_frame_dev = start_frame_dev;
   const int c = head_dim / 2;
   g.n_f = c - 2 * (c / 3);
   g.n_h = c / 3;
@@ -526,7 +571,7 @@ extern "C" int sfb_qk_norm_rope(const void* q_in, long long ldq, const void* k_i
   hs.q[0] = (bf16*)q_out; hs.k[0] = (bf16*)k_out; hs.v[0] = (bf16*)v_out;
   hs.groups = 1; hs.group_cols = C; hs.token_offset = 0;
   return dispatch_nv(C, "sfb_qk_norm_rope", [&](auto nv) {
-    qk_norm_rope_kernel<decltype(nv)::value><<<(rows + ROW_WARPS - 1) / ROW_WARPS, ROW_WARPS * 32, 0, (cudaStream_t)stream>>>(
+    qk_norm_rope_kernel<decltype(nv)::value, false><<<(rows + ROW_WARPS - 1) / ROW_WARPS, ROW_WARPS * 32, 0, (cudaStream_t)stream>>>(
         (const bf16*)q_in, ldq, (const bf16*)k_in, ldk, (const bf16*)v_in, ldv, (const bf16*)wq, (const bf16*)wk, eps,
         cos_tab, sin_tab, head_dim, g, rows, hs, q_out_row, q_out_batch, kv_out_row, kv_out_batch);
     return check_cuda(cudaGetLastError(), "qk_norm_rope launch");
@@ -549,7 +594,7 @@ extern "C" int sfb_qk_norm_rope_sp(const void* q_in, long long ldq, const void* 
   if (start_frame < 0 || start_frame + F > tab_rows || Hh > tab_rows || Ww > tab_rows) { set_error("sfb_qk_norm_rope_sp: position beyond the %d-row RoPE table", tab_rows); return SFB_ERR_INVALID; }
   if ((ldq % 8) || (ldk % 8) || (ldv % 8) || (q_dst_row % 8) || (kv_dst_row % 8)) { set_error("sfb_qk_norm_rope_sp: strides must be multiples of 8"); return SFB_ERR_INVALID; }
   RopeGeom g;
-  g.L = F * Hh * Ww; g.Hh = Hh; g.Ww = Ww; g.start_frame = start_frame;
+  g.L = F * Hh * Ww; g.Hh = Hh; g.Ww = Ww; g.start_frame = start_frame; g.start_frame_dev = nullptr;
   const int c = head_dim / 2;
   g.n_f = c - 2 * (c / 3);
   g.n_h = c / 3;
@@ -557,11 +602,38 @@ extern "C" int sfb_qk_norm_rope_sp(const void* q_in, long long ldq, const void* 
   for (int i = 0; i < groups; ++i) { hs.q[i] = (bf16*)q_dst[i]; hs.k[i] = (bf16*)k_dst[i]; hs.v[i] = (bf16*)v_dst[i]; }
   hs.groups = groups; hs.group_cols = C / groups; hs.token_offset = token_offset;
   return dispatch_nv(C, "sfb_qk_norm_rope_sp", [&](auto nv) {
-    qk_norm_rope_kernel<decltype(nv)::value><<<(rows + ROW_WARPS - 1) / ROW_WARPS, ROW_WARPS * 32, 0, (cudaStream_t)stream>>>(
+    qk_norm_rope_kernel<decltype(nv)::value, true><<<(rows + ROW_WARPS - 1) / ROW_WARPS, ROW_WARPS * 32, 0, (cudaStream_t)stream>>>(
         (const bf16*)q_in, ldq, (const bf16*)k_in, ldk, (const bf16*)v_in, ldv, (const bf16*)wq, (const bf16*)wk, eps,
         cos_tab, sin_tab, head_dim, g, rows, hs, q_dst_row, 0, kv_dst_row, 0);
     return check_cuda(cudaGetLastError(), "qk_norm_rope_sp launch");
   });
+}
+
+// tensors_dev: DEVICE array of n_tensors pointers to [batch, rows, row_bytes] caches with the same geometry.
+// Moves rows [src_row, src_row + n_rows) to [dst_row, dst_row + n_rows), dst_row < src_row (memmove semantics).
+extern "C" int sfb_kv_roll(const void* const* tensors_dev, int n_tensors, int batch, long long batch_stride_bytes,
+                           long long row_bytes, long long dst_row, long long src_row, long long n_rows, void* stream) {
+  if (n_tensors <= 0 || batch <= 0 || n_rows <= 0) return SFB_OK;
+  if (dst_row < 0 || src_row <= dst_row || (row_bytes % 16) || (batch_stride_bytes % 16)) {
+    set_error("sfb_kv_roll: need 0 <= dst_row < src_row and 16-byte rows (dst %lld src %lld row_bytes %lld)", dst_row, src_row, row_bytes);
+    return SFB_ERR_INVALID;
+  }
+  const int sms = device_sm_count();
+  if (sms <= 0) return SFB_ERR_CUDA;
+  const long long shift = src_row - dst_row;
+  for (long long done = 0; done < n_rows; done += shift) {
+    const long long n = (n_rows - done) < shift ? (n_rows - done) : shift;
+    const long long n_v = n * row_bytes / 16;
+    long long bx = (n_v + 256 * 4 - 1) / (256 * 4);
+    const long long cap = (8LL * sms + (long long)n_tensors * batch - 1) / ((long long)n_tensors * batch);   // ~8 blocks per SM in total
+    if (bx > cap) bx = cap;
+    if (bx < 1) bx = 1;
+    kv_roll_kernel<<<dim3((unsigned)bx, n_tensors, batch), 256, 0, (cudaStream_t)stream>>>(
+        reinterpret_cast<const uint4* const*>(tensors_dev), batch_stride_bytes / 16, (dst_row + done) * row_bytes / 16,
+        shift * row_bytes / 16, n_v);
+    if (int e = check_cuda(cudaGetLastError(), "kv_roll launch")) return e;
+  }
+  return SFB_OK;
 }
 
 extern "C" int sfb_patchify(const void* x, long long sb, long long sc, long long sf, long long sy, long long sx,

@@ -138,6 +138,7 @@ class B200CausalWanModel(nn.Module):
         self._sp: Optional[UlyssesGroup] = None   # Ulysses head-parallel group (one long video over several GPUs)
         self._sp_kv: Dict[int, tuple] = {}        # data_ptr of a head-sharded cache tensor -> (pool, element offset)
         self._sp_buf: Dict[int, tuple] = {}       # chunk length -> (q buffer, attention-output buffer) peer tensors
+        self._ptr_tables: Dict[tuple, torch.Tensor] = {}   # cache tensors' data pointers -> device pointer table (kv_roll)
         # CUDA graphs: a cached forward is ~430 launches issued from Python; replaying the whole forward as one graph
         # removes the launch gaps (measured 29.6 -> 28.0 ms at S = 18720).  One graph per distinct static signature
         # (shapes, cache pointers, cache plan), captured on its second occurrence.
@@ -230,6 +231,19 @@ class B200CausalWanModel(nn.Module):
             sp.sync_host()
             self._sp_buf[L] = buf
         return buf
+
+    def _pointer_table(self, tensors, dev) -> torch.Tensor:
+        """int64 device tensor of data pointers (argument of the multi-tensor roll kernel), cached per tensor set so
+        that a replayed CUDA graph keeps reading a live buffer."""
+        key = tuple(t.data_ptr() for t in tensors)
+        tab = self._ptr_tables.get(key)
+        if tab is None:
+            if len(self._ptr_tables) > 64:
+                self._ptr_tables.clear()
+                self._graphs.clear()       # captured graphs may reference the dropped tables
+            tab = torch.tensor(key, dtype=torch.int64, device=dev) if dev.type == "cuda" else torch.zeros(len(key), dtype=torch.int64)
+            self._ptr_tables[key] = tab
+        return tab
 
     def set_sampler_tables(self, timesteps: torch.Tensor, sigmas: torch.Tensor) -> None:
         """FlowMatchScheduler tables (utils/scheduler.py:118-141) used by the fused flow->x0 epilogue."""
@@ -341,6 +355,8 @@ class B200CausalWanModel(nn.Module):
         need_ctx = any(not c["is_init"] for c in crossattn_cache[:NL])
         frame_tokens = fs
         start_frame = current_start // frame_tokens
+        if start_frame + F_ > 1024:      # the reference's RoPE table has 1024 positions per axis (causal_model.py:483-488)
+            raise ValueError(f"frame index {start_frame + F_ - 1} beyond the 1024-entry RoPE table")
         sink_tokens = self.sink_size * frame_tokens
         idx = self._mirror.read(kv_cache[:NL])   # KV-cache plans (host integers; ref causal_model.py:195-236)
         plans = [plan_cache_update(g, l, current_start, L, kv_cache[i]["k"].shape[1], self.local_attn_size,
@@ -371,13 +387,18 @@ class B200CausalWanModel(nn.Module):
         if not eligible:
             return self._device_forward(x, t, context, env)
         kv, ca, NL = env["kv_cache"], env["crossattn_cache"], env["NL"]
-        key = (tuple(x.shape), tuple(t.shape), t.dtype, env["current_start"], env["return_x0"], env["skip_output"], tuple(env["plans"]),
+        # Static signature of the device work.  The chunk position enters the kernels only through the RoPE frame offset,
+        # which is passed in device memory under replay, and the cache plan only through its device-visible fields -- so
+        # in the steady state of a rolling-window video (same roll, same write slot, same window every chunk) ONE graph
+        # per forward kind serves every chunk.
+        key = (tuple(x.shape), tuple(t.shape), t.dtype, env["return_x0"], env["skip_output"],
+               tuple((p.roll, p.roll_src, p.roll_dst, p.roll_len, p.write_start, p.write_end, p.attn_start, p.attn_end)
+                     for p in env["plans"]),
                tuple(c["k"].data_ptr() for c in kv[:NL]), tuple(c["v"].data_ptr() for c in kv[:NL]),
                tuple(c["k"].data_ptr() for c in ca[:NL]), tuple(c["v"].data_ptr() for c in ca[:NL]))
         ent = self._graphs.get(key)
         if ent is None:                       # first occurrence: run eagerly (also warms every lazy initialisation)
-            # bounded: a long / rolling rollout meets a new (current_start, plan) every chunk and each captured graph
-            # owns ~430 nodes plus a private pool -- evict the least recently used entries beyond the cap
+            # bounded: each captured graph owns ~430 nodes plus a private pool -- evict the least recently used
             while len(self._graphs) >= self.max_cuda_graphs:
                 self._graphs.pop(next(iter(self._graphs)))
             self._graphs[key] = "seen"
@@ -388,14 +409,20 @@ class B200CausalWanModel(nn.Module):
         if ent == "seen":                     # second occurrence: capture
             xs = torch.empty(x.shape, dtype=x.dtype, device=dev)
             ts = torch.empty(t.shape, dtype=t.dtype, device=dev)
+            sf = torch.zeros(1, dtype=torch.int32, device=dev) if sp is None else None
             graph = torch.cuda.CUDAGraph()
             before = ops.launches
             with torch.cuda.graph(graph):
-                outs = self._device_forward(xs, ts, context, env)
-            ent = (graph, xs, ts, outs, ops.launches - before)
+                outs = self._device_forward(xs, ts, context, dict(env, start_frame_dev=sf))
+            ent = (graph, xs, ts, outs, ops.launches - before, sf, env["start_frame"])
             ops.launches = before
             self._graphs[key] = ent
-        graph, xs, ts, outs, n_launches = ent
+        graph, xs, ts, outs, n_launches, sf, sf_captured = ent
+        if sf is not None:
+            sf.fill_(env["start_frame"])
+        elif sf_captured != env["start_frame"]:   # Ulysses: the frame offset is baked into the captured kernels
+            self._graphs[key] = "seen"
+            return self._device_forward(x, t, context, env)
         xs.copy_(x)
         ts.copy_(t)
         graph.replay()
@@ -446,6 +473,18 @@ class B200CausalWanModel(nn.Module):
         mod = ws["mod"]
         mstride = 6 * C   # elements between consecutive (b, f) rows of one layer's table
 
+        # ---- rolling window: evict the oldest chunk of every layer's cache before anything is appended ----------
+        # (reference causal_model.py:212-221 shifts inside each layer's attention call; nothing in between reads the
+        # caches, so all layers move in ONE kernel per phase)
+        rolls: Dict[tuple, List[int]] = {}
+        for i in range(NL):
+            if plans[i].roll and plans[i].roll_len > 0:
+                kc = kv_cache[i]["k"]
+                rolls.setdefault((plans[i].roll_dst, plans[i].roll_src, plans[i].roll_len, tuple(kc.shape), tuple(kc.stride())), []).append(i)
+        for (dst, src, n, _, _), layers in rolls.items():
+            tensors = [kv_cache[i][name] for i in layers for name in ("k", "v")]
+            ops.kv_roll(tensors, self._pointer_table(tensors, dev), dst, src, n)
+
         for i, blk in enumerate(self.blocks):
             pb = pk["blocks"][i]
             cache, plan = kv_cache[i], plans[i]
@@ -457,10 +496,6 @@ class B200CausalWanModel(nn.Module):
             kc, vc = cache["k"], cache["v"]
             if kc.shape[0] != B or kc.shape[2] != NHg or kc.shape[3] != D:
                 raise ValueError(f"kv_cache[{i}]['k'] shape {tuple(kc.shape)} does not match B={B}, H={NHg}, D={D}")
-            if plan.roll:
-                for c_ in (kc, vc):
-                    c_[:, plan.roll_dst:plan.roll_dst + plan.roll_len] = \
-                        c_[:, plan.roll_src:plan.roll_src + plan.roll_len].clone()
             k_slot = kc[:, plan.write_start:plan.write_end]
             v_slot = vc[:, plan.write_start:plan.write_end]
             if sp is not None:
@@ -496,7 +531,8 @@ class B200CausalWanModel(nn.Module):
             if sp is None:
                 ops.qk_norm_rope(ws["q_lin"], ws["k_lin"], v_src, sa.norm_q.weight, sa.norm_k.weight, self.eps,
                                  pk["cos"], pk["sin"], B, L, D, (F_, Hh, Ww), start_frame,
-                                 q_out=ws["q"].view(B, L, C), k_out=k_slot, v_out=v_slot)
+                                 q_out=ws["q"].view(B, L, C), k_out=k_slot, v_out=v_slot,
+                                 start_frame_dev=env.get("start_frame_dev"))
                 if skip_output and i == NL - 1:
                     break   # cache-refresh pass: nothing after the last layer's K/V append is consumed
                 ops.attention(q4, kc[:, plan.attn_start:plan.attn_end], vc[:, plan.attn_start:plan.attn_end],

@@ -169,8 +169,11 @@ class CudaOps:
 
     @_op
     def qk_norm_rope(self, q_in, k_in, v_in, wq, wk, eps, cos_tab, sin_tab, B, L, head_dim, grid, start_frame,
-                     q_out, k_out, v_out):
-        """q_in/k_in/v_in [B*L, C]; q_out [B, L, C]-like view; k_out/v_out [B, L, H, D] cache-slot views."""
+                     q_out, k_out, v_out, start_frame_dev=None):
+        """q_in/k_in/v_in [B*L, C]; q_out [B, L, C]-like view; k_out/v_out [B, L, H, D] cache-slot views.
+        start_frame_dev: optional int32 device scalar that overrides start_frame at run time (graph replay)."""
+        if start_frame_dev is not None:
+            assert start_frame_dev.dtype == torch.int32 and start_frame_dev.numel() == 1
         _check_2d(q_in, "q_in"); _check_2d(k_in, "k_in")
         C = q_in.shape[1]
         F_, Hh, Ww = grid
@@ -179,7 +182,7 @@ class CudaOps:
         _lib.check(self.lib.sfb_qk_norm_rope(
             q_in.data_ptr(), q_in.stride(0), k_in.data_ptr(), k_in.stride(0), _ptr(v_in),
             v_in.stride(0) if v_in is not None else 0, wq.data_ptr(), wk.data_ptr(), eps, cos_tab.data_ptr(),
-            sin_tab.data_ptr(), cos_tab.shape[0], B, L, C, head_dim, F_, Hh, Ww, start_frame,
+            sin_tab.data_ptr(), cos_tab.shape[0], B, L, C, head_dim, F_, Hh, Ww, start_frame, _ptr(start_frame_dev),
             q_out.data_ptr(), q_out.stride(1), q_out.stride(0), k_out.data_ptr(), v_out.data_ptr(),
             k_out.stride(1), k_out.stride(0), self._stream()), "sfb_qk_norm_rope")
 
@@ -229,6 +232,21 @@ class CudaOps:
     def peer_barrier(self, sp):
         _lib.check(self.lib.sfb_peer_barrier(_lib.ptr_array(sp.flags.ptrs), sp.rank, sp.world, self._stream()),
                    "sfb_peer_barrier")
+
+    # -- rolling KV window -----------------------------------------------------------------
+    @_op
+    def kv_roll(self, tensors, table, dst_row: int, src_row: int, n_rows: int):
+        """Shift rows [src_row, src_row + n_rows) of every [B, S, H, D] cache tensor in `tensors` to dst_row (< src_row)
+        -- the eviction of the rolling window (causal_model.py:212-221) for all layers' K and V in one call.
+        `table` = int64 device tensor holding the tensors' data pointers (built once per cache, see model.py)."""
+        t0 = tensors[0]
+        for t in tensors:
+            assert t.shape == t0.shape and t.stride() == t0.stride() and t.dtype == t0.dtype
+        assert t0.stride(3) == 1 and t0.stride(2) == t0.shape[3] and t0.stride(1) == t0.shape[2] * t0.shape[3]
+        assert table.dtype == torch.int64 and table.numel() == len(tensors) and table.is_cuda
+        es = t0.element_size()
+        _lib.check(self.lib.sfb_kv_roll(table.data_ptr(), len(tensors), t0.shape[0], t0.stride(0) * es, t0.stride(1) * es,
+                                        dst_row, src_row, n_rows, self._stream()), "sfb_kv_roll")
 
     # -- embeddings -----------------------------------------------------------------------
     @_op

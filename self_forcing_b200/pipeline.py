@@ -74,8 +74,10 @@ class CausalInferencePipeline(torch.nn.Module):
             events["init"][0].record()
 
         # Step 1: KV / cross-attention caches (allocated once, reset by rebinding like the reference :112-132)
-        if (self.kv_cache1 is None or self.kv_cache1[0]["k"].shape[0] != batch_size
-                or self.kv_cache1[0]["k"].device != noise.device):
+        want_tokens = self.local_attn_size * self.frame_seq_length if self.local_attn_size != -1 else 32760
+        kc0 = None if self.kv_cache1 is None else self.kv_cache1[0]["k"]
+        if (kc0 is None or kc0.shape[0] != batch_size or kc0.device != noise.device or kc0.dtype != noise.dtype
+                or kc0.shape[1] != want_tokens):      # another batch / device / dtype / resolution: new caches
             self._initialize_kv_cache(batch_size, noise.dtype, noise.device)
             self._initialize_crossattn_cache(batch_size, noise.dtype, noise.device)
         else:

@@ -71,8 +71,10 @@ class TorchOps:
         y.copy_(O.rms_norm(x, weight, eps))
 
     def qk_norm_rope(self, q_in, k_in, v_in, wq, wk, eps, cos_tab, sin_tab, B, L, head_dim, grid, start_frame,
-                     q_out, k_out, v_out):
+                     q_out, k_out, v_out, start_frame_dev=None):
         self.launches += 1
+        if start_frame_dev is not None:
+            start_frame = int(start_frame_dev)
         C = q_in.shape[1]
         H = C // head_dim
         ang = O.rope_angle_table(head_dim)
@@ -122,6 +124,10 @@ class TorchOps:
     def peer_barrier(self, sp):
         import torch.distributed as dist
         dist.barrier(group=sp.group)
+
+    def kv_roll(self, tensors, table, dst_row, src_row, n_rows):
+        for t in tensors:
+            t[:, dst_row:dst_row + n_rows] = t[:, src_row:src_row + n_rows].clone()
 
     def patchify(self, x, out):
         self.launches += 1

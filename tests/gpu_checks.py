@@ -312,6 +312,22 @@ def check_ln_row_offset(rows=300, C=1536, seed=0):
     return _against_double("ln_modulate row_offset", run, dict(y=torch.zeros(rows, C, device="cuda", dtype=BF)))
 
 
+def check_kv_roll(n_tensors=6, B=2, S=700, H=12, D=128, dst=100, src=230, n=470, seed=0):
+    """Rolling-window eviction kernel (all layers' K and V in one call, several phases because n > src - dst) against
+    the reference's clone-and-assign (causal_model.py:212-221); rows outside the moved range must be untouched."""
+    ops = _ops()
+    pool = _randn(n_tensors, B, S + 3, H, D, seed=seed)
+    tensors = [pool[i, :, :S] for i in range(n_tensors)]          # non-contiguous batch stride, like views of one pool
+    ref = [t.clone() for t in tensors]
+    for r in ref:
+        r[:, dst:dst + n] = r[:, src:src + n].clone()
+    table = torch.tensor([t.data_ptr() for t in tensors], dtype=torch.int64, device="cuda")
+    ops.kv_roll(tensors, table, dst, src, n)
+    torch.cuda.synchronize()
+    m = dict(err_mismatch=float(sum((a != b).sum() for a, b in zip(tensors, ref))))
+    return _finish("kv_roll", m, 0.0)
+
+
 def check_patchify(B=2, F_=3, H=12, W=20, seed=0):
     x = _randn(B, F_, 16, H, W, seed=seed).permute(0, 2, 1, 3, 4)      # the wrapper's permuted view
 
@@ -727,6 +743,9 @@ ALL = {
     "qk_norm_rope_c5120": lambda: check_qk_norm_rope(B=1, F_=2, Hh=4, Ww=6, C=5120, start_frame=0, seed=4),
     "gemm_gate_row_offset": lambda: check_gemm(M=700, N=512, K=256, epilogue=3, rows_per_gate=130, block_n=512, gate_row_offset=77),
     "gemm_gate_row_offset_1cta": lambda: check_gemm(M=300, N=384, K=256, epilogue=3, rows_per_gate=70, block_n=128, gate_row_offset=33),
+    "kv_roll": check_kv_roll,
+    "kv_roll_single_phase": lambda: check_kv_roll(n_tensors=2, B=1, S=3120, dst=1560, src=3000, n=120, seed=1),
+    "kv_roll_framewise_1p3b": lambda: check_kv_roll(n_tensors=4, B=1, S=6 * 1560, dst=1560, src=2 * 1560, n=4 * 1560, seed=2),
     "patchify": check_patchify,
     "sinusoid": check_sinusoid,
     "skinny_linear": check_skinny_linear,

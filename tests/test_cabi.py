@@ -34,7 +34,7 @@ def test_binding_covers_header(lib_path):
                                    "sfb_causal_conv3d_workspace_bytes"}
     assert declared == set(_lib.SIGNATURES), declared ^ set(_lib.SIGNATURES)
     lib = _lib.load(lib_path)
-    assert lib.sfb_abi_version() == 8
+    assert lib.sfb_abi_version() == 9
     assert isinstance(lib.sfb_last_error(), bytes)
 
 

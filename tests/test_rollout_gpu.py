@@ -199,6 +199,45 @@ def test_rolling_sink_cache_on_gpu_matches_reference_golden():
         assert rel_l2(kv[i]["k"].cpu(), g["k"][i]) <= TOL and rel_l2(kv[i]["v"].cpu(), g["v"][i]) <= TOL
 
 
+def test_rolling_window_pipeline_on_gpu_matches_reference_golden():
+    """SURVEY.md 8f rank 4 (long-video driver): local window of 2 frames + 1 sink frame at 1560 tokens / frame, four
+    one-frame chunks THROUGH THE PIPELINE on the GPU (roll kernel + CUDA-graph replay) vs the unmodified reference."""
+    from helpers import ROLLING_ROLLOUT_CASES
+    g = golden("rollout_rolling.pt")["rolling_window"]
+    pipe, *_, noise = make_product_pipeline(ROLLING_ROLLOUT_CASES["rolling_window"], "cuda")
+    assert pipe.local_attn_size == 2
+    with patched_randn_like(3):
+        _, lat = pipe.inference(noise, ["synthetic"], return_latents=True)
+    assert pipe.kv_cache1[0]["k"].shape[1] == 2 * 1560
+    assert (int(pipe.kv_cache1[0]["global_end_index"]), int(pipe.kv_cache1[-1]["local_end_index"])) == tuple(g["final_index"])
+    assert rel_l2(lat.cpu(), g["latents"]) <= TOL
+
+
+def test_long_rolling_video_vs_oracle_on_gpu():
+    """A video longer than its window: 21 latent frames in chunks of 3 with local_attn_size = 12 frames and a 3-frame
+    sink (each eviction shifts 6 kept frames left by 3: two phases of the roll kernel), product vs the oracle on the
+    same GPU.  In the steady state every chunk has the same cache plan, so ONE captured graph per forward kind is
+    replayed for all remaining chunks (the RoPE frame offset is a device-side argument)."""
+    case = dict(frames=21, num_frame_per_block=3, independent_first_frame=False, shift=5.0, local_attn_size=12, sink_size=3)
+    pipe, cfg, params, pe, noise = make_product_pipeline(case, "cuda")
+    with patched_randn_like(3):
+        _, lat = pipe.inference(noise, ["synthetic"], return_latents=True)
+    tr = _oracle_rollout_gpu(cfg, params, case, pe, noise)
+    assert (int(pipe.kv_cache1[0]["global_end_index"]), int(pipe.kv_cache1[0]["local_end_index"])) == tr.index_trace[-1]
+    assert tr.index_trace[-1] == (21 * 1560, 12 * 1560)
+    err = rel_l2(lat, tr.latents)
+    assert err <= TOL, err
+    model = pipe.generator.model
+    captured = sum(1 for g in model._graphs.values() if g != "seen")
+    # fill phase: one graph per chunk position (4); steady state: first forward of a chunk (roll), re-denoising forwards,
+    # refresh forward -> 3 more, however many chunks follow
+    assert 1 <= captured <= 8, captured
+    with patched_randn_like(3):      # and again: replays only, identical bits
+        _, lat2 = pipe.inference(noise, ["synthetic"], return_latents=True)
+    assert torch.equal(lat, lat2)
+    assert sum(1 for g in model._graphs.values() if g != "seen") == captured
+
+
 def test_bidirectional_teacher_forward_on_gpu_matches_reference_golden():
     """BASELINE config 5 at tiny size: B200WanModel through the CUDA kernels vs the unmodified reference WanModel."""
     from oracle.make_golden import BIDIR, bidirectional_cfg, bidirectional_inputs
