@@ -190,6 +190,99 @@ def reference_bidirectional(ref):
     return dict(flow=out.clone(), seq_len=L)
 
 
+def _attention_with_k_lens(q, k, v, q_lens=None, k_lens=None, **kw):
+    """flash_attn_varlen_func's semantics at the reference's call site (wan/modules/attention.py:88-150) restated with
+    SDPA: sample b attends to its first k_lens[b] keys only.  The reference's own CPU fallback (`attention.attention`,
+    :189-202) prints "Padding mask is disabled" and ignores k_lens, so a CPU run of the PADDED path needs this stand-in
+    for the third-party kernel (flash_attn 2.8.3, not runnable without CUDA); everything else stays the unmodified
+    reference."""
+    B, Lq, Lk = q.shape[0], q.shape[1], k.shape[1]
+    mask = None
+    if k_lens is not None:
+        mask = (torch.arange(Lk)[None, :] < k_lens.to(torch.long)[:, None])[:, None, None, :].expand(B, 1, Lq, Lk)
+    out = torch.nn.functional.scaled_dot_product_attention(q.transpose(1, 2).to(torch.bfloat16), k.transpose(1, 2).to(torch.bfloat16),
+                                                           v.transpose(1, 2).to(torch.bfloat16), attn_mask=mask)
+    return out.transpose(1, 2).contiguous()
+
+
+def reference_bidirectional_padded(ref):
+    """The same two samples pushed through the unmodified WanModel with seq_len LARGER than the samples (the model pads
+    every sample with zero tokens to seq_len and passes k_lens = seq_lens to attention, model.py:684-693,150-156)."""
+    import wan.modules.model as ref_model
+    cfg = bidirectional_cfg()
+    params = O.make_random_params(cfg, seed=9)
+    kw = cfg.reference_kwargs()
+    kw.pop("local_attn_size"), kw.pop("sink_size")
+    model = ref.WanModel(**kw)
+    model.load_state_dict(params, strict=False)
+    model = model.to(torch.bfloat16).eval()
+    x, t, ctx = bidirectional_inputs()
+    L = x.shape[2] * (x.shape[3] // 2) * (x.shape[4] // 2)
+    saved = ref_model.flash_attention
+    ref_model.flash_attention = _attention_with_k_lens
+    try:
+        with torch.no_grad():
+            out = model(list(x), t=t, context=[c[:300] for c in ctx], seq_len=L + 16)
+    finally:
+        ref_model.flash_attention = saved
+    return dict(flow=out.clone(), seq_len=L + 16, context_rows=300)
+
+
+# Training-time (cache-free) forward with block masks (SURVEY.md section 8f rank 3): tiny width, several mask shapes.
+TRAIN = dict(dim=256, ffn_dim=256, num_heads=2, num_layers=2, text_dim=512, frame_hw=(8, 12), batch=2)
+TRAIN_CASES = {
+    "causal_chunks_of_2": dict(frames=4, num_frame_per_block=2, local_attn_size=-1, independent_first_frame=False, tf=False),
+    "causal_local_window": dict(frames=5, num_frame_per_block=1, local_attn_size=2, independent_first_frame=False, tf=False),
+    "causal_lone_first_frame": dict(frames=5, num_frame_per_block=2, local_attn_size=-1, independent_first_frame=True, tf=False),
+    "teacher_forcing": dict(frames=4, num_frame_per_block=2, local_attn_size=-1, independent_first_frame=False, tf=True),
+}
+
+
+def train_cfg(case: dict) -> O.OracleConfig:
+    r = TRAIN
+    return O.OracleConfig(dim=r["dim"], ffn_dim=r["ffn_dim"], num_heads=r["num_heads"], num_layers=r["num_layers"],
+                          text_dim=r["text_dim"], local_attn_size=case["local_attn_size"])
+
+
+def train_inputs(case: dict):
+    r = TRAIN
+    g = torch.Generator().manual_seed(31)
+    x = torch.randn(r["batch"], 16, case["frames"], *r["frame_hw"], generator=g).to(torch.bfloat16)
+    clean = torch.randn(r["batch"], 16, case["frames"], *r["frame_hw"], generator=g).to(torch.bfloat16)
+    ctx = torch.randn(r["batch"], 512, r["text_dim"], generator=g).to(torch.bfloat16)
+    t = torch.randint(0, 1000, (r["batch"], case["frames"]), generator=g).float()
+    aug = torch.randint(0, 100, (r["batch"], case["frames"]), generator=g).float()
+    return x, clean, t, aug, ctx
+
+
+def reference_train_forward(ref):
+    """The unmodified CausalWanModel._forward_train (causal_model.py:895-1069) -- FlexAttention block masks, no cache.
+    The reference compiles flex_attention with Inductor (:24-25), which cannot be lowered on a CPU: the module attribute
+    is rebound to torch's uncompiled flex_attention (same op, eager arithmetic)."""
+    from torch.nn.attention.flex_attention import flex_attention as eager_flex
+    cm = ref.causal_model
+    saved = cm.flex_attention
+    cm.flex_attention = eager_flex
+    out = {}
+    try:
+        for name, case in TRAIN_CASES.items():
+            cfg = train_cfg(case)
+            model = ref.CausalWanModel(**cfg.reference_kwargs())
+            model.load_state_dict(O.make_random_params(cfg, seed=13), strict=False)
+            model = model.to(torch.bfloat16).eval()
+            model.num_frame_per_block = case["num_frame_per_block"]
+            model.independent_first_frame = case["independent_first_frame"]
+            x, clean, t, aug, ctx = train_inputs(case)
+            kw = dict(clean_x=clean, aug_t=aug) if case["tf"] else {}
+            with torch.no_grad():
+                flow = model(x, t=t, context=list(ctx), seq_len=x.shape[2] * 24, **kw)
+            out[name] = dict(flow=flow.clone(), case=case)
+            print(name, flow.shape, float(flow.float().abs().mean()))
+    finally:
+        cm.flex_attention = saved
+    return out
+
+
 # 50-step sampler (SURVEY.md section 8f rank 2): CFG + UniPC on the same cached forward, separate pos / neg caches.
 # `sampling_steps` is the reference pipeline's own attribute (hard-wired to 50 in its constructor,
 # causal_diffusion_inference.py:66); the fixture lowers it on the instance so the CPU run stays short -- the solver
@@ -425,6 +518,8 @@ def main():
     torch.save(reference_rolling(ref), os.path.join(GOLDEN, "model_rolling.pt"))
     torch.save(reference_masks(ref), os.path.join(GOLDEN, "block_masks.pt"))
     torch.save(reference_bidirectional(ref), os.path.join(GOLDEN, "bidirectional_tiny.pt"))
+    torch.save(reference_bidirectional_padded(ref), os.path.join(GOLDEN, "bidirectional_padded.pt"))
+    torch.save(reference_train_forward(ref), os.path.join(GOLDEN, "train_forward_tiny.pt"))
 
     diff = {"unipc_trace_bf16": reference_unipc_trace(ref, torch.bfloat16),
             "unipc_trace_fp32": reference_unipc_trace(ref, torch.float32)}

@@ -54,6 +54,29 @@ __device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {
   return *reinterpret_cast<uint32_t*>(&t);
 }
 
+// kernel<<<grid, block, smem, stream>>>(args...) with a thread-block-cluster width.
+// (Programmatic dependent launch -- griddepcontrol.wait after each kernel's prologue, launch_dependents at its top, the
+// programmatic-stream-serialisation attribute on every per-layer launch, captured into the CUDA graphs -- was measured
+// on the full rollout and removed: 1026 ms with it vs 1007 ms without, profiles/r02g_*; graph replay already hides the
+// launch latency and early-resident dependent CTAs only compete with the tail of the running kernel.)
+template <class... KArgs, class... Args>
+inline cudaError_t launch_cluster(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream,
+                                  int cluster_x, Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = cluster_x;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  return cudaLaunchKernelEx(&cfg, kern, KArgs(args)...);
+}
+
 // One lane of a fully active warp (always the same one).  Role warps stay warp-uniform -- every lane runs the
 // loop control and the mbarrier waits -- and only the TMA / tcgen05 issue is predicated on this, which lets the
 // compiler keep descriptors in uniform registers instead of wrapping every UTCHMMA / UTMALDG in a per-thread

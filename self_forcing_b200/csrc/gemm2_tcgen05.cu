@@ -343,8 +343,8 @@ static int launch_gemm2(const CUtensorMap& ta, const CUtensorMap& tb, const Pair
   if (timing && dbg_buf == nullptr) cudaMalloc(&dbg_buf, 512 * 16 * sizeof(long long));
   q.dbg = timing ? dbg_buf : nullptr;
   if (timing) cudaMemsetAsync(dbg_buf, 0, 512 * 16 * sizeof(long long), stream);
-  cfg.gridDim = dim3(CL * clusters);
-  if (int e = check_cuda(cudaLaunchKernelEx(&cfg, kern, ta, tb, pm.out[0], pm.out[1], pm.out[2], pm.res, q), "gemm2 launch"))
+  if (int e = check_cuda(launch_cluster(kern, dim3(CL * clusters), dim3(G2_THREADS), G2_SMEM_BYTES, stream, CL, ta, tb, pm.out[0],
+                                    pm.out[1], pm.out[2], pm.res, q), "gemm2 launch"))
     return e;
   if (timing) {
     static long long h[512 * 16];

@@ -2,6 +2,7 @@
 // driver entry point (so the .so has no link-time dependency on libcuda and loads on a CPU box).
 #include <stdarg.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include "common.cuh"

@@ -607,7 +607,12 @@ class B200WanModel(B200CausalWanModel):
     (`e [B, 6, C]`, model.py:697-700) and the text K/V are recomputed per call.  So this class only supplies scratch
     K/V (one buffer shared by all layers -- nothing persists) and forwards to the same kernel schedule; under
     `enable_ulysses` it is the head-parallel forward of wan/distributed/xdit_context_parallel.py:66-192.
-    Limitation: all samples must have exactly `seq_len` tokens (no padded sequences / k_lens masking)."""
+
+    Samples shorter than `seq_len`: the reference zero-pads every sample to seq_len tokens and hands k_lens = seq_lens
+    to flash_attn (model.py:684-693,150-156), so the valid tokens of a sample only ever see that sample's own valid
+    tokens and every other op is row-wise -- the padded rows change nothing that is returned (unpatchify drops them,
+    :745-771).  The B200 forward therefore runs the exact-length problem: no padded rows are computed at all.  Samples
+    of different shapes in one call run one after the other (their token grids, hence RoPE, differ)."""
 
     def __init__(self, *args, **kwargs):
         kwargs.pop("local_attn_size", None)
@@ -622,12 +627,22 @@ class B200WanModel(B200CausalWanModel):
     def forward(self, x, t, context, seq_len, clip_fea=None, y=None, return_x0: bool = False, **unsupported):
         if any(v is not None and v is not False for v in unsupported.values()):
             raise NotImplementedError(f"B200WanModel: unsupported arguments {sorted(unsupported)} (t2v forward only)")
+        if isinstance(x, (list, tuple)) and len({tuple(u.shape) for u in x}) > 1:
+            # mixed shapes: one exact-length forward per sample; the reference stacks the outputs (model.py:771), which
+            # only works if they happen to share a shape -- same behaviour here
+            ctx = context if isinstance(context, (list, tuple)) else list(context)
+            outs = [self.forward([u], t[i:i + 1], [ctx[i]], seq_len, return_x0=return_x0) for i, u in enumerate(x)]
+            if return_x0:
+                return torch.cat([o[0] for o in outs]), torch.cat([o[1] for o in outs])
+            return torch.cat(outs)
         if isinstance(x, (list, tuple)):
             x = torch.stack(list(x))
         B, _, F_, H, W = x.shape
         L = F_ * (H // 2) * (W // 2)
-        if L != seq_len:
-            raise NotImplementedError(f"B200WanModel needs full-length samples: {L} tokens != seq_len {seq_len}")
+        if L > seq_len:
+            raise ValueError(f"sample of {L} tokens exceeds seq_len {seq_len}")      # reference: assert seq_lens.max() <= seq_len
+        if self._sp is not None and L % self._sp.world:
+            raise NotImplementedError(f"Ulysses mode needs the {L} tokens of a sample to split evenly over {self._sp.world} ranks")
         dev, dt = x.device, self.patch_embedding.weight.dtype
         key = (B, L, str(dev))
         if key not in self._scratch:

@@ -313,8 +313,15 @@ def test_bidirectional_model_matches_reference_golden():
     assert out.shape == g["flow"].shape and rel_l2(out, g["flow"]) <= 1e-2
     out2 = model(x, t=t, context=ctx, seq_len=g["seq_len"])        # scratch buffers are reusable
     assert torch.equal(out, out2)
-    with pytest.raises(NotImplementedError):
-        model(x, t=t, context=ctx, seq_len=g["seq_len"] + 8)      # padded sequences are not supported
+    # samples shorter than seq_len (the reference pads them and masks the padded keys): exact-length forward
+    gp = golden("bidirectional_padded.pt")
+    outp = model(list(x), t=t, context=[c[:gp["context_rows"]] for c in ctx], seq_len=gp["seq_len"])
+    assert outp.shape == gp["flow"].shape and rel_l2(outp, gp["flow"]) <= 1e-2
+    with pytest.raises(ValueError):
+        model(x, t=t, context=ctx, seq_len=g["seq_len"] - 8)      # a sample longer than seq_len (reference asserts)
+    # a one-frame sample under the same seq_len (its own token grid, hence its own RoPE positions)
+    a = model([x[1][:, :1]], t=t[1:], context=[ctx[1]], seq_len=g["seq_len"])
+    assert a.shape == (1, 16, 1, *x.shape[3:])
 
 
 def test_bidirectional_wrapper_surface():

@@ -131,3 +131,17 @@ def test_bidirectional_forward_matches_reference_golden():
     with torch.no_grad():
         out = O.bidirectional_forward(O.make_random_params(cfg, seed=9), cfg, x, t, ctx)
     assert torch.equal(out, g["flow"])
+
+
+def test_bidirectional_padded_samples_match_reference_golden():
+    """Samples shorter than seq_len (model.py:684-693 zero-pads them and attention gets k_lens): the valid tokens of a
+    sample only see that sample's own tokens, so the exact-length restatement must reproduce the reference's padded
+    run (golden made with flash_attn's k_lens semantics restated over SDPA, oracle/make_golden.py)."""
+    from oracle.make_golden import bidirectional_cfg, bidirectional_inputs
+    g = golden("bidirectional_padded.pt")
+    x, t, ctx = bidirectional_inputs()
+    cfg = bidirectional_cfg()
+    ctx = torch.cat([ctx[:, :g["context_rows"]], torch.zeros_like(ctx[:, g["context_rows"]:])], dim=1)   # model.py:704-709
+    with torch.no_grad():
+        out = O.bidirectional_forward(O.make_random_params(cfg, seed=9), cfg, x, t, ctx)
+    assert rel_l2(out, g["flow"]) <= 2e-3      # masked vs unmasked SDPA kernels round differently

@@ -251,6 +251,10 @@ def test_bidirectional_teacher_forward_on_gpu_matches_reference_golden():
     out = model(list(x), t=t, context=list(ctx), seq_len=g["seq_len"])
     assert rel_l2(out.cpu(), g["flow"]) <= TOL
     assert torch.equal(out, model(x, t=t, context=ctx, seq_len=g["seq_len"]))
+    # samples shorter than seq_len (reference: zero padding + k_lens, model.py:684-693): exact-length forward on the GPU
+    gp = golden("bidirectional_padded.pt")
+    outp = model(list(x), t=t, context=[c[:gp["context_rows"]] for c in ctx], seq_len=gp["seq_len"])
+    assert rel_l2(outp.cpu(), gp["flow"]) <= TOL
 
 
 def test_cfg_unipc_pipeline_matches_reference_golden():
