@@ -305,11 +305,165 @@ class B200CausalWanModel(nn.Module):
 
     # ------------------------------------------------------------------ forward
     def forward(self, *args, **kwargs):
+        """Dispatch like the reference (causal_model.py:1071-1079): with a KV cache the cached inference forward, without
+        one the cache-free training-time forward (block-masked attention over the whole video; forward only)."""
         if kwargs.get("kv_cache", None) is None:
-            raise NotImplementedError(
-                "B200CausalWanModel implements the KV-cached inference path only "
-                "(reference _forward_train / FlexAttention is out of scope)")
+            return self._forward_train(*args, **kwargs)
         return self._forward_inference(*args, **kwargs)
+
+    # ------------------------------------------------------------------ training-time forward (no cache)
+    def attention_windows(self, num_frames: int, frame_tokens: int, teacher_forcing: bool):
+        """The reference's FlexAttention block masks (causal_model.py:518-723) as dense rectangles: a list of
+        (q_lo, q_hi, kv_lo, kv_hi) -- query rows [q_lo, q_hi) attend keys [kv_lo, kv_hi) -- in execution order.
+        Block-wise causal: a chunk sees everything before its own end (only the last `local_attn_size` frames if set;
+        a lone first frame if independent_first_frame).  Teacher forcing: sequence = [clean | noisy]; clean chunks are
+        block-causal among themselves, noisy chunk c sees the clean chunks before it plus itself -- two intervals,
+        made ONE rectangle by staging the noisy chunk's K/V over the clean chunk's rows (kv_lo < 0 marks that
+        staging step: copy rows [-kv_lo - 1 ...) -- see _forward_train), walked from the last chunk to the first so that
+        every clean chunk is overwritten only after all its readers are done.  masks.py holds the same intervals as
+        BlockMask tables; tests check both against the reference's masks."""
+        blk = frame_tokens * self.num_frame_per_block
+        total = num_frames * frame_tokens
+        chunks = []                      # (first row, last row + 1, ends[] value of the rows: :533-546 / :680-696)
+        s = 0
+        if self.independent_first_frame and not teacher_forcing:
+            chunks.append((0, frame_tokens, frame_tokens))
+            s = frame_tokens
+        while s < total:
+            chunks.append((s, min(s + blk, total), s + blk))     # a ragged last chunk keeps its nominal end
+            s += blk
+        wins = []
+        for lo, hi, end in chunks:
+            kv_lo = 0 if (self.local_attn_size == -1 or teacher_forcing) else max(0, end - self.local_attn_size * frame_tokens)
+            # kv < ends[q]: a ragged last chunk keeps its nominal end, which under teacher forcing reaches into the
+            # noisy half that follows the clean rows (the reference's mask does exactly that, :611-613,632-635)
+            wins.append((lo, hi, kv_lo, min(end, total * (2 if teacher_forcing else 1))))
+        if teacher_forcing:
+            for lo, hi, _ in reversed(chunks):
+                wins.append((total + lo, total + hi, -(lo + 1), hi))        # stage noisy K/V rows over clean rows [lo, hi), then [0, hi)
+        return wins
+
+    @torch.no_grad()
+    def _forward_train(self, x, t, context, seq_len, clean_x=None, aug_t=None, clip_fea=None, y=None, add_condition=None,
+                       return_x0: bool = False, **unsupported):
+        """CausalWanModel._forward_train (causal_model.py:895-1069), forward only: all frames of the video at once, per-frame
+        timesteps t [B, F], causality from the block mask; clean_x [B, 16, F, H, W] switches teacher forcing on (the
+        sequence becomes [clean | noisy], aug_t = timesteps of the clean half, RoPE restarts for the noisy half, the head
+        runs on the noisy half).  Same kernels as the cached forward; the mask is executed as dense attention calls over
+        the rectangles of attention_windows().  Returns flow [B, 16, F, H, W] (and x0 [B, F, 16, H, W] with return_x0)."""
+        if add_condition is not None or clip_fea is not None or y is not None:
+            raise NotImplementedError("pose / image conditioning is not part of the t2v path")
+        if any(v is not None for v in unsupported.values()):
+            raise NotImplementedError(f"unsupported arguments {sorted(unsupported)}")
+        if self._sp is not None:
+            raise NotImplementedError("the training-time forward is not head-parallel")
+        if isinstance(x, (list, tuple)):
+            x = torch.stack(list(x))
+        if isinstance(clean_x, (list, tuple)):
+            clean_x = torch.stack(list(clean_x))
+        if isinstance(context, (list, tuple)):
+            context = torch.stack([torch.cat([u, u.new_zeros(self.text_len - u.size(0), u.size(1))]) for u in context])
+        tf = clean_x is not None
+        if tf and self.independent_first_frame:
+            raise NotImplementedError("teacher forcing with an independent first frame (the reference raises too, :941-942)")
+        ops, pk = self.ops, (self._packed or self._pack())
+        B, Cin, F_, H, W = x.shape
+        Hh, Ww = H // 2, W // 2
+        fs, L = Hh * Ww, F_ * Hh * Ww
+        assert L <= seq_len and t.shape == (B, F_), f"timestep shape {tuple(t.shape)} != {(B, F_)}"
+        C, NL, D, NH = self.dim, self.num_layers, self.head_dim, self.num_heads
+        dev, bf = x.device, self.patch_embedding.weight.dtype
+        halves = 2 if tf else 1
+        Lt, Fm = halves * L, halves * F_            # tokens / modulation frames per sample
+        R = B * Lt
+        key = ("train", B, Lt, Fm, str(dev))
+        ws = self._ws.get(key)
+        if ws is None:
+            def e(*shape):
+                return torch.empty(*shape, dtype=bf, device=dev)
+            ws = dict(tok=e(L, self.in_dim * 4), x=e(R, C), h=e(R, C), q_lin=e(R, C), k_lin=e(R, C), q=e(R, C), attn=e(R, C),
+                      ffn=e(R, self.ffn_dim), sin=e(B * Fm, self.freq_dim), e1=e(B * Fm, C), e=e(B * Fm, C),
+                      e0=e(B * Fm, 6 * C), mod=e(NL, B * Fm, 6, C), head_mod=e(1, B * Fm, 2, C), head_out=e(B * L, self.out_dim * 4),
+                      ctx_h=e(B * self.text_len, C), ctx=e(B * self.text_len, C), ctx_k=e(B * self.text_len, C),
+                      k=e(B, Lt, NH, D), v=e(B, Lt, NH, D), ck=e(B, self.text_len, NH, D), cv=e(B, self.text_len, NH, D))
+            self._ws[key] = ws
+        X = ws["x"].view(B, Lt, C)
+
+        # ---- embeddings: [clean | noisy] token rows per sample (causal_model.py:966-976,1011-1020) ---------------
+        for b in range(B):
+            for hf, src in enumerate((clean_x, x) if tf else (x,)):
+                ops.patchify(src[b:b + 1], ws["tok"])
+                ops.gemm(ws["tok"], pk["patch_w"], self.patch_embedding.bias, X[b, hf * L:(hf + 1) * L])
+        tt = (torch.cat([aug_t if aug_t is not None else torch.zeros_like(t), t], dim=1) if tf else t).contiguous()
+        ops.sinusoid(tt.reshape(-1), ws["sin"], self.freq_dim)
+        te, tp = self.time_embedding, self.time_projection
+        ops.skinny_linear(ws["sin"], te[0].weight, te[0].bias, ws["e1"], silu_in=False)
+        ops.skinny_linear(ws["e1"], te[2].weight, te[2].bias, ws["e"], silu_in=True)
+        ops.skinny_linear(ws["e"], tp[1].weight, tp[1].bias, ws["e0"], silu_in=True)
+        ops.modulation_table(pk["mod"], ws["e0"], ws["mod"], e_row_stride=6 * C, e_group_stride=C)
+        ops.modulation_table(pk["head_mod"], ws["e"], ws["head_mod"], e_row_stride=C, e_group_stride=0)
+        if context.shape[1] < self.text_len:
+            context = torch.cat([context, context.new_zeros(B, self.text_len - context.shape[1], context.shape[2])], dim=1)
+        tx = self.text_embedding
+        ops.gemm(context.reshape(B * self.text_len, self.text_dim).contiguous(), tx[0].weight, tx[0].bias, ws["ctx_h"], epilogue=EPI_GELU)
+        ops.gemm(ws["ctx_h"], tx[2].weight, tx[2].bias, ws["ctx"])
+
+        windows = self.attention_windows(F_, fs, tf)
+        kv_table = self._pointer_table([ws["k"], ws["v"]], dev)
+        scale = 1.0 / math.sqrt(D)
+        mstride = 6 * C
+        Q4, A4 = ws["q"].view(B, Lt, NH, D), ws["attn"].view(B, Lt, NH, D)
+        for i, blk in enumerate(self.blocks):
+            pb, m = pk["blocks"][i], ws["mod"][i]
+            sa, ca = blk.self_attn, blk.cross_attn
+            ops.ln_modulate(ws["x"], ws["h"], shift=m[:, 0], scale=m[:, 1], mod_stride=mstride, rows_per_mod=fs, eps=self.eps)
+            ops.gemm(ws["h"], pb["wqkv"], pb["bqkv"], None, seg_cols=C, outs=[ws["q_lin"], ws["k_lin"], ws["v"].view(R, C)])
+            # RoPE positions restart at frame 0 for every half of every sample (causal_model.py:127-136)
+            for b in range(B):
+                for hf in range(halves):
+                    r0 = b * Lt + hf * L
+                    ops.qk_norm_rope(ws["q_lin"][r0:r0 + L], ws["k_lin"][r0:r0 + L], None, sa.norm_q.weight, sa.norm_k.weight,
+                                     self.eps, pk["cos"], pk["sin"], 1, L, D, (F_, Hh, Ww), 0,
+                                     q_out=ws["q"][r0:r0 + L].view(1, L, C), k_out=ws["k"][b:b + 1, hf * L:(hf + 1) * L],
+                                     v_out=ws["v"][b:b + 1, hf * L:(hf + 1) * L])
+            for q_lo, q_hi, kv_lo, kv_hi in windows:
+                if kv_lo < 0:       # teacher forcing: stage this noisy chunk's K / V over its clean twin's rows
+                    dst = -kv_lo - 1
+                    ops.kv_roll([ws["k"], ws["v"]], kv_table, dst, L + dst, q_hi - q_lo)
+                    kv_lo = 0
+                ops.attention(Q4[:, q_lo:q_hi], ws["k"][:, kv_lo:kv_hi], ws["v"][:, kv_lo:kv_hi], A4[:, q_lo:q_hi], scale)
+            ops.gemm(ws["attn"], sa.o.weight, sa.o.bias, ws["x"], epilogue=EPI_GATE_RES, residual=ws["x"],
+                     gate=m[:, 2], gate_stride=mstride, rows_per_gate=fs)
+            # cross attention: text K / V recomputed per call (no cache on this path, model.py:175-180)
+            ops.gemm(ws["ctx"], pb["wkv_c"], pb["bkv_c"], None, seg_cols=C, outs=[ws["ctx_k"], ws["cv"].view(B * self.text_len, C)])
+            ops.rmsnorm(ws["ctx_k"], ws["ck"].view(B * self.text_len, C), ca.norm_k.weight, self.eps)
+            ops.ln_affine(ws["x"], ws["h"], blk.norm3.weight, blk.norm3.bias, self.eps)
+            ops.gemm(ws["h"], ca.q.weight, ca.q.bias, ws["q_lin"])
+            ops.rmsnorm(ws["q_lin"], ws["q"], ca.norm_q.weight, self.eps)
+            ops.attention(Q4, ws["ck"], ws["cv"], A4, scale)
+            ops.gemm(ws["attn"], ca.o.weight, ca.o.bias, ws["x"], epilogue=EPI_RESIDUAL, residual=ws["x"])
+            ops.ln_modulate(ws["x"], ws["h"], shift=m[:, 3], scale=m[:, 4], mod_stride=mstride, rows_per_mod=fs, eps=self.eps)
+            ops.gemm(ws["h"], blk.ffn[0].weight, blk.ffn[0].bias, ws["ffn"], epilogue=EPI_GELU)
+            ops.gemm(ws["ffn"], blk.ffn[2].weight, blk.ffn[2].bias, ws["x"], epilogue=EPI_GATE_RES, residual=ws["x"],
+                     gate=m[:, 5], gate_stride=mstride, rows_per_gate=fs)
+
+        # ---- head on the noisy half (causal_model.py:1058-1062), modulated by the un-projected embedding of t -------
+        hm = ws["head_mod"][0]
+        for b in range(B):
+            r0 = b * Lt + (halves - 1) * L
+            ops.ln_modulate(ws["x"][r0:r0 + L], ws["h"][r0:r0 + L], shift=hm[:, 0], scale=hm[:, 1], mod_stride=2 * C,
+                            rows_per_mod=fs, eps=self.eps, row_offset=r0)
+            ops.gemm(ws["h"][r0:r0 + L], self.head.head.weight, self.head.head.bias, ws["head_out"][b * L:(b + 1) * L])
+        flow = torch.empty(B, F_, self.out_dim, H, W, dtype=bf, device=dev)
+        if return_x0:
+            if self._sampler_tables is None:
+                raise RuntimeError("return_x0 needs set_sampler_tables() (done by B200DiffusionWrapper)")
+            x0 = torch.empty_like(flow)
+            ops.head_finish(ws["head_out"], x.permute(0, 2, 1, 3, 4), t.contiguous(), self._sampler_tables[0],
+                            self._sampler_tables[1], flow, x0)
+            return flow.permute(0, 2, 1, 3, 4), x0
+        ops.head_finish(ws["head_out"], x.permute(0, 2, 1, 3, 4), t.contiguous(), None, None, flow, None)
+        return flow.permute(0, 2, 1, 3, 4)
 
     @torch.no_grad()
     def _forward_inference(self, x, t, context, seq_len, clip_fea=None, y=None, add_condition=None,

@@ -69,12 +69,20 @@ class B200DiffusionWrapper(nn.Module):
                 current_start: Optional[int] = None, classify_mode: bool = False,
                 concat_time_embeddings: bool = False, clean_x=None, aug_t=None, cache_start: Optional[int] = None,
                 add_condition=None, clip_feature=None, y=None, refresh_only: bool = False):
-        if classify_mode or clean_x is not None:
-            raise NotImplementedError("training-time modes (GAN classify branch, teacher forcing) are out of scope")
+        if classify_mode:
+            raise NotImplementedError("the GAN classify branch is a training-only head (out of scope)")
+        if kv_cache is None and not isinstance(self.model, B200WanModel):
+            # cache-free forward of the causal model (wan_wrapper.py:301-337: training-time rollouts, teacher forcing with
+            # clean_x / aug_t): block-masked attention over the whole video, forward only
+            flow, x0 = self.model(noisy_image_or_video.permute(0, 2, 1, 3, 4), t=timestep,
+                                  context=conditional_dict["prompt_embeds"], seq_len=self.seq_len,
+                                  clean_x=None if clean_x is None else clean_x.permute(0, 2, 1, 3, 4), aug_t=aug_t,
+                                  return_x0=True)
+            return flow.permute(0, 2, 1, 3, 4), x0
+        if clean_x is not None:
+            raise NotImplementedError("teacher forcing applies to the causal model")
         if kv_cache is None:
             # bidirectional forward (wan_wrapper.py:329-337): [B, F] timesteps must be uniform per sample (:282-283)
-            if not isinstance(self.model, B200WanModel):
-                raise NotImplementedError("the causal model without a KV cache is the training forward (out of scope)")
             t0 = timestep[:, 0]
             if not bool((timestep == t0[:, None]).all()):
                 raise ValueError("the bidirectional model takes one timestep per sample")

@@ -198,11 +198,17 @@ def test_state_dict_is_reference_compatible():
     m.load_state_dict(sd, strict=True)
 
 
-def test_training_path_raises():
+def test_cache_free_call_dispatches_to_the_training_forward():
+    """forward() without a kv_cache is the training-time forward (reference causal_model.py:1071-1079; parity in
+    tests/test_train_forward.py); pose / image conditioning still raises."""
     from self_forcing_b200.model import B200CausalWanModel
-    m = B200CausalWanModel(dim=256, ffn_dim=256, num_heads=2, num_layers=1, text_dim=512, ops=TorchOps())
+    m = B200CausalWanModel(dim=256, ffn_dim=256, num_heads=2, num_layers=1, text_dim=512, ops=TorchOps()).to(torch.bfloat16)
+    m.init_weights(0)
+    x = torch.zeros(1, 16, 1, 8, 8, dtype=torch.bfloat16)
+    out = m(x, t=torch.zeros(1, 1), context=torch.zeros(1, 512, 512, dtype=torch.bfloat16), seq_len=100)
+    assert out.shape == x.shape
     with pytest.raises(NotImplementedError):
-        m(torch.zeros(1, 16, 1, 8, 8), t=torch.zeros(1, 1), context=torch.zeros(1, 512, 512), seq_len=100)
+        m(x, t=torch.zeros(1, 1), context=torch.zeros(1, 512, 512, dtype=torch.bfloat16), seq_len=100, y=[x[0]])
 
 
 # --------------------------------------------------------------------------------------------------
