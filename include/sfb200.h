@@ -21,7 +21,7 @@
 extern "C" {
 #endif
 
-#define SFB_ABI_VERSION 8
+#define SFB_ABI_VERSION 9
 
 const char* sfb_last_error(void);
 int sfb_abi_version(void);

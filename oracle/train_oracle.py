@@ -42,7 +42,7 @@ def masked_attention(q: Tensor, k: Tensor, v: Tensor, mask: Tensor) -> Tensor:
     qh, kh, vh = (torch.cat([t, t.new_zeros(B, pad, H, D)], dim=1).transpose(2, 1) for t in (q, k, v))
     scores = qh.to(torch.float32) @ kh.to(torch.float32).transpose(-2, -1)
     scores = scores * (1.0 / (D ** 0.5))
-    scores = torch.where(mask[None, None], scores, torch.full_like(scores, float("-inf")))
+    scores = torch.where(mask.to(scores.device)[None, None], scores, torch.full_like(scores, float("-inf")))
     probs = torch._safe_softmax(scores, dim=-1)
     out = probs.to(q.dtype) @ vh                                    # [B, H, Lp, D]
     out = out.transpose(1, 2).contiguous().transpose(1, 2)          # flex_attention returns the query's memory layout
