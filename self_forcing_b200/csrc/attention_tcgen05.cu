@@ -33,52 +33,9 @@
 #include <stdlib.h>
 
 #include "common.cuh"
+#include "attention_sched.cuh"
 
 namespace sfb {
-
-struct AttnParams {
-  int Lq, Skv, H, B;
-  int n_kv_tiles;
-  int kv_tail;            // valid columns in the last KV tile (1..128)
-  int n_qpairs;           // ceil(Lq / 256)
-  int items;              // B * H * n_qpairs
-  int split;              // 1: contiguous step ranges per CTA (partials in ws), 0: whole items per CTA
-  int heads_per_group;    // (batch, head) pairs processed together; groups run one after the other so that the
-  int n_groups;           //   K/V of the heads in flight stays L2-resident (every K/V tile is read by all q tiles)
-  float scale_log2;       // softmax_scale * log2(e)
-  __nv_bfloat16* out[8];  // query rows [d * rows_per_dst, (d + 1) * rows_per_dst) go to out[d] (Ulysses: peer-mapped
-  int rows_per_dst;       //   buffers, the epilogue stores are the reverse all-to-all); one destination otherwise
-  long long out_row_stride, out_batch_stride;   // elements
-  float* ws;              // [group][grid][2 slots][2 tiles][128*128 O^T + 128 m + 128 l] floats (split mode)
-  long long* dbg;         // diagnostic phase timers [grid][8] (SFB_ATTN_TIMING=1), else nullptr
-};
-
-constexpr int ATT_BM = 128, ATT_BN = 128, ATT_D = 128;
-constexpr int ATT_THREADS = 384;
-constexpr int ATT_TILE_BYTES = 128 * 128 * 2;    // 32 KB: two 16 KB halves (d 0-63 | d 64-127)
-constexpr int ATT_HALF_BYTES = 128 * 64 * 2;
-constexpr int ATT_KV_STAGES = 2;
-constexpr int ATT_SMEM_BYTES = 2 * ATT_TILE_BYTES + 2 * ATT_KV_STAGES * ATT_TILE_BYTES + 1024 + 256;
-constexpr int ATT_SLOT_FLOATS = ATT_BM * ATT_D + 2 * ATT_BM;   // one (tile, segment) partial
-constexpr int ATT_MIN_SPLIT_KV_TILES = 48;                     // shorter KV (measured: S = 4680 is better whole, S >= 9360 split): whole items per CTA
-constexpr int ATT_MAX_GROUPS = 4;
-constexpr long long ATT_L2_BUDGET = 72ll << 20;                // K + V bytes of the heads in flight (L2 is 126 MB; measured: 3 groups of 4 heads beat 4 x 3 and 6 x 2 at S = 32760)
-
-// Work of one head group: items_g = (heads in the group) x n_qpairs items of n_kv steps, linearised item-major.
-__host__ __device__ __forceinline__ int att_group_items(int grp, const AttnParams& p) {
-  const int bh0 = grp * p.heads_per_group;
-  const int nbh = (p.B * p.H - bh0) < p.heads_per_group ? (p.B * p.H - bh0) : p.heads_per_group;
-  return nbh * p.n_qpairs;
-}
-// first KV step (in the group's linearised item x step space) of CTA c, and the owner of a step
-__host__ __device__ __forceinline__ long long att_range_start(int c, int grid, int items_g, const AttnParams& p) {
-  if (p.split) return ((long long)c * items_g * p.n_kv_tiles) / grid;
-  return (((long long)c * items_g) / grid) * p.n_kv_tiles;
-}
-__host__ __device__ __forceinline__ int att_step_owner(long long step, int grid, int items_g, const AttnParams& p) {
-  const long long G = (long long)items_g * p.n_kv_tiles;
-  return (int)(((step + 1) * grid - 1) / G);   // largest c with floor(c * G / grid) <= step   (split mode)
-}
 
 __device__ __forceinline__ float fast_exp2(float x) {
   float y;
@@ -148,51 +105,65 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_con
     if (warp == 0) {
       // ------------------------------ TMA producer (warp-uniform, one lane issues) ----
       {
-        uint32_t seg = 0, g = 0;   // segment counter, ring counter (KV steps issued so far)
+        uint32_t seg = 0, g = 0;   // segment counter, ring counter (KV tiles issued so far)
         for (int grp = 0; grp < p.n_groups; ++grp) {
-        const int items_g = att_group_items(grp, p);
-        const long long range_end = att_range_start(blockIdx.x + 1, gridDim.x, items_g, p);
-        for (long long cur = att_range_start(blockIdx.x, gridDim.x, items_g, p); cur < range_end; ++seg) {
-          const int item = (int)(cur / n_kv);
-          const int j0 = (int)(cur - (long long)item * n_kv);
-          const int j1 = (range_end - cur) < (long long)(n_kv - j0) ? j0 + (int)(range_end - cur) : n_kv;
-          const int qp = item % p.n_qpairs, bh = grp * p.heads_per_group + item / p.n_qpairs;
+        const int range_end = att_range_start(blockIdx.x + 1, gridDim.x, grp, p);
+        for (int cur = att_range_start(blockIdx.x, gridDim.x, grp, p); cur < range_end; ++seg) {
+          const AttSeg sg = att_decode(cur, range_end, p);
+          const int bh = grp * p.heads_per_group + sg.bh_local;
           const int head = bh % p.H, batch = bh / p.H;
-          const int q_row0 = qp * (2 * ATT_BM);
+          const int q_row0 = sg.qp * (2 * ATT_BM);
           mbar_wait(q_empty, (seg & 1) ^ 1);           // previous segment's QK^T MMAs have retired
           if (elect_one()) {
             mbar_expect_tx(q_full, 2 * ATT_TILE_BYTES);
 #pragma unroll
             for (int t = 0; t < 2; ++t)
 #pragma unroll
-              for (int hf = 0; hf < 2; ++hf)
+              for (int hf = 0; hf < 2; ++hf)   // half item: the one query tile in both slots
                 tma_load_4d(q_smem + t * ATT_TILE_BYTES + hf * ATT_HALF_BYTES, &tma_q, q_full, hf * 64, head,
-                            q_row0 + t * ATT_BM, batch);
+                            q_row0 + (sg.half ? 0 : t * ATT_BM), batch);
           }
           __syncwarp();
-          for (int j = j0; j < j1; ++j, ++g) {
-            const int st = g & 1;
-            const uint32_t ph = (g >> 1) & 1;
-            mbar_wait(&k_empty[st], ph ^ 1);
+          // KV tiles of the segment, one ring entry each (a half item's step is two tiles)
+          const int kv_lo = sg.half ? 2 * sg.j0 : sg.j0;
+          const int kv_hi = sg.half ? (2 * sg.j1 < n_kv ? 2 * sg.j1 : n_kv) : sg.j1;
+          auto load_k = [&](int j, uint32_t e) {
+            mbar_wait(&k_empty[e & 1], ((e >> 1) & 1) ^ 1);
             if (elect_one()) {
-              mbar_expect_tx(&k_full[st], ATT_TILE_BYTES);
+              mbar_expect_tx(&k_full[e & 1], ATT_TILE_BYTES);
 #pragma unroll
               for (int hf = 0; hf < 2; ++hf)
-                tma_load_4d(k_smem + st * ATT_TILE_BYTES + hf * ATT_HALF_BYTES, &tma_k, &k_full[st], hf * 64, head,
+                tma_load_4d(k_smem + (e & 1) * ATT_TILE_BYTES + hf * ATT_HALF_BYTES, &tma_k, &k_full[e & 1], hf * 64, head,
                             j * ATT_BN, batch);
             }
             __syncwarp();
-            mbar_wait(&v_empty[st], ph ^ 1);
+          };
+          auto load_v = [&](int j, uint32_t e) {
+            mbar_wait(&v_empty[e & 1], ((e >> 1) & 1) ^ 1);
             if (elect_one()) {
-              mbar_expect_tx(&v_full[st], ATT_TILE_BYTES);
+              mbar_expect_tx(&v_full[e & 1], ATT_TILE_BYTES);
 #pragma unroll
               for (int hf = 0; hf < 2; ++hf)
-                tma_load_4d(v_smem + st * ATT_TILE_BYTES + hf * ATT_HALF_BYTES, &tma_v, &v_full[st], hf * 64, head,
+                tma_load_4d(v_smem + (e & 1) * ATT_TILE_BYTES + hf * ATT_HALF_BYTES, &tma_v, &v_full[e & 1], hf * 64, head,
                             j * ATT_BN, batch);
             }
             __syncwarp();
+          };
+          if (!sg.half) {
+            for (int j = kv_lo; j < kv_hi; ++j, ++g) { load_k(j, g); load_v(j, g); }
+          } else {
+            // two ring entries per step: both K tiles first (they only wait for the QK^T two entries back), then the V
+            // tiles (which wait for the PV two entries back -- a later event)
+            for (int j = kv_lo; j < kv_hi; j += 2) {
+              const bool two = j + 1 < kv_hi;
+              load_k(j, g);
+              if (two) load_k(j + 1, g + 1);
+              load_v(j, g);
+              if (two) load_v(j + 1, g + 1);
+              g += two ? 2 : 1;
+            }
           }
-          cur += j1 - j0;
+          cur += sg.j1 - sg.j0;
         }
         }
       }
@@ -223,62 +194,123 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_con
           }
         };
 
-        uint32_t seg = 0, g = 0;
+        uint32_t seg = 0, g = 0;     // segment counter, ring counter (KV tiles consumed so far)
+        uint32_t sc[2] = {0, 0};     // score tiles committed so far per query-tile slot (parity of s_full / p_half)
         for (int grp = 0; grp < p.n_groups; ++grp) {
-        const int items_g = att_group_items(grp, p);
-        const long long range_end = att_range_start(blockIdx.x + 1, gridDim.x, items_g, p);
-        for (long long cur = att_range_start(blockIdx.x, gridDim.x, items_g, p); cur < range_end; ++seg) {
-          const int item = (int)(cur / n_kv);
-          const int j0 = (int)(cur - (long long)item * n_kv);
-          const int n = (range_end - cur) < (long long)(n_kv - j0) ? (int)(range_end - cur) : (n_kv - j0);
+        const int range_end = att_range_start(blockIdx.x + 1, gridDim.x, grp, p);
+        for (int cur = att_range_start(blockIdx.x, gridDim.x, grp, p); cur < range_end; ++seg) {
+          const AttSeg sg = att_decode(cur, range_end, p);
+          const int n = sg.j1 - sg.j0;
           mbar_wait(q_full, seg & 1);
-          mbar_wait(&k_full[g & 1], (g >> 1) & 1);
-          tc_fence_after();
-          if (elect_one()) {
-            issue_qk(0, g & 1);
-            umma_commit(&s_full[0]);
-            issue_qk(1, g & 1);
-            umma_commit(&s_full[1]);
-            umma_commit(&k_empty[g & 1]);
-            if (n == 1) umma_commit(q_empty);
-          }
-          __syncwarp();
-          for (int i = 0; i < n; ++i, ++g) {
-            const int vst = g & 1;
-            const uint32_t vph = (g >> 1) & 1;
-            const bool has_next = (i + 1) < n;
-            const int kst = (g + 1) & 1;
-            const uint32_t kph = ((g + 1) >> 1) & 1;
-            for (int t = 0; t < 2; ++t) {
-              // P arrives in two halves (64 KV columns each): the first half's PV overlaps the softmax of the second
-              mbar_wait(&p_half[2 * t], g & 1);
-              if (t == 0) mbar_wait(&v_full[vst], vph);
-              if (i == 0) mbar_wait(&o_free[t], (seg & 1) ^ 1);   // previous segment's epilogue has read O_t
-              tc_fence_after();
-              if (elect_one()) issue_pv(t, vst, i > 0, 0);
-              __syncwarp();
-              mbar_wait(&p_half[2 * t + 1], g & 1);
-              tc_fence_after();
-              if (has_next && t == 0) {
-                mbar_wait(&k_full[kst], kph);
+          if (!sg.half) {
+            // ---- full item: both query tiles walk the same KV tiles; one ring entry per step ----
+            mbar_wait(&k_full[g & 1], (g >> 1) & 1);
+            tc_fence_after();
+            if (elect_one()) {
+              issue_qk(0, g & 1);
+              umma_commit(&s_full[0]);
+              issue_qk(1, g & 1);
+              umma_commit(&s_full[1]);
+              umma_commit(&k_empty[g & 1]);
+              if (n == 1) umma_commit(q_empty);
+            }
+            __syncwarp();
+            for (int i = 0; i < n; ++i, ++g) {
+              const int vst = g & 1;
+              const uint32_t vph = (g >> 1) & 1;
+              const bool has_next = (i + 1) < n;
+              const int kst = (g + 1) & 1;
+              const uint32_t kph = ((g + 1) >> 1) & 1;
+              for (int t = 0; t < 2; ++t) {
+                // P arrives in two halves (64 KV columns each): the first half's PV overlaps the softmax of the second
+                mbar_wait(&p_half[2 * t], sc[t] & 1);
+                if (t == 0) mbar_wait(&v_full[vst], vph);
+                if (i == 0) mbar_wait(&o_free[t], (seg & 1) ^ 1);   // previous segment's epilogue has read O_t
                 tc_fence_after();
-              }
-              if (elect_one()) {
-                issue_pv(t, vst, true, 1);
-                if (t == 1) umma_commit(&v_empty[vst]);
-                if (has_next) {
-                  issue_qk(t, kst);
-                  umma_commit(&s_full[t]);
-                  if (t == 1) {
-                    umma_commit(&k_empty[kst]);
-                    if (i + 2 == n) umma_commit(q_empty);   // that was the segment's last QK^T: Q smem reusable
-                  }
-                } else {
-                  umma_commit(&o_final[t]);
+                if (elect_one()) issue_pv(t, vst, i > 0, 0);
+                __syncwarp();
+                mbar_wait(&p_half[2 * t + 1], sc[t] & 1);
+                tc_fence_after();
+                if (has_next && t == 0) {
+                  mbar_wait(&k_full[kst], kph);
+                  tc_fence_after();
                 }
+                if (elect_one()) {
+                  issue_pv(t, vst, true, 1);
+                  if (t == 1) umma_commit(&v_empty[vst]);
+                  if (has_next) {
+                    issue_qk(t, kst);
+                    umma_commit(&s_full[t]);
+                    if (t == 1) {
+                      umma_commit(&k_empty[kst]);
+                      if (i + 2 == n) umma_commit(q_empty);   // that was the segment's last QK^T: Q smem reusable
+                    }
+                  } else {
+                    umma_commit(&o_final[t]);
+                  }
+                }
+                __syncwarp();
+                ++sc[t];
+              }
+            }
+          } else {
+            // ---- half item: ONE query tile (in both Q slots); slot t takes KV tiles kv_lo + t, kv_lo + t + 2, ... each
+            //      its own ring entry; O_0 and O_1 are partial sums over disjoint KV tiles, merged by the softmax warps ----
+            const int kv_lo = 2 * sg.j0, kv_hi = 2 * sg.j1 < n_kv ? 2 * sg.j1 : n_kv;
+            const int cnt = kv_hi - kv_lo;
+            const int n_t[2] = {(cnt + 1) >> 1, cnt >> 1};
+            for (int t = 0; t < 2; ++t) {
+              if (n_t[t] == 0) continue;
+              const uint32_t e = g + t;
+              mbar_wait(&k_full[e & 1], (e >> 1) & 1);
+              tc_fence_after();
+              if (elect_one()) {
+                issue_qk(t, e & 1);
+                umma_commit(&s_full[t]);
+                umma_commit(&k_empty[e & 1]);
+                if ((int)t == cnt - 1) umma_commit(q_empty);
               }
               __syncwarp();
             }
+            for (int i = 0; i < n_t[0]; ++i) {
+              for (int t = 0; t < 2; ++t) {
+                if (i >= n_t[t]) continue;
+                const uint32_t e = g + 2 * i + t, e2 = e + 2;
+                const int vst = e & 1;
+                const bool has_next = (i + 1) < n_t[t];
+                mbar_wait(&p_half[2 * t], sc[t] & 1);
+                mbar_wait(&v_full[vst], (e >> 1) & 1);
+                if (i == 0) mbar_wait(&o_free[t], (seg & 1) ^ 1);
+                tc_fence_after();
+                if (elect_one()) issue_pv(t, vst, i > 0, 0);
+                __syncwarp();
+                mbar_wait(&p_half[2 * t + 1], sc[t] & 1);
+                tc_fence_after();
+                if (has_next) {
+                  mbar_wait(&k_full[e2 & 1], (e2 >> 1) & 1);
+                  tc_fence_after();
+                }
+                if (elect_one()) {
+                  issue_pv(t, vst, true, 1);
+                  umma_commit(&v_empty[vst]);
+                  if (has_next) {
+                    issue_qk(t, e2 & 1);
+                    umma_commit(&s_full[t]);
+                    umma_commit(&k_empty[e2 & 1]);
+                    if (2 * (i + 1) + t == cnt - 1) umma_commit(q_empty);
+                  } else {
+                    umma_commit(&o_final[t]);
+                  }
+                }
+                __syncwarp();
+                ++sc[t];
+              }
+            }
+            if (n_t[1] == 0) {           // slot 1 had no KV tile in this segment: keep its per-segment barrier in step
+              if (elect_one()) umma_commit(&o_final[1]);
+              __syncwarp();
+            }
+            g += cnt;
           }
           cur += n;
         }
@@ -306,21 +338,22 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_con
         t_prev = now;
       }
     };
-    uint32_t seg = 0, g = 0;
+    uint32_t seg = 0, sc = 0;   // segment counter, score tiles of THIS query-tile slot consumed so far
+    float2* xchg = reinterpret_cast<float2*>(bars + 32);   // [2 segment parities][128 rows] (m, l) of slot 1 -> slot 0's warps (half items)
     for (int grp = 0; grp < p.n_groups; ++grp) {
-    const int items_g = att_group_items(grp, p);
-    const long long range_begin = att_range_start(blockIdx.x, gridDim.x, items_g, p);
-    const long long range_end = att_range_start(blockIdx.x + 1, gridDim.x, items_g, p);
-    for (long long cur = range_begin; cur < range_end; ++seg) {
-      const int item = (int)(cur / n_kv);
-      const int j0 = (int)(cur - (long long)item * n_kv);
-      const int j1 = (range_end - cur) < (long long)(n_kv - j0) ? j0 + (int)(range_end - cur) : n_kv;
+    const int range_begin = att_range_start(blockIdx.x, gridDim.x, grp, p);
+    const int range_end = att_range_start(blockIdx.x + 1, gridDim.x, grp, p);
+    for (int cur = range_begin; cur < range_end; ++seg) {
+      const AttSeg sg = att_decode(cur, range_end, p);
+      // KV tiles of this slot: every tile of the segment (full item) or every other one (half item)
+      const int jb = sg.half ? 2 * sg.j0 + t : sg.j0, js = sg.half ? 2 : 1;
+      const int je = sg.half ? (2 * sg.j1 < n_kv ? 2 * sg.j1 : n_kv) : sg.j1;
       float m_ref = -INFINITY;   // reference max (raw score units) the stored exponentials are relative to
       float l = 0.f;             // running sum of exponentials relative to m_ref
 
-      for (int j = j0; j < j1; ++j, ++g) {
+      for (int j = jb; j < je; j += js, ++sc) {
         stamp(5);
-        mbar_wait(&s_full[t], g & 1);
+        mbar_wait(&s_full[t], sc & 1);
         tc_fence_after();
         stamp(0);
         if (j == n_kv - 1 && p.kv_tail < ATT_BN) {
@@ -358,7 +391,7 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_con
           mx3 = fmaxf(mx3, __uint_as_float(s[i + 3]));
         }
         const float mx = fmaxf(fmaxf(mx0, mx1), fmaxf(mx2, mx3));
-        if (j == j0) {
+        if (j == jb) {
           m_ref = mx;
         } else {
           const float m_new = fmaxf(m_ref, mx);
@@ -414,55 +447,99 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_con
       // segment epilogue
       mbar_wait(&o_final[t], seg & 1);
       tc_fence_after();
-      const int qp = item % p.n_qpairs, bh = grp * p.heads_per_group + item / p.n_qpairs;
+      const int bh = grp * p.heads_per_group + sg.bh_local;
       const int head = bh % p.H, batch = bh / p.H;
-      if (j0 == 0 && j1 == n_kv) {
-        // whole item: O_t / l -> bf16 -> global, one query row per thread (256 contiguous bytes)
-        const int row = qp * (2 * ATT_BM) + t * ATT_BM + r_local;
-        const float inv_l = 1.0f / l;
-        const int dst = row / p.rows_per_dst;
-        __nv_bfloat16* orow = p.out[dst < 8 ? dst : 0] + (long long)batch * p.out_batch_stride +
-                              (long long)(row - dst * p.rows_per_dst) * p.out_row_stride + head * ATT_D;
-#pragma unroll 1
-        for (int c = 0; c < 4; ++c) {
-          uint32_t o[32];
-          tmem_ld32(o_addr + c * 32, o);
-          tmem_ld_wait();
-          if (row < p.Lq) {
-#pragma unroll
-            for (int gq = 0; gq < 4; ++gq) {
-              uint4 w;
-              w.x = pack_bf16(__uint_as_float(o[gq * 8 + 0]) * inv_l, __uint_as_float(o[gq * 8 + 1]) * inv_l);
-              w.y = pack_bf16(__uint_as_float(o[gq * 8 + 2]) * inv_l, __uint_as_float(o[gq * 8 + 3]) * inv_l);
-              w.z = pack_bf16(__uint_as_float(o[gq * 8 + 4]) * inv_l, __uint_as_float(o[gq * 8 + 5]) * inv_l);
-              w.w = pack_bf16(__uint_as_float(o[gq * 8 + 6]) * inv_l, __uint_as_float(o[gq * 8 + 7]) * inv_l);
-              *reinterpret_cast<uint4*>(orow + c * 32 + gq * 8) = w;
-            }
+      const bool whole = sg.j0 == 0 && sg.j1 == sg.item_steps;
+      if (sg.half && t == 1) {
+        // half item, slot 1: hand (m, l) to slot 0's warp of the same TMEM lane quarter, which reads O_1 itself
+        xchg[(seg & 1) * ATT_BM + r_local] = make_float2(m_ref, l);
+        tc_fence_before();
+        named_barrier_arrive(1, 2 * ATT_BM);
+      } else {
+        // rows of this thread: O_t scaled by w_own (+ O_1 scaled by w_oth for a half item), row sum l
+        float w_own = 1.f, w_oth = 0.f;
+        bool two = false;
+        if (sg.half) {
+          named_barrier_sync(1, 2 * ATT_BM);
+          tc_fence_after();
+          const float2 ml = xchg[(seg & 1) * ATT_BM + r_local];
+          two = ((2 * sg.j1 < n_kv ? 2 * sg.j1 : n_kv) - 2 * sg.j0) > 1;   // slot 1 had at least one KV tile (segment-uniform)
+          if (two) {
+            const float m_new = fmaxf(m_ref, ml.x);
+            w_own = fast_exp2((m_ref - m_new) * sl2);
+            w_oth = fast_exp2((ml.x - m_new) * sl2);
+            l = l * w_own + ml.y * w_oth;
+            m_ref = m_new;
           }
         }
-      } else {
-        // partial item: park (O^T, m, l) in this CTA's workspace slot (first segment -> 0, last -> 1)
-        float* slot = p.ws + ((((long long)grp * gridDim.x + blockIdx.x) * 2 + (cur == range_begin ? 0 : 1)) * 2 + t) *
-                                 ATT_SLOT_FLOATS;
+        const uint32_t o_oth = o_addr + 128;   // O_1 (same TMEM lanes)
+        const int row = sg.qp * (2 * ATT_BM) + t * ATT_BM + r_local;
+        if (whole) {
+          // whole item: O / l -> bf16 -> global, one query row per thread (256 contiguous bytes)
+          const float inv_l = 1.0f / l;
+          const float a_own = w_own * inv_l, a_oth = w_oth * inv_l;
+          const int dst = row / p.rows_per_dst;
+          __nv_bfloat16* orow = p.out[dst < 8 ? dst : 0] + (long long)batch * p.out_batch_stride +
+                                (long long)(row - dst * p.rows_per_dst) * p.out_row_stride + head * ATT_D;
 #pragma unroll 1
-        for (int c = 0; c < 4; ++c) {
-          uint32_t o[32];
-          tmem_ld32(o_addr + c * 32, o);
-          tmem_ld_wait();
+          for (int c = 0; c < 4; ++c) {
+            uint32_t o[32];
+            tmem_ld32(o_addr + c * 32, o);
+            tmem_ld_wait();
 #pragma unroll
-          for (int i = 0; i < 32; ++i) slot[(c * 32 + i) * ATT_BM + r_local] = __uint_as_float(o[i]);   // coalesced
+            for (int i = 0; i < 32; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * a_own);
+            if (two) {
+              uint32_t o2[32];
+              tmem_ld32(o_oth + c * 32, o2);
+              tmem_ld_wait();
+#pragma unroll
+              for (int i = 0; i < 32; ++i) o[i] = __float_as_uint(fmaf(__uint_as_float(o2[i]), a_oth, __uint_as_float(o[i])));
+            }
+            if (row < p.Lq) {
+#pragma unroll
+              for (int gq = 0; gq < 4; ++gq) {
+                uint4 w;
+                w.x = pack_bf16(__uint_as_float(o[gq * 8 + 0]), __uint_as_float(o[gq * 8 + 1]));
+                w.y = pack_bf16(__uint_as_float(o[gq * 8 + 2]), __uint_as_float(o[gq * 8 + 3]));
+                w.z = pack_bf16(__uint_as_float(o[gq * 8 + 4]), __uint_as_float(o[gq * 8 + 5]));
+                w.w = pack_bf16(__uint_as_float(o[gq * 8 + 6]), __uint_as_float(o[gq * 8 + 7]));
+                *reinterpret_cast<uint4*>(orow + c * 32 + gq * 8) = w;
+              }
+            }
+          }
+        } else {
+          // partial item: park (O^T, m, l) in this CTA's workspace slot (first segment -> 0, last -> 1)
+          float* slot = p.ws + ((((long long)grp * gridDim.x + blockIdx.x) * 2 + (cur == range_begin ? 0 : 1)) * 2 + t) *
+                                   ATT_SLOT_FLOATS;
+#pragma unroll 1
+          for (int c = 0; c < 4; ++c) {
+            uint32_t o[32];
+            tmem_ld32(o_addr + c * 32, o);
+            tmem_ld_wait();
+            if (two) {
+              uint32_t o2[32];
+              tmem_ld32(o_oth + c * 32, o2);
+              tmem_ld_wait();
+#pragma unroll
+              for (int i = 0; i < 32; ++i)
+                o[i] = __float_as_uint(fmaf(__uint_as_float(o2[i]), w_oth, __uint_as_float(o[i]) * w_own));
+            }
+#pragma unroll
+            for (int i = 0; i < 32; ++i) slot[(c * 32 + i) * ATT_BM + r_local] = __uint_as_float(o[i]);   // coalesced
+          }
+          slot[ATT_BM * ATT_D + r_local] = m_ref;
+          slot[ATT_BM * ATT_D + ATT_BM + r_local] = l;
         }
-        slot[ATT_BM * ATT_D + r_local] = m_ref;
-        slot[ATT_BM * ATT_D + ATT_BM + r_local] = l;
+        tc_fence_before();
+        mbar_arrive(&o_free[t]);
+        if (sg.half) mbar_arrive(&o_free[1]);   // slot 0's warps have read O_1 as well
       }
-      tc_fence_before();
-      mbar_arrive(&o_free[t]);
-      cur += j1 - j0;
+      cur += sg.j1 - sg.j0;
     }
     }
     if (timing) {
       for (int k = 0; k < 6; ++k) p.dbg[blockIdx.x * 8 + k] = tm[k];
-      p.dbg[blockIdx.x * 8 + 6] = g;
+      p.dbg[blockIdx.x * 8 + 6] = sc;
     }
   }
 
@@ -479,20 +556,20 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_con
 __global__ void __launch_bounds__(128)
 attention_combine_kernel(const AttnParams p, int grid_fwd) {
   const int t = blockIdx.y, r = threadIdx.x;
-  const int n_kv = p.n_kv_tiles;
   const int qp = blockIdx.x % p.n_qpairs, bh = blockIdx.x / p.n_qpairs;
   const int head = bh % p.H, batch = bh / p.H;
   const int grp = bh / p.heads_per_group;
   const int item = (bh - grp * p.heads_per_group) * p.n_qpairs + qp;   // item index inside its head group
-  const int items_g = att_group_items(grp, p);
-  const long long s0 = (long long)item * n_kv, s1 = s0 + n_kv - 1;
-  const int c0 = att_step_owner(s0, grid_fwd, items_g, p), c1 = att_step_owner(s1, grid_fwd, items_g, p);
+  const bool half = p.half_last && qp == p.n_qpairs - 1;
+  if (half && t == 1) return;   // a half item has one query tile; its two slots were merged inside the CTA (slot 0)
+  const long long s0 = att_item_first_step(item, p), s1 = s0 + (half ? p.n_half_steps : p.n_kv_tiles) - 1;
+  const int c0 = att_step_owner(s0, grid_fwd, grp, p), c1 = att_step_owner(s1, grid_fwd, grp, p);
   if (c0 == c1) return;   // the item was computed whole by one CTA
   const int row = qp * (2 * ATT_BM) + t * ATT_BM + r;
   if (row >= p.Lq) return;
   auto slot_of = [&](int c) {
-    const int first_item = (int)(att_range_start(c, grid_fwd, items_g, p) / n_kv);
-    return p.ws + ((((long long)grp * grid_fwd + c) * 2 + (first_item == item ? 0 : 1)) * 2 + t) * ATT_SLOT_FLOATS;
+    const bool first = att_range_start(c, grid_fwd, grp, p) >= s0;   // CTA c's first segment belongs to this item
+    return p.ws + ((((long long)grp * grid_fwd + c) * 2 + (first ? 0 : 1)) * 2 + t) * ATT_SLOT_FLOATS;
   };
   // an item is cut by at most a few CTA boundaries: keep the segment pointers and weights in registers
   constexpr int MAX_SEG = 8;
@@ -581,51 +658,13 @@ static int attention_launch(const void* q, long long q_row_stride, long long q_b
   const int sms = device_sm_count();
   if (sms <= 0) return SFB_ERR_CUDA;
   AttnParams p{};
-  p.Lq = Lq; p.Skv = Skv; p.H = H; p.B = B;
-  p.n_kv_tiles = (Skv + ATT_BN - 1) / ATT_BN;
-  p.kv_tail = Skv - (p.n_kv_tiles - 1) * ATT_BN;
-  p.n_qpairs = (Lq + 2 * ATT_BM - 1) / (2 * ATT_BM);
-  p.items = B * H * p.n_qpairs;
+  const int grid = att_plan(p, B, Lq, Skv, H, sms, workspace != nullptr ? workspace_bytes : 0);
   p.scale_log2 = softmax_scale * 1.4426950408889634f;
   for (int d = 0; d < 8; ++d) p.out[d] = static_cast<__nv_bfloat16*>(out_dst[d < n_dst ? d : 0]);
   p.rows_per_dst = rows_per_dst;
   p.out_row_stride = out_row_stride;
   p.out_batch_stride = out_batch_stride;
   p.ws = static_cast<float*>(workspace);
-  // Long KV windows: one contiguous range of (item, KV step) work per SM, whatever the item count (also when there
-  // are fewer items than SMs -- head-parallel ranks and frame-wise rollouts).  Short ones: whole items per CTA.
-  int grid = p.items < sms ? p.items : sms;
-  p.heads_per_group = B * H;
-  p.n_groups = 1;
-  const long long slot_bytes = (long long)sms * 2 * 2 * ATT_SLOT_FLOATS * (long long)sizeof(float);   // per group
-  const char* nosplit = getenv("SFB_ATTN_NOSPLIT");
-  // (with >= 8 items per SM whole items already balance to within a few per cent, and consecutive CTAs walk the same
-  // head's K/V together -- no partials, natural L2 locality: the 14B teacher has 5120 items)
-  p.split = (p.items % sms != 0 && p.items < 8 * sms && p.n_kv_tiles >= ATT_MIN_SPLIT_KV_TILES && workspace != nullptr &&
-             workspace_bytes >= slot_bytes && !(nosplit && nosplit[0] == '1')) ? 1 : 0;
-  if (p.split) {
-    grid = sms;
-    // head groups: keep K + V of the (batch, head) pairs in flight within the L2 budget
-    const long long kv_bytes_per_head = 2ll * Skv * ATT_D * 2;
-    long long hg_max = ATT_L2_BUDGET / kv_bytes_per_head;
-    if (hg_max < 1) hg_max = 1;
-    int groups = (int)((B * H + hg_max - 1) / hg_max);
-    const int groups_fit = (int)(workspace_bytes / slot_bytes);
-    if (groups > ATT_MAX_GROUPS) groups = ATT_MAX_GROUPS;
-    if (groups > groups_fit) groups = groups_fit;
-    if (const char* env = getenv("SFB_ATTN_GROUPS")) { const int gq = atoi(env); if (gq >= 1 && gq <= groups_fit && gq <= ATT_MAX_GROUPS) groups = gq; }
-    p.n_groups = groups;
-    p.heads_per_group = (B * H + groups - 1) / groups;
-    p.n_groups = (B * H + p.heads_per_group - 1) / p.heads_per_group;
-    // the merge kernel keeps at most 8 segments of an item in registers: never cut an item into more pieces
-    const int last_heads = B * H - (p.n_groups - 1) * p.heads_per_group;
-    const int min_items = last_heads * p.n_qpairs;
-    if ((grid + min_items - 1) / min_items + 1 > 8) grid = min_items * 6;
-  }
-  if (const char* cap = getenv("SFB_ATTN_GRID")) {   // diagnostic: run on fewer SMs
-    const int g = atoi(cap);
-    if (g > 0 && g < grid) grid = g;
-  }
 
   static long long* dbg_buf = nullptr;
   static int timing = -1;

@@ -178,6 +178,9 @@ __device__ __forceinline__ void tma_store_wait_read() {
 __device__ __forceinline__ void named_barrier_sync(int id, int threads) {
   asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(threads) : "memory");
 }
+__device__ __forceinline__ void named_barrier_arrive(int id, int threads) {
+  asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(threads) : "memory");
+}
 
 // ------------------------------------------------------------------------------------
 // tcgen05 / TMEM

@@ -726,6 +726,10 @@ ALL = {
     "attn_split_batch": lambda: check_attention(B=2, Lq=1560, S=9360, H=12, seed=6),
     "attn_split_3way": lambda: check_attention(Lq=1300, S=40000, H=32, seed=7),
     "attn_whole_items": lambda: check_attention(Lq=1560, S=4680, H=12, seed=8),
+    "attn_half_even_kv": lambda: check_attention(B=2, Lq=400, S=1024, H=3, seed=11),          # lone 4th query tile, 8 KV tiles
+    "attn_half_two_kv": lambda: check_attention(Lq=100, S=200, H=5, seed=12),                 # half items only, one step each
+    "attn_half_cross_full": lambda: check_attention(Lq=4680, S=512, H=12, seed=13),           # cross-attention of a chunk
+    "attn_half_split_long": lambda: check_attention(Lq=4680, S=18720, H=12, seed=14),         # split schedule with half items
     "ln_modulate": check_ln_modulate,
     "ln_affine": check_ln_affine,
     "rmsnorm": check_rmsnorm,
