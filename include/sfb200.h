@@ -21,7 +21,7 @@
 extern "C" {
 #endif
 
-#define SFB_ABI_VERSION 9
+#define SFB_ABI_VERSION 10
 
 const char* sfb_last_error(void);
 int sfb_abi_version(void);
@@ -51,6 +51,24 @@ int sfb_gemm_bf16(const void* x, long long ldx, const void* w, long long ldw, co
                   const void* gate, long long gate_stride, int rows_per_gate, int gate_row_offset,
                   int block_n, void* workspace, long long workspace_bytes, void* stream);
 
+/* sfb_gemm_bf16 with per-row statistics, so that the row-wise norms around a projection need no pass of their own.
+ * A statistics record is float[2] = (mean, M2 = sum (x - mean)^2) of one row over SFB_STATS_CHUNK consecutive columns,
+ * laid out [row][chunk]; chunks are merged with Chan's parallel-variance formula.  Needs the CTA-pair tiles (M > 128, N and
+ * seg_cols multiples of 256; block_n 0 / 512 / 515).
+ *   stats_out != NULL: records of the bf16 OUTPUT rows, [M][N / SFB_STATS_CHUNK].
+ *   ln_stats  != NULL: records of the INPUT rows x, [M][K / SFB_STATS_CHUNK]; the affine LayerNorm in front of the Linear
+ *     (norm3 + cross-attention q, causal_model.py:324 -> model.py:172) is folded into the epilogue:
+ *       y[r][n] = bf16(rstd_r * (acc[r][n] - mean_r * ln_sc[n][0]) + ln_sc[n][1])
+ *     where w = bf16(W * norm_weight) (per input channel), ln_sc[n] = (sum_c w[n][c], bias[n] + sum_c norm_bias[c] W[n][c])
+ *     as float[2]; epilogue SFB_EPI_BIAS with bias == NULL. */
+#define SFB_STATS_CHUNK 128
+int sfb_gemm_bf16_stats(const void* x, long long ldx, const void* w, long long ldw, const void* bias,
+                        int M, int N, int K, int epilogue,
+                        void* out0, long long ldo0, void* out1, long long ldo1, void* out2, long long ldo2, int seg_cols,
+                        const void* residual, long long ldr,
+                        const void* gate, long long gate_stride, int rows_per_gate, int gate_row_offset,
+                        int block_n, void* stats_out, const void* ln_stats, const void* ln_sc, float ln_eps, void* stream);
+
 /* Scratch (bytes) for the stream-K schedule of the CTA-pair GEMM (used when whole tiles would leave the last wave
  * badly filled, e.g. 4680 x 1536 outputs = 114 tiles on 74 CTA pairs): caller-owned, zero-initialised once, one launch
  * at a time per workspace.  workspace == NULL disables stream-K. */
@@ -64,6 +82,17 @@ int sfb_attention_fwd(const void* q, long long q_row_stride, long long q_batch_s
                       void* out, long long out_row_stride, long long out_batch_stride,
                       int B, int Lq, int Skv, int H, int head_dim, float softmax_scale,
                       void* workspace, long long workspace_bytes, void* stream);
+
+/* sfb_attention_fwd with the WanRMSNorm of the query (model.py:70-86,172) folded in: q is the UN-normalised projection,
+ * q_stats its statistics records [B * Lq][q_chunks] over the full channel width (from sfb_gemm_bf16_stats), and the
+ * row's factor rsqrt(mean(q^2) + q_eps) multiplies its scores inside the softmax; the caller multiplies the norm's weight
+ * into K once per prompt (k' = k * w_q per channel). */
+int sfb_attention_fwd_qnorm(const void* q, long long q_row_stride, long long q_batch_stride,
+                            const void* k, const void* v, long long kv_row_stride, long long kv_batch_stride,
+                            void* out, long long out_row_stride, long long out_batch_stride,
+                            int B, int Lq, int Skv, int H, int head_dim, float softmax_scale,
+                            const void* q_stats, int q_chunks, float q_eps,
+                            void* workspace, long long workspace_bytes, void* stream);
 
 /* Scratch (bytes) sfb_attention_fwd uses to spread long KV windows evenly over all SMs: the (item, KV step)
  * space is cut into one contiguous range per SM and partial (O, max, sum) results of split items are merged

@@ -14,12 +14,14 @@ LIB_PATH = os.path.join(HERE, "libsfb200.so")
 P, LL, I, F = c_void_p, c_longlong, c_int, c_float
 PP = ctypes.POINTER(c_void_p)
 FP = ctypes.POINTER(c_float)   # host array of floats
-ABI_VERSION = 9
+ABI_VERSION = 10
 
 # name -> argtypes, mirroring include/sfb200.h one to one
 SIGNATURES = {
     "sfb_gemm_bf16": [P, LL, P, LL, P, I, I, I, I, P, LL, P, LL, P, LL, I, P, LL, P, LL, I, I, I, P, LL, P],
+    "sfb_gemm_bf16_stats": [P, LL, P, LL, P, I, I, I, I, P, LL, P, LL, P, LL, I, P, LL, P, LL, I, I, I, P, P, P, F, P],
     "sfb_attention_fwd": [P, LL, LL, P, P, LL, LL, P, LL, LL, I, I, I, I, I, F, P, LL, P],
+    "sfb_attention_fwd_qnorm": [P, LL, LL, P, P, LL, LL, P, LL, LL, I, I, I, I, I, F, P, I, F, P, LL, P],
     "sfb_modulation_table": [P, P, P, I, I, I, I, LL, LL, P],
     "sfb_ln_modulate": [P, LL, P, LL, I, I, F, P, P, LL, I, I, P],
     "sfb_ln_affine": [P, LL, P, LL, I, I, F, P, P, P],

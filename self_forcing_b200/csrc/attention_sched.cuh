@@ -20,6 +20,9 @@ struct AttnParams {
   int heads_per_group;    // (batch, head) pairs processed together; groups run one after the other so that the
   int n_groups;           //   K/V of the heads in flight stays L2-resident (every K/V tile is read by all q tiles)
   float scale_log2;       // softmax_scale * log2(e)
+  const float2* q_stats;  // if set: statistics records of the (un-normalised) query rows [B * Lq][q_chunks] (common.cuh); the row's
+  int q_chunks;           //   RMSNorm factor rsqrt(mean(q^2) + q_eps) over ALL heads multiplies its scores (WanRMSNorm folded into
+  float q_eps;            //   the softmax scale; the norm's weight is folded into K by the caller)
   __nv_bfloat16* out[8];  // query rows [d * rows_per_dst, (d + 1) * rows_per_dst) go to out[d] (Ulysses: peer-mapped
   int rows_per_dst;       //   buffers, the epilogue stores are the reverse all-to-all); one destination otherwise
   long long out_row_stride, out_batch_stride;   // elements

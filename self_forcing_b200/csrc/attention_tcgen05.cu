@@ -48,6 +48,9 @@ __device__ __forceinline__ void setmaxnreg_inc() { asm volatile("setmaxnreg.inc.
 template <int REGS>
 __device__ __forceinline__ void setmaxnreg_dec() { asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(REGS)); }
 
+// TIMING = true: diagnostic build with per-phase clock64 timers in one softmax warp (SFB_ATTN_TIMING=1); the timers cost
+// ~15 registers in the softmax warps, so the shipping instantiation compiles them out.
+template <bool TIMING>
 __global__ void __launch_bounds__(ATT_THREADS, 1)
 attention_fwd_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_constant__ CUtensorMap tma_k,
                      const __grid_constant__ CUtensorMap tma_v, const AttnParams p) {
@@ -101,7 +104,7 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_con
   // per head group, this CTA owns one contiguous range of (item, KV step) work: see att_range_start
 
   if (warp < 4) {
-    setmaxnreg_dec<104>();
+    setmaxnreg_dec<104>();   // frees (168 - 104) x 128 = 8192 registers of the CTA pool = exactly the (200 - 168) x 256 the softmax warps take (112 here deadlocks the inc)
     if (warp == 0) {
       // ------------------------------ TMA producer (warp-uniform, one lane issues) ----
       {
@@ -326,13 +329,12 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_con
     const uint32_t lane_base = (uint32_t)(quarter * 32) << 16;
     const uint32_t s_addr = tmem_base + lane_base + t * 128;
     const uint32_t o_addr = tmem_base + lane_base + 256 + t * 128;
-    const float sl2 = p.scale_log2;
 
-    const bool timing = p.dbg != nullptr && warp == 4 && lane == 0;
+    const bool timing = TIMING && p.dbg != nullptr && warp == 4 && lane == 0;
     long long tm[6] = {0, 0, 0, 0, 0, 0};
     long long t_prev = timing ? clock64() : 0;
     auto stamp = [&](int k) {
-      if (timing) {
+      if (TIMING && timing) {
         const long long now = clock64();
         tm[k] += now - t_prev;
         t_prev = now;
@@ -350,6 +352,13 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_con
       const int je = sg.half ? (2 * sg.j1 < n_kv ? 2 * sg.j1 : n_kv) : sg.j1;
       float m_ref = -INFINITY;   // reference max (raw score units) the stored exponentials are relative to
       float l = 0.f;             // running sum of exponentials relative to m_ref
+      float sl2 = p.scale_log2;  // softmax scale of this thread's row (x log2 e)
+      if (p.q_stats != nullptr) {
+        const int bh_s = grp * p.heads_per_group + sg.bh_local;
+        const int row_s = sg.qp * (2 * ATT_BM) + (sg.half ? 0 : t * ATT_BM) + r_local;
+        sl2 *= stats_rms_rstd(p.q_stats + ((long long)(bh_s / p.H) * p.Lq + (row_s < p.Lq ? row_s : p.Lq - 1)) * p.q_chunks,
+                              p.q_chunks, p.q_eps);
+      }
 
       for (int j = jb; j < je; j += js, ++sc) {
         stamp(5);
@@ -537,7 +546,7 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_con
       cur += sg.j1 - sg.j0;
     }
     }
-    if (timing) {
+    if (TIMING && timing) {
       for (int k = 0; k < 6; ++k) p.dbg[blockIdx.x * 8 + k] = tm[k];
       p.dbg[blockIdx.x * 8 + 6] = sc;
     }
@@ -583,11 +592,13 @@ attention_combine_kernel(const AttnParams p, int grid_fwd) {
     if (i < nseg) m = fmaxf(m, seg_ptr[i][ATT_BM * ATT_D + r]);
   }
   float L = 0.f;
+  float sl2 = p.scale_log2;
+  if (p.q_stats != nullptr) sl2 *= stats_rms_rstd(p.q_stats + ((long long)batch * p.Lq + row) * p.q_chunks, p.q_chunks, p.q_eps);
 #pragma unroll
   for (int i = 0; i < MAX_SEG; ++i) {
     w[i] = 0.f;
     if (i < nseg) {
-      w[i] = exp2f((seg_ptr[i][ATT_BM * ATT_D + r] - m) * p.scale_log2);
+      w[i] = exp2f((seg_ptr[i][ATT_BM * ATT_D + r] - m) * sl2);
       L += seg_ptr[i][ATT_BM * ATT_D + ATT_BM + r] * w[i];
     }
   }
@@ -630,7 +641,8 @@ static int attention_launch(const void* q, long long q_row_stride, long long q_b
                             const void* v, long long kv_row_stride, long long kv_batch_stride, void* const* out_dst,
                             int n_dst, int rows_per_dst, long long out_row_stride, long long out_batch_stride, int B,
                             int Lq, int Skv, int H, int head_dim, float softmax_scale, void* workspace,
-                            long long workspace_bytes, cudaStream_t stream) {
+                            long long workspace_bytes, cudaStream_t stream, const void* q_stats = nullptr, int q_chunks = 0,
+                            float q_eps = 0.f) {
   if (head_dim != ATT_D) { set_error("sfb_attention_fwd: head_dim %d unsupported (128 only)", head_dim); return SFB_ERR_INVALID; }
   if (B <= 0 || Lq <= 0 || Skv <= 0 || H <= 0) { set_error("sfb_attention_fwd: empty problem B=%d Lq=%d Skv=%d H=%d", B, Lq, Skv, H); return SFB_ERR_INVALID; }
   if ((q_row_stride % 8) || (kv_row_stride % 8) || (out_row_stride % 8) || (q_batch_stride % 8) ||
@@ -665,6 +677,10 @@ static int attention_launch(const void* q, long long q_row_stride, long long q_b
   p.out_row_stride = out_row_stride;
   p.out_batch_stride = out_batch_stride;
   p.ws = static_cast<float*>(workspace);
+  p.q_stats = static_cast<const float2*>(q_stats);
+  p.q_chunks = q_chunks;
+  p.q_eps = q_eps;
+  if (q_stats != nullptr && q_chunks <= 0) { set_error("sfb_attention_fwd_qnorm: q_chunks must be positive"); return SFB_ERR_INVALID; }
 
   static long long* dbg_buf = nullptr;
   static int timing = -1;
@@ -677,10 +693,15 @@ static int attention_launch(const void* q, long long q_row_stride, long long q_b
 
   // (measured in round 1 and removed: a degree-3 polynomial exp2 on the FMA pipe for 25 / 50 % of the exponentials --
   // 1115 / 1063 vs 1166 TFLOP/s at Lq 4680 x S 32760 -- and integer-ALU bf16 packing of P: the softmax is issue-bound)
-  auto kern = attention_fwd_kernel;
-  static SmemOptIn optin;
-  if (int e = optin.ensure(kern, ATT_SMEM_BYTES, "cudaFuncSetAttribute(attention)")) return e;
-  kern<<<grid, ATT_THREADS, ATT_SMEM_BYTES, stream>>>(tq, tk, tv, p);
+  if (timing) {
+    static SmemOptIn optin_t;
+    if (int e = optin_t.ensure(attention_fwd_kernel<true>, ATT_SMEM_BYTES, "cudaFuncSetAttribute(attention, timing)")) return e;
+    attention_fwd_kernel<true><<<grid, ATT_THREADS, ATT_SMEM_BYTES, stream>>>(tq, tk, tv, p);
+  } else {
+    static SmemOptIn optin;
+    if (int e = optin.ensure(attention_fwd_kernel<false>, ATT_SMEM_BYTES, "cudaFuncSetAttribute(attention)")) return e;
+    attention_fwd_kernel<false><<<grid, ATT_THREADS, ATT_SMEM_BYTES, stream>>>(tq, tk, tv, p);
+  }
   if (int e = check_cuda(cudaGetLastError(), "attention launch")) return e;
   if (timing) {   // diagnostic: per-phase cycles of one softmax warp, averaged over CTAs, per KV step
     static long long h[512 * 8];
@@ -715,6 +736,20 @@ extern "C" int sfb_attention_fwd(const void* q, long long q_row_stride, long lon
   return sfb::attention_launch(q, q_row_stride, q_batch_stride, k, v, kv_row_stride, kv_batch_stride, dst, 1,
                                Lq > 0 ? Lq : 1, out_row_stride, out_batch_stride, B, Lq, Skv, H, head_dim, softmax_scale,
                                workspace, workspace_bytes, reinterpret_cast<cudaStream_t>(stream_));
+}
+
+// sfb_attention_fwd with WanRMSNorm of the query rows folded into the softmax scale: q holds the UN-normalised projection,
+// q_stats its statistics records [B * Lq][q_chunks] over the full channel width (written by sfb_gemm_bf16_stats), and the
+// caller has multiplied the norm's weight into K.  Replaces norm_q + attention of wan/modules/model.py:172,189.
+extern "C" int sfb_attention_fwd_qnorm(const void* q, long long q_row_stride, long long q_batch_stride, const void* k,
+                                       const void* v, long long kv_row_stride, long long kv_batch_stride, void* out,
+                                       long long out_row_stride, long long out_batch_stride, int B, int Lq, int Skv,
+                                       int H, int head_dim, float softmax_scale, const void* q_stats, int q_chunks,
+                                       float q_eps, void* workspace, long long workspace_bytes, void* stream_) {
+  void* dst[1] = {out};
+  return sfb::attention_launch(q, q_row_stride, q_batch_stride, k, v, kv_row_stride, kv_batch_stride, dst, 1,
+                               Lq > 0 ? Lq : 1, out_row_stride, out_batch_stride, B, Lq, Skv, H, head_dim, softmax_scale,
+                               workspace, workspace_bytes, reinterpret_cast<cudaStream_t>(stream_), q_stats, q_chunks, q_eps);
 }
 
 // Head-parallel (Ulysses) form, one sample: this rank attends with ITS head group (H = heads per group) for ALL Lq

@@ -332,4 +332,32 @@ __host__ __device__ constexpr uint32_t umma_idesc_bf16(uint32_t M, uint32_t N, u
          ((M >> 4) << 24);
 }
 
+// ---- row statistics records shared by the GEMM epilogues and their consumers (see GemmParams::stats_out) ----
+constexpr int STATS_CHUNK = 128;
+
+// mean and 1/sqrt(var + eps) of a row from its chunk records (Chan et al. parallel variance)
+__device__ __forceinline__ void stats_mean_rstd(const float2* __restrict__ rec, int chunks, float eps, float& mean, float& rstd) {
+  float m = 0.f;
+  for (int j = 0; j < chunks; ++j) m += __ldg(&rec[j]).x;
+  m /= (float)chunks;
+  float m2 = 0.f;
+  for (int j = 0; j < chunks; ++j) {
+    const float2 r = __ldg(&rec[j]);
+    const float d = r.x - m;
+    m2 += r.y + (float)STATS_CHUNK * d * d;
+  }
+  mean = m;
+  rstd = rsqrtf(m2 / (float)(chunks * STATS_CHUNK) + eps);
+}
+// 1/sqrt(mean(x^2) + eps) of a row from its chunk records
+__device__ __forceinline__ float stats_rms_rstd(const float2* __restrict__ rec, int chunks, float eps) {
+  float ss = 0.f;
+  for (int j = 0; j < chunks; ++j) {
+    const float2 r = __ldg(&rec[j]);
+    ss += r.y + (float)STATS_CHUNK * r.x * r.x;
+  }
+  return rsqrtf(ss / (float)(chunks * STATS_CHUNK) + eps);
+}
+
+
 }  // namespace sfb

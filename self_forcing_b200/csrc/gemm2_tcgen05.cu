@@ -42,8 +42,9 @@ constexpr int G2_SUB_BYTES = G2_ROWS * G2_SUB * 2;
 constexpr int G2_A_BYTES = G2_ROWS * G2_BK * 2;
 constexpr int G2_B_BYTES = (G2_BN / 2) * G2_BK * 2;
 constexpr int G2_STAGE_BYTES = G2_A_BYTES + G2_B_BYTES;
-constexpr int G2_AUX_BYTES = 128 + 3 * G2_BN * 2 + 128;   // barriers + TMEM slot | bias [256] | gate [2][256] (bf16)
-constexpr int G2_SMEM_BYTES = G2_STAGES * G2_STAGE_BYTES + G2_NSUB * G2_SUB_BYTES + 1024 + G2_AUX_BYTES;
+constexpr int G2_AUX_BYTES = 128 + G2_BN * 8 + 128;   // barriers + TMEM slot | bias [256] + gate [2][256] (bf16)  OR  ln_sc [256] (float2)
+// no slack for aligning the dynamic shared memory: the kernel declares it 1024-byte aligned and traps if it is not
+constexpr int G2_SMEM_BYTES = G2_STAGES * G2_STAGE_BYTES + G2_NSUB * G2_SUB_BYTES + G2_AUX_BYTES;
 constexpr int G2_THREADS = 64 + 256;   // producer warp, MMA warp, 8 epilogue warps
 static_assert(G2_SMEM_BYTES <= 227 * 1024, "shared memory budget");
 
@@ -73,8 +74,9 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_consta
                   const __grid_constant__ CUtensorMap tma_out2, const __grid_constant__ CUtensorMap tma_res,
                   const GemmParams p) {
   constexpr int CL = 2 * NP;   // CTAs per cluster
-  extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = smem_raw;
+  if (smem_u32(smem) & 1023u) __trap();   // the 128-byte swizzle of the TMA boxes / UMMA descriptors needs 1024-byte aligned tiles
   uint8_t* stage_out = smem + G2_STAGES * G2_STAGE_BYTES;   // [G2_NSUB][128 rows][128 B], swizzled
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(stage_out + G2_NSUB * G2_SUB_BYTES);
   uint64_t* empty_bar = full_bar + G2_STAGES;
@@ -84,6 +86,7 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_consta
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(res_full + 1);
   __nv_bfloat16* bias_s = reinterpret_cast<__nv_bfloat16*>(reinterpret_cast<uint8_t*>(full_bar) + 128);   // [256]
   __nv_bfloat16* gate_s = bias_s + G2_BN;                                                                 // [2][256]
+  float2* ln_sc_s = reinterpret_cast<float2*>(bias_s);   // [256] (column sum, constant) of the LayerNorm fold; aliases bias / gate (unused then)
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -218,6 +221,7 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_consta
       // this warp's previous TMA stores have read their staging rows
       if (elect_one()) tma_store_wait_read<0>();
       __syncwarp();
+      if (it > 0) named_barrier_sync(1, 256);   // every warp has finished reading the previous tile's bias / gate / ln_sc vectors
       // bias and gate vectors of this tile -> shared memory (the loads overlap the end of the main loop).  A 128-row tile
       // meets at most two gate vectors unless rows_per_gate is tiny; that rare case reads the gate from global memory.
       int g_lo = 0;
@@ -233,6 +237,14 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_consta
         }
       }
       if (p.bias != nullptr && !phantom) bias_s[tid_e] = p.bias[n0 + tid_e];
+      // LayerNorm folded into this GEMM: mean / rstd of this thread's input row (overlaps the end of the main loop)
+      const bool do_ln = EPI == EPI_BIAS && p.ln_stats != nullptr;
+      float ln_mean = 0.f, ln_rstd = 1.f;
+      if (do_ln && !phantom) {
+        ln_sc_s[tid_e] = __ldg(p.ln_sc + n0 + tid_e);
+        const int rr = row0 + r_local < p.M ? row0 + r_local : p.M - 1;
+        stats_mean_rstd(p.ln_stats + (long long)rr * (p.K / STATS_CHUNK), p.K / STATS_CHUNK, p.ln_eps, ln_mean, ln_rstd);
+      }
       named_barrier_sync(1, 256);    // staging buffers free in every warp; bias / gate visible
       if (HAS_RES && !phantom && warp == 2 && elect_one()) {
         mbar_expect_tx(res_full, G2_NSUB * G2_SUB_BYTES);
@@ -253,6 +265,10 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_consta
         const __nv_bfloat16* gsm = gate_s + (grow_idx - g_lo) * G2_BN;                    // gate_smem
         const __nv_bfloat16* ggl = EPI == EPI_GATE_RES ? p.gate + (long long)grow_idx * p.gate_stride + n0 : nullptr;
         const bool has_bias = p.bias != nullptr;
+        // statistics of this thread's 128 output columns, shifted by the first value (x0) so that a large row mean
+        // does not cancel: sd = sum (x - x0), sd2 = sum (x - x0)^2
+        const bool do_stats = p.stats_out != nullptr;
+        float x0 = 0.f, sd = 0.f, sd2 = 0.f;
 #pragma unroll 1
         for (int j = 0; j < 2; ++j) {
           const int sb = half * 2 + j;
@@ -270,7 +286,27 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_consta
             if (has_bias) bq = *reinterpret_cast<const uint4*>(bias_s + col);
             if (EPI == EPI_GATE_RES)
               gq = gate_smem ? *reinterpret_cast<const uint4*>(gsm + col) : __ldg(reinterpret_cast<const uint4*>(ggl + col));
-            *slot = gemm_epilogue_vals<EPI, true>(&v[c * 8], has_bias, bq, gq, res);
+            if (do_ln) {
+              const float4* scp = reinterpret_cast<const float4*>(ln_sc_s + col);   // (colsum, const) pairs, warp-uniform address: smem broadcast
+#pragma unroll
+              for (int q4 = 0; q4 < 4; ++q4) {
+                const float4 sc2 = scp[q4];
+                v[c * 8 + 2 * q4] = __float_as_uint(fmaf(ln_rstd, fmaf(-ln_mean, sc2.x, __uint_as_float(v[c * 8 + 2 * q4])), sc2.y));
+                v[c * 8 + 2 * q4 + 1] = __float_as_uint(fmaf(ln_rstd, fmaf(-ln_mean, sc2.z, __uint_as_float(v[c * 8 + 2 * q4 + 1])), sc2.w));
+              }
+            }
+            const uint4 o8 = gemm_epilogue_vals<EPI, true>(&v[c * 8], has_bias, bq, gq, res);
+            *slot = o8;
+            if (do_stats) {
+              const uint32_t ow[4] = {o8.x, o8.y, o8.z, o8.w};
+              if (j == 0 && c == 0) x0 = bf_lo(ow[0]);
+#pragma unroll
+              for (int q4 = 0; q4 < 4; ++q4) {
+                const float d0 = bf_lo(ow[q4]) - x0, d1 = bf_hi(ow[q4]) - x0;
+                sd += d0 + d1;
+                sd2 = fmaf(d0, d0, fmaf(d1, d1, sd2));
+              }
+            }
           }
           fence_proxy_async();
           __syncwarp();
@@ -278,6 +314,11 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_consta
             tma_store_2d(omap, stage_out + sb * G2_SUB_BYTES + quarter * (32 * 128), seg_col0 + sb * G2_SUB, row0 + quarter * 32);
             tma_store_commit();
           }
+        }
+        if (do_stats && row < p.M) {
+          const float inv = 1.0f / (float)STATS_CHUNK;
+          p.stats_out[(long long)row * (p.N / STATS_CHUNK) + n_blk * (G2_BN / STATS_CHUNK) + half] =
+              make_float2(x0 + sd * inv, fmaxf(sd2 - sd * sd * inv, 0.f));
         }
       }
       tc_fence_before();

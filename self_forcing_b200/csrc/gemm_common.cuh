@@ -22,6 +22,13 @@ struct GemmParams {
   int rows_per_gate;
   int gate_row_offset;         // chunk-global index of row 0 (sequence-parallel callers hold a slice of the rows)
   long long* dbg;              // SFB_GEMM_TIMING=1: per-CTA clock64 timeline [grid][16], else nullptr
+  // Row statistics (CTA-pair kernel only).  A statistics record is float2 (mean, M2 = sum (x - mean)^2) of one row over
+  // one chunk of STATS_CHUNK consecutive columns, laid out [row][chunk]; chunks are merged with Chan's formula, so the
+  // result does not depend on the size of the row mean.
+  float2* stats_out;           // if set: statistics of the bf16 OUTPUT rows, [M][N / STATS_CHUNK]
+  const float2* ln_stats;      // if set (EPI_BIAS, bias == nullptr): statistics of the INPUT rows, [M][K / STATS_CHUNK] -- the
+  float ln_eps;                //   LayerNorm of the input is folded into the epilogue:
+  const float2* ln_sc;         //   y[r][n] = rstd_r * (acc[r][n] - mean_r * ln_sc[n].x) + ln_sc[n].y   with the weights pre-scaled by the norm's affine weight
 };
 
 __device__ __forceinline__ float gelu_tanh_f(float x) {

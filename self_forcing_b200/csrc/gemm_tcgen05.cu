@@ -185,12 +185,14 @@ int launch_gemm_cluster(int epi, int pairs_per_cluster, const void* x, long long
 
 }  // namespace sfb
 
-extern "C" int sfb_gemm_bf16(const void* x, long long ldx, const void* w, long long ldw, const void* bias,
-                             int M, int N, int K, int epilogue, void* out0, long long ldo0, void* out1,
-                             long long ldo1, void* out2, long long ldo2, int seg_cols, const void* residual,
-                             long long ldr, const void* gate, long long gate_stride, int rows_per_gate,
-                             int gate_row_offset, int block_n, void* workspace, long long workspace_bytes,
-                             void* stream_) {
+// sfb_gemm_bf16 plus row statistics (include/sfb200.h): stats_out = statistics of the output rows, ln_stats / ln_sc =
+// LayerNorm of the input folded into the epilogue.  Both need the CTA-pair kernel (N, seg_cols multiples of 256).
+extern "C" int sfb_gemm_bf16_stats(const void* x, long long ldx, const void* w, long long ldw, const void* bias,
+                                   int M, int N, int K, int epilogue, void* out0, long long ldo0, void* out1,
+                                   long long ldo1, void* out2, long long ldo2, int seg_cols, const void* residual,
+                                   long long ldr, const void* gate, long long gate_stride, int rows_per_gate,
+                                   int gate_row_offset, int block_n, void* stats_out, const void* ln_stats,
+                                   const void* ln_sc, float ln_eps, void* stream_) {
   using namespace sfb;
   cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
   if (M <= 0 || N <= 0 || K <= 0) { set_error("sfb_gemm_bf16: empty problem M=%d N=%d K=%d", M, N, K); return SFB_ERR_INVALID; }
@@ -236,6 +238,15 @@ extern "C" int sfb_gemm_bf16(const void* x, long long ldx, const void* w, long l
   p.residual = static_cast<const __nv_bfloat16*>(residual); p.ldr = ldr;
   p.gate = static_cast<const __nv_bfloat16*>(gate); p.gate_stride = gate_stride; p.rows_per_gate = rows_per_gate;
   p.gate_row_offset = gate_row_offset;
+  p.stats_out = static_cast<float2*>(stats_out);
+  p.ln_stats = static_cast<const float2*>(ln_stats);
+  p.ln_sc = static_cast<const float2*>(ln_sc);
+  p.ln_eps = ln_eps;
+  if ((stats_out != nullptr || ln_stats != nullptr) && !pair) { set_error("sfb_gemm_bf16_stats: row statistics need the CTA-pair kernel (N and seg_cols multiples of 256, M > 128)"); return SFB_ERR_INVALID; }
+  if (ln_stats != nullptr && (epilogue != EPI_BIAS || bias != nullptr || ln_sc == nullptr || K % STATS_CHUNK)) {
+    set_error("sfb_gemm_bf16_stats: the LayerNorm fold takes the plain epilogue, no bias (it lives in ln_sc), and K a multiple of %d", STATS_CHUNK);
+    return SFB_ERR_INVALID;
+  }
 
   CUtensorMap ta, tb;
   {
@@ -258,6 +269,18 @@ extern "C" int sfb_gemm_bf16(const void* x, long long ldx, const void* w, long l
     case 128: return dispatch_epi<128>(epilogue, ta, tb, p, sms, stream);
     default: return dispatch_epi<256>(epilogue, ta, tb, p, sms, stream);
   }
+}
+
+extern "C" int sfb_gemm_bf16(const void* x, long long ldx, const void* w, long long ldw, const void* bias,
+                             int M, int N, int K, int epilogue, void* out0, long long ldo0, void* out1,
+                             long long ldo1, void* out2, long long ldo2, int seg_cols, const void* residual,
+                             long long ldr, const void* gate, long long gate_stride, int rows_per_gate,
+                             int gate_row_offset, int block_n, void* workspace, long long workspace_bytes,
+                             void* stream_) {
+  (void)workspace; (void)workspace_bytes;
+  return sfb_gemm_bf16_stats(x, ldx, w, ldw, bias, M, N, K, epilogue, out0, ldo0, out1, ldo1, out2, ldo2, seg_cols, residual,
+                             ldr, gate, gate_stride, rows_per_gate, gate_row_offset, block_n, nullptr, nullptr, nullptr,
+                             0.f, stream_);
 }
 
 // Kept for ABI stability: the GEMM needs no scratch any more (the stream-K schedule that used it was measured and

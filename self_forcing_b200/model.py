@@ -26,13 +26,14 @@ GPUs (ulysses.py).  `B200WanModel` (bottom of this file) is the bidirectional te
 from __future__ import annotations
 
 import math
+import os
 from typing import Dict, List, Optional
 
 import torch
 from torch import nn
 
 from .cache import IndexMirror, plan_cache_update
-from .ops import EPI_GATE_RES, EPI_GELU, EPI_RESIDUAL
+from .ops import EPI_GATE_RES, EPI_GELU, EPI_RESIDUAL, STATS_CHUNK
 from .ulysses import UlyssesGroup, shard_rows
 
 
@@ -139,6 +140,10 @@ class B200CausalWanModel(nn.Module):
         self._sp_kv: Dict[int, tuple] = {}        # data_ptr of a head-sharded cache tensor -> (pool, element offset)
         self._sp_buf: Dict[int, tuple] = {}       # chunk length -> (q buffer, attention-output buffer) peer tensors
         self._ptr_tables: Dict[tuple, torch.Tensor] = {}   # cache tensors' data pointers -> device pointer table (kv_roll)
+        # Cross-attention with its two norms folded away (norm3 into the q projection's epilogue, norm_q into the softmax
+        # scale and the cached K): on by default where the ops provide row statistics (the CTA-pair GEMM: dim % 256 == 0).
+        self.fold_cross_norms = os.environ.get("SFB_NO_FOLD", "0") != "1"   # (the variable is a diagnostic A/B knob)
+        self._ck_fold: Dict[tuple, torch.Tensor] = {}      # (layer, data_ptr of the cross-attention K cache) -> K * norm_q.weight
         # CUDA graphs: a cached forward is ~430 launches issued from Python; replaying the whole forward as one graph
         # removes the launch gaps (measured 29.6 -> 28.0 ms at S = 18720).  One graph per distinct static signature
         # (shapes, cache pointers, cache plan), captured on its second occurrence.
@@ -178,6 +183,7 @@ class B200CausalWanModel(nn.Module):
     def invalidate_packed(self) -> None:
         self._packed = None
         self._graphs.clear()
+        self._ck_fold.clear()
 
     def _apply(self, fn, *a, **k):
         self.invalidate_packed()
@@ -274,6 +280,19 @@ class B200CausalWanModel(nn.Module):
                 wkv_c=torch.cat([ca.k.weight, ca.v.weight]).detach().contiguous(),
                 bkv_c=torch.cat([ca.k.bias, ca.v.bias]).detach().contiguous()))
         pk["blocks"] = blocks
+        pk["fold"] = bool(self.fold_cross_norms and getattr(self.ops, "supports_row_stats", False) and self.dim % 256 == 0)
+        if pk["fold"]:
+            # norm3 (affine LayerNorm) folded into the cross-attention q projection (include/sfb200.h: sfb_gemm_bf16_stats):
+            #   Linear(LN(x) * w3 + b3) = rstd * (x @ (W * w3)^T - mean * colsum(W * w3)) + (b + W @ b3)
+            # and norm_q's weight folded into the cached text K (its row factor goes into the softmax scale).
+            for b, pb in zip(self.blocks, blocks):
+                ca = b.cross_attn
+                wf = (ca.q.weight.detach().float() * b.norm3.weight.detach().float()[None, :]).to(dt)
+                pb["wq_c_fold"] = wf.contiguous()
+                pb["sc_c"] = torch.stack([wf.float().sum(dim=1),
+                                          ca.q.bias.detach().float() + ca.q.weight.detach().float() @ b.norm3.bias.detach().float()],
+                                         dim=1).contiguous()
+                pb["gk_fold"] = (ca.norm_k.weight.detach().float() * ca.norm_q.weight.detach().float()).to(dt).contiguous()
         pk["mod"] = torch.cat([b.modulation.detach() for b in self.blocks]).contiguous()       # [NL, 6, C]
         pk["head_mod"] = self.head.modulation.detach().contiguous()                              # [1, 2, C]
         cos, sin = rope_tables(self.head_dim)
@@ -300,6 +319,9 @@ class B200CausalWanModel(nn.Module):
                       e1=e(B * F_, C), e=e(B * F_, C), e0=e(B * F_, 6 * C), mod=e(self.num_layers, B * F_, 6, C),
                       head_mod=e(1, B * F_, 2, C), head_out=e(R, self.out_dim * 4),
                       ctx_h=e(B * self.text_len, C), ctx=e(B * self.text_len, C), ctx_k=e(B * self.text_len, C))
+            if C % STATS_CHUNK == 0:   # row-statistics records of x (after the self-attention residual) and of the cross q
+                ws["x_stats"] = torch.empty(R, C // STATS_CHUNK, 2, dtype=torch.float32, device=dev)
+                ws["q_stats"] = torch.empty(R, C // STATS_CHUNK, 2, dtype=torch.float32, device=dev)
             self._ws[key] = ws
         return ws
 
@@ -518,7 +540,12 @@ class B200CausalWanModel(nn.Module):
         if return_x0 and self._sampler_tables is None:
             raise RuntimeError("return_x0 needs set_sampler_tables() (done by B200DiffusionWrapper)")
 
-        env = dict(ops=ops, pk=pk, ws=ws, sp=sp, dev=dev, mod_rows=mod_rows, Fm=Fm, B=B, F_=F_, H=H, W=W, Hh=Hh, Ww=Ww, fs=fs, L=L, Lr=Lr, off=off, R=R,
+        # cross-attention norms folded into the neighbouring kernels: per layer, if the folded K of this cache exists (or is
+        # about to be written by this call)
+        fold_ok = pk["fold"] and R > 128
+        fold = tuple(fold_ok and (not crossattn_cache[i]["is_init"] or (i, crossattn_cache[i]["k"].data_ptr()) in self._ck_fold)
+                     for i in range(NL))
+        env = dict(fold=fold, ops=ops, pk=pk, ws=ws, sp=sp, dev=dev, mod_rows=mod_rows, Fm=Fm, B=B, F_=F_, H=H, W=W, Hh=Hh, Ww=Ww, fs=fs, L=L, Lr=Lr, off=off, R=R,
                    C=C, NL=NL, D=D, NH=NH, NHg=NHg, kv_cache=kv_cache, crossattn_cache=crossattn_cache, plans=plans,
                    need_ctx=need_ctx, start_frame=start_frame, current_start=current_start, skip_output=skip_output,
                    return_x0=return_x0)
@@ -545,7 +572,7 @@ class B200CausalWanModel(nn.Module):
         # which is passed in device memory under replay, and the cache plan only through its device-visible fields -- so
         # in the steady state of a rolling-window video (same roll, same write slot, same window every chunk) ONE graph
         # per forward kind serves every chunk.
-        key = (tuple(x.shape), tuple(t.shape), t.dtype, env["return_x0"], env["skip_output"],
+        key = (tuple(x.shape), tuple(t.shape), t.dtype, env["return_x0"], env["skip_output"], env["fold"],
                tuple((p.roll, p.roll_src, p.roll_dst, p.roll_len, p.write_start, p.write_end, p.attn_start, p.attn_end)
                      for p in env["plans"]),
                tuple(c["k"].data_ptr() for c in kv[:NL]), tuple(c["v"].data_ptr() for c in kv[:NL]),
@@ -594,7 +621,7 @@ class B200CausalWanModel(nn.Module):
         C, NL, D, NH, NHg, dev = (env[k] for k in ("C", "NL", "D", "NH", "NHg", "dev"))
         kv_cache, crossattn_cache, plans = env["kv_cache"], env["crossattn_cache"], env["plans"]
         need_ctx, start_frame, skip_output, return_x0 = env["need_ctx"], env["start_frame"], env["skip_output"], env["return_x0"]
-        mod_rows = env["mod_rows"]
+        mod_rows, fold = env["mod_rows"], env["fold"]
         if sp is not None:
             q_peer, attn_peer = env["q_peer"], env["attn_peer"]
 
@@ -672,7 +699,8 @@ class B200CausalWanModel(nn.Module):
                                  vc[0, plan.attn_start:plan.attn_end], scale, sp, attn_peer, Lr)
                 sp.barrier(ops)          # every head group's output columns have landed
                 ops.gemm(attn_peer.local, sa.o.weight, sa.o.bias, ws["x"], epilogue=EPI_GATE_RES, residual=ws["x"],
-                         gate=m[:, 2], gate_stride=mstride, rows_per_gate=mod_rows, gate_row_offset=off)
+                         gate=m[:, 2], gate_stride=mstride, rows_per_gate=mod_rows, gate_row_offset=off,
+                         **(dict(stats_out=ws["x_stats"]) if fold[i] else {}))
             elif B == 1:   # V projection lands directly in its cache slot
                 ops.gemm(ws["h"], pb["wqkv"], pb["bqkv"], None, seg_cols=C,
                          outs=[ws["q_lin"], ws["k_lin"], v_slot.view(L, C)])   # .view: a non-viewable cache layout must raise
@@ -692,7 +720,8 @@ class B200CausalWanModel(nn.Module):
                 ops.attention(q4, kc[:, plan.attn_start:plan.attn_end], vc[:, plan.attn_start:plan.attn_end],
                               ws["attn"].view(B, L, NH, D), scale)
                 ops.gemm(ws["attn"], sa.o.weight, sa.o.bias, ws["x"], epilogue=EPI_GATE_RES, residual=ws["x"],
-                         gate=m[:, 2], gate_stride=mstride, rows_per_gate=mod_rows)
+                         gate=m[:, 2], gate_stride=mstride, rows_per_gate=mod_rows,
+                         **(dict(stats_out=ws["x_stats"]) if fold[i] else {}))
             # -- cross attention --
             cc = crossattn_cache[i]
             if not cc["is_init"]:
@@ -704,11 +733,28 @@ class B200CausalWanModel(nn.Module):
                 ops.gemm(ws["ctx"], pb["wkv_c"], pb["bkv_c"], None, seg_cols=C,
                          outs=[ws["ctx_k"], cv.view(B * self.text_len, C)])
                 ops.rmsnorm(ws["ctx_k"], ck.view(B * self.text_len, C), ca.norm_k.weight, self.eps)
+                if fold[i]:    # K with norm_q's weight multiplied in, kept beside the reference-visible cache entry
+                    kf = self._ck_fold.get((i, ck.data_ptr()))
+                    if kf is None:
+                        if len(self._ck_fold) >= 4 * NL:      # callers that keep re-allocating their caches
+                            self._ck_fold.clear()
+                            self._graphs.clear()
+                        kf = self._ck_fold[(i, ck.data_ptr())] = torch.empty_like(ck)
+                    ops.rmsnorm(ws["ctx_k"], kf.view(B * self.text_len, C), pb["gk_fold"], self.eps)
                 cc["is_init"] = True
-            ops.ln_affine(ws["x"], ws["h"], blk.norm3.weight, blk.norm3.bias, self.eps)
-            ops.gemm(ws["h"], ca.q.weight, ca.q.bias, ws["q_lin"])
-            ops.rmsnorm(ws["q_lin"], ws["q"], ca.norm_q.weight, self.eps)
-            ops.attention(q4, cc["k"], cc["v"], ws["attn"].view(B, Lr, NH, D), scale)
+            if fold[i]:
+                # norm3 -> q -> norm_q -> attention as TWO launches: the q projection reads x directly (LayerNorm applied in
+                # its epilogue from the row statistics the o projection just wrote) and emits the statistics of q; the
+                # attention applies norm_q's row factor inside the softmax
+                ops.gemm(ws["x"], pb["wq_c_fold"], None, ws["q_lin"], stats_out=ws["q_stats"], ln_stats=ws["x_stats"],
+                         ln_sc=pb["sc_c"], ln_eps=self.eps)
+                ops.attention(ws["q_lin"].view(B, Lr, NH, D), self._ck_fold[(i, cc["k"].data_ptr())], cc["v"],
+                              ws["attn"].view(B, Lr, NH, D), scale, q_stats=ws["q_stats"], q_eps=self.eps)
+            else:
+                ops.ln_affine(ws["x"], ws["h"], blk.norm3.weight, blk.norm3.bias, self.eps)
+                ops.gemm(ws["h"], ca.q.weight, ca.q.bias, ws["q_lin"])
+                ops.rmsnorm(ws["q_lin"], ws["q"], ca.norm_q.weight, self.eps)
+                ops.attention(q4, cc["k"], cc["v"], ws["attn"].view(B, Lr, NH, D), scale)
             ops.gemm(ws["attn"], ca.o.weight, ca.o.bias, ws["x"], epilogue=EPI_RESIDUAL, residual=ws["x"])
             # -- feed forward --
             ops.ln_modulate(ws["x"], ws["h"], shift=m[:, 3], scale=m[:, 4], mod_stride=mstride, rows_per_mod=mod_rows,

@@ -11,6 +11,7 @@ import torch
 from . import _lib
 
 EPI_BIAS, EPI_GELU, EPI_RESIDUAL, EPI_GATE_RES, EPI_F32 = 0, 1, 2, 3, 4
+STATS_CHUNK = 128   # columns per row-statistics record (include/sfb200.h: SFB_STATS_CHUNK)
 _T_DTYPE = {torch.float32: 0, torch.int64: 1, torch.float64: 2, torch.bfloat16: 3}
 
 
@@ -49,6 +50,7 @@ class CudaOps:
 
     requires_bf16 = True
     supports_cuda_graphs = True   # every op only enqueues kernels on the current stream (no host sync, no allocation)
+    supports_row_stats = True     # gemm(stats_out= / ln_stats=) and attention(q_stats=): norms folded into the neighbouring kernels
 
     def __init__(self):
         self.lib = _lib.load()
@@ -99,7 +101,9 @@ class CudaOps:
     @_op
     def gemm(self, x, w, bias, out, *, epilogue=EPI_BIAS, residual=None, gate=None, gate_stride=0,
              rows_per_gate=1, gate_row_offset=0, outs: Optional[Sequence[torch.Tensor]] = None, seg_cols=0,
-             block_n=0):
+             block_n=0, stats_out=None, ln_stats=None, ln_sc=None, ln_eps: float = 0.0):
+        """stats_out: fp32 [M, N / 128, 2] receives (mean, M2) records of the output rows; ln_stats [M, K / 128, 2] + ln_sc
+        [N, 2]: the LayerNorm in front of the Linear folded into the epilogue (include/sfb200.h: sfb_gemm_bf16_stats)."""
         _check_2d(x, "x"); _check_2d(w, "w")
         M, K = x.shape
         N = w.shape[0]
@@ -114,6 +118,18 @@ class CudaOps:
             segs.append(None)
         if residual is not None:
             _check_2d(residual, "residual")
+        if stats_out is not None or ln_stats is not None:
+            for s_, shape in ((stats_out, (M, N // STATS_CHUNK, 2)), (ln_stats, (M, K // STATS_CHUNK, 2)), (ln_sc, (N, 2))):
+                assert s_ is None or (s_.dtype == torch.float32 and s_.is_contiguous() and tuple(s_.shape) == shape), \
+                    f"statistics tensor {None if s_ is None else tuple(s_.shape)} != {shape} fp32 contiguous"
+            _lib.check(self.lib.sfb_gemm_bf16_stats(
+                x.data_ptr(), x.stride(0), w.data_ptr(), w.stride(0), _ptr(bias), M, N, K, epilogue,
+                _ptr(segs[0]), segs[0].stride(0), _ptr(segs[1]), segs[1].stride(0) if segs[1] is not None else 0,
+                _ptr(segs[2]), segs[2].stride(0) if segs[2] is not None else 0, seg_cols,
+                _ptr(residual), residual.stride(0) if residual is not None else 0,
+                _ptr(gate), gate_stride, rows_per_gate, gate_row_offset, block_n, _ptr(stats_out), _ptr(ln_stats),
+                _ptr(ln_sc), ln_eps, self._stream()), "sfb_gemm_bf16_stats")
+            return
         _lib.check(self.lib.sfb_gemm_bf16(
             x.data_ptr(), x.stride(0), w.data_ptr(), w.stride(0), _ptr(bias), M, N, K, epilogue,
             _ptr(segs[0]), segs[0].stride(0), _ptr(segs[1]), segs[1].stride(0) if segs[1] is not None else 0,
@@ -124,14 +140,23 @@ class CudaOps:
 
     # -- attention ------------------------------------------------------------------------
     @_op
-    def attention(self, q, k, v, out, scale: float):
-        """q/out [B, Lq, H, D] views, k/v [B, S, H, D] views (the cache window)."""
+    def attention(self, q, k, v, out, scale: float, q_stats=None, q_eps: float = 0.0):
+        """q/out [B, Lq, H, D] views, k/v [B, S, H, D] views (the cache window).  q_stats fp32 [B * Lq, chunks, 2]: q is the
+        un-normalised projection and its full-width RMSNorm factor is applied inside the softmax (sfb_attention_fwd_qnorm)."""
         B, Lq, H, D = q.shape
         S = k.shape[1]
         for t in (q, k, v, out):
             assert t.stride(3) == 1 and t.stride(2) == D and t.dtype == torch.bfloat16
         assert k.stride() == v.stride() and k.shape == v.shape
         ws = self._attn_workspace(q.device)
+        if q_stats is not None:
+            assert q_stats.dtype == torch.float32 and q_stats.is_contiguous() and q_stats.dim() == 3 \
+                and q_stats.shape[0] == B * Lq and q_stats.shape[2] == 2
+            _lib.check(self.lib.sfb_attention_fwd_qnorm(
+                q.data_ptr(), q.stride(1), q.stride(0), k.data_ptr(), v.data_ptr(), k.stride(1), k.stride(0),
+                out.data_ptr(), out.stride(1), out.stride(0), B, Lq, S, H, D, scale, q_stats.data_ptr(), q_stats.shape[1],
+                q_eps, ws.data_ptr(), ws.numel(), self._stream()), "sfb_attention_fwd_qnorm")
+            return
         _lib.check(self.lib.sfb_attention_fwd(
             q.data_ptr(), q.stride(1), q.stride(0), k.data_ptr(), v.data_ptr(), k.stride(1), k.stride(0),
             out.data_ptr(), out.stride(1), out.stride(0), B, Lq, S, H, D, scale, ws.data_ptr(), ws.numel(),

@@ -19,10 +19,33 @@ class TorchOps:
         self.launches = 0
         self.log = []
 
+    @staticmethod
+    def _stats_records(y):
+        """(mean, M2) per 128-column chunk of every row, like the GEMM epilogue writes them."""
+        c = y.float().reshape(y.shape[0], -1, 128)
+        mean = c.mean(dim=2)
+        return torch.stack([mean, ((c - mean[..., None]) ** 2).sum(dim=2)], dim=2)
+
+    @staticmethod
+    def _stats_mean_var(rec):
+        mean = rec[..., 0].mean(dim=1)
+        m2 = (rec[..., 1] + 128.0 * (rec[..., 0] - mean[:, None]) ** 2).sum(dim=1)
+        return mean, m2 / (128.0 * rec.shape[1])
+
     def gemm(self, x, w, bias, out, *, epilogue=EPI_BIAS, residual=None, gate=None, gate_stride=0,
-             rows_per_gate=1, gate_row_offset=0, outs=None, seg_cols=0, block_n=0):
+             rows_per_gate=1, gate_row_offset=0, outs=None, seg_cols=0, block_n=0, stats_out=None, ln_stats=None,
+             ln_sc=None, ln_eps=0.0):
         self.launches += 1
         self.log.append("gemm")
+        if ln_stats is not None:      # LayerNorm of x folded into the epilogue (include/sfb200.h: sfb_gemm_bf16_stats)
+            assert epilogue == EPI_BIAS and bias is None
+            mean, var = self._stats_mean_var(ln_stats)
+            acc = x.float() @ w.float().t()
+            y = (torch.rsqrt(var + ln_eps)[:, None] * (acc - mean[:, None] * ln_sc[:, 0][None]) + ln_sc[:, 1][None]).to(out.dtype)
+            out.copy_(y)
+            if stats_out is not None:
+                stats_out.copy_(self._stats_records(y))
+            return
         if epilogue == EPI_F32:
             out.copy_(F.linear(x.float(), w.float(), None if bias is None else bias.float()))
             return
@@ -35,15 +58,25 @@ class TorchOps:
             M = x.shape[0]
             g = gate[(torch.arange(M) + gate_row_offset) // rows_per_gate]   # gate is a [groups, C] strided view
             y = residual + y * g
+        if stats_out is not None:
+            stats_out.copy_(self._stats_records(y))
         if outs is not None:
             for i, o in enumerate(outs):
                 o.copy_(y[:, i * seg_cols:(i + 1) * seg_cols])
         else:
             out.copy_(y)
 
-    def attention(self, q, k, v, out, scale):
+    def attention(self, q, k, v, out, scale, q_stats=None, q_eps=0.0):
         self.launches += 1
         self.log.append("attention")
+        if q_stats is not None:       # RMSNorm row factor of q applied to the scores (sfb_attention_fwd_qnorm)
+            self.log.append("attention_qnorm")
+            B, Lq, H, D = q.shape
+            ms = (q_stats[..., 1] + 128.0 * q_stats[..., 0] ** 2).sum(dim=1) / (128.0 * q_stats.shape[1])
+            rstd = torch.rsqrt(ms + q_eps).reshape(B, 1, Lq, 1)
+            s_ = torch.einsum("blhd,bshd->bhls", q.float(), k.float()) * scale * rstd
+            out.copy_(torch.einsum("bhls,bshd->blhd", torch.softmax(s_, dim=-1).to(v.dtype).float(), v.float()).to(out.dtype))
+            return
         out.copy_(O.dense_attention(q, k, v))
 
     def modulation_table(self, mod, e, out, e_row_stride, e_group_stride):

@@ -85,6 +85,93 @@ def check_gemm(M=300, N=256, K=192, epilogue=0, block_n=0, rows_per_gate=100, se
     return _finish(f"gemm M{M} N{N} K{K} epi{epilogue} bn{block_n}", m, 3e-3)
 
 
+def _stats_ref(y):
+    """(mean, M2) per 128-column chunk of every row (include/sfb200.h: statistics records)."""
+    c = y.float().reshape(y.shape[0], -1, 128)
+    mean = c.mean(dim=2)
+    return torch.stack([mean, ((c - mean[..., None]) ** 2).sum(dim=2)], dim=2)
+
+
+def check_gemm_stats(M=700, N=512, K=256, epilogue=3, rows_per_gate=130, seed=0, mean_shift=0.0, block_n=0):
+    """Row statistics of the OUTPUT written by the pair kernel's epilogue (any epilogue); a large common offset in the
+    rows (mean_shift) must not cost accuracy in M2 (shifted sums + Chan's merge)."""
+    ops = _ops()
+    x = _randn(M, K, seed=seed)
+    w = _randn(N, K, seed=seed + 1, scale=1.0 / math.sqrt(K))
+    b = _randn(N, seed=seed + 2, scale=0.5)
+    res = (_randn(M, N, seed=seed + 3).float() + mean_shift).to(BF)
+    groups = (M + rows_per_gate - 1) // rows_per_gate
+    gate = _randn(groups, N, seed=seed + 4)
+    out = torch.full((M, N), float("nan"), device="cuda", dtype=BF)
+    stats = torch.full((M, N // 128, 2), float("nan"), device="cuda")
+    kw = dict(residual=res) if epilogue in (2, 3) else {}
+    if epilogue == 3:
+        kw.update(gate=gate, gate_stride=N, rows_per_gate=rows_per_gate)
+    ops.gemm(x, w, b, out, epilogue=epilogue, stats_out=stats, block_n=block_n, **kw)
+    ref = _stats_ref(out)                       # statistics of the bf16 values the kernel stored
+    var = ref[..., 1].sum(1) / N
+    m = dict(err_mean=float((stats[..., 0] - ref[..., 0]).abs().max() / (1.0 + abs(mean_shift))),
+             err_m2=float(((stats[..., 1] - ref[..., 1]).abs() / (ref[..., 1] + 1e-3)).max()),
+             nan=int(torch.isnan(stats).sum() + torch.isnan(out.float()).sum()), var_mean=float(var.mean()))
+    assert m["nan"] == 0, f"unwritten statistics / output: {m}"
+    return _finish(f"gemm_stats M{M} N{N} K{K} epi{epilogue} shift{mean_shift}", m, 2e-3)
+
+
+def check_gemm_lnfold(M=700, N=512, K=256, seed=0, mean_shift=0.0):
+    """norm3 folded into the cross-attention q projection: producer GEMM writes x and its statistics, consumer GEMM applies
+    the LayerNorm in its epilogue and writes the statistics of q.  Reference: fp32 LayerNorm (affine) -> Linear."""
+    ops = _ops()
+    eps = 1e-6
+    a = _randn(M, K, seed=seed)
+    wp = _randn(K, K, seed=seed + 1, scale=1.0 / math.sqrt(K))
+    res = (_randn(M, K, seed=seed + 2).float() + mean_shift).to(BF)
+    x = torch.empty(M, K, device="cuda", dtype=BF)
+    x_stats = torch.full((M, K // 128, 2), float("nan"), device="cuda")
+    ops.gemm(a, wp, None, x, epilogue=2, residual=res, stats_out=x_stats)            # x = res + a @ wp^T, with statistics
+    wq = _randn(N, K, seed=seed + 3, scale=1.0 / math.sqrt(K))
+    bq = _randn(N, seed=seed + 4, scale=0.5)
+    w3 = (1.0 + 0.1 * _randn(K, seed=seed + 5).float()).to(BF)
+    b3 = _randn(K, seed=seed + 6, scale=0.1)
+    wf = (wq.float() * w3.float()[None, :]).to(BF)
+    sc = torch.stack([wf.float().sum(1), bq.float() + wq.float() @ b3.float()], dim=1).contiguous()
+    q = torch.full((M, N), float("nan"), device="cuda", dtype=BF)
+    q_stats = torch.full((M, N // 128, 2), float("nan"), device="cuda")
+    ops.gemm(x, wf, None, q, stats_out=q_stats, ln_stats=x_stats, ln_sc=sc, ln_eps=eps)
+    h = F.layer_norm(x.float(), (K,), w3.float(), b3.float(), eps)
+    ref = h @ wq.float().t() + bq.float()                                              # fp32 reference, no intermediate rounding
+    ref_rounded = (h.to(BF).float() @ wq.float().t() + bq.float()).to(BF)              # what the reference's op chain produces
+    qs_ref = _stats_ref(q)
+    m = dict(err_rel_l2=rel_l2(q, ref), ref_chain_rel_l2=rel_l2(ref_rounded, ref),
+             err_qstats=float(((q_stats - qs_ref).abs() / (qs_ref.abs() + 1e-2)).max()) * 1e-1,
+             nan=int(torch.isnan(q.float()).sum() + torch.isnan(q_stats).sum()))
+    assert m["nan"] == 0, f"unwritten output: {m}"
+    # no further from the fp32 result than the reference's own bf16 op chain (x 1.5), and within the GEMM tolerance
+    assert m["err_rel_l2"] <= max(1.5 * m["ref_chain_rel_l2"], 1e-3), m
+    return _finish(f"gemm_lnfold M{M} N{N} K{K} shift{mean_shift}", m, 4e-3)
+
+
+def check_attention_qnorm(B=1, Lq=300, S=512, H=2, seed=0):
+    """WanRMSNorm of q folded into the softmax scale + norm weight folded into K, against norm -> attention."""
+    ops = _ops()
+    D, eps = 128, 1e-6
+    C = H * D
+    q_lin = _randn(B * Lq, C, seed=seed, scale=2.0)
+    gq = (1.0 + 0.1 * _randn(C, seed=seed + 1).float()).to(BF)
+    k = _randn(B, S, H, D, seed=seed + 2)
+    v = _randn(B, S, H, D, seed=seed + 3)
+    scale = 1.0 / math.sqrt(D)
+    q_stats = _stats_ref(q_lin).contiguous()
+    kf = (k.float() * gq.float().view(1, 1, H, D)).to(BF)
+    out = torch.full((B, Lq, H, D), float("nan"), device="cuda", dtype=BF)
+    ops.attention(q_lin.view(B, Lq, H, D), kf, v, out, scale, q_stats=q_stats, q_eps=eps)
+    qn = (q_lin.float() * torch.rsqrt(q_lin.float().pow(2).mean(dim=1, keepdim=True) + eps) * gq.float())
+    ref = _attn_ref(qn.view(B, Lq, H, D), k, v, scale)
+    m = dict(err_rel_l2=rel_l2(out, ref), nan=int(torch.isnan(out.float()).sum()))
+    assert m["nan"] == 0, f"attention produced NaN / left rows unwritten: {m}"
+    return _finish(f"attention_qnorm B{B} Lq{Lq} S{S} H{H}", m, 6e-3)
+
+
+
 def check_gemm_segments(M=300, C=256, K=128, seed=0, block_n=0):
     """QKV-style call: one GEMM, three destinations with different row strides (V into a cache slot)."""
     ops = _ops()
@@ -713,6 +800,16 @@ ALL = {
     "gemm_pair_persistent_gelu": lambda: check_gemm(M=4680, N=8960, K=256, epilogue=1, block_n=512),
     "gemm_pair_gate": lambda: check_gemm(M=1000, N=768, K=320, epilogue=3, rows_per_gate=70, block_n=512),
     "gemm_pair_o_proj": lambda: check_gemm(M=4680, N=1536, K=1536, epilogue=3, rows_per_gate=1560, block_n=512),
+    "gemm_stats_gate": check_gemm_stats,
+    "gemm_stats_bias_shifted": lambda: check_gemm_stats(M=300, N=256, K=128, epilogue=2, seed=3, mean_shift=40.0),
+    "gemm_stats_o_proj": lambda: check_gemm_stats(M=4680, N=1536, K=1536, epilogue=3, rows_per_gate=1560, seed=4),
+    "gemm_stats_ffn2_cluster": lambda: check_gemm_stats(M=4680, N=1536, K=8960, epilogue=3, rows_per_gate=1560, seed=5),
+    "gemm_lnfold": check_gemm_lnfold,
+    "gemm_lnfold_shifted": lambda: check_gemm_lnfold(M=300, N=256, K=512, seed=7, mean_shift=25.0),
+    "gemm_lnfold_cross_q": lambda: check_gemm_lnfold(M=4680, N=1536, K=1536, seed=8),
+    "attn_qnorm": check_attention_qnorm,
+    "attn_qnorm_cross": lambda: check_attention_qnorm(Lq=4680, S=512, H=12, seed=2),
+    "attn_qnorm_batch_split": lambda: check_attention_qnorm(B=2, Lq=1300, S=7000, H=4, seed=3),
     "attn_small": lambda: check_attention(),
     "attn_one_tile": lambda: check_attention(Lq=128, S=128, H=1),
     "attn_tail": lambda: check_attention(Lq=72, S=72, H=3),

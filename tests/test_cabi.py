@@ -34,7 +34,7 @@ def test_binding_covers_header(lib_path):
                                    "sfb_causal_conv3d_workspace_bytes"}
     assert declared == set(_lib.SIGNATURES), declared ^ set(_lib.SIGNATURES)
     lib = _lib.load(lib_path)
-    assert lib.sfb_abi_version() == 9
+    assert lib.sfb_abi_version() == _lib.ABI_VERSION == int(re.search(r"#define SFB_ABI_VERSION (\d+)", open(os.path.join(ROOT, "include", "sfb200.h")).read()).group(1))
     assert isinstance(lib.sfb_last_error(), bytes)
 
 

@@ -211,62 +211,7 @@ def test_cache_free_call_dispatches_to_the_training_forward():
         m(x, t=torch.zeros(1, 1), context=torch.zeros(1, 512, 512, dtype=torch.bfloat16), seq_len=100, y=[x[0]])
 
 
-# --------------------------------------------------------------------------------------------------
-# attention work schedule (self_forcing_b200/csrc/attention_tcgen05.cu: att_range_start / att_step_owner):
-# a Python model of the integer arithmetic the forward and the combine kernel must agree on
-# --------------------------------------------------------------------------------------------------
-def _range_start(c, grid, items, n_kv, split=True):
-    return (c * items * n_kv) // grid if split else ((c * items) // grid) * n_kv
-
-
-def _owner(step, grid, items, n_kv):
-    return ((step + 1) * grid - 1) // (items * n_kv)
-
-
-def _segments(c, grid, items, n_kv, split=True):
-    cur, end, out = _range_start(c, grid, items, n_kv, split), _range_start(c + 1, grid, items, n_kv, split), []
-    while cur < end:
-        item = cur // n_kv
-        j0 = cur - item * n_kv
-        j1 = min(n_kv, j0 + (end - cur))
-        out.append((item, j0, j1))
-        cur += j1 - j0
-    return out
-
-
-@pytest.mark.parametrize("items,n_kv,grid", [(228, 37, 148), (228, 256, 148), (84, 256, 84), (336, 74, 148),
-                                             (149, 16, 148), (1000, 17, 148), (32 * 6, 313, 148), (5, 100, 5)])
-def test_attention_split_schedule_is_consistent(items, n_kv, grid):
-    covered = {}
-    for c in range(grid):
-        segs = _segments(c, grid, items, n_kv)
-        partial = [(i, s) for i, s in enumerate(segs) if not (s[1] == 0 and s[2] == n_kv)]
-        # only the first and the last segment of a CTA can be partial -> two workspace slots per CTA suffice
-        assert all(i in (0, len(segs) - 1) for i, _ in partial)
-        for i, (item, j0, j1) in enumerate(segs):
-            for j in range(j0, j1):
-                assert (item, j) not in covered
-                covered[(item, j)] = c
-                assert _owner(item * n_kv + j, grid, items, n_kv) == c
-            if (j0, j1) != (0, n_kv):
-                # slot rule of the combine kernel: slot 0 iff the CTA's range starts inside this item
-                slot_fwd = 0 if i == 0 else 1
-                slot_comb = 0 if _range_start(c, grid, items, n_kv) // n_kv == item else 1
-                assert slot_fwd == slot_comb
-    assert len(covered) == items * n_kv
-    # the load is balanced to within one KV step
-    sizes = [_range_start(c + 1, grid, items, n_kv) - _range_start(c, grid, items, n_kv) for c in range(grid)]
-    assert max(sizes) - min(sizes) <= 1
-
-
-def test_attention_whole_item_schedule_never_splits():
-    for items, n_kv, grid in [(228, 4, 148), (84, 256, 84), (7, 3, 7)]:
-        seen = []
-        for c in range(grid):
-            for item, j0, j1 in _segments(c, grid, items, n_kv, split=False):
-                assert (j0, j1) == (0, n_kv)
-                seen.append(item)
-        assert seen == list(range(items))
+# (the attention work schedule is checked against the kernel's own host/device functions in tests/test_attention_schedule.py)
 
 
 def test_reference_arm_runs_on_rank0_only():
@@ -372,3 +317,33 @@ def test_wrapper_loads_a_checkpoint_directory(tmp_path):
     assert w.model.num_layers == 1 and w.scheduler.shift == 5.0 and w.seq_len == 32760
     with pytest.raises(FileNotFoundError):
         B200DiffusionWrapper(model_path=str(tmp_path / "missing"), ops=TorchOps())
+
+
+def test_cross_attention_norm_fold_matches_the_unfolded_schedule():
+    """norm3 folded into the cross-attention q projection and norm_q into the softmax scale / cached K (model.py: `fold`):
+    in fp32 the folded schedule is the unfolded one up to rounding, on a multi-chunk cached rollout."""
+    from self_forcing_b200.model import B200CausalWanModel
+
+    class StatsOps(TorchOps):
+        supports_row_stats = True
+
+    def run(ops):
+        torch.manual_seed(0)
+        m = B200CausalWanModel(dim=256, ffn_dim=256, num_heads=2, num_layers=2, text_dim=512, ops=ops)
+        m.init_weights(3)
+        fs, F_ = 8 * 20, 2                  # 160 tokens per frame -> 320 rows per forward (> 128: fold eligible)
+        kv = m.allocate_kv_cache(1, 3 * F_ * fs, torch.float32, torch.device("cpu"))
+        ca = [dict(k=torch.zeros(1, 512, 2, 128), v=torch.zeros(1, 512, 2, 128), is_init=False) for _ in range(2)]
+        ctx = torch.randn(1, 512, 512)
+        outs = []
+        for chunk in range(3):
+            x = torch.randn(1, 16, F_, 16, 40)
+            outs.append(m(x, t=torch.full((1, F_), 500.0), context=ctx, seq_len=32760, kv_cache=kv, crossattn_cache=ca,
+                          current_start=chunk * F_ * fs))
+        return torch.stack(outs), ops.log
+
+    ref, log_ref = run(TorchOps())
+    got, log_fold = run(StatsOps())
+    assert log_fold.count("gemm") == log_ref.count("gemm")
+    assert log_fold.count("attention_qnorm") == 2 * 3 and log_ref.count("attention_qnorm") == 0
+    assert rel_l2(got, ref) <= 2e-5

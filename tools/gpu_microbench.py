@@ -66,6 +66,31 @@ def main():
                    cublas_ms=tmed, cublas_tflops=fl / tmed / 1e9)
         print(json.dumps(rec), flush=True)
         out.append(rec)
+    # the cross-attention q projection with norm3 folded in (+ statistics of q) and the o projection writing statistics
+    for name, epi, use_ln in [("cross_q_fold", 0, True), ("o_proj_stats", 3, False), ("cross_q_stats_only", 0, False)]:
+        if only and not any(o in "gemm_" + name for o in only):
+            continue
+        N = K = 1536
+        x = torch.randn(M, K, device="cuda").to(BF)
+        w = (torch.randn(N, K, device="cuda") / math.sqrt(K)).to(BF)
+        b = torch.randn(N, device="cuda").to(BF)
+        res = torch.randn(M, N, device="cuda").to(BF)
+        gate = torch.randn(3, N, device="cuda").to(BF)
+        y = torch.empty(M, N, device="cuda", dtype=BF)
+        st_in = torch.rand(M, K // 128, 2, device="cuda") + 0.5
+        st_out = torch.empty(M, N // 128, 2, device="cuda")
+        sc = torch.randn(N, 2, device="cuda")
+        kw = dict(epilogue=epi, stats_out=st_out)
+        if epi == 3:
+            kw.update(residual=res, gate=gate, gate_stride=N, rows_per_gate=1560)
+        if use_ln:
+            kw.update(ln_stats=st_in, ln_sc=sc, ln_eps=1e-6)
+        bias = None if use_ln else b
+        med, best = timeit(lambda: ops.gemm(x, w, bias, y, **kw), flush=flush)
+        fl = 2.0 * M * N * K
+        rec = dict(kernel="gemm_" + name, M=M, N=N, K=K, ms=med, ms_best=best, tflops=fl / med / 1e9)
+        print(json.dumps(rec), flush=True)
+        out.append(rec)
     for name, Lq, S, H in [("self_S4680", 4680, 4680, 12), ("self_S18720", 4680, 18720, 12),
                            ("self_S32760", 4680, 32760, 12), ("cross_S512", 4680, 512, 12),
                            ("frame_S32760", 1560, 32760, 12)]:
