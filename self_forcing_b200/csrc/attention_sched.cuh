@@ -12,6 +12,7 @@ struct AttnParams {
   int n_kv_tiles;
   int kv_tail;            // valid columns in the last KV tile (1..128)
   int n_qpairs;           // ceil(Lq / 256)
+  int n_qtiles;           // ceil(Lq / 128)
   int half_last;          // 1: the last query pair of every head has an empty second tile and runs as a HALF item
   int n_half_steps;       // steps of a half item = ceil(n_kv_tiles / 2) (two KV tiles per step, one per softmax warpgroup)
   int steps_per_head;     // (n_qpairs - half_last) * n_kv_tiles + half_last * n_half_steps
@@ -60,21 +61,40 @@ __host__ __device__ __forceinline__ long long att_item_first_step(int item, cons
   return (long long)(item / p.n_qpairs) * p.steps_per_head + (long long)(item % p.n_qpairs) * p.n_kv_tiles;
 }
 struct AttSeg {
-  int bh_local, qp;   // head (group-local) and query pair of the item
+  int bh_local;       // head (group-local) of the item
+  int q_tile;         // first 128-row query tile of the item
   int j0, j1;         // steps [j0, j1) of the item
   int item_steps;     // n_kv (full item) or n_half
+  int advance;        // how far the segment moves the CTA's cursor
   bool half;
 };
+// WHOLE-ITEM mode (short KV, p.split == 0) linearises single query TILES, head-major: a CTA owns a contiguous range of
+// tiles and walks it pair by pair -- two consecutive tiles of one head form a full item (the pair need not start at an
+// even tile), a tile left alone at the end of the range or of the head runs as a half item.  Lq = 4680, H = 12: 444
+// tiles = exactly 3 per SM (a pair + a half item) where whole pairs gave 228 items = two rounds on 148 SMs.
+// SPLIT mode linearises (item, step) with fixed, even-aligned pairs (see att_item_first_step).
 __host__ __device__ __forceinline__ AttSeg att_decode(int cur, int range_end, const AttnParams& p) {
   AttSeg s;
+  if (!p.split) {
+    s.bh_local = cur / p.n_qtiles;
+    s.q_tile = cur - s.bh_local * p.n_qtiles;
+    s.half = !((range_end - cur) >= 2 && s.q_tile + 1 < p.n_qtiles);
+    s.item_steps = s.half ? p.n_half_steps : p.n_kv_tiles;
+    s.j0 = 0;
+    s.j1 = s.item_steps;
+    s.advance = s.half ? 1 : 2;
+    return s;
+  }
   s.bh_local = cur / p.steps_per_head;
   const int r = cur - s.bh_local * p.steps_per_head;
   const int full_steps = (p.n_qpairs - p.half_last) * p.n_kv_tiles;
   s.half = r >= full_steps;
-  s.qp = s.half ? p.n_qpairs - 1 : r / p.n_kv_tiles;
-  s.j0 = s.half ? r - full_steps : r - s.qp * p.n_kv_tiles;
+  const int qp = s.half ? p.n_qpairs - 1 : r / p.n_kv_tiles;
+  s.q_tile = 2 * qp;
+  s.j0 = s.half ? r - full_steps : r - qp * p.n_kv_tiles;
   s.item_steps = s.half ? p.n_half_steps : p.n_kv_tiles;
   s.j1 = (range_end - cur) < (s.item_steps - s.j0) ? s.j0 + (range_end - cur) : s.item_steps;
+  s.advance = s.j1 - s.j0;
   return s;
 }
 // Split mode cuts the group's work into one contiguous range per CTA by COST, not by step count: a half-item step moves
@@ -94,7 +114,7 @@ __host__ __device__ __forceinline__ long long att_cost_start(long long step, con
 }
 // first step (in the group's linearised space) of CTA c, and the owner of a step
 __host__ __device__ __forceinline__ int att_range_start(int c, int grid, int grp, const AttnParams& p) {
-  if (!p.split) return (int)att_item_first_step((int)(((long long)c * att_group_items(grp, p)) / grid), p);
+  if (!p.split) return (int)(((long long)c * att_group_heads(grp, p) * p.n_qtiles) / grid);   // tiles
   const long long hc = att_head_cost(p);
   const long long b = ((long long)c * att_group_heads(grp, p) * hc) / grid;
   const long long head = b / hc, r = b - head * hc;
@@ -115,6 +135,7 @@ inline int att_plan(AttnParams& p, int B, int Lq, int Skv, int H, int sms, long 
   p.n_kv_tiles = (Skv + ATT_BN - 1) / ATT_BN;
   p.kv_tail = Skv - (p.n_kv_tiles - 1) * ATT_BN;
   p.n_qpairs = (Lq + 2 * ATT_BM - 1) / (2 * ATT_BM);
+  p.n_qtiles = (Lq + ATT_BM - 1) / ATT_BM;
   p.items = B * H * p.n_qpairs;
   p.half_last = (Lq - (p.n_qpairs - 1) * 2 * ATT_BM) <= ATT_BM ? 1 : 0;
   if (const char* env = getenv("SFB_ATTN_NOHALF")) { if (env[0] == '1') p.half_last = 0; }   // diagnostic: pad the lone last tile to a pair
@@ -122,7 +143,9 @@ inline int att_plan(AttnParams& p, int B, int Lq, int Skv, int H, int sms, long 
   p.steps_per_head = (p.n_qpairs - p.half_last) * p.n_kv_tiles + p.half_last * p.n_half_steps;
   // Long KV windows: one contiguous range of (item, KV step) work per SM, whatever the item count (also when there
   // are fewer items than SMs -- head-parallel ranks and frame-wise rollouts).  Short ones: whole items per CTA.
-  int grid = p.items < sms ? p.items : sms;
+  const int tiles = B * H * p.n_qtiles;
+  // whole-item mode: one tile per CTA (a half item: n_kv / 2 steps) if that fits the machine, else at least a pair per CTA
+  int grid = tiles <= sms ? tiles : ((tiles + 1) / 2 < sms ? (tiles + 1) / 2 : sms);
   p.heads_per_group = B * H;
   p.n_groups = 1;
   const long long slot_bytes = (long long)sms * 2 * 2 * ATT_SLOT_FLOATS * (long long)sizeof(float);   // per group

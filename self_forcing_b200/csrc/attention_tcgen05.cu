@@ -115,7 +115,7 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_con
           const AttSeg sg = att_decode(cur, range_end, p);
           const int bh = grp * p.heads_per_group + sg.bh_local;
           const int head = bh % p.H, batch = bh / p.H;
-          const int q_row0 = sg.qp * (2 * ATT_BM);
+          const int q_row0 = sg.q_tile * ATT_BM;
           mbar_wait(q_empty, (seg & 1) ^ 1);           // previous segment's QK^T MMAs have retired
           if (elect_one()) {
             mbar_expect_tx(q_full, 2 * ATT_TILE_BYTES);
@@ -166,7 +166,7 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_con
               g += two ? 2 : 1;
             }
           }
-          cur += sg.j1 - sg.j0;
+          cur += sg.advance;
         }
         }
       }
@@ -315,7 +315,7 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_con
             }
             g += cnt;
           }
-          cur += n;
+          cur += sg.advance;
         }
         }
       }
@@ -355,7 +355,7 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_con
       float sl2 = p.scale_log2;  // softmax scale of this thread's row (x log2 e)
       if (p.q_stats != nullptr) {
         const int bh_s = grp * p.heads_per_group + sg.bh_local;
-        const int row_s = sg.qp * (2 * ATT_BM) + (sg.half ? 0 : t * ATT_BM) + r_local;
+        const int row_s = sg.q_tile * ATT_BM + (sg.half ? 0 : t * ATT_BM) + r_local;
         sl2 *= stats_rms_rstd(p.q_stats + ((long long)(bh_s / p.H) * p.Lq + (row_s < p.Lq ? row_s : p.Lq - 1)) * p.q_chunks,
                               p.q_chunks, p.q_eps);
       }
@@ -482,7 +482,7 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_con
           }
         }
         const uint32_t o_oth = o_addr + 128;   // O_1 (same TMEM lanes)
-        const int row = sg.qp * (2 * ATT_BM) + t * ATT_BM + r_local;
+        const int row = sg.q_tile * ATT_BM + t * ATT_BM + r_local;
         if (whole) {
           // whole item: O / l -> bf16 -> global, one query row per thread (256 contiguous bytes)
           const float inv_l = 1.0f / l;
@@ -543,7 +543,7 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_con
         mbar_arrive(&o_free[t]);
         if (sg.half) mbar_arrive(&o_free[1]);   // slot 0's warps have read O_1 as well
       }
-      cur += sg.j1 - sg.j0;
+      cur += sg.advance;
     }
     }
     if (TIMING && timing) {

@@ -20,50 +20,64 @@ static int check(int B, int Lq, int Skv, int H, int sms, long long ws_bytes) {
   const int q_tiles = (Lq + ATT_BM - 1) / ATT_BM;
   if (p.half_last != (q_tiles % 2)) fail("half_last", p.half_last, q_tiles);
   for (int grp = 0; grp < p.n_groups; ++grp) {
-    const long long G = att_group_steps(grp, p);
-    const int items_g = att_group_items(grp, p);
+    const long long G = p.split ? att_group_steps(grp, p) : (long long)att_group_heads(grp, p) * p.n_qtiles;
     if (att_range_start(0, grid, grp, p) != 0 || att_range_start(grid, grid, grp, p) != G) fail("range ends", G, 0);
-    // KV tiles seen per (item, query-tile slot): every tile exactly once per slot for full items; for half items each
-    // tile in exactly one slot (slot parity = tile parity relative to the segment start)
-    std::map<long long, int> seen;   // key (item * 2 + slot) * n_kv + tile
-    std::vector<int> pieces(items_g, 0);
+    // every (head, query tile, KV tile) must be computed exactly once
+    std::map<long long, int> seen;                 // key (head * n_qtiles + tile) * n_kv + kv tile
+    std::map<long long, int> pieces;               // key head * n_qtiles + first tile of the item -> number of segments
+    const int heads = att_group_heads(grp, p);
     for (int c = 0; c < grid; ++c) {
       const int r0 = att_range_start(c, grid, grp, p), r1 = att_range_start(c + 1, grid, grp, p);
       if (r1 < r0) fail("range order", r0, r1);
       for (int cur = r0; cur < r1;) {
         const AttSeg sg = att_decode(cur, r1, p);
-        if (sg.j1 <= sg.j0 || sg.j1 > sg.item_steps) { fail("segment", sg.j0, sg.j1); break; }
-        const int item = sg.bh_local * p.n_qpairs + sg.qp;
-        if (item >= items_g) { fail("item", item, items_g); break; }
-        if (att_item_first_step(item, p) + sg.j0 != cur) fail("first step", cur, item);
-        if (sg.half != (p.half_last && sg.qp == p.n_qpairs - 1)) fail("half flag", item, sg.half);
-        if (sg.item_steps != (sg.half ? p.n_half_steps : p.n_kv_tiles)) fail("item steps", item, sg.item_steps);
-        if (!p.split && !(sg.j0 == 0 && sg.j1 == sg.item_steps)) fail("whole-item mode cut an item", item, c);
-        pieces[item]++;
-        for (int s = cur; s < cur + (sg.j1 - sg.j0); ++s)
-          if (att_step_owner(s, grid, grp, p) != c && p.split) fail("owner", s, c);
+        if (sg.j1 <= sg.j0 || sg.j1 > sg.item_steps || sg.advance < 1) { fail("segment", sg.j0, sg.j1); break; }
+        if (sg.bh_local >= heads || sg.q_tile >= p.n_qtiles) { fail("item", sg.bh_local, sg.q_tile); break; }
+        if (!sg.half && sg.q_tile + 1 >= p.n_qtiles) fail("pair runs past the head's tiles", sg.bh_local, sg.q_tile);
+        if (sg.item_steps != (sg.half ? p.n_half_steps : p.n_kv_tiles)) fail("item steps", sg.q_tile, sg.item_steps);
+        if (!p.split && !(sg.j0 == 0 && sg.j1 == sg.item_steps)) fail("whole-item mode cut an item", sg.q_tile, c);
+        if (p.split) {
+          const int item = sg.bh_local * p.n_qpairs + sg.q_tile / 2;
+          if (sg.q_tile & 1) fail("split-mode pair not even-aligned", sg.q_tile, 0);
+          if (att_item_first_step(item, p) + sg.j0 != cur) fail("first step", cur, item);
+          if (sg.half != (p.half_last && sg.q_tile / 2 == p.n_qpairs - 1)) fail("half flag", item, sg.half);
+          for (int s = cur; s < cur + sg.advance; ++s)
+            if (att_step_owner(s, grid, grp, p) != c) fail("owner", s, c);
+        }
+        pieces[(long long)sg.bh_local * p.n_qtiles + sg.q_tile]++;
+        const long long base = (long long)sg.bh_local * p.n_qtiles + sg.q_tile;
         if (sg.half) {
           const int lo = 2 * sg.j0, hi = 2 * sg.j1 < p.n_kv_tiles ? 2 * sg.j1 : p.n_kv_tiles;
-          for (int j = lo; j < hi; ++j) seen[((long long)item * 2 + ((j - lo) & 1)) * p.n_kv_tiles + j]++;
+          for (int j = lo; j < hi; ++j) seen[base * p.n_kv_tiles + j]++;
         } else {
           for (int j = sg.j0; j < sg.j1; ++j)
-            for (int t = 0; t < 2; ++t) seen[((long long)item * 2 + t) * p.n_kv_tiles + j]++;
+            for (int t = 0; t < 2; ++t) seen[(base + t) * p.n_kv_tiles + j]++;
         }
-        cur += sg.j1 - sg.j0;
+        cur += sg.advance;
       }
     }
-    for (int item = 0; item < items_g; ++item) {
-      const bool half = p.half_last && (item % p.n_qpairs) == p.n_qpairs - 1;
-      if (pieces[item] < 1 || pieces[item] > 8) fail("pieces", item, pieces[item]);
-      for (int j = 0; j < p.n_kv_tiles; ++j) {
-        const int a = seen[((long long)item * 2) * p.n_kv_tiles + j], b = seen[((long long)item * 2 + 1) * p.n_kv_tiles + j];
-        if (half ? (a + b != 1) : (a != 1 || b != 1)) fail("coverage", item, j);
-      }
+    for (int h = 0; h < heads; ++h)
+      for (int q = 0; q < p.n_qtiles; ++q)
+        for (int j = 0; j < p.n_kv_tiles; ++j)
+          if (seen[((long long)h * p.n_qtiles + q) * p.n_kv_tiles + j] != 1) fail("coverage", h * 1000 + q, j);
+    for (auto& kv : pieces) {
+      if (kv.second < 1 || kv.second > 8) fail("pieces", kv.first, kv.second);
       if (p.split) {   // the combine kernel's view
+        const int h = (int)(kv.first / p.n_qtiles), q = (int)(kv.first % p.n_qtiles);
+        const int item = h * p.n_qpairs + q / 2;
+        const bool half = p.half_last && q / 2 == p.n_qpairs - 1;
         const long long s0 = att_item_first_step(item, p), s1 = s0 + (half ? p.n_half_steps : p.n_kv_tiles) - 1;
         const int c0 = att_step_owner(s0, grid, grp, p), c1 = att_step_owner(s1, grid, grp, p);
-        if (c1 - c0 + 1 != pieces[item]) fail("combine piece count", item, c1 - c0 + 1);
+        if (c1 - c0 + 1 != kv.second) fail("combine piece count", item, c1 - c0 + 1);
       }
+    }
+    if (!p.split) {   // whole-item mode: tiles are dealt out evenly (to within one tile)
+      int lo = 1 << 30, hi = 0;
+      for (int c = 0; c < grid; ++c) {
+        const int n = att_range_start(c + 1, grid, grp, p) - att_range_start(c, grid, grp, p);
+        lo = n < lo ? n : lo; hi = n > hi ? n : hi;
+      }
+      if (hi - lo > 1) fail("tile balance", lo, hi);
     }
   }
   return fails;
