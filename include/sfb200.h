@@ -131,6 +131,17 @@ int sfb_qk_norm_rope(const void* q_in, long long ldq, const void* k_in, long lon
                      const int* start_frame_dev, void* q_out, long long q_out_row, long long q_out_batch,
                      void* k_out, void* v_out, long long kv_out_row, long long kv_out_batch, void* stream);
 
+/* sfb_qk_norm_rope with the RMS statistics of the q / k rows taken from the statistics records of the QKV projection
+ * (sfb_gemm_bf16_stats, stats_out [B*L][stats_ld] records): q's chunks start at record q_chunk0, k's at k_chunk0.  The rows are
+ * streamed (no reduction pass), head_dim 128. */
+int sfb_qk_norm_rope_stats(const void* q_in, long long ldq, const void* k_in, long long ldk, const void* v_in, long long ldv,
+                           const void* wq, const void* wk, float eps, const void* stats, int stats_ld, int q_chunk0,
+                           int k_chunk0, const float* cos_tab, const float* sin_tab,
+                           int tab_rows, int B, int L, int C, int head_dim, int F, int Hh, int Ww, int start_frame,
+                           const int* start_frame_dev,
+                           void* q_out, long long q_out_row, long long q_out_batch,
+                           void* k_out, void* v_out, long long kv_out_row, long long kv_out_batch, void* stream);
+
 /* ---- Ulysses head-parallel attention for one long video (wan/distributed/xdit_context_parallel.py:66-192) ----
  * Every rank holds a contiguous slice of the chunk's tokens with ALL heads for the token-wise work and ONE head
  * group for attention.  The two all-to-alls per block are plain stores into peer-mapped memory issued by the

@@ -27,6 +27,7 @@ SIGNATURES = {
     "sfb_ln_affine": [P, LL, P, LL, I, I, F, P, P, P],
     "sfb_rmsnorm": [P, LL, P, LL, I, I, F, P, P],
     "sfb_qk_norm_rope": [P, LL, P, LL, P, LL, P, P, F, P, P, I, I, I, I, I, I, I, I, I, P, P, LL, LL, P, P, LL, LL, P],
+    "sfb_qk_norm_rope_stats": [P, LL, P, LL, P, LL, P, P, F, P, I, I, I, P, P, I, I, I, I, I, I, I, I, I, P, P, LL, LL, P, P, LL, LL, P],
     "sfb_kv_roll": [P, I, I, LL, LL, LL, LL, LL, P],
     "sfb_patchify": [P, LL, LL, LL, LL, LL, P, I, I, I, I, I, P],
     "sfb_sinusoid": [P, I, P, I, I, P],

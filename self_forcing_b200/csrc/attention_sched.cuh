@@ -3,6 +3,7 @@
 // exhaustively on the CPU (tests/test_attention_schedule.py).
 #pragma once
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 #include <stdlib.h>
 
 namespace sfb {
@@ -27,7 +28,7 @@ struct AttnParams {
   __nv_bfloat16* out[8];  // query rows [d * rows_per_dst, (d + 1) * rows_per_dst) go to out[d] (Ulysses: peer-mapped
   int rows_per_dst;       //   buffers, the epilogue stores are the reverse all-to-all); one destination otherwise
   long long out_row_stride, out_batch_stride;   // elements
-  float* ws;              // [group][grid][2 slots][2 tiles][128*128 O^T + 128 m + 128 l] floats (split mode)
+  float* ws;              // [group][grid][2 slots][2 tiles][64*128 half2 (O/l)^T + 128 m + 128 l] (split mode)
   long long* dbg;         // diagnostic phase timers [grid][8] (SFB_ATTN_TIMING=1), else nullptr
 };
 
@@ -38,7 +39,7 @@ constexpr int ATT_HALF_BYTES = 128 * 64 * 2;
 constexpr int ATT_KV_STAGES = 2;
 constexpr int ATT_XCHG_BYTES = 2 * ATT_BM * 8;      // half items: (m, l) of slot 1's rows, double buffered by segment parity
 constexpr int ATT_SMEM_BYTES = 2 * ATT_TILE_BYTES + 2 * ATT_KV_STAGES * ATT_TILE_BYTES + 1024 + 256 + ATT_XCHG_BYTES;
-constexpr int ATT_SLOT_FLOATS = ATT_BM * ATT_D + 2 * ATT_BM;   // one (tile, segment) partial
+constexpr int ATT_SLOT_FLOATS = ATT_BM * ATT_D / 2 + 2 * ATT_BM;   // one (tile, segment) partial: O / l as fp16 pairs [64 column pairs][128 rows], then m, l (fp32)
 constexpr int ATT_MIN_SPLIT_KV_TILES = 48;                     // shorter KV (measured: S = 4680 is better whole, S >= 9360 split): whole items per CTA
 constexpr int ATT_MAX_GROUPS = 4;
 constexpr long long ATT_L2_BUDGET = 72ll << 20;                // K + V bytes of the heads in flight (L2 is 126 MB; measured: 3 groups of 4 heads beat 4 x 3 and 6 x 2 at S = 32760)

@@ -48,6 +48,100 @@ __device__ __forceinline__ void setmaxnreg_inc() { asm volatile("setmaxnreg.inc.
 template <int REGS>
 __device__ __forceinline__ void setmaxnreg_dec() { asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(REGS)); }
 
+// ---- MMA issue helpers (one elected lane calls them) --------------------------------------------------------------
+struct AttMmaCtx {
+  uint32_t tmem_base, q_addr, k_addr, v_addr;   // TMEM base column, shared-memory addresses of the Q / K / V tiles
+};
+__device__ __forceinline__ void att_issue_qk(const AttMmaCtx& c, int t, int kst) {
+  constexpr uint32_t idesc_qk = umma_idesc_bf16(ATT_BM, ATT_BN, 0, 0);   // A, B K-major
+  const uint32_t qa = c.q_addr + t * ATT_TILE_BYTES, ka = c.k_addr + kst * ATT_TILE_BYTES;
+#pragma unroll
+  for (int k = 0; k < ATT_D / 16; ++k) {
+    const uint32_t off = (k >> 2) * ATT_HALF_BYTES + (k & 3) * 32;
+    umma_ss(c.tmem_base + t * 128, umma_desc_sw128(qa + off, 16, 1024), umma_desc_sw128(ka + off, 16, 1024), idesc_qk, k != 0);
+  }
+}
+__device__ __forceinline__ void att_issue_pv(const AttMmaCtx& c, int t, int vst, bool acc, int half) {
+  constexpr uint32_t idesc_pv = umma_idesc_bf16(ATT_BM, ATT_D, 0, 1);    // B (=V) MN-major
+  const uint32_t va = c.v_addr + vst * ATT_TILE_BYTES;
+#pragma unroll
+  for (int k = half * 4; k < half * 4 + 4; ++k) {
+    // A: P_t rows on TMEM lanes, 16 bf16 of K per 8 32-bit columns.
+    // B: V tile [kv][d], d contiguous -> MN-major; 16 kv rows = 2048 B; d halves 16 KB apart.
+    umma_ts(c.tmem_base + 256 + t * 128, c.tmem_base + t * 128 + k * 8, umma_desc_sw128(va + k * 2048, ATT_HALF_BYTES, 1024),
+            idesc_pv, (acc || k != 0) ? 1u : 0u);
+  }
+}
+
+// MMA schedule of a HALF item (called by the whole MMA warp): ONE query tile (in both Q slots); slot t takes the KV tiles
+// kv_lo + t, kv_lo + t + 2, ... each its own ring entry; O_0 and O_1 are partial sums over disjoint KV tiles, merged by
+// the softmax warps.  Kept out of line: one item in ~37 takes this path, and inlined it cost the main loop registers
+// (the MMA warp runs under a 104-register cap).  g = ring entries consumed so far, sc[t] = score tiles committed per slot.
+__device__ __forceinline__ void att_mma_half_item(AttMmaCtx c, uint64_t* bars, int kv_lo, int cnt, uint32_t seg, uint32_t g,
+                                               uint32_t* sc) {
+  uint64_t* q_empty = bars + 1;
+  uint64_t* k_full = bars + 2;
+  uint64_t* k_empty = bars + 4;
+  uint64_t* v_full = bars + 6;
+  uint64_t* v_empty = bars + 8;
+  uint64_t* s_full = bars + 10;
+  uint64_t* p_half = bars + 18;
+  uint64_t* o_final = bars + 14;
+  uint64_t* o_free = bars + 16;
+  const int n_t[2] = {(cnt + 1) >> 1, cnt >> 1};
+  for (int t = 0; t < 2; ++t) {
+    if (n_t[t] == 0) continue;
+    const uint32_t e = g + t;
+    mbar_wait(&k_full[e & 1], (e >> 1) & 1);
+    tc_fence_after();
+    if (elect_one()) {
+      att_issue_qk(c, t, e & 1);
+      umma_commit(&s_full[t]);
+      umma_commit(&k_empty[e & 1]);
+      if ((int)t == cnt - 1) umma_commit(q_empty);
+    }
+    __syncwarp();
+  }
+  for (int i = 0; i < n_t[0]; ++i) {
+    for (int t = 0; t < 2; ++t) {
+      if (i >= n_t[t]) continue;
+      const uint32_t e = g + 2 * i + t, e2 = e + 2;
+      const int vst = e & 1;
+      const bool has_next = (i + 1) < n_t[t];
+      mbar_wait(&p_half[2 * t], sc[t] & 1);
+      mbar_wait(&v_full[vst], (e >> 1) & 1);
+      if (i == 0) mbar_wait(&o_free[t], (seg & 1) ^ 1);
+      tc_fence_after();
+      if (elect_one()) att_issue_pv(c, t, vst, i > 0, 0);
+      __syncwarp();
+      mbar_wait(&p_half[2 * t + 1], sc[t] & 1);
+      tc_fence_after();
+      if (has_next) {
+        mbar_wait(&k_full[e2 & 1], (e2 >> 1) & 1);
+        tc_fence_after();
+      }
+      if (elect_one()) {
+        att_issue_pv(c, t, vst, true, 1);
+        umma_commit(&v_empty[vst]);
+        if (has_next) {
+          att_issue_qk(c, t, e2 & 1);
+          umma_commit(&s_full[t]);
+          umma_commit(&k_empty[e2 & 1]);
+          if (2 * (i + 1) + t == cnt - 1) umma_commit(q_empty);
+        } else {
+          umma_commit(&o_final[t]);
+        }
+      }
+      __syncwarp();
+      ++sc[t];
+    }
+  }
+  if (n_t[1] == 0) {           // slot 1 had no KV tile in this segment: keep its per-segment barrier in step
+    if (elect_one()) umma_commit(&o_final[1]);
+    __syncwarp();
+  }
+}
+
 // TIMING = true: diagnostic build with per-phase clock64 timers in one softmax warp (SFB_ATTN_TIMING=1); the timers cost
 // ~15 registers in the softmax warps, so the shipping instantiation compiles them out.
 template <bool TIMING>
@@ -173,29 +267,7 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_con
     } else if (warp == 1) {
       // ------------------------------ MMA issuer (warp-uniform, one lane issues) -----
       {
-        constexpr uint32_t idesc_qk = umma_idesc_bf16(ATT_BM, ATT_BN, 0, 0);   // A, B K-major
-        constexpr uint32_t idesc_pv = umma_idesc_bf16(ATT_BM, ATT_D, 0, 1);    // B (=V) MN-major
-        const uint32_t q_addr = smem_u32(q_smem), k_addr = smem_u32(k_smem), v_addr = smem_u32(v_smem);
-
-        auto issue_qk = [&](int t, int kst) {
-          const uint32_t qa = q_addr + t * ATT_TILE_BYTES, ka = k_addr + kst * ATT_TILE_BYTES;
-#pragma unroll
-          for (int k = 0; k < ATT_D / 16; ++k) {
-            const uint32_t off = (k >> 2) * ATT_HALF_BYTES + (k & 3) * 32;
-            umma_ss(tmem_base + t * 128, umma_desc_sw128(qa + off, 16, 1024), umma_desc_sw128(ka + off, 16, 1024),
-                    idesc_qk, k != 0);
-          }
-        };
-        auto issue_pv = [&](int t, int vst, bool acc, int half) {
-          const uint32_t va = v_addr + vst * ATT_TILE_BYTES;
-#pragma unroll
-          for (int k = half * 4; k < half * 4 + 4; ++k) {
-            // A: P_t rows on TMEM lanes, 16 bf16 of K per 8 32-bit columns.
-            // B: V tile [kv][d], d contiguous -> MN-major; 16 kv rows = 2048 B; d halves 16 KB apart.
-            umma_ts(tmem_base + 256 + t * 128, tmem_base + t * 128 + k * 8,
-                    umma_desc_sw128(va + k * 2048, ATT_HALF_BYTES, 1024), idesc_pv, (acc || k != 0) ? 1u : 0u);
-          }
-        };
+        const AttMmaCtx mc{tmem_base, smem_u32(q_smem), smem_u32(k_smem), smem_u32(v_smem)};
 
         uint32_t seg = 0, g = 0;     // segment counter, ring counter (KV tiles consumed so far)
         uint32_t sc[2] = {0, 0};     // score tiles committed so far per query-tile slot (parity of s_full / p_half)
@@ -210,9 +282,9 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_con
             mbar_wait(&k_full[g & 1], (g >> 1) & 1);
             tc_fence_after();
             if (elect_one()) {
-              issue_qk(0, g & 1);
+              att_issue_qk(mc, 0, g & 1);
               umma_commit(&s_full[0]);
-              issue_qk(1, g & 1);
+              att_issue_qk(mc, 1, g & 1);
               umma_commit(&s_full[1]);
               umma_commit(&k_empty[g & 1]);
               if (n == 1) umma_commit(q_empty);
@@ -230,7 +302,7 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_con
                 if (t == 0) mbar_wait(&v_full[vst], vph);
                 if (i == 0) mbar_wait(&o_free[t], (seg & 1) ^ 1);   // previous segment's epilogue has read O_t
                 tc_fence_after();
-                if (elect_one()) issue_pv(t, vst, i > 0, 0);
+                if (elect_one()) att_issue_pv(mc, t, vst, i > 0, 0);
                 __syncwarp();
                 mbar_wait(&p_half[2 * t + 1], sc[t] & 1);
                 tc_fence_after();
@@ -239,10 +311,10 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_con
                   tc_fence_after();
                 }
                 if (elect_one()) {
-                  issue_pv(t, vst, true, 1);
+                  att_issue_pv(mc, t, vst, true, 1);
                   if (t == 1) umma_commit(&v_empty[vst]);
                   if (has_next) {
-                    issue_qk(t, kst);
+                    att_issue_qk(mc, t, kst);
                     umma_commit(&s_full[t]);
                     if (t == 1) {
                       umma_commit(&k_empty[kst]);
@@ -257,62 +329,10 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_con
               }
             }
           } else {
-            // ---- half item: ONE query tile (in both Q slots); slot t takes KV tiles kv_lo + t, kv_lo + t + 2, ... each
-            //      its own ring entry; O_0 and O_1 are partial sums over disjoint KV tiles, merged by the softmax warps ----
+            // ---- half item (out of line: att_mma_half_item) ----
             const int kv_lo = 2 * sg.j0, kv_hi = 2 * sg.j1 < n_kv ? 2 * sg.j1 : n_kv;
             const int cnt = kv_hi - kv_lo;
-            const int n_t[2] = {(cnt + 1) >> 1, cnt >> 1};
-            for (int t = 0; t < 2; ++t) {
-              if (n_t[t] == 0) continue;
-              const uint32_t e = g + t;
-              mbar_wait(&k_full[e & 1], (e >> 1) & 1);
-              tc_fence_after();
-              if (elect_one()) {
-                issue_qk(t, e & 1);
-                umma_commit(&s_full[t]);
-                umma_commit(&k_empty[e & 1]);
-                if ((int)t == cnt - 1) umma_commit(q_empty);
-              }
-              __syncwarp();
-            }
-            for (int i = 0; i < n_t[0]; ++i) {
-              for (int t = 0; t < 2; ++t) {
-                if (i >= n_t[t]) continue;
-                const uint32_t e = g + 2 * i + t, e2 = e + 2;
-                const int vst = e & 1;
-                const bool has_next = (i + 1) < n_t[t];
-                mbar_wait(&p_half[2 * t], sc[t] & 1);
-                mbar_wait(&v_full[vst], (e >> 1) & 1);
-                if (i == 0) mbar_wait(&o_free[t], (seg & 1) ^ 1);
-                tc_fence_after();
-                if (elect_one()) issue_pv(t, vst, i > 0, 0);
-                __syncwarp();
-                mbar_wait(&p_half[2 * t + 1], sc[t] & 1);
-                tc_fence_after();
-                if (has_next) {
-                  mbar_wait(&k_full[e2 & 1], (e2 >> 1) & 1);
-                  tc_fence_after();
-                }
-                if (elect_one()) {
-                  issue_pv(t, vst, true, 1);
-                  umma_commit(&v_empty[vst]);
-                  if (has_next) {
-                    issue_qk(t, e2 & 1);
-                    umma_commit(&s_full[t]);
-                    umma_commit(&k_empty[e2 & 1]);
-                    if (2 * (i + 1) + t == cnt - 1) umma_commit(q_empty);
-                  } else {
-                    umma_commit(&o_final[t]);
-                  }
-                }
-                __syncwarp();
-                ++sc[t];
-              }
-            }
-            if (n_t[1] == 0) {           // slot 1 had no KV tile in this segment: keep its per-segment barrier in step
-              if (elect_one()) umma_commit(&o_final[1]);
-              __syncwarp();
-            }
+            att_mma_half_item(mc, bars, kv_lo, cnt, seg, g, sc);
             g += cnt;
           }
           cur += sg.advance;
@@ -517,27 +537,34 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_con
             }
           }
         } else {
-          // partial item: park (O^T, m, l) in this CTA's workspace slot (first segment -> 0, last -> 1)
+          // partial item: park ((O / l)^T as fp16, m, l) in this CTA's workspace slot (first segment -> 0, last -> 1).  The
+          // normalised partial is a convex combination of V rows (no overflow) and fp16's 2^-11 is 8x below the bf16
+          // rounding of the final output; it halves the bytes every split item sends through memory twice.
           float* slot = p.ws + ((((long long)grp * gridDim.x + blockIdx.x) * 2 + (cur == range_begin ? 0 : 1)) * 2 + t) *
                                    ATT_SLOT_FLOATS;
+          __half2* slot_h = reinterpret_cast<__half2*>(slot);
+          const float inv_l = 1.0f / l;
+          const float a_own = w_own * inv_l, a_oth = w_oth * inv_l;
 #pragma unroll 1
           for (int c = 0; c < 4; ++c) {
             uint32_t o[32];
             tmem_ld32(o_addr + c * 32, o);
             tmem_ld_wait();
+#pragma unroll
+            for (int i = 0; i < 32; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * a_own);
             if (two) {
               uint32_t o2[32];
               tmem_ld32(o_oth + c * 32, o2);
               tmem_ld_wait();
 #pragma unroll
-              for (int i = 0; i < 32; ++i)
-                o[i] = __float_as_uint(fmaf(__uint_as_float(o2[i]), w_oth, __uint_as_float(o[i]) * w_own));
+              for (int i = 0; i < 32; ++i) o[i] = __float_as_uint(fmaf(__uint_as_float(o2[i]), a_oth, __uint_as_float(o[i])));
             }
 #pragma unroll
-            for (int i = 0; i < 32; ++i) slot[(c * 32 + i) * ATT_BM + r_local] = __uint_as_float(o[i]);   // coalesced
+            for (int i = 0; i < 16; ++i)   // column pair (2i, 2i + 1) of this row: 4 bytes per lane, coalesced over rows
+              slot_h[(c * 16 + i) * ATT_BM + r_local] = __floats2half2_rn(__uint_as_float(o[2 * i]), __uint_as_float(o[2 * i + 1]));
           }
-          slot[ATT_BM * ATT_D + r_local] = m_ref;
-          slot[ATT_BM * ATT_D + ATT_BM + r_local] = l;
+          slot[ATT_BM * ATT_D / 2 + r_local] = m_ref;
+          slot[ATT_BM * ATT_D / 2 + ATT_BM + r_local] = l;
         }
         tc_fence_before();
         mbar_arrive(&o_free[t]);
@@ -582,6 +609,7 @@ attention_combine_kernel(const AttnParams p, int grid_fwd) {
   };
   // an item is cut by at most a few CTA boundaries: keep the segment pointers and weights in registers
   constexpr int MAX_SEG = 8;
+  constexpr int ML = ATT_BM * ATT_D / 2;   // float index of the (m, l) vectors behind the fp16 partial
   const int nseg = (c1 - c0 + 1) < MAX_SEG ? (c1 - c0 + 1) : MAX_SEG;
   const float* seg_ptr[MAX_SEG];
   float w[MAX_SEG];
@@ -589,7 +617,7 @@ attention_combine_kernel(const AttnParams p, int grid_fwd) {
 #pragma unroll
   for (int i = 0; i < MAX_SEG; ++i) {
     seg_ptr[i] = i < nseg ? slot_of(c0 + i) : nullptr;
-    if (i < nseg) m = fmaxf(m, seg_ptr[i][ATT_BM * ATT_D + r]);
+    if (i < nseg) m = fmaxf(m, seg_ptr[i][ML + r]);
   }
   float L = 0.f;
   float sl2 = p.scale_log2;
@@ -597,9 +625,9 @@ attention_combine_kernel(const AttnParams p, int grid_fwd) {
 #pragma unroll
   for (int i = 0; i < MAX_SEG; ++i) {
     w[i] = 0.f;
-    if (i < nseg) {
-      w[i] = exp2f((seg_ptr[i][ATT_BM * ATT_D + r] - m) * sl2);
-      L += seg_ptr[i][ATT_BM * ATT_D + ATT_BM + r] * w[i];
+    if (i < nseg) {   // weight of the segment's NORMALISED partial: l_s 2^{(m_s - m) c}
+      w[i] = exp2f((seg_ptr[i][ML + r] - m) * sl2) * seg_ptr[i][ML + ATT_BM + r];
+      L += w[i];
     }
   }
   const float inv_l = 1.0f / L;
@@ -611,8 +639,13 @@ attention_combine_kernel(const AttnParams p, int grid_fwd) {
 #pragma unroll
     for (int i = 0; i < MAX_SEG; ++i) {
       if (i < nseg) {
+        const __half2* sh = reinterpret_cast<const __half2*>(seg_ptr[i]);
 #pragma unroll
-        for (int j = 0; j < 8; ++j) acc[j] += seg_ptr[i][(col + j) * ATT_BM + r] * w[i];
+        for (int j = 0; j < 4; ++j) {
+          const float2 v2 = __half22float2(sh[(col / 2 + j) * ATT_BM + r]);
+          acc[2 * j] = fmaf(v2.x, w[i], acc[2 * j]);
+          acc[2 * j + 1] = fmaf(v2.y, w[i], acc[2 * j + 1]);
+        }
       }
     }
     uint4 o;

@@ -286,6 +286,75 @@ qk_norm_rope_kernel(const __nv_bfloat16* __restrict__ q_in, long long ldq, const
   }
 }
 
+// Streaming form of qk_norm_rope: the RMS statistics of the q and k rows come from the statistics records the QKV
+// projection's epilogue wrote (sfb_gemm_bf16_stats), so a row no longer has to sit in registers between a reduction pass
+// and an apply pass -- every 16-byte vector is loaded, normalised, rotated and stored on its own.  (The resident-row
+// kernel above spills 35 registers under its 64-register cap: profiles/r02_sass_summary.json.)
+template <int NV>
+__global__ void __launch_bounds__(ROW_WARPS * 32, row_kernel_blocks(NV))
+qk_rope_stream_kernel(const __nv_bfloat16* __restrict__ q_in, long long ldq, const __nv_bfloat16* __restrict__ k_in,
+                      long long ldk, const __nv_bfloat16* __restrict__ v_in, long long ldv,
+                      const __nv_bfloat16* __restrict__ wq, const __nv_bfloat16* __restrict__ wk, float eps,
+                      const float2* __restrict__ stats, int stats_ld, int q_chunk0, int k_chunk0,
+                      const float* __restrict__ cos_tab, const float* __restrict__ sin_tab, RopeGeom g, int rows,
+                      __nv_bfloat16* __restrict__ q_out, __nv_bfloat16* __restrict__ k_out, __nv_bfloat16* __restrict__ v_out,
+                      long long q_out_row, long long q_out_batch, long long kv_out_row, long long kv_out_batch) {
+  constexpr int C = NV * 256, CHUNKS = C / STATS_CHUNK, HALF = 64;   // head_dim 128
+  const int row = blockIdx.x * ROW_WARPS + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (row >= rows) return;
+  // sum of squares of the q and k rows from their chunk records (mean, M2): sum x^2 = M2 + n mean^2
+  float ssq = 0.f, ssk = 0.f;
+  const float2* rec = stats + (long long)row * stats_ld;
+  for (int j = lane; j < CHUNKS; j += 32) {
+    const float2 a = __ldg(rec + q_chunk0 + j), b = __ldg(rec + k_chunk0 + j);
+    ssq += a.y + (float)STATS_CHUNK * a.x * a.x;
+    ssk += b.y + (float)STATS_CHUNK * b.x * b.x;
+  }
+  const float rstd_q = rsqrtf(warp_sum(ssq) * (1.0f / C) + eps), rstd_k = rsqrtf(warp_sum(ssk) * (1.0f / C) + eps);
+
+  const int b = row / g.L, n = row - b * g.L;
+  const int fhw = g.Hh * g.Ww;
+  const int f = n / fhw, rem = n - f * fhw;
+  const int hh = rem / g.Ww, ww = rem - hh * g.Ww;
+  const int pos_f = (g.start_frame_dev != nullptr ? __ldg(g.start_frame_dev) : g.start_frame) + f;
+  // a lane's vectors all start at complex pair (lane % 16) * 4 of their head: 4 (cos, sin) pairs per token and lane
+  float cs4[4], sn4[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int pi = (lane & 15) * 4 + i;
+    const int pos = pi < g.n_f ? pos_f : (pi < g.n_f + g.n_h ? hh : ww);
+    cs4[i] = __ldg(cos_tab + pos * HALF + pi);
+    sn4[i] = __ldg(sin_tab + pos * HALF + pi);
+  }
+  const __nv_bfloat16* qs = q_in + row * ldq;
+  const __nv_bfloat16* ks = k_in + row * ldk;
+  __nv_bfloat16* qd = q_out + b * q_out_batch + n * q_out_row;
+  __nv_bfloat16* kd = k_out + b * kv_out_batch + n * kv_out_row;
+  uint4 rq[NV], rk[NV];
+#pragma unroll
+  for (int k = 0; k < NV; ++k) { rq[k] = ldg16(qs + (k * 32 + lane) * 8); rk[k] = ldg16(ks + (k * 32 + lane) * 8); }
+#pragma unroll
+  for (int which = 0; which < 2; ++which) {
+#pragma unroll
+    for (int k = 0; k < NV; ++k) {
+      float v[8], o[8];
+      rms_apply<NV>(which == 0 ? rq[k] : rk[k], which == 0 ? wq : wk, which == 0 ? rstd_q : rstd_k, k, lane, v);
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        o[2 * i] = v[2 * i] * cs4[i] - v[2 * i + 1] * sn4[i];
+        o[2 * i + 1] = v[2 * i] * sn4[i] + v[2 * i + 1] * cs4[i];
+      }
+      *reinterpret_cast<uint4*>((which == 0 ? qd : kd) + (k * 32 + lane) * 8) = pack8(o);
+    }
+  }
+  if (v_in != nullptr) {
+    __nv_bfloat16* vd = v_out + b * kv_out_batch + n * kv_out_row;
+#pragma unroll
+    for (int k = 0; k < NV; ++k) *reinterpret_cast<uint4*>(vd + (k * 32 + lane) * 8) = ldg16(v_in + row * ldv + (k * 32 + lane) * 8);
+  }
+}
+
 // ------------------------------------------------------------------------------------
 // KV-cache roll (reference causal_model.py:212-221: `cache[:, sink:sink+keep] = cache[:, sink+ev:sink+ev+keep].clone()`)
 // for ALL layers' K and V tensors in one launch per phase: rows [dst, dst + n) <- rows [dst + shift, dst + shift + n),
@@ -575,6 +644,34 @@ extern "C" int sfb_qk_norm_rope(const void* q_in, long long ldq, const void* k_i
         (const bf16*)q_in, ldq, (const bf16*)k_in, ldk, (const bf16*)v_in, ldv, (const bf16*)wq, (const bf16*)wk, eps,
         cos_tab, sin_tab, head_dim, g, rows, hs, q_out_row, q_out_batch, kv_out_row, kv_out_batch);
     return check_cuda(cudaGetLastError(), "qk_norm_rope launch");
+  });
+}
+
+// sfb_qk_norm_rope with the row statistics supplied by the QKV projection (include/sfb200.h).
+extern "C" int sfb_qk_norm_rope_stats(const void* q_in, long long ldq, const void* k_in, long long ldk, const void* v_in,
+                                      long long ldv, const void* wq, const void* wk, float eps, const void* stats,
+                                      int stats_ld, int q_chunk0, int k_chunk0, const float* cos_tab,
+                                      const float* sin_tab, int tab_rows, int B, int L, int C, int head_dim, int F, int Hh,
+                                      int Ww, int start_frame, const int* start_frame_dev, void* q_out, long long q_out_row,
+                                      long long q_out_batch, void* k_out, void* v_out, long long kv_out_row,
+                                      long long kv_out_batch, void* stream) {
+  if (B <= 0 || L <= 0 || L != F * Hh * Ww) { set_error("sfb_qk_norm_rope_stats: L=%d != F*H*W=%d*%d*%d", L, F, Hh, Ww); return SFB_ERR_INVALID; }
+  if (head_dim != 128 || C % head_dim) { set_error("sfb_qk_norm_rope_stats: head_dim %d (128 only) / C=%d", head_dim, C); return SFB_ERR_INVALID; }
+  if (stats == nullptr || q_chunk0 < 0 || k_chunk0 < 0 || stats_ld < q_chunk0 + C / STATS_CHUNK || stats_ld < k_chunk0 + C / STATS_CHUNK) { set_error("sfb_qk_norm_rope_stats: statistics records [%d] do not cover chunks %d / %d + %d", stats_ld, q_chunk0, k_chunk0, C / STATS_CHUNK); return SFB_ERR_INVALID; }
+  if (start_frame < 0 || start_frame + F > tab_rows || Hh > tab_rows || Ww > tab_rows) { set_error("sfb_qk_norm_rope_stats: position beyond the %d-row RoPE table (start_frame=%d F=%d)", tab_rows, start_frame, F); return SFB_ERR_INVALID; }
+  if ((ldq % 8) || (ldk % 8) || (ldv % 8) || (q_out_row % 8) || (kv_out_row % 8) || (q_out_batch % 8) || (kv_out_batch % 8)) { set_error("sfb_qk_norm_rope_stats: strides must be multiples of 8"); return SFB_ERR_INVALID; }
+  RopeGeom g;
+  g.L = L; g.Hh = Hh; g.Ww = Ww; g.start_frame = start_frame; g.start_frame_dev = start_frame_dev;
+  const int c = head_dim / 2;
+  g.n_f = c - 2 * (c / 3);
+  g.n_h = c / 3;
+  const int rows = B * L;
+  return dispatch_nv(C, "sfb_qk_norm_rope_stats", [&](auto nv) {
+    qk_rope_stream_kernel<decltype(nv)::value><<<(rows + ROW_WARPS - 1) / ROW_WARPS, ROW_WARPS * 32, 0, (cudaStream_t)stream>>>(
+        (const bf16*)q_in, ldq, (const bf16*)k_in, ldk, (const bf16*)v_in, ldv, (const bf16*)wq, (const bf16*)wk, eps,
+        (const float2*)stats, stats_ld, q_chunk0, k_chunk0, cos_tab, sin_tab, g, rows, (bf16*)q_out, (bf16*)k_out,
+        (bf16*)v_out, q_out_row, q_out_batch, kv_out_row, kv_out_batch);
+    return check_cuda(cudaGetLastError(), "qk_norm_rope_stats launch");
   });
 }
 

@@ -205,8 +205,21 @@ extern "C" int sfb_gemm_bf16_stats(const void* x, long long ldx, const void* w, 
   // block_n: 0 = choose; 64 / 128 / 256 = one-CTA tiles of 128 x block_n; 512 = CTA-pair tiles of 256 x 256 (tcgen05
   // cta_group::2, gemm2_tcgen05.cu) -- the default whenever N and the segments are multiples of 256; 515 = pair tiles in
   // clusters of two pairs sharing A by TMA multicast (default for long-K, narrow-N problems: FFN2).
-  if (block_n == 0 && N % 256 == 0 && seg_cols % 256 == 0 && M > 128 && epilogue != EPI_F32)
-    block_n = (K >= 4096 && N <= 2048 && M >= 2048) ? 515 : 512;
+  if (block_n == 0 && N % 256 == 0 && seg_cols % 256 == 0 && M > 128 && epilogue != EPI_F32) {
+    block_n = 512;
+    if (K >= 4096 && N <= 2048 && M >= 2048) {
+      // clusters of two pairs (A multicast) win 4-5 % on long-K problems at equal SM fill (measured: 33 of them are co-resident
+      // on 148 SMs); choose them unless whole pairs fill the machine better (M = 9360, N = 1536: 222 tiles = 3 exact rounds
+      // of 74 pairs against 111 super tiles on 33 clusters)
+      const int sms_ = device_sm_count();
+      const int pairs = sms_ / 2, quads = sms_ * 33 / 148 > 0 ? sms_ * 33 / 148 : 1;
+      const int mb = (M + 255) / 256, nb = N / 256;
+      const int t1 = mb * nb, t2 = mb * ((nb + 1) / 2);
+      const double eff1 = (double)t1 / (((t1 + pairs - 1) / pairs) * pairs);
+      const double eff2 = (double)t2 / (((t2 + quads - 1) / quads) * quads) * (4.0 * quads / sms_) * ((double)nb / (2 * ((nb + 1) / 2)));
+      if (eff2 >= 0.98 * eff1) block_n = 515;
+    }
+  }
   if (block_n == 0) {
     // narrow problems take 128-wide tiles so the tile count fills the SMs
     block_n = (N % 256 == 0 && N >= 4096) ? 256 : (N % 128 == 0 ? 128 : 64);

@@ -322,6 +322,7 @@ class B200CausalWanModel(nn.Module):
             if C % STATS_CHUNK == 0:   # row-statistics records of x (after the self-attention residual) and of the cross q
                 ws["x_stats"] = torch.empty(R, C // STATS_CHUNK, 2, dtype=torch.float32, device=dev)
                 ws["q_stats"] = torch.empty(R, C // STATS_CHUNK, 2, dtype=torch.float32, device=dev)
+                ws["qkv_stats"] = torch.empty(R, 3 * C // STATS_CHUNK, 2, dtype=torch.float32, device=dev)
             self._ws[key] = ws
         return ws
 
@@ -666,6 +667,10 @@ class B200CausalWanModel(nn.Module):
             tensors = [kv_cache[i][name] for i in layers for name in ("k", "v")]
             ops.kv_roll(tensors, self._pointer_table(tensors, dev), dst, src, n)
 
+        # QK-RMSNorm statistics from the QKV projection's epilogue: qk_norm_rope then streams its rows (no reduction pass)
+        stream_rope = pk["fold"] and R > 128 and D == 128 and sp is None
+        qkv_stats = dict(stats_out=ws["qkv_stats"]) if stream_rope else {}
+        rope_stats = dict(stats=ws["qkv_stats"], q_chunk0=0, k_chunk0=C // STATS_CHUNK) if stream_rope else {}
         for i, blk in enumerate(self.blocks):
             pb = pk["blocks"][i]
             cache, plan = kv_cache[i], plans[i]
@@ -703,18 +708,18 @@ class B200CausalWanModel(nn.Module):
                          **(dict(stats_out=ws["x_stats"]) if fold[i] else {}))
             elif B == 1:   # V projection lands directly in its cache slot
                 ops.gemm(ws["h"], pb["wqkv"], pb["bqkv"], None, seg_cols=C,
-                         outs=[ws["q_lin"], ws["k_lin"], v_slot.view(L, C)])   # .view: a non-viewable cache layout must raise
+                         outs=[ws["q_lin"], ws["k_lin"], v_slot.view(L, C)], **qkv_stats)   # .view: a non-viewable cache layout must raise
                 v_src = None
             else:
                 ops.gemm(ws["h"], pb["wqkv"], pb["bqkv"], None, seg_cols=C,
-                         outs=[ws["q_lin"], ws["k_lin"], ws["v_lin"]])
+                         outs=[ws["q_lin"], ws["k_lin"], ws["v_lin"]], **qkv_stats)
                 v_src = ws["v_lin"]
             q4 = ws["q"].view(B, Lr, NH, D)
             if sp is None:
                 ops.qk_norm_rope(ws["q_lin"], ws["k_lin"], v_src, sa.norm_q.weight, sa.norm_k.weight, self.eps,
                                  pk["cos"], pk["sin"], B, L, D, (F_, Hh, Ww), start_frame,
                                  q_out=ws["q"].view(B, L, C), k_out=k_slot, v_out=v_slot,
-                                 start_frame_dev=env.get("start_frame_dev"))
+                                 start_frame_dev=env.get("start_frame_dev"), **rope_stats)
                 if skip_output and i == NL - 1:
                     break   # cache-refresh pass: nothing after the last layer's K/V append is consumed
                 ops.attention(q4, kc[:, plan.attn_start:plan.attn_end], vc[:, plan.attn_start:plan.attn_end],

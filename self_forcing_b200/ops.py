@@ -194,9 +194,11 @@ class CudaOps:
 
     @_op
     def qk_norm_rope(self, q_in, k_in, v_in, wq, wk, eps, cos_tab, sin_tab, B, L, head_dim, grid, start_frame,
-                     q_out, k_out, v_out, start_frame_dev=None):
+                     q_out, k_out, v_out, start_frame_dev=None, stats=None, q_chunk0=0, k_chunk0=0):
         """q_in/k_in/v_in [B*L, C]; q_out [B, L, C]-like view; k_out/v_out [B, L, H, D] cache-slot views.
-        start_frame_dev: optional int32 device scalar that overrides start_frame at run time (graph replay)."""
+        start_frame_dev: optional int32 device scalar that overrides start_frame at run time (graph replay).
+        stats: fp32 [B*L, chunks, 2] statistics records of the QKV projection's output rows (gemm(stats_out=)); q's
+        records start at chunk q_chunk0, k's at k_chunk0 -- the rows are then streamed (sfb_qk_norm_rope_stats)."""
         if start_frame_dev is not None:
             assert start_frame_dev.dtype == torch.int32 and start_frame_dev.numel() == 1
         _check_2d(q_in, "q_in"); _check_2d(k_in, "k_in")
@@ -204,6 +206,17 @@ class CudaOps:
         F_, Hh, Ww = grid
         assert cos_tab.dtype == torch.float32 and cos_tab.is_contiguous() and sin_tab.is_contiguous()
         assert k_out.stride() == v_out.stride()
+        if stats is not None:
+            assert stats.dtype == torch.float32 and stats.is_contiguous() and stats.dim() == 3 and stats.shape[0] == B * L \
+                and stats.shape[2] == 2
+            _lib.check(self.lib.sfb_qk_norm_rope_stats(
+                q_in.data_ptr(), q_in.stride(0), k_in.data_ptr(), k_in.stride(0), _ptr(v_in),
+                v_in.stride(0) if v_in is not None else 0, wq.data_ptr(), wk.data_ptr(), eps, stats.data_ptr(),
+                stats.shape[1], q_chunk0, k_chunk0, cos_tab.data_ptr(), sin_tab.data_ptr(), cos_tab.shape[0], B, L, C,
+                head_dim, F_, Hh, Ww, start_frame, _ptr(start_frame_dev), q_out.data_ptr(), q_out.stride(1),
+                q_out.stride(0), k_out.data_ptr(), v_out.data_ptr(), k_out.stride(1), k_out.stride(0), self._stream()),
+                "sfb_qk_norm_rope_stats")
+            return
         _lib.check(self.lib.sfb_qk_norm_rope(
             q_in.data_ptr(), q_in.stride(0), k_in.data_ptr(), k_in.stride(0), _ptr(v_in),
             v_in.stride(0) if v_in is not None else 0, wq.data_ptr(), wk.data_ptr(), eps, cos_tab.data_ptr(),

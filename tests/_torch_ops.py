@@ -104,8 +104,15 @@ class TorchOps:
         y.copy_(O.rms_norm(x, weight, eps))
 
     def qk_norm_rope(self, q_in, k_in, v_in, wq, wk, eps, cos_tab, sin_tab, B, L, head_dim, grid, start_frame,
-                     q_out, k_out, v_out, start_frame_dev=None):
+                     q_out, k_out, v_out, start_frame_dev=None, stats=None, q_chunk0=0, k_chunk0=0):
         self.launches += 1
+        if stats is not None:     # the records must describe the rows handed in (sfb_qk_norm_rope_stats)
+            self.log.append("qk_norm_rope_stats")
+            nc = q_in.shape[1] // 128
+            for x, c0 in ((q_in, q_chunk0), (k_in, k_chunk0)):
+                rec = stats[:, c0:c0 + nc]
+                ss = (rec[..., 1] + 128.0 * rec[..., 0] ** 2).sum(dim=1)
+                assert torch.allclose(ss, x.float().pow(2).sum(dim=1), rtol=1e-3, atol=1e-3)
         if start_frame_dev is not None:
             start_frame = int(start_frame_dev)
         C = q_in.shape[1]

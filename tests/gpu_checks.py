@@ -302,6 +302,34 @@ def check_qk_norm_rope(B=2, F_=2, Hh=5, Ww=7, C=1536, start_frame=3, seed=0, wit
     return _against_double("qk_norm_rope", run, outs, exact=("vc",))
 
 
+def check_qk_norm_rope_stats(B=2, F_=2, Hh=5, Ww=7, C=1536, start_frame=3, seed=0, with_v=True):
+    """Streaming form fed by the QKV projection's statistics records against the resident-row kernel: the only difference
+    is the summation order of the row's sum of squares -> at most a last-bit difference of the normalisation factor."""
+    ops = _ops()
+    D = 128
+    H = C // D
+    L = F_ * Hh * Ww
+    qkv = _randn(B * L, 3 * C, seed=seed)
+    wq, wk = _randn(C, seed=seed + 1) * 0.1 + 1, _randn(C, seed=seed + 2) * 0.1 + 1
+    from self_forcing_b200.model import rope_tables
+    cos, sin = (t.cuda() for t in rope_tables(D))
+    stats = _stats_ref(qkv).contiguous()
+    outs = []
+    for use_stats in (False, True):
+        q = torch.zeros(B, L, C, device="cuda", dtype=BF)
+        kc = torch.zeros(B, L + 11, H, D, device="cuda", dtype=BF)
+        vc = torch.zeros_like(kc)
+        kw = dict(stats=stats, q_chunk0=0, k_chunk0=C // 128) if use_stats else {}
+        ops.qk_norm_rope(qkv[:, :C], qkv[:, C:2 * C], qkv[:, 2 * C:] if with_v else None, wq, wk, 1e-6, cos, sin, B, L, D,
+                         (F_, Hh, Ww), start_frame, q_out=q, k_out=kc[:, 5:5 + L], v_out=vc[:, 5:5 + L], **kw)
+        outs.append((q, kc, vc))
+    (q0, k0, v0), (q1, k1, v1) = outs
+    m = dict(err_q=rel_l2(q1, q0), err_k=rel_l2(k1, k0), err_v_mismatch=float((v1 != v0).sum()),
+             q_mismatch_frac=float((q1 != q0).float().mean()), k_mismatch_frac=float((k1 != k0).float().mean()))
+    assert m["err_v_mismatch"] == 0 and m["q_mismatch_frac"] <= 2e-3 and m["k_mismatch_frac"] <= 2e-3, m
+    return _finish("qk_norm_rope_stats", m, 1e-4)
+
+
 class _FakeGroup:
     """Stands in for UlyssesGroup in single-GPU kernel checks: `world` ranks emulated in one process."""
     def __init__(self, world, rank):
@@ -832,6 +860,8 @@ ALL = {
     "rmsnorm": check_rmsnorm,
     "qk_norm_rope": check_qk_norm_rope,
     "qk_norm_rope_nov": lambda: check_qk_norm_rope(B=1, with_v=False),
+    "qk_norm_rope_stats": check_qk_norm_rope_stats,
+    "qk_norm_rope_stats_chunk": lambda: check_qk_norm_rope_stats(B=1, F_=3, Hh=30, Ww=52, start_frame=6, seed=5, with_v=False),
     "qk_norm_rope_sp": check_qk_norm_rope_sp,
     "qk_norm_rope_sp4": lambda: check_qk_norm_rope_sp(P=4, Hh=8),
     "attn_sp": check_attention_sp,

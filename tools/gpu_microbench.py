@@ -134,6 +134,10 @@ def main():
             ("rmsnorm", 2 * L * C * 2, lambda: ops.rmsnorm(x, y, w, 1e-6)),
             ("qk_norm_rope", 6 * L * C * 2, lambda: ops.qk_norm_rope(qkv[:, :C], qkv[:, C:2 * C], qkv[:, 2 * C:], w, w, 1e-6, cos, sin, 1, L, 128, (3, 30, 52), 0, q_out=qo, k_out=kc, v_out=vc)),
         ]
+        qkv_stats = torch.rand(L, 36, 2, device="cuda") + 0.5
+        cases.append(("qk_norm_rope_stats", 6 * L * C * 2, lambda: ops.qk_norm_rope(
+            qkv[:, :C], qkv[:, C:2 * C], qkv[:, 2 * C:], w, w, 1e-6, cos, sin, 1, L, 128, (3, 30, 52), 0, q_out=qo, k_out=kc,
+            v_out=vc, stats=qkv_stats, q_chunk0=0, k_chunk0=12)))
         for name, nbytes, fn in cases:
             for _ in range(3): fn()
             torch.cuda.synchronize()

@@ -12,16 +12,23 @@ cap() {   # name, kernel regex, launches to skip, microbench selector...
       -o $OUT/${TAG}_${name} python tools/gpu_microbench.py "$@" > $OUT/${TAG}_ncu_${name}.log 2>&1
   echo "ncu ${name} rc=$?"
 }
-cap attn_S4680   attention_fwd_kernel 3 attn_self_S4680
-cap attn_S18720  attention_fwd_kernel 3 attn_self_S18720
-cap attn_S32760  attention_fwd_kernel 3 attn_self_S32760
-cap attn_cross   attention_fwd_kernel 3 attn_cross_S512
-cap gemm_qkv     gemm2_bf16_kernel 3 gemm_qkv
-cap gemm_o_proj  gemm2_bf16_kernel 3 gemm_o_proj
-cap gemm_ffn1    gemm2_bf16_kernel 3 gemm_ffn1
-cap gemm_ffn2    gemm2_bf16_kernel 3 gemm_ffn2
-cap ln_modulate  "ln_kernel.*Lb0" 3 elementwise
-cap ln_affine    "ln_kernel.*Lb1" 3 elementwise
-cap rmsnorm      "rmsnorm_kernel" 3 elementwise
-cap qk_norm_rope "qk_norm_rope_kernel" 3 elementwise
+# one plain run of everything that is captured below (must exit 0 before any capture)
+python tools/gpu_microbench.py attn_ gemm_qkv gemm_o_proj gemm_cross_q gemm_ffn elementwise > $OUT/${TAG}_plain_all.log 2>&1 || { echo "plain run failed"; tail -5 $OUT/${TAG}_plain_all.log; exit 1; }
+capq() {   # like cap, without the per-capture plain run (covered by the run above)
+  local name=$1 regex=$2 skip=$3; shift 3
+  timeout 240 ncu --set full --clock-control none --import-source on -k regex:${regex} -s ${skip} -c 1 -f \
+      -o $OUT/${TAG}_${name} python tools/gpu_microbench.py "$@" > $OUT/${TAG}_ncu_${name}.log 2>&1
+  echo "ncu ${name} rc=$?"
+}
+capq attn_S4680   attention_fwd_kernel 3 attn_self_S4680
+capq attn_S18720  attention_fwd_kernel 3 attn_self_S18720
+capq attn_S32760  attention_fwd_kernel 3 attn_self_S32760
+capq attn_cross   attention_fwd_kernel 3 attn_cross_S512
+capq gemm_qkv     gemm2_bf16_kernel 3 gemm_qkv
+capq gemm_o_proj_stats  gemm2_bf16_kernel 3 gemm_o_proj_stats
+capq gemm_cross_q_fold  gemm2_bf16_kernel 3 gemm_cross_q_fold
+capq gemm_ffn1    gemm2_bf16_kernel 3 gemm_ffn1
+capq gemm_ffn2    gemm2_bf16_kernel 3 gemm_ffn2
+capq ln_modulate  "ln_kernel.*Lb0" 3 elementwise
+capq qk_rope_stream "qk_rope_stream_kernel" 3 elementwise
 ls -la $OUT | grep ${TAG}_ | grep ncu-rep

@@ -25,6 +25,9 @@ KEEP = ["gpu__time_duration.sum", "sm__pipe_tensor_cycles_active.avg.pct_of_peak
 SHAPES = {"attn_S4680": "Lq 4680, S 4680, H 12", "attn_S18720": "Lq 4680, S 18720, H 12", "attn_S32760": "Lq 4680, S 32760, H 12",
           "attn_cross": "Lq 4680, S 512, H 12", "gemm_qkv": "4680 x 4608 x 1536 bias", "gemm_o_proj": "4680 x 1536 x 1536 gate+residual",
           "gemm_ffn1": "4680 x 8960 x 1536 GELU", "gemm_ffn2": "4680 x 1536 x 8960 gate+residual",
+          "gemm_o_proj_stats": "4680 x 1536 x 1536 gate+residual + row statistics of the output",
+          "gemm_cross_q_fold": "4680 x 1536 x 1536, LayerNorm folded into the epilogue + row statistics of the output",
+          "qk_rope_stream": "4680 x 1536 q,k -> q, cache (statistics from the QKV epilogue)",
           "ln_modulate": "4680 x 1536", "ln_affine": "4680 x 1536", "rmsnorm": "4680 x 1536", "qk_norm_rope": "4680 x 1536 q,k -> q, cache"}
 
 
