@@ -425,21 +425,10 @@ def run_product_arm(args) -> None:
 
     # ---- timed region 1b: the same K steps with every attention launch bracketed by CUDA events (roofline leg;
     # individual launches cannot be timed inside a graph replay, so this pass launches eagerly).
-    # An eager forward is ~430 launches issued from Python; whenever the host falls behind, the GPU idles between an
-    # event and the kernel behind it and the event pair times the HOST (measured: the 30 us cross-attention launch read
-    # 35 / 47 / 87 us on three boxes).  So every profiled forward is preceded by ~20 ms of queued tensor-core work (plain
-    # cuBLAS GEMMs: same power state as the rollout, unlike a sleep): the host enqueues the whole forward while the GPU is
-    # busy and the kernels then run back to back, event pairs timing the kernels only.
-    burn_a = torch.randn(8192, 8192, device=dev, dtype=torch.bfloat16)
-    burn_c = torch.empty_like(burn_a)
-    model_forward = gen.model._device_forward
-
-    def forward_behind_queued_work(*a, **k):
-        for _ in range(24):
-            torch.matmul(burn_a, burn_a, out=burn_c)
-        return model_forward(*a, **k)
-
-    gen.model._device_forward = forward_behind_queued_work
+    # (Event pairs around the ~30 us kernels also time the host whenever it falls behind -- the cross-attention launch read
+    # 35 / 47 / 87 us on three boxes; queueing each forward behind 20 ms of cuBLAS work removes the gaps but leaves the
+    # chip at the GEMM's lower power-capped clock and read every kernel 10 % slow.  So: plain eager launches; per-kernel GPU
+    # times without host gaps are in the ncu launch list, profiles/r02q_ncu_launch_shares.json.)
     ops.start_profile(only={"attention", "attention_sp"})
     barrier()
     for _ in range(args.steps):
@@ -447,7 +436,6 @@ def run_product_arm(args) -> None:
     barrier()
     row1 = clocks.mark() if clocks else 0
     attn_prof = ops.stop_profile()
-    gen.model._device_forward = model_forward
 
     # ---- timed region 2: end to end with host buffers ------------------------------------------
     host_step()
@@ -460,12 +448,9 @@ def run_product_arm(args) -> None:
     clk = clocks.stop(row0, None) if clocks else None
 
     # ---- per-kernel breakdown of one more (untimed) rollout --------------------------------------
-    gen.model._device_forward = forward_behind_queued_work
     ops.start_profile()
     resident_step()
     prof = ops.stop_profile()
-    gen.model._device_forward = model_forward
-    del burn_a, burn_c
 
     def shutdown():
         """Tear the process group down; never let a stuck teardown turn a finished measurement into a hang."""
@@ -531,7 +516,7 @@ def run_product_arm(args) -> None:
             gbs = nbytes / (gk[1] * 1e-3) / 1e9
             hbm_lines.append({"kernel": kname, "bound": "hbm", "achieved": gbs, "peak": pk["hbm"], "unit": "GB/s",
                               "frac": gbs / pk["hbm"], "bytes_per_launch": passes * Lrows * C * 2.0,
-                              "note": "per-launch CUDA events of the eager breakdown pass, each forward queued behind ~20 ms of GEMM work so that the kernels run back to back"})
+                              "note": "per-launch CUDA events of the eager breakdown pass (event pairs around ~10 us kernels include host launch gaps; GPU-only times: profiles/r02q_ncu_launch_shares.json)"})
     total_fl = rollout_flops(cf)
     traffic, traffic_src = ncu_traffic()
     # per-shape view of the projections (event-timed eager launches of the breakdown pass)

@@ -588,7 +588,7 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_con
 }
 
 // Merges the partial segments of every split item: out = sum_s O_s 2^{(m_s - m) c} / sum_s l_s 2^{(m_s - m) c}.
-// grid (items, 2 query tiles), 128 threads = one query row each.
+// grid (items, 2 query tiles, 4 column quarters), 128 threads = one query row each.
 __global__ void __launch_bounds__(128)
 attention_combine_kernel(const AttnParams p, int grid_fwd) {
   const int t = blockIdx.y, r = threadIdx.x;
@@ -634,7 +634,9 @@ attention_combine_kernel(const AttnParams p, int grid_fwd) {
   const int dst = row / p.rows_per_dst;
   __nv_bfloat16* orow = p.out[dst] + (long long)batch * p.out_batch_stride +
                         (long long)(row - dst * p.rows_per_dst) * p.out_row_stride + head * ATT_D;
-  for (int col = 0; col < ATT_D; col += 8) {
+  // blockIdx.z = quarter of the head's columns: 4x the blocks of a row-per-thread kernel whose occupancy (about two
+  // 128-thread blocks per SM do any work) left it latency-bound (38.7 us per launch in profiles/r02q_ncu_launch_shares.json)
+  for (int col = blockIdx.z * (ATT_D / 4); col < (blockIdx.z + 1) * (ATT_D / 4); col += 8) {
     float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
 #pragma unroll
     for (int i = 0; i < MAX_SEG; ++i) {
@@ -747,7 +749,7 @@ static int attention_launch(const void* q, long long q_row_stride, long long q_b
             acc[5] / steps, (acc[0] + acc[1] + acc[2] + acc[3] + acc[4] + acc[5]) / steps);
   }
   if (p.split) {
-    attention_combine_kernel<<<dim3(p.items, 2), 128, 0, stream>>>(p, grid);
+    attention_combine_kernel<<<dim3(p.items, 2, 4), 128, 0, stream>>>(p, grid);
     return check_cuda(cudaGetLastError(), "attention combine launch");
   }
   return SFB_OK;
