@@ -53,6 +53,8 @@ class B200T5Encoder:
         self.device = torch.device(device) if device is not None else torch.device("cpu")
         self.w: Dict[str, torch.Tensor] = {}
         self._bias: Dict[int, List[torch.Tensor]] = {}
+        self.use_cuda_graphs = True
+        self._graphs: Dict[tuple, object] = {}     # (ids shape, has mask) -> "seen" | (graph, static ids, static mask, static output, launches)
 
     @property
     def ops(self):
@@ -87,6 +89,7 @@ class B200T5Encoder:
             self.w[b + "qkv"] = torch.cat([get(b + "attn.q.weight"), get(b + "attn.k.weight"), get(b + "attn.v.weight")]).contiguous()
             self.w[b + "fc1_gate"] = torch.cat([get(b + "ffn.fc1.weight"), get(b + "ffn.gate.0.weight")]).contiguous()
         self._bias.clear()
+        self._graphs.clear()
         return missing, unexpected
 
     def _position_bias(self, L: int) -> List[torch.Tensor]:
@@ -99,9 +102,39 @@ class B200T5Encoder:
 
     @torch.no_grad()
     def __call__(self, ids: torch.Tensor, mask: Optional[torch.Tensor] = None) -> torch.Tensor:
-        """ids [B, L] int64, mask [B, L] (non-zero = real token) -> bf16 [B, L, dim]."""
+        """ids [B, L] int64, mask [B, L] (non-zero = real token) -> bf16 [B, L, dim].
+
+        The per-head attention makes one prompt ~6300 small launches (measured: 93 ms, launch-bound), so the forward of
+        a given (B, L) is replayed as ONE CUDA graph from its third call on (first call eager, second captures)."""
         if not self.w:
             raise RuntimeError("B200T5Encoder: load_state_dict first")
+        dev = torch.device(self.device)
+        if not (self.use_cuda_graphs and dev.type == "cuda" and getattr(self.ops, "supports_cuda_graphs", False)
+                and getattr(self.ops, "_prof", None) is None):
+            return self._forward(ids, mask)
+        key = (tuple(ids.shape), mask is not None)
+        ent = self._graphs.get(key)
+        if ent is None:
+            self._graphs[key] = "seen"
+            return self._forward(ids, mask)
+        if ent == "seen":
+            ids_s = ids.to(dev).clone()
+            mask_s = None if mask is None else mask.to(dev).clone()
+            graph = torch.cuda.CUDAGraph()
+            before = self.ops.launches
+            with torch.cuda.graph(graph):
+                out_s = self._forward(ids_s, mask_s)
+            ent = self._graphs[key] = (graph, ids_s, mask_s, out_s, self.ops.launches - before)
+            self.ops.launches = before
+        graph, ids_s, mask_s, out_s, n_launches = ent
+        ids_s.copy_(ids)
+        if mask_s is not None:
+            mask_s.copy_(mask)
+        graph.replay()
+        self.ops.launches += n_launches
+        return out_s.clone()
+
+    def _forward(self, ids: torch.Tensor, mask: Optional[torch.Tensor] = None) -> torch.Tensor:
         ops, dev = self.ops, self.device
         B, L = ids.shape
         C, A, Fd, H = self.dim, self.dim_attn, self.dim_ffn, self.num_heads

@@ -779,6 +779,12 @@ def check_t5_encoder():
     enc.load_state_dict(T.make_random_t5_params(cfg, seed=T5_CASE["seed"]))
     ids, mask = t5_case_inputs()
     out = enc(ids.cuda(), mask.cuda()).cpu()
+    # second call captures the forward as a CUDA graph, third and fourth replay it (the fourth with other inputs in between)
+    out2 = enc(ids.cuda(), mask.cuda()).cpu()
+    out3 = enc(ids.cuda(), mask.cuda()).cpu()
+    enc(ids.flip(1).cuda().contiguous(), mask.cuda())
+    out4 = enc(ids.cuda(), mask.cuda()).cpu()
+    assert torch.equal(out, out2) and torch.equal(out, out3) and torch.equal(out, out4), "graph replay differs from the eager forward"
     for u, n in zip(out, T5_CASE["lengths"]):
         u[n:] = 0
     torch.cuda.synchronize()
