@@ -43,6 +43,37 @@ __device__ __forceinline__ float fast_exp2(float x) {
   return y;
 }
 
+// 2^x for two values on the FMA / ALU pipes only (no MUFU, no conversion-pipe instruction): round x to the nearest
+// integer with the magic-number add (t = x + 1.5 * 2^23 holds round(x) in its low mantissa bits), evaluate a degree-3
+// minimax polynomial of 2^f on f = x - round(x) in [-0.5, 0.5] (max relative error 7.5e-5, 26x below the bf16 rounding
+// of P) and add round(x) to the exponent field.  Packed f32x2 arithmetic: 6 FMA-pipe + 4 ALU instructions per pair.
+// (Round 1's polynomial used floorf + float-to-int conversion, which issue on the same quarter-rate pipe as MUFU.)
+__device__ __forceinline__ float2 exp2_poly2(float2 x) {
+  x.x = fmaxf(x.x, -125.0f);
+  x.y = fmaxf(x.y, -125.0f);
+  const float2 t = __fadd2_rn(x, make_float2(12582912.0f, 12582912.0f));
+  const float2 xi = __fadd2_rn(t, make_float2(-12582912.0f, -12582912.0f));
+  const float2 f = __ffma2_rn(xi, make_float2(-1.0f, -1.0f), x);
+  float2 p = __ffma2_rn(f, make_float2(0.05517132207751274f, 0.05517132207751274f), make_float2(0.24261054396629333f, 0.24261054396629333f));
+  p = __ffma2_rn(p, f, make_float2(0.6932609677314758f, 0.6932609677314758f));
+  p = __ffma2_rn(p, f, make_float2(0.9999281167984009f, 0.9999281167984009f));
+  float2 e;
+  e.x = __int_as_float(__float_as_int(p.x) + (__float_as_int(t.x) << 23));
+  e.y = __int_as_float(__float_as_int(p.y) + (__float_as_int(t.y) << 23));
+  return e;
+}
+// Which of the 16 column pairs of a 32-column chunk take the polynomial (bit i = pair i); the others use MUFU.EX2.
+// The exponentials (16 / clk / SM on the XU pipe) need exactly as many cycles per KV step as the MMAs; moving a share of
+// them to the FMA pipe takes the softmax off the critical path.
+// 64 bits: 16 per 32-column chunk of the KV tile (bit 16 c + i = pair i of chunk c).  Measured on B200, same box
+// (tools/build_attn_variants.sh, profiles/r02w_attn_poly_share.json), Lq 4680 x S 18720 / 32760: no polynomial 443 / 752 us;
+// every 8th pair 445 / 750; **every 4th pair (25 %) 433 / 730 us (+2.4 .. 3 %)**; 31 % concentrated in the later chunks
+// 447 / 761; 37.5 % 468 / 789; 44 % 464 / 781; 50 % 480 / 814 -- beyond a quarter the extra FMA-pipe work costs more than
+// the MUFU cycles it frees (and shares that touch the first chunk spill: the 128 score registers are all live there).
+#ifndef ATT_POLY_MASK
+#define ATT_POLY_MASK 0x8888888888888888ull
+#endif
+
 template <int REGS>
 __device__ __forceinline__ void setmaxnreg_inc() { asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(REGS)); }
 template <int REGS>
@@ -455,8 +486,12 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_con
             const float2 x = __ffma2_rn(make_float2(__uint_as_float(s[c * 32 + 2 * i]), __uint_as_float(s[c * 32 + 2 * i + 1])),
                                         sl2v, negv);
             float2 e;
-            e.x = fast_exp2(x.x);
-            e.y = fast_exp2(x.y);
+            if ((ATT_POLY_MASK >> (16 * c + i)) & 1ull) {
+              e = exp2_poly2(x);
+            } else {
+              e.x = fast_exp2(x.x);
+              e.y = fast_exp2(x.y);
+            }
             if (i & 1) sum_b = __fadd2_rn(sum_b, e); else sum_a = __fadd2_rn(sum_a, e);
             pk[i] = pack_bf16(e.x, e.y);
           }
@@ -726,8 +761,8 @@ static int attention_launch(const void* q, long long q_row_stride, long long q_b
   }
   p.dbg = timing ? dbg_buf : nullptr;
 
-  // (measured in round 1 and removed: a degree-3 polynomial exp2 on the FMA pipe for 25 / 50 % of the exponentials --
-  // 1115 / 1063 vs 1166 TFLOP/s at Lq 4680 x S 32760 -- and integer-ALU bf16 packing of P: the softmax is issue-bound)
+  // (measured in round 1 and removed: integer-ALU bf16 packing of P; a polynomial exp2 built on floorf + float-to-int,
+  // which issue on the quarter-rate conversion pipe -- the magic-number form above replaced it)
   if (timing) {
     static SmemOptIn optin_t;
     if (int e = optin_t.ensure(attention_fwd_kernel<true>, ATT_SMEM_BYTES, "cudaFuncSetAttribute(attention, timing)")) return e;

@@ -544,8 +544,20 @@ class B200CausalWanModel(nn.Module):
         # cross-attention norms folded into the neighbouring kernels: per layer, if the folded K of this cache exists (or is
         # about to be written by this call)
         fold_ok = pk["fold"] and R > 128
-        fold = tuple(fold_ok and (not crossattn_cache[i]["is_init"] or (i, crossattn_cache[i]["k"].data_ptr()) in self._ck_fold)
-                     for i in range(NL))
+        for i in range(NL):       # entries this call will fill: right shape, and a buffer for the folded K (allocations stay
+            cc = crossattn_cache[i]    # out of the device work so that it can be captured as a CUDA graph)
+            if cc["is_init"]:
+                continue
+            ck = cc["k"]
+            if ck.shape != (B, self.text_len, NH, D) or not ck.is_contiguous() or not cc["v"].is_contiguous():
+                ck = torch.empty(B, self.text_len, NH, D, dtype=self.patch_embedding.weight.dtype, device=dev)
+                cc["k"], cc["v"] = ck, torch.empty_like(ck)
+            if fold_ok and (i, ck.data_ptr()) not in self._ck_fold:
+                if len(self._ck_fold) >= 4 * NL:      # callers that keep re-allocating their caches
+                    self._ck_fold.clear()
+                    self._graphs.clear()
+                self._ck_fold[(i, ck.data_ptr())] = torch.empty_like(ck)
+        fold = tuple(fold_ok and (i, crossattn_cache[i]["k"].data_ptr()) in self._ck_fold for i in range(NL))
         env = dict(fold=fold, ops=ops, pk=pk, ws=ws, sp=sp, dev=dev, mod_rows=mod_rows, Fm=Fm, B=B, F_=F_, H=H, W=W, Hh=Hh, Ww=Ww, fs=fs, L=L, Lr=Lr, off=off, R=R,
                    C=C, NL=NL, D=D, NH=NH, NHg=NHg, kv_cache=kv_cache, crossattn_cache=crossattn_cache, plans=plans,
                    need_ctx=need_ctx, start_frame=start_frame, current_start=current_start, skip_output=skip_output,
@@ -564,7 +576,7 @@ class B200CausalWanModel(nn.Module):
     def _run_device_work(self, x, t, context, env):
         """Runs (or replays) all kernels of one forward.  `env` = the prelude's local variables."""
         ops, sp, dev = env["ops"], env["sp"], env["dev"]
-        eligible = (self.use_cuda_graphs and not env["need_ctx"] and dev.type == "cuda"
+        eligible = (self.use_cuda_graphs and dev.type == "cuda"
                     and getattr(ops, "supports_cuda_graphs", False) and getattr(ops, "_prof", None) is None)
         if not eligible:
             return self._device_forward(x, t, context, env)
@@ -573,7 +585,12 @@ class B200CausalWanModel(nn.Module):
         # which is passed in device memory under replay, and the cache plan only through its device-visible fields -- so
         # in the steady state of a rolling-window video (same roll, same write slot, same window every chunk) ONE graph
         # per forward kind serves every chunk.
+        # The first forward of a prompt also fills the cross-attention cache from the text context: its own signature,
+        # with the context as a third static input.
+        need_ctx = env["need_ctx"]
+        fills = tuple(not c["is_init"] for c in ca[:NL]) if need_ctx else None
         key = (tuple(x.shape), tuple(t.shape), t.dtype, env["return_x0"], env["skip_output"], env["fold"],
+               fills, (tuple(context.shape), context.dtype) if need_ctx else None,
                tuple((p.roll, p.roll_src, p.roll_dst, p.roll_len, p.write_start, p.write_end, p.attn_start, p.attn_end)
                      for p in env["plans"]),
                tuple(c["k"].data_ptr() for c in kv[:NL]), tuple(c["v"].data_ptr() for c in kv[:NL]),
@@ -591,15 +608,16 @@ class B200CausalWanModel(nn.Module):
         if ent == "seen":                     # second occurrence: capture
             xs = torch.empty(x.shape, dtype=x.dtype, device=dev)
             ts = torch.empty(t.shape, dtype=t.dtype, device=dev)
+            cs = torch.empty_like(context) if need_ctx else None
             sf = torch.zeros(1, dtype=torch.int32, device=dev) if sp is None else None
             graph = torch.cuda.CUDAGraph()
             before = ops.launches
             with torch.cuda.graph(graph):
-                outs = self._device_forward(xs, ts, context, dict(env, start_frame_dev=sf))
-            ent = (graph, xs, ts, outs, ops.launches - before, sf, env["start_frame"])
+                outs = self._device_forward(xs, ts, cs if need_ctx else context, dict(env, start_frame_dev=sf, replay_sets_flags=True))
+            ent = (graph, xs, ts, outs, ops.launches - before, sf, env["start_frame"], cs)
             ops.launches = before
             self._graphs[key] = ent
-        graph, xs, ts, outs, n_launches, sf, sf_captured = ent
+        graph, xs, ts, outs, n_launches, sf, sf_captured, cs = ent
         if sf is not None:
             sf.fill_(env["start_frame"])
         elif sf_captured != env["start_frame"]:   # Ulysses: the frame offset is baked into the captured kernels
@@ -607,8 +625,13 @@ class B200CausalWanModel(nn.Module):
             return self._device_forward(x, t, context, env)
         xs.copy_(x)
         ts.copy_(t)
+        if cs is not None:
+            cs.copy_(context)
         graph.replay()
         ops.launches += n_launches
+        if need_ctx:
+            for c in ca[:NL]:
+                c["is_init"] = True
         if outs is None:
             return None
         if outs == "gather":
@@ -730,23 +753,14 @@ class B200CausalWanModel(nn.Module):
             # -- cross attention --
             cc = crossattn_cache[i]
             if not cc["is_init"]:
-                ck, cv = cc["k"], cc["v"]
-                if ck.shape != (B, self.text_len, NH, D) or not ck.is_contiguous() or not cv.is_contiguous():
-                    ck = torch.empty(B, self.text_len, NH, D, dtype=ws["x"].dtype, device=dev)
-                    cv = torch.empty_like(ck)
-                    cc["k"], cc["v"] = ck, cv
+                ck, cv = cc["k"], cc["v"]       # shape-checked (and the folded-K buffer allocated) by the host prelude
                 ops.gemm(ws["ctx"], pb["wkv_c"], pb["bkv_c"], None, seg_cols=C,
                          outs=[ws["ctx_k"], cv.view(B * self.text_len, C)])
                 ops.rmsnorm(ws["ctx_k"], ck.view(B * self.text_len, C), ca.norm_k.weight, self.eps)
                 if fold[i]:    # K with norm_q's weight multiplied in, kept beside the reference-visible cache entry
-                    kf = self._ck_fold.get((i, ck.data_ptr()))
-                    if kf is None:
-                        if len(self._ck_fold) >= 4 * NL:      # callers that keep re-allocating their caches
-                            self._ck_fold.clear()
-                            self._graphs.clear()
-                        kf = self._ck_fold[(i, ck.data_ptr())] = torch.empty_like(ck)
-                    ops.rmsnorm(ws["ctx_k"], kf.view(B * self.text_len, C), pb["gk_fold"], self.eps)
-                cc["is_init"] = True
+                    ops.rmsnorm(ws["ctx_k"], self._ck_fold[(i, ck.data_ptr())].view(B * self.text_len, C), pb["gk_fold"], self.eps)
+                if not env.get("replay_sets_flags"):
+                    cc["is_init"] = True
             if fold[i]:
                 # norm3 -> q -> norm_q -> attention as TWO launches: the q projection reads x directly (LayerNorm applied in
                 # its epilogue from the row statistics the o projection just wrote) and emits the statistics of q; the
