@@ -242,7 +242,13 @@ def test_long_rolling_video_vs_oracle_on_gpu():
     with patched_randn_like(3):      # and again: replays only, identical bits
         _, lat2 = pipe.inference(noise, ["synthetic"], return_latents=True)
     assert torch.equal(lat, lat2)
-    assert sum(1 for g in model._graphs.values() if g != "seen") == captured
+    # the only signature that recurs once per ROLLOUT rather than per chunk is the prompt's first forward (it also fills
+    # the cross-attention cache): its graph is captured here, on its second occurrence
+    assert sum(1 for g in model._graphs.values() if g != "seen") == captured + 1
+    with patched_randn_like(3):      # third rollout: every forward is a replay, still the same bits
+        _, lat3 = pipe.inference(noise, ["synthetic"], return_latents=True)
+    assert torch.equal(lat, lat3)
+    assert sum(1 for g in model._graphs.values() if g != "seen") == captured + 1
 
 
 def test_bidirectional_teacher_forward_on_gpu_matches_reference_golden():
