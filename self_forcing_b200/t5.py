@@ -188,7 +188,10 @@ class B200TextEncoder(torch.nn.Module):
             self.text_encoder.load_state_dict(state_dict)
 
     def forward(self, text_prompts: List[str]) -> dict:
-        ids, mask = self.tokenizer(text_prompts)
+        try:      # the reference's HuggingfaceTokenizer returns the mask only on request (wan_wrapper.py:38-40)
+            ids, mask = self.tokenizer(text_prompts, return_mask=True, add_special_tokens=True)
+        except TypeError:
+            ids, mask = self.tokenizer(text_prompts)
         context = self.text_encoder(ids, mask)
         for u, n in zip(context, mask.gt(0).sum(dim=1).long()):
             u[int(n):] = 0.0                                    # padding rows are zero (wan_wrapper.py:47-48)
