@@ -425,45 +425,50 @@ __global__ void sinusoid_kernel(const void* __restrict__ t, int t_dtype, __nv_bf
 // skinny linear: y[m][n] = bf16(sum_k in(x[m][k]) w[n][k] + b[n]), M <= 8 per pass; in = id | silu
 // ------------------------------------------------------------------------------------
 constexpr int SKINNY_M = 8;
+// Each block stages the (activated) input rows once and its 8 warps then walk `cols_per_warp` output columns each: with
+// one column per warp every block repeated the staging (8 x K loads + SiLU exponentials) for 24 KB of weights and the
+// three time-MLP launches took 36 us each against ~6 us of weight streaming (profiles/r02q_ncu_launch_shares.json).
 __global__ void __launch_bounds__(256)
 skinny_linear_kernel(const __nv_bfloat16* __restrict__ x, long long ldx, const __nv_bfloat16* __restrict__ w,
                      long long ldw, const __nv_bfloat16* __restrict__ bias, __nv_bfloat16* __restrict__ y,
-                     long long ldy, int M, int N, int K, int silu_in) {
+                     long long ldy, int M, int N, int K, int silu_in, int cols_per_warp) {
   extern __shared__ float xs[];   // [SKINNY_M][K] fp32 (already activated)
   const int m0 = blockIdx.y * SKINNY_M;
   const int mcount = min(SKINNY_M, M - m0);
-  for (int i = threadIdx.x; i < SKINNY_M * K; i += blockDim.x) {
+  for (int i = threadIdx.x; i < mcount * K; i += blockDim.x) {
     const int m = i / K, k = i - m * K;
-    float v = 0.f;
-    if (m < mcount) {
-      v = __bfloat162float(x[(m0 + m) * ldx + k]);
-      if (silu_in) v = bf16r(v / (1.0f + __expf(-v)));
-    }
+    float v = __bfloat162float(x[(m0 + m) * ldx + k]);
+    if (silu_in) v = bf16r(v / (1.0f + __expf(-v)));
     xs[i] = v;
   }
   __syncthreads();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int n = blockIdx.x * 8 + warp;
-  if (n >= N) return;
-  float acc[SKINNY_M];
+  for (int c = 0; c < cols_per_warp; ++c) {
+    const int n = (blockIdx.x * 8 + warp) * cols_per_warp + c;
+    if (n >= N) return;
+    float acc[SKINNY_M];
 #pragma unroll
-  for (int m = 0; m < SKINNY_M; ++m) acc[m] = 0.f;
-  for (int k0 = lane * 8; k0 < K; k0 += 256) {
-    float wv[8];
-    unpack8(ldg16(w + n * ldw + k0), wv);
+    for (int m = 0; m < SKINNY_M; ++m) acc[m] = 0.f;
+    for (int k0 = lane * 8; k0 < K; k0 += 256) {
+      float wv[8];
+      unpack8(ldg16(w + n * ldw + k0), wv);
 #pragma unroll
-    for (int m = 0; m < SKINNY_M; ++m) {
-      const float4 a = *reinterpret_cast<const float4*>(xs + m * K + k0);
-      const float4 c = *reinterpret_cast<const float4*>(xs + m * K + k0 + 4);
-      acc[m] += a.x * wv[0] + a.y * wv[1] + a.z * wv[2] + a.w * wv[3] + c.x * wv[4] + c.y * wv[5] + c.z * wv[6] +
-                c.w * wv[7];
+      for (int m = 0; m < SKINNY_M; ++m) {
+        if (m < mcount) {   // block-uniform
+          const float4 a = *reinterpret_cast<const float4*>(xs + m * K + k0);
+          const float4 c4 = *reinterpret_cast<const float4*>(xs + m * K + k0 + 4);
+          acc[m] += a.x * wv[0] + a.y * wv[1] + a.z * wv[2] + a.w * wv[3] + c4.x * wv[4] + c4.y * wv[5] + c4.z * wv[6] +
+                    c4.w * wv[7];
+        }
+      }
     }
-  }
 #pragma unroll
-  for (int m = 0; m < SKINNY_M; ++m) acc[m] = warp_sum(acc[m]);
-  if (lane == 0) {
-    const float bv = bias ? __bfloat162float(bias[n]) : 0.f;
-    for (int m = 0; m < mcount; ++m) y[(m0 + m) * ldy + n] = __float2bfloat16_rn(acc[m] + bv);
+    for (int m = 0; m < SKINNY_M; ++m)
+      if (m < mcount) acc[m] = warp_sum(acc[m]);
+    if (lane == 0) {
+      const float bv = bias ? __bfloat162float(bias[n]) : 0.f;
+      for (int m = 0; m < mcount; ++m) y[(m0 + m) * ldy + n] = __float2bfloat16_rn(acc[m] + bv);
+    }
   }
 }
 
@@ -756,9 +761,13 @@ extern "C" int sfb_skinny_linear(const void* x, long long ldx, const void* w, lo
   static SmemOptIn optin;
   if (smem > 48 * 1024)
     if (int e = optin.ensure(skinny_linear_kernel, (int)smem, "cudaFuncSetAttribute(skinny)")) return e;
-  dim3 grid((N + 7) / 8, (M + SKINNY_M - 1) / SKINNY_M);
+  // about two blocks per SM for the wide projection (N = 9216: 288 blocks of 32 columns), one column per warp when narrow
+  const int sms = device_sm_count();
+  int cpw = N / (8 * 2 * (sms > 0 ? sms : 148));
+  cpw = cpw < 1 ? 1 : (cpw > 8 ? 8 : cpw);
+  dim3 grid((N + 8 * cpw - 1) / (8 * cpw), (M + SKINNY_M - 1) / SKINNY_M);
   skinny_linear_kernel<<<grid, 256, smem, (cudaStream_t)stream>>>((const bf16*)x, ldx, (const bf16*)w, ldw,
-                                                                (const bf16*)bias, (bf16*)y, ldy, M, N, K, silu_in);
+                                                                (const bf16*)bias, (bf16*)y, ldy, M, N, K, silu_in, cpw);
   return check_cuda(cudaGetLastError(), "skinny_linear launch");
 }
 
