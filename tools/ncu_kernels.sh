@@ -3,6 +3,7 @@
 # Each capture runs only after the same command exited 0 without ncu.  Reports land in gpurun_out/<tag>_<name>.ncu-rep;
 # tools/ncu_summary.py turns them into profiles/<tag>_ncu_kernels.json (read by bench.py for roofline.traffic).
 TAG=${1:-r02}
+ONLY=${2:-.}      # regex on the capture names (default: all)
 OUT=gpurun_out
 mkdir -p $OUT
 cap() {   # name, kernel regex, launches to skip, microbench selector...
@@ -16,6 +17,7 @@ cap() {   # name, kernel regex, launches to skip, microbench selector...
 python tools/gpu_microbench.py attn_ gemm_qkv gemm_o_proj gemm_cross_q gemm_ffn elementwise > $OUT/${TAG}_plain_all.log 2>&1 || { echo "plain run failed"; tail -5 $OUT/${TAG}_plain_all.log; exit 1; }
 capq() {   # like cap, without the per-capture plain run (covered by the run above)
   local name=$1 regex=$2 skip=$3; shift 3
+  [[ $name =~ $ONLY ]] || return 0
   timeout 240 ncu --set full --clock-control none --import-source on -k regex:${regex} -s ${skip} -c 1 -f \
       -o $OUT/${TAG}_${name} python tools/gpu_microbench.py "$@" > $OUT/${TAG}_ncu_${name}.log 2>&1
   echo "ncu ${name} rc=$?"
