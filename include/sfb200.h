@@ -21,7 +21,7 @@
 extern "C" {
 #endif
 
-#define SFB_ABI_VERSION 10
+#define SFB_ABI_VERSION 11
 
 const char* sfb_last_error(void);
 int sfb_abi_version(void);
@@ -109,6 +109,12 @@ int sfb_modulation_table(const void* mod, const void* e, void* out, int NL, int 
 int sfb_ln_modulate(const void* x, long long ldx, void* y, long long ldy, int rows, int C, float eps,
                     const void* shift, const void* scale, long long mod_stride, int rows_per_mod, int row_offset,
                     void* stream);
+
+/* sfb_ln_modulate with the row's (mean, rstd) merged from the statistics records [rows][stats_ld] that the GEMM which
+ * produced x wrote (sfb_gemm_bf16_stats, stats_out): the rows are streamed, no reduction pass. */
+int sfb_ln_modulate_stats(const void* x, long long ldx, void* y, long long ldy, int rows, int C, float eps,
+                          const void* shift, const void* scale, long long mod_stride, int rows_per_mod, int row_offset,
+                          const void* stats, int stats_ld, void* stream);
 
 /* y = bf16(LN(x) * weight + bias)   (norm3, causal_model.py:268-270,324). */
 int sfb_ln_affine(const void* x, long long ldx, void* y, long long ldy, int rows, int C, float eps,

@@ -14,7 +14,7 @@ LIB_PATH = os.path.join(HERE, "libsfb200.so")
 P, LL, I, F = c_void_p, c_longlong, c_int, c_float
 PP = ctypes.POINTER(c_void_p)
 FP = ctypes.POINTER(c_float)   # host array of floats
-ABI_VERSION = 10
+ABI_VERSION = 11
 
 # name -> argtypes, mirroring include/sfb200.h one to one
 SIGNATURES = {
@@ -24,6 +24,7 @@ SIGNATURES = {
     "sfb_attention_fwd_qnorm": [P, LL, LL, P, P, LL, LL, P, LL, LL, I, I, I, I, I, F, P, I, F, P, LL, P],
     "sfb_modulation_table": [P, P, P, I, I, I, I, LL, LL, P],
     "sfb_ln_modulate": [P, LL, P, LL, I, I, F, P, P, LL, I, I, P],
+    "sfb_ln_modulate_stats": [P, LL, P, LL, I, I, F, P, P, LL, I, I, P, I, P],
     "sfb_ln_affine": [P, LL, P, LL, I, I, F, P, P, P],
     "sfb_rmsnorm": [P, LL, P, LL, I, I, F, P, P],
     "sfb_qk_norm_rope": [P, LL, P, LL, P, LL, P, P, F, P, P, I, I, I, I, I, I, I, I, I, P, P, LL, LL, P, P, LL, LL, P],

@@ -135,6 +135,52 @@ ln_kernel(const __nv_bfloat16* __restrict__ x, long long ldx, __nv_bfloat16* __r
   }
 }
 
+// Streaming form of LayerNorm + adaLN modulation: the row's (mean, rstd) come from the statistics records the GEMM that
+// produced x wrote in its epilogue (sfb_gemm_bf16_stats), so there is no reduction pass over the data and every 16-byte
+// vector is loaded, normalised, modulated and stored on its own.  (The resident-row kernel above is instruction-bound:
+// three unpack passes, 52 % issue-active at 2.9 TB/s -- profiles/r02_ncu_kernels.json.)
+template <int NV>
+__global__ void __launch_bounds__(ROW_WARPS * 32, row_kernel_blocks(NV))
+ln_stream_kernel(const __nv_bfloat16* __restrict__ x, long long ldx, __nv_bfloat16* __restrict__ y, long long ldy, int rows,
+                 float eps, const __nv_bfloat16* __restrict__ shift, const __nv_bfloat16* __restrict__ scale,
+                 long long mod_stride, int rows_per_mod, int row_offset, const float2* __restrict__ stats, int stats_ld) {
+  constexpr int C = NV * 256, CHUNKS = C / STATS_CHUNK;
+  const int row = blockIdx.x * ROW_WARPS + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (row >= rows) return;
+  // Chan's merge of the chunk records, one record (or a few) per lane
+  const float2* rec = stats + (long long)row * stats_ld;
+  float msum = 0.f;
+  for (int j = lane; j < CHUNKS; j += 32) msum += __ldg(rec + j).x;
+  const float mean = warp_sum(msum) * (1.0f / CHUNKS);
+  float m2 = 0.f;
+  for (int j = lane; j < CHUNKS; j += 32) {
+    const float2 r = __ldg(rec + j);
+    const float d = r.x - mean;
+    m2 += r.y + (float)STATS_CHUNK * d * d;
+  }
+  const float rstd = rsqrtf(warp_sum(m2) * (1.0f / C) + eps);
+  const long long mrow = (long long)((row + row_offset) / rows_per_mod) * mod_stride;
+#pragma unroll
+  for (int k = 0; k < NV; ++k) {
+    const int c0 = (k * 32 + lane) * 8;
+    float v[8], o[8];
+    unpack8(ldg16(x + row * ldx + c0), v);
+    const uint4 scq = ldg16(scale + mrow + c0), shq = ldg16(shift + mrow + c0);
+    const uint32_t scw[4] = {scq.x, scq.y, scq.z, scq.w}, shw[4] = {shq.x, shq.y, shq.z, shq.w};
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      // bf16(bf16(LN(x)) * bf16(1 + scale)) + shift, two elements at a time (same rounding chain as ln_kernel)
+      const uint32_t n2 = round_pair((v[2 * i] - mean) * rstd, (v[2 * i + 1] - mean) * rstd);
+      const uint32_t s2 = round_pair(1.0f + bf_lo(scw[i]), 1.0f + bf_hi(scw[i]));
+      const uint32_t p2 = mul_bf16x2(n2, s2);
+      o[2 * i] = bf_lo(p2) + bf_lo(shw[i]);
+      o[2 * i + 1] = bf_hi(p2) + bf_hi(shw[i]);
+    }
+    *reinterpret_cast<uint4*>(y + row * ldy + c0) = pack8(o);
+  }
+}
+
 // ------------------------------------------------------------------------------------
 // RMSNorm over the full channel width (+ optional 3-D RoPE), NV = C / 256
 // ------------------------------------------------------------------------------------
@@ -602,6 +648,20 @@ extern "C" int sfb_ln_modulate(const void* x, long long ldx, void* y, long long 
         (const bf16*)x, ldx, (bf16*)y, ldy, rows, eps, (const bf16*)shift, (const bf16*)scale, mod_stride, rows_per_mod,
         row_offset, nullptr, nullptr);
     return check_cuda(cudaGetLastError(), "ln_modulate launch");
+  });
+}
+
+// sfb_ln_modulate with the row statistics supplied by the GEMM that produced x (include/sfb200.h).
+extern "C" int sfb_ln_modulate_stats(const void* x, long long ldx, void* y, long long ldy, int rows, int C, float eps,
+                                     const void* shift, const void* scale, long long mod_stride, int rows_per_mod,
+                                     int row_offset, const void* stats, int stats_ld, void* stream) {
+  if (rows <= 0 || rows_per_mod <= 0 || row_offset < 0 || (ldx % 8) || (ldy % 8) || (mod_stride % 8)) { set_error("sfb_ln_modulate_stats: bad arguments"); return SFB_ERR_INVALID; }
+  if (stats == nullptr || stats_ld < C / STATS_CHUNK) { set_error("sfb_ln_modulate_stats: statistics records [%d] do not cover C=%d", stats_ld, C); return SFB_ERR_INVALID; }
+  return dispatch_nv(C, "sfb_ln_modulate_stats", [&](auto nv) {
+    ln_stream_kernel<decltype(nv)::value><<<(rows + ROW_WARPS - 1) / ROW_WARPS, ROW_WARPS * 32, 0, (cudaStream_t)stream>>>(
+        (const bf16*)x, ldx, (bf16*)y, ldy, rows, eps, (const bf16*)shift, (const bf16*)scale, mod_stride, rows_per_mod,
+        row_offset, (const float2*)stats, stats_ld);
+    return check_cuda(cudaGetLastError(), "ln_modulate_stats launch");
   });
 }
 

@@ -96,4 +96,4 @@ int make_tmap_bf16(CUtensorMap* out, const void* base, int rank, const uint64_t*
 
 extern "C" const char* sfb_last_error(void) { return sfb::g_err; }
 
-extern "C" int sfb_abi_version(void) { return 10; }
+extern "C" int sfb_abi_version(void) { return 11; }

@@ -691,6 +691,9 @@ class B200CausalWanModel(nn.Module):
             ops.kv_roll(tensors, self._pointer_table(tensors, dev), dst, src, n)
 
         # QK-RMSNorm statistics from the QKV projection's epilogue: qk_norm_rope then streams its rows (no reduction pass)
+        stream_ln = pk["fold"] and R > 128 and os.environ.get("SFB_NO_STREAM_LN", "0") != "1"   # adaLN LayerNorms stream their rows too (statistics of x from its producer; the variable is an A/B knob)
+        x_stats_out = dict(stats_out=ws["x_stats"]) if stream_ln else {}
+        x_stats_in = dict(stats=ws["x_stats"]) if stream_ln else {}
         stream_rope = pk["fold"] and R > 128 and D == 128 and sp is None
         qkv_stats = dict(stats_out=ws["qkv_stats"]) if stream_rope else {}
         rope_stats = dict(stats=ws["qkv_stats"], q_chunk0=0, k_chunk0=C // STATS_CHUNK) if stream_rope else {}
@@ -700,8 +703,10 @@ class B200CausalWanModel(nn.Module):
             m = mod[i]   # [B*F, 6, C]
             sa, ca = blk.self_attn, blk.cross_attn
             # -- self attention --
+            # (x_stats always describes the current x from here on: every GEMM that writes x writes its records too;
+            # the patch embedding in front of layer 0 is a one-CTA GEMM without statistics)
             ops.ln_modulate(ws["x"], ws["h"], shift=m[:, 0], scale=m[:, 1], mod_stride=mstride, rows_per_mod=mod_rows,
-                            eps=self.eps, row_offset=off)
+                            eps=self.eps, row_offset=off, **(x_stats_in if i > 0 else {}))
             kc, vc = cache["k"], cache["v"]
             if kc.shape[0] != B or kc.shape[2] != NHg or kc.shape[3] != D:
                 raise ValueError(f"kv_cache[{i}]['k'] shape {tuple(kc.shape)} does not match B={B}, H={NHg}, D={D}")
@@ -728,7 +733,7 @@ class B200CausalWanModel(nn.Module):
                 sp.barrier(ops)          # every head group's output columns have landed
                 ops.gemm(attn_peer.local, sa.o.weight, sa.o.bias, ws["x"], epilogue=EPI_GATE_RES, residual=ws["x"],
                          gate=m[:, 2], gate_stride=mstride, rows_per_gate=mod_rows, gate_row_offset=off,
-                         **(dict(stats_out=ws["x_stats"]) if fold[i] else {}))
+                         **(x_stats_out if (fold[i] or stream_ln) else {}))
             elif B == 1:   # V projection lands directly in its cache slot
                 ops.gemm(ws["h"], pb["wqkv"], pb["bqkv"], None, seg_cols=C,
                          outs=[ws["q_lin"], ws["k_lin"], v_slot.view(L, C)], **qkv_stats)   # .view: a non-viewable cache layout must raise
@@ -749,7 +754,7 @@ class B200CausalWanModel(nn.Module):
                               ws["attn"].view(B, L, NH, D), scale)
                 ops.gemm(ws["attn"], sa.o.weight, sa.o.bias, ws["x"], epilogue=EPI_GATE_RES, residual=ws["x"],
                          gate=m[:, 2], gate_stride=mstride, rows_per_gate=mod_rows,
-                         **(dict(stats_out=ws["x_stats"]) if fold[i] else {}))
+                         **(x_stats_out if (fold[i] or stream_ln) else {}))
             # -- cross attention --
             cc = crossattn_cache[i]
             if not cc["is_init"]:
@@ -774,13 +779,14 @@ class B200CausalWanModel(nn.Module):
                 ops.gemm(ws["h"], ca.q.weight, ca.q.bias, ws["q_lin"])
                 ops.rmsnorm(ws["q_lin"], ws["q"], ca.norm_q.weight, self.eps)
                 ops.attention(q4, cc["k"], cc["v"], ws["attn"].view(B, Lr, NH, D), scale)
-            ops.gemm(ws["attn"], ca.o.weight, ca.o.bias, ws["x"], epilogue=EPI_RESIDUAL, residual=ws["x"])
+            ops.gemm(ws["attn"], ca.o.weight, ca.o.bias, ws["x"], epilogue=EPI_RESIDUAL, residual=ws["x"], **x_stats_out)
             # -- feed forward --
             ops.ln_modulate(ws["x"], ws["h"], shift=m[:, 3], scale=m[:, 4], mod_stride=mstride, rows_per_mod=mod_rows,
-                            eps=self.eps, row_offset=off)
+                            eps=self.eps, row_offset=off, **x_stats_in)
             ops.gemm(ws["h"], blk.ffn[0].weight, blk.ffn[0].bias, ws["ffn"], epilogue=EPI_GELU)
             ops.gemm(ws["ffn"], blk.ffn[2].weight, blk.ffn[2].bias, ws["x"], epilogue=EPI_GATE_RES,
-                     residual=ws["x"], gate=m[:, 5], gate_stride=mstride, rows_per_gate=mod_rows, gate_row_offset=off)
+                     residual=ws["x"], gate=m[:, 5], gate_stride=mstride, rows_per_gate=mod_rows, gate_row_offset=off,
+                     **x_stats_out)
 
         if skip_output:
             return None
@@ -788,7 +794,7 @@ class B200CausalWanModel(nn.Module):
         # ---- head ------------------------------------------------------------------------------
         hm = ws["head_mod"][0]   # [B*F, 2, C]
         ops.ln_modulate(ws["x"], ws["h"], shift=hm[:, 0], scale=hm[:, 1], mod_stride=2 * C, rows_per_mod=mod_rows,
-                        eps=self.eps, row_offset=off)
+                        eps=self.eps, row_offset=off, **(x_stats_in if NL > 0 else {}))
         ops.gemm(ws["h"], self.head.head.weight, self.head.head.bias, ws["head_out"])
         if env.get("defer_gather"):
             return "gather"          # Ulysses under graph capture: the NCCL gather + unpatchify run outside the graph

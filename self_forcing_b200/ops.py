@@ -173,8 +173,18 @@ class CudaOps:
                    "sfb_modulation_table")
 
     @_op
-    def ln_modulate(self, x, y, shift, scale, mod_stride: int, rows_per_mod: int, eps: float, row_offset: int = 0):
+    def ln_modulate(self, x, y, shift, scale, mod_stride: int, rows_per_mod: int, eps: float, row_offset: int = 0,
+                    stats=None):
+        """stats: fp32 [rows, C / 128, 2] statistics records of x from the GEMM that wrote it -> streaming kernel."""
         _check_2d(x, "x"); _check_2d(y, "y")
+        if stats is not None:
+            assert stats.dtype == torch.float32 and stats.is_contiguous() and stats.dim() == 3 \
+                and stats.shape[0] == x.shape[0] and stats.shape[2] == 2
+            _lib.check(self.lib.sfb_ln_modulate_stats(
+                x.data_ptr(), x.stride(0), y.data_ptr(), y.stride(0), x.shape[0], x.shape[1], eps, shift.data_ptr(),
+                scale.data_ptr(), mod_stride, rows_per_mod, row_offset, stats.data_ptr(), stats.shape[1], self._stream()),
+                "sfb_ln_modulate_stats")
+            return
         _lib.check(self.lib.sfb_ln_modulate(x.data_ptr(), x.stride(0), y.data_ptr(), y.stride(0), x.shape[0],
                                             x.shape[1], eps, shift.data_ptr(), scale.data_ptr(), mod_stride,
                                             rows_per_mod, row_offset, self._stream()), "sfb_ln_modulate")

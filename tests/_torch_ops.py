@@ -89,8 +89,13 @@ class TorchOps:
                 base = r * e_row_stride + g * e_group_stride
                 out[:, r, g] = mod[:, g] + ef[base:base + C]
 
-    def ln_modulate(self, x, y, shift, scale, mod_stride, rows_per_mod, eps, row_offset=0):
+    def ln_modulate(self, x, y, shift, scale, mod_stride, rows_per_mod, eps, row_offset=0, stats=None):
         self.launches += 1
+        if stats is not None:     # the records must describe the rows handed in (sfb_ln_modulate_stats)
+            self.log.append("ln_modulate_stats")
+            mean, var = self._stats_mean_var(stats)
+            xf = x.float()
+            assert torch.allclose(mean, xf.mean(dim=1), rtol=1e-4, atol=1e-4) and torch.allclose(var, xf.var(dim=1, unbiased=False), rtol=1e-3, atol=1e-4)
         n = F.layer_norm(x, (x.shape[1],), None, None, eps)
         idx = (torch.arange(x.shape[0]) + row_offset) // rows_per_mod
         y.copy_(n * (1 + scale[idx]) + shift[idx])

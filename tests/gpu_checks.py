@@ -265,6 +265,26 @@ def check_ln_modulate(rows=777, C=1536, rpm=200, seed=0):
     return _against_double("ln_modulate", run, dict(y=torch.zeros(rows, C, device="cuda", dtype=BF)))
 
 
+def check_ln_modulate_stats(rows=777, C=1536, rpm=200, seed=0, mean_shift=0.3, row_offset=0):
+    """Streaming form fed by statistics records against the resident-row kernel (only the summation order of the row
+    statistics differs) and against the torch double."""
+    ops = _ops()
+    x = (_randn(rows, C, seed=seed, scale=2.0).float() + mean_shift).to(BF)
+    tab = _randn((rows + row_offset + rpm - 1) // rpm, 6, C, seed=seed + 1, scale=0.5)
+    stats = _stats_ref(x).contiguous()
+    kw = dict(shift=tab[:, 3], scale=tab[:, 4], mod_stride=6 * C, rows_per_mod=rpm, eps=1e-6, row_offset=row_offset)
+    y0 = torch.zeros(rows, C, device="cuda", dtype=BF)
+    y1 = torch.full((rows, C), float("nan"), device="cuda", dtype=BF)
+    ops.ln_modulate(x, y0, **kw)
+    ops.ln_modulate(x, y1, stats=stats, **kw)
+    yr = torch.zeros(rows, C, device="cuda", dtype=BF)
+    TorchOps().ln_modulate(x, yr, **kw)
+    m = dict(err_vs_resident=rel_l2(y1, y0), err_vs_double=rel_l2(y1, yr), mismatch_frac=float((y1 != y0).float().mean()),
+             nan=int(torch.isnan(y1.float()).sum()))
+    assert m["nan"] == 0 and m["mismatch_frac"] <= 5e-3, m
+    return _finish("ln_modulate_stats", m, 3e-3)
+
+
 def check_ln_affine(rows=333, C=1536, seed=0):
     x = _randn(rows, C, seed=seed, scale=2.0) - 0.2
     w, b = _randn(C, seed=seed + 1) * 0.1 + 1, _randn(C, seed=seed + 2) * 0.1
@@ -862,6 +882,9 @@ ALL = {
     "attn_half_cross_full": lambda: check_attention(Lq=4680, S=512, H=12, seed=13),           # cross-attention of a chunk
     "attn_half_split_long": lambda: check_attention(Lq=4680, S=18720, H=12, seed=14),         # split schedule with half items
     "ln_modulate": check_ln_modulate,
+    "ln_modulate_stats": check_ln_modulate_stats,
+    "ln_modulate_stats_chunk": lambda: check_ln_modulate_stats(rows=4680, rpm=1560, seed=3, mean_shift=-1.5),
+    "ln_modulate_stats_offset": lambda: check_ln_modulate_stats(rows=300, rpm=130, seed=4, mean_shift=20.0, row_offset=77),
     "ln_affine": check_ln_affine,
     "rmsnorm": check_rmsnorm,
     "qk_norm_rope": check_qk_norm_rope,

@@ -134,6 +134,9 @@ def main():
             ("rmsnorm", 2 * L * C * 2, lambda: ops.rmsnorm(x, y, w, 1e-6)),
             ("qk_norm_rope", 6 * L * C * 2, lambda: ops.qk_norm_rope(qkv[:, :C], qkv[:, C:2 * C], qkv[:, 2 * C:], w, w, 1e-6, cos, sin, 1, L, 128, (3, 30, 52), 0, q_out=qo, k_out=kc, v_out=vc)),
         ]
+        x_stats = torch.rand(L, 12, 2, device="cuda") + 0.5
+        cases.append(("ln_modulate_stats", 2 * L * C * 2, lambda: ops.ln_modulate(x, y, shift=tab[:, 0], scale=tab[:, 1], mod_stride=6 * C,
+                                                                                rows_per_mod=1560, eps=1e-6, stats=x_stats)))
         qkv_stats = torch.rand(L, 36, 2, device="cuda") + 0.5
         cases.append(("qk_norm_rope_stats", 6 * L * C * 2, lambda: ops.qk_norm_rope(
             qkv[:, :C], qkv[:, C:2 * C], qkv[:, 2 * C:], w, w, 1e-6, cos, sin, 1, L, 128, (3, 30, 52), 0, q_out=qo, k_out=kc,

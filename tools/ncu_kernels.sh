@@ -31,6 +31,6 @@ capq gemm_o_proj_stats  gemm2_bf16_kernel 3 gemm_o_proj_stats
 capq gemm_cross_q_fold  gemm2_bf16_kernel 3 gemm_cross_q_fold
 capq gemm_ffn1    gemm2_bf16_kernel 3 gemm_ffn1
 capq gemm_ffn2    gemm2_bf16_kernel 3 gemm_ffn2
-capq ln_modulate  "ln_kernel.*Lb0" 3 elementwise
+capq ln_modulate  "ln_kernel" 3 elementwise
 capq qk_rope_stream "qk_rope_stream_kernel" 3 elementwise
 ls -la $OUT | grep ${TAG}_ | grep ncu-rep
