@@ -690,10 +690,12 @@ class B200CausalWanModel(nn.Module):
             tensors = [kv_cache[i][name] for i in layers for name in ("k", "v")]
             ops.kv_roll(tensors, self._pointer_table(tensors, dev), dst, src, n)
 
-        # QK-RMSNorm statistics from the QKV projection's epilogue: qk_norm_rope then streams its rows (no reduction pass)
-        stream_ln = pk["fold"] and R > 128 and os.environ.get("SFB_NO_STREAM_LN", "0") != "1"   # adaLN LayerNorms stream their rows too (statistics of x from its producer; the variable is an A/B knob)
+        # Row statistics instead of reduction passes: every GEMM that writes the residual stream x
+        # also writes its records, and the adaLN LayerNorms stream their rows (SFB_NO_STREAM_LN=1: A/B knob) ...
+        stream_ln = pk["fold"] and R > 128 and os.environ.get("SFB_NO_STREAM_LN", "0") != "1"
         x_stats_out = dict(stats_out=ws["x_stats"]) if stream_ln else {}
         x_stats_in = dict(stats=ws["x_stats"]) if stream_ln else {}
+        # ... and the QKV projection writes the q / k records that let qk_norm_rope stream as well
         stream_rope = pk["fold"] and R > 128 and D == 128 and sp is None
         qkv_stats = dict(stats_out=ws["qkv_stats"]) if stream_rope else {}
         rope_stats = dict(stats=ws["qkv_stats"], q_chunk0=0, k_chunk0=C // STATS_CHUNK) if stream_rope else {}
