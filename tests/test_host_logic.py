@@ -347,3 +347,44 @@ def test_cross_attention_norm_fold_matches_the_unfolded_schedule():
     assert log_fold.count("gemm") == log_ref.count("gemm")
     assert log_fold.count("attention_qnorm") == 2 * 3 and log_ref.count("attention_qnorm") == 0
     assert rel_l2(got, ref) <= 2e-5
+
+
+def test_cross_attention_fold_falls_back_for_caches_filled_elsewhere():
+    """The folded cross-attention needs a private copy of the text K with norm_q's weight multiplied in.  A cache entry
+    that is already initialised but has no such copy (filled by another model instance) must take the unfolded schedule
+    -- same result -- and the copy table stays bounded when callers keep re-allocating their caches."""
+    from self_forcing_b200.model import B200CausalWanModel
+
+    class StatsOps(TorchOps):
+        supports_row_stats = True
+
+    def make():
+        m = B200CausalWanModel(dim=256, ffn_dim=256, num_heads=2, num_layers=2, text_dim=512, ops=StatsOps())
+        m.init_weights(5)
+        return m
+
+    torch.manual_seed(1)
+    fs, F_ = 8 * 20, 1
+    ctx = torch.randn(1, 512, 512)
+    x = torch.randn(1, 16, F_, 16, 40)
+    t = torch.full((1, F_), 300.0)
+
+    def caches(m):
+        kv = m.allocate_kv_cache(1, 2 * fs, torch.float32, torch.device("cpu"))
+        ca = [dict(k=torch.zeros(1, 512, 2, 128), v=torch.zeros(1, 512, 2, 128), is_init=False) for _ in range(2)]
+        return kv, ca
+
+    a = make()
+    kv_a, ca = caches(a)
+    ref = a(x, t=t, context=ctx, seq_len=32760, kv_cache=kv_a, crossattn_cache=ca, current_start=0)
+    assert a.ops.log.count("attention_qnorm") == 2 and all(c["is_init"] for c in ca)
+    b = make()                                    # same weights, but it never saw these cache entries being filled
+    kv_b, _ = caches(b)
+    out = b(x, t=t, context=ctx, seq_len=32760, kv_cache=kv_b, crossattn_cache=ca, current_start=0)
+    assert b.ops.log.count("attention_qnorm") == 0            # unfolded schedule for both layers
+    assert rel_l2(out, ref) <= 2e-5
+    # a caller that re-allocates its cross-attention cache on every call cannot grow the table without bound
+    for _ in range(12):
+        kv_c, ca_c = caches(a)
+        a(x, t=t, context=ctx, seq_len=32760, kv_cache=kv_c, crossattn_cache=ca_c, current_start=0)
+    assert len(a._ck_fold) <= 4 * a.num_layers
