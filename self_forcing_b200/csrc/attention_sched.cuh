@@ -40,6 +40,7 @@ constexpr int ATT_KV_STAGES = 2;
 constexpr int ATT_XCHG_BYTES = 2 * ATT_BM * 8;      // half items: (m, l) of slot 1's rows, double buffered by segment parity
 constexpr int ATT_SMEM_BYTES = 2 * ATT_TILE_BYTES + 2 * ATT_KV_STAGES * ATT_TILE_BYTES + 1024 + 256 + ATT_XCHG_BYTES;
 constexpr int ATT_SLOT_FLOATS = ATT_BM * ATT_D / 2 + 2 * ATT_BM;   // one (tile, segment) partial: O / l as fp16 pairs [64 column pairs][128 rows], then m, l (fp32)
+constexpr int ATT_MIN_SPLIT_KV_TILES_MANY_TILES = 160;          // same, when there are at least two query tiles per SM (see att_plan)
 constexpr int ATT_MIN_SPLIT_KV_TILES = 48;                     // shorter KV (measured: S = 4680 is better whole, S >= 9360 split): whole items per CTA
 constexpr int ATT_MAX_GROUPS = 4;
 constexpr long long ATT_L2_BUDGET = 72ll << 20;                // K + V bytes of the heads in flight (L2 is 126 MB; measured: 3 groups of 4 heads beat 4 x 3 and 6 x 2 at S = 32760)
@@ -153,7 +154,11 @@ inline int att_plan(AttnParams& p, int B, int Lq, int Skv, int H, int sms, long 
   const char* nosplit = getenv("SFB_ATTN_NOSPLIT");
   // (with >= 8 items per SM whole items already balance to within a few per cent, and consecutive CTAs walk the same
   // head's K/V together -- no partials, natural L2 locality: the 14B teacher has 5120 items)
-  int min_split = ATT_MIN_SPLIT_KV_TILES;
+  // split threshold: with at least two tiles per SM the tile-granular whole-item mode fills the machine by itself and
+  // measured faster than the split up to ~160 KV tiles (S = 9360 / 14040 / 18720: 238.6 / 335.0 / 429.1 -> 226.2 / 322.4 /
+  // 422.9 us, equal at 23400: no partials, no combine pass; beyond that the head groups' L2 residency wins); problems with
+  // fewer tiles (head-parallel ranks, small batches of short chunks) need the split to use all SMs
+  int min_split = tiles >= 2 * sms ? ATT_MIN_SPLIT_KV_TILES_MANY_TILES : ATT_MIN_SPLIT_KV_TILES;
   if (const char* env = getenv("SFB_ATTN_MIN_SPLIT")) { if (atoi(env) > 0) min_split = atoi(env); }   // diagnostic
   p.split = (p.items % sms != 0 && p.items < 8 * sms && p.n_kv_tiles >= min_split &&
              workspace_bytes >= slot_bytes && !(nosplit && nosplit[0] == '1')) ? 1 : 0;
